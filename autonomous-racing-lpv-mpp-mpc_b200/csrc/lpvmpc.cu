@@ -1,0 +1,548 @@
+// Kernels and C-ABI (include/lpvmpc.h) of the B200-native batched LPV-MPC QP solver.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "lpvmpc.h"
+#include "lpv_model.cuh"
+#include "lpv_qp.cuh"
+
+namespace lpv {
+
+// ------------------------------------------------------------------------------------------------
+// Scheduling inside the solve kernel: fills G = -[A_k B_k] of the warp's workspace.
+// Returns (warp-uniform) nonzero when Curvature() failed for any stage.
+template <int KIND>
+__device__ int schedule_into(QP<KIND> &qp, const Params &p, int b, double *x0_eff) {
+  constexpr int NX = QP<KIND>::NX, NB = QP<KIND>::NB;
+  const Layout &L = qp.L;
+  const Model &M = qp.M;
+  const int N = L.N, lane = qp.lane;
+  double *G = qp.w + L.G;
+  const lpvmpc_args &a = p.a;
+  int err = 0;
+  if (a.sched_mode == LPVMPC_SCHED_GIVEN) {
+    for (int e = lane; e < N * NX * NB; e += 32) {
+      const int k = e / (NX * NB), rc = e - k * NX * NB, r = rc / NB, c = rc - r * NB;
+      const double v = (c < NX) ? a.A[((size_t)b * N + k) * NX * NX + r * NX + c]
+                                : a.Bm[((size_t)b * N + k) * NX * NU + r * NU + (c - NX)];
+      G[e] = -v;
+    }
+    for (int r = lane; r < NX; r += 32) x0_eff[r] = a.x0[(size_t)b * NX + r];
+  } else if (a.sched_mode == LPVMPC_SCHED_PREDICT) {
+    if (lane == 0) {
+      double st[NX], Ai[NX * NX], Bi[NX * NU];
+      const double *xs = a.x_sched ? a.x_sched + (size_t)b * NX : a.x0 + (size_t)b * NX;
+#pragma unroll
+      for (int r = 0; r < NX; ++r) st[r] = xs[r];
+      const double *up = a.u_prev + (size_t)b * N * NU;
+      const int lap = a.lap ? a.lap[b] : a.lap_all;
+      for (int i = 0; i < N; ++i) {
+        if (KIND == LPVMPC_CONTROLLER) {
+          const double cur = (lap == 0) ? curvature(M.track, M.nseg, st[4], err) : a.curv_ref[(size_t)b * N + i];
+          ctrl_stage(M, a.Cf_new, a.Cf_new, a.vel_ref[(size_t)b * (N + 1) + i], st[1], st[3], st[5], cur, up[i * NU], Ai, Bi);
+        } else {
+          const double cur = curvature(M.track, M.nseg, a.SS[(size_t)b * (N + 1) + i], err);
+          plan_stage(M, st[0], st[1], st[3], st[4], cur, up[i * NU], Ai, Bi);
+        }
+#pragma unroll
+        for (int r = 0; r < NX; ++r) {
+#pragma unroll
+          for (int c = 0; c < NX; ++c) G[(size_t)(i * NX + r) * NB + c] = -Ai[r * NX + c];
+#pragma unroll
+          for (int c = 0; c < NU; ++c) G[(size_t)(i * NX + r) * NB + NX + c] = -Bi[r * NU + c];
+        }
+        if (a.A_out) for (int e = 0; e < NX * NX; ++e) a.A_out[((size_t)b * N + i) * NX * NX + e] = Ai[e];
+        if (a.B_out) for (int e = 0; e < NX * NU; ++e) a.B_out[((size_t)b * N + i) * NX * NU + e] = Bi[e];
+        propagate<NX>(Ai, Bi, up + i * NU, st);
+        if (a.states_out) for (int r = 0; r < NX; ++r) a.states_out[((size_t)b * N + i) * NX + r] = st[r];
+        if (i == 0) {
+#pragma unroll
+          for (int r = 0; r < NX; ++r) x0_eff[r] = a.x0_from_prediction ? st[r] : a.x0[(size_t)b * NX + r];
+        }
+      }
+    }
+  } else {  // ESTIMATE: stages are independent
+    for (int i = lane; i < N; i += 32) {
+      double Ai[NX * NX], Bi[NX * NU];
+      const double *t = a.traj + ((size_t)b * N + i) * 6;
+      const double delta = a.u_prev[((size_t)b * N + i) * NU];
+      if (KIND == LPVMPC_CONTROLLER) {
+        const double cur = curvature(M.track, M.nseg, t[4], err);
+        ctrl_stage(M, M.Cf, M.Cr, t[0], t[1], t[3], t[5], cur, delta, Ai, Bi);
+      } else {
+        const double cur = curvature(M.track, M.nseg, t[5], err);
+        plan_stage(M, t[0], t[1], t[3], t[4], cur, delta, Ai, Bi);
+      }
+      for (int r = 0; r < NX; ++r) {
+        for (int c = 0; c < NX; ++c) G[(size_t)(i * NX + r) * NB + c] = -Ai[r * NX + c];
+        for (int c = 0; c < NU; ++c) G[(size_t)(i * NX + r) * NB + NX + c] = -Bi[r * NU + c];
+      }
+      if (a.A_out) for (int e = 0; e < NX * NX; ++e) a.A_out[((size_t)b * N + i) * NX * NX + e] = Ai[e];
+      if (a.B_out) for (int e = 0; e < NX * NU; ++e) a.B_out[((size_t)b * N + i) * NX * NU + e] = Bi[e];
+    }
+    for (int r = lane; r < NX; r += 32) x0_eff[r] = a.x0[(size_t)b * NX + r];
+  }
+  __syncwarp();
+  return __any_sync(kFull, err);
+}
+
+// One warp per QP, persistent over the batch.
+template <int KIND, bool SMEM>
+__global__ void __launch_bounds__(32) lpv_solve_kernel(const __grid_constant__ Params p) {
+  extern __shared__ double smem[];
+  constexpr int NX = QP<KIND>::NX;
+  const int lane = threadIdx.x;
+  const Layout &L = p.L;
+  double *w = SMEM ? smem : p.gws + (size_t)blockIdx.x * L.total;
+  QP<KIND> qp(L, p.M, w, lane);
+  const lpvmpc_args &a = p.a;
+  for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+    double *x0_eff = w + L.xt;  // free until the first ADMM step
+    const int sched_err = schedule_into<KIND>(qp, p, b, x0_eff);
+    Outcome out;
+    out.status = LPVMPC_UNSOLVED; out.iter = 0; out.rho_updates = 0; out.polish_status = 0;
+    out.obj = nan(""); out.pri_res = nan(""); out.dua_res = nan("");
+    bool solved_path = false;
+    double c = 1.0;
+    if (sched_err) out.status = LPVMPC_SCHEDULE_ERROR;
+    else {
+      qp.build(p, b, x0_eff);
+      if (qp.bounds_invalid()) out.status = LPVMPC_DATA_ERROR;
+      else {
+        if (p.S.scaling) c = qp.scale(p.S.scaling);
+        else {
+          for (int j = lane; j < L.nz; j += 32) { w[L.D + j] = 1.0; w[L.Dinv + j] = 1.0; }
+          for (int i = lane; i < L.m; i += 32) { w[L.E + i] = 1.0; w[L.Einv + i] = 1.0; }
+          __syncwarp();
+        }
+        qp.classify();
+        admm_run<KIND>(qp, p.S, c, out, p, b);
+        solved_path = true;
+      }
+    }
+    const bool has_sol = solved_path &&
+                         !(out.status == LPVMPC_PRIMAL_INFEASIBLE || out.status == LPVMPC_PRIMAL_INFEASIBLE_INACCURATE ||
+                           out.status == LPVMPC_DUAL_INFEASIBLE || out.status == LPVMPC_DUAL_INFEASIBLE_INACCURATE ||
+                           out.status == LPVMPC_NON_CVX);
+    // unpack: x = D x_bar (PathFollowingLPVMPC.py:157-158 split)
+    const double *x = w + L.x, *D = w + L.D;
+    for (int j = lane; j < L.nz; j += 32) {
+      const double v = has_sol ? D[j] * x[j] : nan("");
+      if (j < L.nx) a.x_pred[(size_t)b * L.nx + j] = v;
+      else a.u_pred[(size_t)b * (L.nz - L.nx) + (j - L.nx)] = v;
+    }
+    if (a.y || a.active_lo || a.active_up) {
+      const double *y = w + L.y, *E = w + L.E;
+      const int8_t *ty = qp.types();
+      const double cinv = 1.0 / c;
+      for (int i = lane; i < L.m; i += 32) {
+        const size_t o = (size_t)b * L.m + Spec<KIND>::ref_row(L, i);
+        if (a.y) a.y[o] = has_sol ? cinv * (E[i] * y[i]) : nan("");
+        const int t = solved_path ? ty[i] : 0;
+        if (a.active_lo) a.active_lo[o] = (t & 4) ? 1 : 0;
+        if (a.active_up) a.active_up[o] = (t & 8) ? 1 : 0;
+      }
+    }
+    if (lane == 0) {
+      a.status[b] = out.status;
+      if (a.iters) a.iters[b] = out.iter;
+      if (a.rho_updates) a.rho_updates[b] = out.rho_updates;
+      if (a.polish_status) a.polish_status[b] = out.polish_status;
+      if (a.obj) a.obj[b] = out.obj;
+      if (a.pri_res) a.pri_res[b] = out.pri_res;
+      if (a.dua_res) a.dua_res[b] = out.dua_res;
+    }
+    __syncwarp();
+    (void)NX;
+  }
+}
+
+// Stand-alone LPVPrediction / _EstimateABC: one thread per QP (the roll-out is serial in k).
+template <int KIND>
+__global__ void __launch_bounds__(128) lpv_schedule_kernel(const __grid_constant__ Params p, int *sched_err) {
+  constexpr int NX = Spec<KIND>::NX;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= p.B) return;
+  const Model &M = p.M;
+  const lpvmpc_args &a = p.a;
+  const int N = p.L.N;
+  int err = 0;
+  double st[NX], Ai[NX * NX], Bi[NX * NU];
+  if (a.sched_mode == LPVMPC_SCHED_ESTIMATE) {
+    for (int i = 0; i < N; ++i) {
+      const double *t = a.traj + ((size_t)b * N + i) * 6;
+      const double delta = a.u_prev[((size_t)b * N + i) * NU];
+      if (KIND == LPVMPC_CONTROLLER) ctrl_stage(M, M.Cf, M.Cr, t[0], t[1], t[3], t[5], curvature(M.track, M.nseg, t[4], err), delta, Ai, Bi);
+      else plan_stage(M, t[0], t[1], t[3], t[4], curvature(M.track, M.nseg, t[5], err), delta, Ai, Bi);
+      if (a.A_out) for (int e = 0; e < NX * NX; ++e) a.A_out[((size_t)b * N + i) * NX * NX + e] = Ai[e];
+      if (a.B_out) for (int e = 0; e < NX * NU; ++e) a.B_out[((size_t)b * N + i) * NX * NU + e] = Bi[e];
+    }
+  } else {
+    const double *xs = a.x_sched ? a.x_sched + (size_t)b * NX : a.x0 + (size_t)b * NX;
+    for (int r = 0; r < NX; ++r) st[r] = xs[r];
+    const double *up = a.u_prev + (size_t)b * N * NU;
+    const int lap = a.lap ? a.lap[b] : a.lap_all;
+    for (int i = 0; i < N; ++i) {
+      if (KIND == LPVMPC_CONTROLLER) {
+        const double cur = (lap == 0) ? curvature(M.track, M.nseg, st[4], err) : a.curv_ref[(size_t)b * N + i];
+        ctrl_stage(M, a.Cf_new, a.Cf_new, a.vel_ref[(size_t)b * (N + 1) + i], st[1], st[3], st[5], cur, up[i * NU], Ai, Bi);
+      } else {
+        plan_stage(M, st[0], st[1], st[3], st[4], curvature(M.track, M.nseg, a.SS[(size_t)b * (N + 1) + i], err), up[i * NU], Ai, Bi);
+      }
+      if (a.A_out) for (int e = 0; e < NX * NX; ++e) a.A_out[((size_t)b * N + i) * NX * NX + e] = Ai[e];
+      if (a.B_out) for (int e = 0; e < NX * NU; ++e) a.B_out[((size_t)b * N + i) * NX * NU + e] = Bi[e];
+      propagate<NX>(Ai, Bi, up + i * NU, st);
+      if (a.states_out) for (int r = 0; r < NX; ++r) a.states_out[((size_t)b * N + i) * NX + r] = st[r];
+    }
+  }
+  if (sched_err) sched_err[b] = err;
+}
+
+}  // namespace lpv
+
+// ================================================================================================
+// Host side: handle, layout, staging, C-ABI
+// ================================================================================================
+using lpv::Layout;
+using lpv::Params;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Field {  // one staged array of lpvmpc_args
+  size_t off_args;   // offsetof the pointer inside lpvmpc_args
+  size_t elem;       // bytes per problem
+  bool output;
+};
+
+inline int align2(int v) { return (v + 1) & ~1; }
+
+Layout make_layout(int kind, int N, int delay) {
+  const int NX = kind == LPVMPC_CONTROLLER ? 6 : 5, NUc = 2, NB = NX + NUc;
+  Layout L;
+  std::memset(&L, 0, sizeof(L));
+  L.N = N; L.nx = NX * (N + 1); L.nz = L.nx + NUc * N; L.md = L.nx;
+  L.ms = kind == LPVMPC_CONTROLLER ? 6 * N + delay : L.nz;
+  L.m = L.md + L.ms;
+  int o = 0;
+  auto take = [&](int n) { const int r = o; o += align2(n); return r; };
+  L.G = take(N * NX * NB); L.gI = take(L.md); L.sc = take(L.ms);
+  L.Pxx = take((N + 1) * NX * NX); L.Puu = take(N * NUc * NUc); L.Pud = take((N > 1 ? N - 1 : 0) * NUc);
+  L.q = take(L.nz); L.D = take(L.nz); L.Dinv = take(L.nz);
+  L.E = take(L.m); L.Einv = take(L.m); L.l = take(L.m); L.u = take(L.m); L.z = take(L.m); L.y = take(L.m);
+  L.x = take(L.nz); L.xp = take(L.nz); L.xt = take(L.nz); L.tn = take(L.nz);
+  L.dy = take(L.m); L.tm = take(L.m);
+  L.K = take((N + 1) * NB * NB); L.T = take((N + 1) * NB * NB); L.So = take(NB * NB);
+  L.type = take((L.m + 7) / 8);
+  L.total = o;
+  return L;
+}
+
+}  // namespace
+
+struct lpvmpc_handle {
+  lpvmpc_cfg cfg;
+  Layout L;
+  lpv::Model M;
+  int n, d;
+  int device;
+  int sm_count;
+  int smem_optin;
+  bool smem_mode;
+  int grid_cap;           // resident CTAs (persistent grid)
+  size_t ws_bytes;
+  double *d_track = nullptr;
+  double *d_gws = nullptr;
+  // staging for the host API
+  char *d_stage = nullptr, *h_stage = nullptr;
+  size_t stage_bytes = 0;
+  cudaStream_t stream = nullptr;
+  long long launches = 0;
+  std::string err;
+};
+
+namespace {
+
+int fail(lpvmpc_handle *h, int code, const std::string &msg) {
+  if (h) h->err = msg; else g_create_error = msg;
+  return code;
+}
+#define CUDA_TRY(h, expr)                                                                     \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return fail(h, LPVMPC_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));     \
+  } while (0)
+
+Params make_params(const lpvmpc_handle *h, int B, const lpvmpc_args *a) {
+  Params p;
+  p.L = h->L; p.M = h->M; p.S = h->cfg.settings; p.a = *a; p.B = B; p.gws = h->d_gws;
+  return p;
+}
+
+int validate_args(lpvmpc_handle *h, int B, const lpvmpc_args *a, bool solve) {
+  if (!h || !a) return fail(h, LPVMPC_E_ARG, "null handle/args");
+  if (B < 0 || B > h->cfg.max_batch) return fail(h, LPVMPC_E_ARG, "batch exceeds max_batch");
+  const bool ctrl = h->cfg.kind == LPVMPC_CONTROLLER;
+  if (a->sched_mode < 0 || a->sched_mode > 2) return fail(h, LPVMPC_E_ARG, "bad sched_mode");
+  if (solve) {
+    if (!a->x0 || !a->x_pred || !a->u_pred || !a->status) return fail(h, LPVMPC_E_ARG, "x0, x_pred, u_pred, status are required");
+    if (ctrl && !a->vel_ref) return fail(h, LPVMPC_E_ARG, "controller needs vel_ref");
+    if (!ctrl && !a->max_ey) return fail(h, LPVMPC_E_ARG, "planner needs max_ey");
+    if (ctrl && h->cfg.steering_delay > 0 && !a->old_steering) return fail(h, LPVMPC_E_ARG, "steering_delay needs old_steering");
+    if (a->sched_mode == LPVMPC_SCHED_GIVEN && (!a->A || !a->Bm)) return fail(h, LPVMPC_E_ARG, "SCHED_GIVEN needs A and Bm");
+  }
+  if (a->sched_mode == LPVMPC_SCHED_PREDICT) {
+    if (!a->u_prev || (!a->x0 && !a->x_sched)) return fail(h, LPVMPC_E_ARG, "PREDICT needs x0/x_sched and u_prev");
+    if (ctrl && !a->vel_ref) return fail(h, LPVMPC_E_ARG, "controller PREDICT needs vel_ref");
+    if (ctrl && !a->curv_ref && (a->lap || a->lap_all != 0)) return fail(h, LPVMPC_E_ARG, "controller PREDICT with lap != 0 needs curv_ref");
+    if (!ctrl && !a->SS) return fail(h, LPVMPC_E_ARG, "planner PREDICT needs SS");
+  }
+  if (a->sched_mode == LPVMPC_SCHED_ESTIMATE && (!a->traj || !a->u_prev)) return fail(h, LPVMPC_E_ARG, "ESTIMATE needs traj and u_prev");
+  return LPVMPC_OK;
+}
+
+template <int KIND>
+int launch_solve(lpvmpc_handle *h, const Params &p, cudaStream_t s) {
+  const int grid = p.B < h->grid_cap ? p.B : h->grid_cap;
+  if (grid == 0) return LPVMPC_OK;
+  if (h->smem_mode) lpv::lpv_solve_kernel<KIND, true><<<grid, 32, h->ws_bytes, s>>>(p);
+  else lpv::lpv_solve_kernel<KIND, false><<<grid, 32, 0, s>>>(p);
+  ++h->launches;
+  CUDA_TRY(h, cudaGetLastError());
+  return LPVMPC_OK;
+}
+
+// The staged fields of lpvmpc_args for the host API: {offset, bytes per problem, is_output}
+std::vector<Field> staged_fields(const lpvmpc_handle *h) {
+  const int n = h->n, d = h->d, N = h->L.N, nz = h->L.nz, m = h->L.m, delay = h->cfg.steering_delay;
+  const size_t D = sizeof(double);
+  std::vector<Field> f;
+#define IN(name, cnt) f.push_back({offsetof(lpvmpc_args, name), (size_t)(cnt), false})
+#define OUT(name, cnt) f.push_back({offsetof(lpvmpc_args, name), (size_t)(cnt), true})
+  IN(x0, n * D); IN(x_sched, n * D); IN(A, N * n * n * D); IN(Bm, N * n * d * D); IN(C, N * n * D);
+  IN(u_prev, N * d * D); IN(vel_ref, (N + 1) * D); IN(curv_ref, N * D); IN(SS, (N + 1) * D); IN(lap, sizeof(int32_t));
+  IN(traj, N * 6 * D); IN(u_old, d * D); IN(old_steering, (delay > 0 ? delay : 1) * D); IN(max_ey, D);
+  IN(ey_lo, (N + 1) * D); IN(ey_hi, (N + 1) * D);
+  OUT(x_pred, (N + 1) * n * D); OUT(u_pred, N * d * D); OUT(status, sizeof(int32_t)); OUT(iters, sizeof(int32_t));
+  OUT(rho_updates, sizeof(int32_t)); OUT(polish_status, sizeof(int32_t)); OUT(obj, D); OUT(pri_res, D); OUT(dua_res, D);
+  OUT(active_lo, m); OUT(active_up, m); OUT(y, m * D); OUT(A_out, N * n * n * D); OUT(B_out, N * n * d * D);
+  OUT(states_out, N * n * D); OUT(xs, nz * D); OUT(zs, m * D); OUT(ys, m * D);
+#undef IN
+#undef OUT
+  return f;
+}
+
+inline void *&ptr_at(lpvmpc_args *a, size_t off) { return *reinterpret_cast<void **>(reinterpret_cast<char *>(a) + off); }
+inline const void *cptr_at(const lpvmpc_args *a, size_t off) {
+  return *reinterpret_cast<void *const *>(reinterpret_cast<const char *>(a) + off);
+}
+inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+}  // namespace
+
+extern "C" {
+
+int lpvmpc_abi_version(void) { return LPVMPC_ABI_VERSION; }
+
+void lpvmpc_default_settings(lpvmpc_settings *s) {
+  if (!s) return;
+  s->rho = 0.1; s->sigma = 1e-6; s->alpha = 1.6;
+  s->eps_abs = 1e-3; s->eps_rel = 1e-3; s->eps_prim_inf = 1e-4; s->eps_dual_inf = 1e-4;
+  s->delta = 1e-6; s->adaptive_rho_tolerance = 5.0;
+  s->max_iter = 4000; s->check_termination = 25; s->scaling = 10;
+  s->adaptive_rho = 1; s->adaptive_rho_interval = 0;
+  s->polish = 1; s->polish_refine_iter = 3; s->scaled_termination = 0;
+}
+
+int lpvmpc_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+const char *lpvmpc_last_error(const lpvmpc_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
+  if (!cfg || !out) return fail(nullptr, LPVMPC_E_ARG, "null cfg/out");
+  *out = nullptr;
+  if (cfg->abi_version != LPVMPC_ABI_VERSION) return fail(nullptr, LPVMPC_E_ARG, "abi_version mismatch");
+  if (cfg->kind != LPVMPC_CONTROLLER && cfg->kind != LPVMPC_PLANNER) return fail(nullptr, LPVMPC_E_ARG, "bad kind");
+  if (cfg->N < 2 || cfg->N > 4096) return fail(nullptr, LPVMPC_E_ARG, "horizon N must be in [2, 4096]");
+  if (cfg->max_batch < 1) return fail(nullptr, LPVMPC_E_ARG, "max_batch must be >= 1");
+  if (!cfg->track || cfg->n_track_seg < 1) return fail(nullptr, LPVMPC_E_ARG, "track table required");
+  if (cfg->steering_delay < 0 || cfg->steering_delay > cfg->N || (cfg->kind == LPVMPC_PLANNER && cfg->steering_delay))
+    return fail(nullptr, LPVMPC_E_ARG, "bad steering_delay");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(nullptr, LPVMPC_E_CUDA, "no CUDA device: this library has no CPU fallback");
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, LPVMPC_E_ARG, "bad device ordinal");
+  lpvmpc_handle *h = new (std::nothrow) lpvmpc_handle();
+  if (!h) return fail(nullptr, LPVMPC_E_ARG, "out of host memory");
+  h->cfg = *cfg;
+  h->cfg.track = nullptr;
+  h->device = cfg->device;
+  h->n = cfg->kind == LPVMPC_CONTROLLER ? 6 : 5;
+  h->d = 2;
+  h->L = make_layout(cfg->kind, cfg->N, cfg->steering_delay);
+  auto bail = [&](int code) { std::string m = h->err; lpvmpc_destroy(h); g_create_error = m; return code; };
+#define CTRY(expr)                                                                                   \
+  do {                                                                                               \
+    cudaError_t e__ = (expr);                                                                        \
+    if (e__ != cudaSuccess) { h->err = std::string(#expr) + ": " + cudaGetErrorString(e__); return bail(LPVMPC_E_CUDA); } \
+  } while (0)
+  CTRY(cudaSetDevice(h->device));
+  cudaDeviceProp prop;
+  CTRY(cudaGetDeviceProperties(&prop, h->device));
+  if (prop.major < 10) { h->err = "built for sm_100a (B200); device is older"; return bail(LPVMPC_E_UNSUPPORTED); }
+  h->sm_count = prop.multiProcessorCount;
+  h->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  h->ws_bytes = (size_t)h->L.total * sizeof(double);
+  h->smem_mode = h->ws_bytes <= (size_t)h->smem_optin;
+  if (h->smem_mode) {
+    int per_sm = (int)(prop.sharedMemPerMultiprocessor / (h->ws_bytes + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 32) per_sm = 32;
+    h->grid_cap = h->sm_count * per_sm;
+    if (cfg->kind == LPVMPC_CONTROLLER)
+      CTRY(cudaFuncSetAttribute(lpv::lpv_solve_kernel<LPVMPC_CONTROLLER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ws_bytes));
+    else
+      CTRY(cudaFuncSetAttribute(lpv::lpv_solve_kernel<LPVMPC_PLANNER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ws_bytes));
+  } else {
+    h->grid_cap = h->sm_count * 16;
+    if (h->grid_cap > cfg->max_batch) h->grid_cap = cfg->max_batch;
+    CTRY(cudaMalloc(&h->d_gws, h->ws_bytes * (size_t)h->grid_cap));
+  }
+  CTRY(cudaMalloc(&h->d_track, sizeof(double) * 6 * (size_t)cfg->n_track_seg));
+  CTRY(cudaMemcpy(h->d_track, cfg->track, sizeof(double) * 6 * (size_t)cfg->n_track_seg, cudaMemcpyHostToDevice));
+  CTRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  lpv::Model &M = h->M;
+  M.dt = cfg->dt; M.lf = cfg->lf; M.lr = cfg->lr; M.m = cfg->m; M.Iz = cfg->Iz; M.Cf = cfg->Cf; M.Cr = cfg->Cr; M.mu = cfg->mu;
+  M.max_vel = cfg->max_vel; M.min_vel = cfg->min_vel;
+  std::memcpy(M.Q, cfg->Q, sizeof(M.Q)); std::memcpy(M.R, cfg->R, sizeof(M.R));
+  std::memcpy(M.dR, cfg->dR, sizeof(M.dR)); std::memcpy(M.L_cf, cfg->L_cf, sizeof(M.L_cf));
+  M.track = h->d_track; M.nseg = cfg->n_track_seg; M.delay = cfg->steering_delay;
+  // staging arena for the host API
+  size_t per = 0;
+  for (const Field &f : staged_fields(h)) per += align256(f.elem * (size_t)cfg->max_batch);
+  per += align256(sizeof(int32_t) * (size_t)cfg->max_batch);  // sched_err of lpvmpc_schedule_host
+  h->stage_bytes = per;
+  CTRY(cudaMalloc(&h->d_stage, per));
+  CTRY(cudaMallocHost(&h->h_stage, per));
+#undef CTRY
+  *out = h;
+  return LPVMPC_OK;
+}
+
+void lpvmpc_destroy(lpvmpc_handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  cudaFree(h->d_track); cudaFree(h->d_gws); cudaFree(h->d_stage);
+  if (h->h_stage) cudaFreeHost(h->h_stage);
+  delete h;
+}
+
+int lpvmpc_get_info(const lpvmpc_handle *h, lpvmpc_info *info) {
+  if (!h || !info) return LPVMPC_E_ARG;
+  info->n = h->n; info->d = h->d; info->N = h->L.N; info->nz = h->L.nz; info->m = h->L.m;
+  info->variant = 1;
+  info->workspace_in_smem = h->smem_mode ? 1 : 0;
+  info->smem_bytes_per_qp = h->smem_mode ? (int)h->ws_bytes : 0;
+  info->workspace_bytes = (long long)(h->stage_bytes + (h->smem_mode ? 0 : h->ws_bytes * (size_t)h->grid_cap));
+  info->kernel_launches = h->launches;
+  return LPVMPC_OK;
+}
+
+int lpvmpc_update_settings(lpvmpc_handle *h, const lpvmpc_settings *s) {
+  if (!h || !s) return LPVMPC_E_ARG;
+  if (s->max_iter < 1 || s->rho <= 0 || s->sigma <= 0 || s->alpha <= 0 || s->alpha >= 2 || s->check_termination < 0 ||
+      s->scaling < 0 || s->delta <= 0 || s->polish_refine_iter < 0)
+    return fail(h, LPVMPC_E_ARG, "invalid settings");
+  h->cfg.settings = *s;
+  return LPVMPC_OK;
+}
+
+int lpvmpc_solve_dev(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, void *stream) {
+  int rc = validate_args(h, B, a, true);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const Params p = make_params(h, B, a);
+  return h->cfg.kind == LPVMPC_CONTROLLER ? launch_solve<LPVMPC_CONTROLLER>(h, p, (cudaStream_t)stream)
+                                          : launch_solve<LPVMPC_PLANNER>(h, p, (cudaStream_t)stream);
+}
+
+int lpvmpc_schedule_dev(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, int32_t *sched_err, void *stream) {
+  int rc = validate_args(h, B, a, false);
+  if (rc) return rc;
+  if (a->sched_mode == LPVMPC_SCHED_GIVEN) return fail(h, LPVMPC_E_ARG, "schedule needs PREDICT or ESTIMATE");
+  if (B == 0) return LPVMPC_OK;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const Params p = make_params(h, B, a);
+  const int grid = (B + 127) / 128;
+  if (h->cfg.kind == LPVMPC_CONTROLLER) lpv::lpv_schedule_kernel<LPVMPC_CONTROLLER><<<grid, 128, 0, (cudaStream_t)stream>>>(p, sched_err);
+  else lpv::lpv_schedule_kernel<LPVMPC_PLANNER><<<grid, 128, 0, (cudaStream_t)stream>>>(p, sched_err);
+  ++h->launches;
+  CUDA_TRY(h, cudaGetLastError());
+  return LPVMPC_OK;
+}
+
+// Host-pointer variants: pack every non-NULL input into one pinned arena, one H2D, kernel, one D2H.
+static int run_host(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, int32_t *sched_err, bool solve) {
+  int rc = validate_args(h, B, a, solve);
+  if (rc) return rc;
+  if (B == 0) return LPVMPC_OK;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  lpvmpc_args dev = *a;
+  const std::vector<Field> fields = staged_fields(h);
+  size_t off = 0, in_end = 0, out_begin = 0;
+  bool first_out = true;
+  std::vector<size_t> offs(fields.size());
+  for (size_t i = 0; i < fields.size(); ++i) {
+    const Field &f = fields[i];
+    if (f.output && first_out) { out_begin = off; first_out = false; }
+    offs[i] = off;
+    if (cptr_at(a, f.off_args)) {
+      const size_t bytes = f.elem * (size_t)B;
+      if (!f.output) std::memcpy(h->h_stage + off, cptr_at(a, f.off_args), bytes);
+      ptr_at(&dev, f.off_args) = h->d_stage + off;
+      off += align256(bytes);
+      if (!f.output) in_end = off;
+    }
+  }
+  size_t se_off = off;
+  int32_t *d_se = nullptr;
+  if (sched_err) { d_se = reinterpret_cast<int32_t *>(h->d_stage + off); off += align256(sizeof(int32_t) * (size_t)B); }
+  if (off > h->stage_bytes) return fail(h, LPVMPC_E_ARG, "staging overflow");
+  if (in_end) CUDA_TRY(h, cudaMemcpyAsync(h->d_stage, h->h_stage, in_end, cudaMemcpyHostToDevice, h->stream));
+  rc = solve ? lpvmpc_solve_dev(h, B, &dev, h->stream) : lpvmpc_schedule_dev(h, B, &dev, d_se, h->stream);
+  if (rc) return rc;
+  if (off > out_begin)
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_stage + out_begin, h->d_stage + out_begin, off - out_begin, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  for (size_t i = 0; i < fields.size(); ++i) {
+    const Field &f = fields[i];
+    if (f.output && cptr_at(a, f.off_args))
+      std::memcpy(const_cast<void *>(cptr_at(a, f.off_args)), h->h_stage + offs[i], f.elem * (size_t)B);
+  }
+  if (sched_err) std::memcpy(sched_err, h->h_stage + se_off, sizeof(int32_t) * (size_t)B);
+  return LPVMPC_OK;
+}
+
+int lpvmpc_solve_host(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a) { return run_host(h, B, a, nullptr, true); }
+
+int lpvmpc_schedule_host(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, int32_t *sched_err) {
+  return run_host(h, B, a, sched_err, false);
+}
+
+}  // extern "C"

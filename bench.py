@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py — LPV-MPC QP solves/s on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A "step" is one pass of the hot path (LPV scheduling -> QP build -> OSQP ADMM solve + polish) over one batch of
+synthetic problems.  Workloads:
+    ctrl4096   4,096 controller QPs, N=8, trajectory-tracking tune, lap=1       (BASELINE configs[1], default)
+    plan16384  16,384 planner QPs, N=40, lateral-box "obstacles"                 (configs[2])
+    ctrl1024N100  1,024 controller QPs, N=100                                     (configs[4])
+Multi-GPU: one process per GPU (torchrun), every rank solves its own batch of the same size (weak scaling, no
+collective on the data path); value = all ranks' QPs / max-over-ranks device time.
+
+`value`   : kernel-path throughput, inputs resident in HBM, CUDA-event timed per step (L2 flushed between steps).
+`e2e`     : same metric through the public host API (numpy in -> numpy out): pinned staging + H2D + kernel + D2H.
+`roofline`: fp64-FMA roofline of the one kernel in the step (algorithmic flops from measured iteration counts).
+`cpu_baseline` / `--impl reference`: the CPU oracle port of the reference loop (C build + OSQP restatement; the
+reference's own OSQP is an absent PyPI dependency), OpenMP over the host cores.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic flop model per QP (1 FMA = 2 flops; condensed block-tridiagonal form)
+FLOP_TABLE = {
+    # (kind, N): F_scale, F_form, F_fac, F_solve, F_iter, F_check
+    ("controller", 8): (14e3, 1.6e3, 7.3e3, 2.6e3, 5.6e3, 2.5e3),
+    ("controller", 20): (34e3, 4.0e3, 18.3e3, 6.4e3, 13.8e3, 6.0e3),
+    ("controller", 100): (168e3, 19.8e3, 91.3e3, 31.7e3, 68.2e3, 29.7e3),
+    ("planner", 40): (62e3, 7.1e3, 22.2e3, 9.2e3, 23.1e3, 11.1e3),
+}
+FP64_PEAK_FILE = os.path.join(ROOT, "profiles", "r1_fp64_peak.jsonl")
+
+WORKLOADS = {
+    "ctrl4096": dict(kind="controller", N=8, B=4096, seed=0),
+    "plan16384": dict(kind="planner", N=40, B=16384, seed=1),
+    "ctrl1024N100": dict(kind="controller", N=100, B=1024, seed=3),
+}
+
+
+def flops_per_qp(kind, N, iters, rho_updates, polished):
+    key = (kind, N)
+    if key not in FLOP_TABLE:  # scale the nearest row per stage
+        base = min((k for k in FLOP_TABLE if k[0] == kind), key=lambda k: abs(k[1] - N))
+        f = [v * N / base[1] for v in FLOP_TABLE[base]]
+    else:
+        f = FLOP_TABLE[key]
+    F_scale, F_form, F_fac, F_solve, F_iter, F_check = f
+    n_fac = 1.0 + rho_updates
+    w = F_scale + F_form + n_fac * F_fac + iters * F_iter + np.ceil(iters / 25.0) * F_check
+    w = w + polished * (F_fac + 4 * F_solve)
+    return w
+
+
+def fp64_peak_tflops():
+    try:
+        with open(FP64_PEAK_FILE) as fh:
+            for line in fh:
+                d = json.loads(line)
+                if d.get("bench") == "dfma_sustained":
+                    return float(d["tflops"]), "profiles/r1_fp64_peak.jsonl (own DFMA microbenchmark, sustained 3 s)"
+    except Exception:
+        pass
+    return 34.2, "fallback: DFMA microbenchmark of round 1"
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return json.load(fh)
+    except Exception:
+        return {"hbm_gbs": 6650.0, "_fallback": True}
+
+
+class ClockSampler(object):
+    """Samples SM clock / throttle reasons of one GPU during the timed region (NVML)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80, "sync_boost": 0x10}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.01)
+
+    def start(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join()
+        return {"sm_mhz": (float(np.median(self.samples)) if self.samples else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def make_workload(name, rank):
+    import lpvmpc_b200 as lp
+    W = lp.workloads
+    spec = WORKLOADS[name]
+    track = lp.Map("L_shape")
+    seed = spec["seed"] + 1000 * rank
+    if spec["kind"] == "controller":
+        w = W.controller_batch(spec["B"], spec["N"], seed=seed, track=track, steer_scale=(0.2 if spec["N"] >= 50 else 1.0))
+        tune, dt = W.CTRL_TT, W.CTRL_DT
+        keys = ("u_prev", "vel_ref", "curv_ref", "lap", "u_old")
+    else:
+        w = W.planner_batch(spec["B"], spec["N"], seed=seed, track=track)
+        tune, dt = W.PLAN, W.PLAN_DT
+        keys = ("SS", "u_prev", "u_old", "max_ey", "ey_lo", "ey_hi")
+    return spec, track, w, tune, dt, keys
+
+
+def cpu_reference_rate(name, threads, repeats=1, sample=None):
+    """QP/s of the CPU oracle port on `threads` host threads, on (a sample of) the workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    spec, track, w, tune, dt, keys = make_workload(name, 0)
+    B = spec["B"] if sample is None else min(sample, spec["B"])
+    st = oracle.default_settings(polish=1)
+    if spec["kind"] == "controller":
+        cfg = oracle.make_cfg("controller", spec["N"], dt, tune["Q"], tune["R"], tune["dR"], track.PointAndTangent)
+        run = lambda: oracle.ctrl_batch(cfg, st, w["x0"][:B], w["u_prev"][:B], w["vel_ref"][:B], w["curv_ref"][:B],
+                                        w["lap"][:B], w["u_old"][:B], threads=threads)
+    else:
+        cfg = oracle.make_cfg("planner", spec["N"], dt, tune["Q"], tune["R"], tune["dR"], track.PointAndTangent, L_cf=tune["L_cf"])
+        run = lambda: oracle.plan_batch(cfg, st, w["x0"][:B], w["SS"][:B], w["u_prev"][:B], w["u_old"][:B], w["max_ey"][:B],
+                                        w["ey_lo"][:B], w["ey_hi"][:B], threads=threads)
+    times = []
+    solved = 0
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        r = run()
+        times.append(time.perf_counter() - t0)
+        solved = int(r["solved"])
+    return B, times, solved
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    spec = WORKLOADS[args.workload]
+    sample = spec["B"] if spec["kind"] == "controller" and spec["N"] <= 20 else max(64, threads * 8)
+    for _ in range(max(args.warmup, 1) if sample <= 4096 else 1):
+        cpu_reference_rate(args.workload, threads, 1, sample=min(sample, 256))
+    B, times, solved = cpu_reference_rate(args.workload, threads, args.steps, sample=sample)
+    total = float(np.sum(times))
+    value = B * len(times) / total
+    line = {
+        "impl": "reference", "metric": "LPV-MPC QP solves/sec", "value": value, "unit": "QP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "kind": spec["kind"], "N": spec["N"], "batch_per_step": B,
+                   "note": "CPU oracle port (C restatement of the reference's LPVPrediction + QP build + OSQP 0.6 "
+                           "algorithm); upstream osqp is an absent PyPI dependency; Python overhead of the reference "
+                           "(about 1.7 ms/QP at N=8) is NOT included, which favours this arm"},
+        "cpu_baseline": {"value": value, "unit": "QP/s", "cores": threads, "kind": "port",
+                         "sample": "%d QPs per step x %d steps (%s of the workload batch)" % (B, len(times), "all" if B == spec["B"] else "a slice")},
+        "e2e": {"value": value, "unit": "QP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "solved_fraction": solved / float(B),
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import lpvmpc_b200 as lp
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+
+    spec, track, w, tune, dt, keys = make_workload(args.workload, rank)
+    B = spec["B"]
+    solver = lp.BatchSolver(spec["kind"], spec["N"], dt, track=track.PointAndTangent, max_batch=B, device=local, **tune)
+    info0 = solver.info()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------------------------------------------------------- device-resident arm
+    tin = {k: torch.as_tensor(w[k]).to(dev) for k in keys}
+    tx0 = torch.as_tensor(w["x0"]).to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    for _ in range(args.warmup):
+        r = solver.solve(tx0, **tin)
+    barrier()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    sampler = ClockSampler(local)
+    launches0 = solver.info()["kernel_launches"]
+    sampler.start()
+    barrier()
+    for i in range(args.steps):
+        flush.zero_()
+        starts[i].record()
+        r = solver.solve(tx0, **tin)
+        ends[i].record()
+    barrier()
+    clocks = sampler.stop()
+    launches = solver.info()["kernel_launches"] - launches0
+    step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, ends)])
+    total_ms = float(step_ms.sum())
+    status = r.status.cpu().numpy()
+    iters = r.iters.cpu().numpy().astype(np.float64)
+    rho_up = r.rho_updates.cpu().numpy().astype(np.float64)
+    pol = (r.polish_status.cpu().numpy() != 0).astype(np.float64)
+    solved = int((status == 1).sum())
+    flops = float(flops_per_qp(spec["kind"], spec["N"], iters, rho_up, pol).sum())
+
+    # ---------------------------------------------------------------- end-to-end arm (host API)
+    hin = {k: w[k] for k in keys}
+    for _ in range(max(1, min(args.warmup, 3))):
+        solver.solve(w["x0"], **hin)
+    barrier()
+    e2e_t = []
+    for i in range(args.steps):
+        t0 = time.perf_counter()
+        rh = solver.solve(w["x0"], **hin)
+        e2e_t.append(time.perf_counter() - t0)
+    barrier()
+    e2e_total = float(np.sum(e2e_t))
+    h2d = int(w["x0"].nbytes + sum(np.asarray(w[k]).nbytes for k in keys))
+    d2h = int(sum(rh[k].nbytes for k in rh if hasattr(rh[k], "nbytes")))
+    assert np.array_equal(rh.status, status), "host and device paths disagree"
+
+    # ---------------------------------------------------------------- reduce over ranks (max time)
+    if dist is not None:
+        t = torch.tensor([total_ms, e2e_total, float(solved), float(flops)], dtype=torch.float64, device=dev)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        total_ms, e2e_total = float(tmax[0]), float(tmax[1])
+        solved_all, flops_rank = float(tsum[2]), flops
+    else:
+        solved_all = float(solved)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    ms_per_step = total_ms / args.steps
+    value = world * B * args.steps / (total_ms * 1e-3)
+    e2e_value = world * B * args.steps / e2e_total
+    peak, peak_src = fp64_peak_tflops()
+    achieved = flops / (ms_per_step * 1e-3) * 1e-12  # this rank's kernel: flops per launch / launch duration
+    in_bytes_qp = h2d / float(B)
+    out_bytes_qp = d2h / float(B)
+    mp = measured_peaks()
+    line = {
+        "metric": "LPV-MPC QP solves/sec", "value": value, "unit": "QP/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "kind": spec["kind"], "N": spec["N"], "batch_per_gpu": B,
+                   "osqp": "defaults (eps 1e-3, rho 0.1 adaptive@100, sigma 1e-6, alpha 1.6, 10 Ruiz passes, max_iter 4000) + polish",
+                   "sched": "fused LPVPrediction (lap=1)", "l2": "flushed between steps (256 MiB memset outside the per-step event pairs)",
+                   "kernel_variant": info0["variant"], "workspace_in_smem": info0["workspace_in_smem"],
+                   "smem_bytes_per_qp": info0["smem_bytes_per_qp"]},
+        "e2e": {"value": e2e_value, "unit": "QP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * e2e_total / args.steps,
+                "latency_ms": {"p50": 1e3 * float(np.percentile(e2e_t, 50)), "p99": 1e3 * float(np.percentile(e2e_t, 99)),
+                               "max": 1e3 * float(np.max(e2e_t))}},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "fp64_fma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "kernel": "lpv_solve_kernel (schedule + build + Ruiz + factor + ADMM + polish, one launch per step)",
+                     "algorithmic_flops_per_launch": flops,
+                     "algorithmic_hbm_bytes_per_launch": (in_bytes_qp + out_bytes_qp) * B,
+                     "hbm_frac_of_measured": ((in_bytes_qp + out_bytes_qp) * B / (ms_per_step * 1e-3) * 1e-9) / float(mp.get("hbm_gbs", 6650.0))},
+        "kernel_latency_ms": {"p50": float(np.percentile(step_ms, 50)), "p99": float(np.percentile(step_ms, 99)), "max": float(step_ms.max())},
+        "solved_fraction": solved_all / float(world * B),
+        "iters": {"mean": float(iters.mean()), "p50": float(np.percentile(iters, 50)), "p99": float(np.percentile(iters, 99)), "max": float(iters.max())},
+    }
+    # CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload on all host cores
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sample = B if spec["kind"] == "controller" and spec["N"] <= 20 else max(64, threads * 8)
+        cpu_reference_rate(args.workload, threads, 1, sample=min(sample, 256))
+        Bs, times, _ = cpu_reference_rate(args.workload, threads, 3 if sample <= 4096 else 1, sample=sample)
+        line["cpu_baseline"] = {"value": Bs * len(times) / float(np.sum(times)), "unit": "QP/s", "cores": threads, "kind": "port",
+                                "sample": "%d QPs x %d passes of the same workload, OpenMP over all host cores; C port without the reference's Python overhead" % (Bs, len(times))}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ctrl4096", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,185 @@
+/*
+ * lpvmpc.h — C-ABI of the B200-native batched LPV-MPC QP solver.
+ *
+ * Drop-in boundary for ONE hot path of euge2838/Autonomous-Racing-LPV-MPP-MPC: per control tick,
+ * LPV scheduling A(rho_k)/B(rho_k) over the horizon -> QP assembly -> OSQP ADMM solve, for a batch
+ * of independent problems.  The reference has no FFI of its own for this path (it is Python calling
+ * the PyPI `osqp` C extension); the interfaces each entry point replaces are the Python methods below
+ * (paths relative to /root/reference/workspace/src/barc/src):
+ *
+ *   lpvmpc_create            PathFollowingLPV_MPC.__init__   ControllerObject/PathFollowingLPVMPC.py:35-84
+ *                            LPV_MPC_Planner.__init__        PlannerObject/LPV_MPC_Planner.py:34-82
+ *                            (+ rospy params MAIN_LAUNCH.launch:5-11,40-44 and Map().PointAndTangent,
+ *                             Utilities/trackInitialization.py:90-202)
+ *   lpvmpc_schedule_*        .LPVPrediction                  PathFollowingLPVMPC.py:166-258, LPV_MPC_Planner.py:242-320
+ *                            _EstimateABC                    PathFollowingLPVMPC.py:732-809, LPV_MPC_Planner.py:519-591
+ *   lpvmpc_solve_*           .solve + osqp_solve_qp          PathFollowingLPVMPC.py:89-162,273-325
+ *                            .solve (OSQP().setup/.solve)    LPV_MPC_Planner.py:86-236
+ *                            (OSQP itself: PyPI `osqp` 0.6.x, setup+solve+polish; not vendored)
+ *
+ * Conventions: plain pointers and sizes only; every call returns 0 or a negative LPVMPC_E_* code and
+ * never throws; lpvmpc_last_error() gives the message.  A handle is bound to one CUDA device and is not
+ * thread-safe; `_dev` calls take DEVICE pointers and are asynchronous on `stream` (a cudaStream_t passed
+ * as void*, NULL = legacy default stream); `_host` calls take HOST pointers, stage through pinned
+ * buffers owned by the handle, and return after the results are in the caller's arrays.
+ * All arrays are row-major fp64 unless stated.  There is no CPU fallback: without a CUDA device every
+ * compute entry point fails with LPVMPC_E_CUDA.
+ *
+ * Sizes: controller n=6 states [vx vy wz epsi s ey], planner n=5 states [vx vy wz ey epsi]; d=2 inputs
+ * [delta a]; nz = n(N+1)+dN decision variables ordered [x_0..x_N, u_0..u_{N-1}] as in the reference
+ * (PathFollowingLPVMPC.py:157-158); m constraint rows in the REFERENCE's OSQP row order:
+ *   controller: 2N state rows, 4N input rows, n(N+1) dynamics rows, then `steering_delay` rows
+ *               (PathFollowingLPVMPC.py:304-308, 329-378, 518-527)
+ *   planner   : n(N+1) dynamics rows, then nz box rows (LPV_MPC_Planner.py:200-202)
+ */
+#ifndef LPVMPC_H
+#define LPVMPC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LPVMPC_ABI_VERSION 1
+
+enum { LPVMPC_CONTROLLER = 0, LPVMPC_PLANNER = 1 };
+
+/* error codes (function return values) */
+enum {
+  LPVMPC_OK = 0,
+  LPVMPC_E_ARG = -1,      /* bad argument / NULL where required / batch > max_batch */
+  LPVMPC_E_CUDA = -2,     /* CUDA runtime error or no device */
+  LPVMPC_E_UNSUPPORTED = -3
+};
+
+/* per-problem status: OSQP's own integers (osqp 0.6 constants.h) plus two of ours */
+enum {
+  LPVMPC_SOLVED = 1,
+  LPVMPC_SOLVED_INACCURATE = 2,
+  LPVMPC_PRIMAL_INFEASIBLE_INACCURATE = 3,
+  LPVMPC_DUAL_INFEASIBLE_INACCURATE = 4,
+  LPVMPC_MAX_ITER_REACHED = -2,
+  LPVMPC_PRIMAL_INFEASIBLE = -3,
+  LPVMPC_DUAL_INFEASIBLE = -4,
+  LPVMPC_NON_CVX = -7,
+  LPVMPC_UNSOLVED = -10,
+  LPVMPC_SCHEDULE_ERROR = -20, /* Curvature(s) had no (unique) segment: the reference raises (utilities.py:46) */
+  LPVMPC_DATA_ERROR = -21      /* l > u: upstream osqp.setup() refuses the problem */
+};
+
+/* scheduling modes of lpvmpc_solve_* */
+enum {
+  LPVMPC_SCHED_GIVEN = 0,   /* A,B(,C) supplied by the caller (what .solve(..., A_L,B_L,C_L, first_it>=10) does) */
+  LPVMPC_SCHED_PREDICT = 1, /* fused .LPVPrediction roll-out inside the solve kernel */
+  LPVMPC_SCHED_ESTIMATE = 2 /* fused _EstimateABC from a given trajectory (warm-up ticks) */
+};
+
+typedef struct {
+  double rho, sigma, alpha;
+  double eps_abs, eps_rel, eps_prim_inf, eps_dual_inf;
+  double delta;                  /* polish regularisation */
+  double adaptive_rho_tolerance;
+  int32_t max_iter;
+  int32_t check_termination;     /* 0 = never check before max_iter (fixed-iteration mode) */
+  int32_t scaling;               /* Ruiz passes */
+  int32_t adaptive_rho;
+  int32_t adaptive_rho_interval; /* 0 = OSQP's deterministic fallback: 4 * check_termination (or 100) */
+  int32_t polish;
+  int32_t polish_refine_iter;
+  int32_t scaled_termination;
+} lpvmpc_settings;
+
+typedef struct {
+  int32_t abi_version;           /* LPVMPC_ABI_VERSION */
+  int32_t kind;                  /* LPVMPC_CONTROLLER / LPVMPC_PLANNER */
+  int32_t N;                     /* horizon */
+  int32_t steering_delay;        /* controller only; extra equality rows u_k[0] = old_steering[k+1] */
+  double dt;
+  double Q[36];                  /* n x n row-major (planner uses the leading 25 entries) */
+  double R[4];                   /* d x d */
+  double dR[2];                  /* input-rate weights */
+  double L_cf[5];                /* planner linear (lap-time) cost */
+  double lf, lr, m, Iz, Cf, Cr, mu; /* rospy params "lf".."mu" */
+  double max_vel, min_vel;       /* /TrajectoryPlanner/max_vel, min_vel */
+  int32_t n_track_seg;           /* rows of PointAndTangent */
+  int32_t max_batch;             /* workspaces are allocated for this many problems */
+  const double *track;           /* HOST pointer, n_track_seg x 6 [x y psi s len kappa]; copied */
+  int32_t device;                /* CUDA device ordinal */
+  int32_t variant;               /* 0 = auto; 1 = generic warp-per-QP kernel; see lpvmpc_info.variant */
+  lpvmpc_settings settings;
+} lpvmpc_cfg;
+
+typedef struct {
+  int32_t n, d, N, nz, m;        /* problem dimensions */
+  int32_t variant;               /* kernel actually selected */
+  int32_t workspace_in_smem;     /* 1: per-QP workspace lives in shared memory; 0: global (L2) workspace */
+  int32_t smem_bytes_per_qp;
+  int64_t workspace_bytes;       /* device bytes owned by the handle */
+  int64_t kernel_launches;       /* kernels launched by this handle so far */
+} lpvmpc_info;
+
+/* Batched arguments of one solve.  Unused pointers may be NULL.  `_dev`: device pointers; `_host`: host. */
+typedef struct {
+  int32_t sched_mode;            /* LPVMPC_SCHED_* */
+  int32_t x0_from_prediction;    /* controller lap-0 quirk: QP x0 := first predicted state (controllerMain.py:329-331) */
+  int32_t lap_all;               /* used when `lap` is NULL (controller PREDICT: 0 => Curvature(s), else curv_ref) */
+  int32_t reserved;
+  double Cf_new;                 /* controller PREDICT tyre stiffness (controllerMain.py:77: 60) */
+  /* inputs */
+  const double *x0;              /* [B,n]      QP initial state (and scheduling state unless x_sched given) */
+  const double *x_sched;         /* [B,n]      optional roll-out start (PREDICT) */
+  const double *A;               /* [B,N,n,n]  GIVEN */
+  const double *Bm;              /* [B,N,n,d]  GIVEN */
+  const double *C;               /* [B,N,n]    GIVEN, optional (reference: zeros) */
+  const double *u_prev;          /* [B,N,d]    PREDICT / ESTIMATE: previous input sequence (steering schedules A,B) */
+  const double *vel_ref;         /* [B,N+1]    controller: tracking reference; entry N is the terminal one */
+  const double *curv_ref;        /* [B,N]      controller PREDICT with lap != 0 */
+  const double *SS;              /* [B,N+1]    planner PREDICT: arc-length per stage */
+  const int32_t *lap;            /* [B]        controller PREDICT, optional */
+  const double *traj;            /* [B,N,6]    ESTIMATE: controller rows [vx vy wz epsi s ey]; planner [vx vy w ey epsi s] */
+  const double *u_old;           /* [B,d]      slew-rate anchor [OldSteering[0], OldAccelera[0]]; NULL = 0 */
+  const double *old_steering;    /* [B,delay]  controller steering_delay rows: OldSteering[1..delay] */
+  const double *max_ey;          /* [B]        planner lateral box */
+  const double *ey_lo, *ey_hi;   /* [B,N+1]    planner optional per-stage lateral box ("obstacles") */
+  /* outputs */
+  double *x_pred;                /* [B,N+1,n] */
+  double *u_pred;                /* [B,N,d]   */
+  int32_t *status;               /* [B] LPVMPC_* status */
+  int32_t *iters;                /* [B] ADMM iterations */
+  int32_t *rho_updates;          /* [B] optional */
+  int32_t *polish_status;        /* [B] optional: 1 ok, -1 unsuccessful, 0 not run */
+  double *obj;                   /* [B] optional objective 0.5 z'Pz + q'z */
+  double *pri_res, *dua_res;     /* [B] optional */
+  uint8_t *active_lo, *active_up;/* [B,m] optional polish active-set guess, reference row order */
+  double *y;                     /* [B,m] optional dual solution, reference row order */
+  double *A_out, *B_out;         /* [B,N,n,n], [B,N,n,d] optional: scheduled matrices (PREDICT/ESTIMATE) */
+  double *states_out;            /* [B,N,n] optional: roll-out states (PREDICT) */
+  double *xs, *zs, *ys;          /* [B,nz],[B,m],[B,m] optional scaled ADMM iterates before polish (parity tests) */
+} lpvmpc_args;
+
+typedef struct lpvmpc_handle lpvmpc_handle;
+
+int lpvmpc_abi_version(void);
+void lpvmpc_default_settings(lpvmpc_settings *s); /* OSQP 0.6 defaults + polish=1 (what the reference runs) */
+int lpvmpc_device_count(void);
+
+int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out);
+void lpvmpc_destroy(lpvmpc_handle *h);
+const char *lpvmpc_last_error(const lpvmpc_handle *h); /* h may be NULL: last create() error */
+int lpvmpc_get_info(const lpvmpc_handle *h, lpvmpc_info *info);
+int lpvmpc_update_settings(lpvmpc_handle *h, const lpvmpc_settings *s);
+
+/* LPVPrediction / _EstimateABC for a batch: A_out [B,N,n,n], B_out [B,N,n,d], states_out [B,N,n] (PREDICT),
+ * sched_err [B] (1 where Curvature failed).  Uses x0 (or x_sched), u_prev, vel_ref, curv_ref/SS, lap, traj. */
+int lpvmpc_schedule_dev(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, int32_t *sched_err, void *stream);
+int lpvmpc_schedule_host(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, int32_t *sched_err);
+
+/* schedule (per sched_mode) + build + OSQP solve (+ polish) + unpack */
+int lpvmpc_solve_dev(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, void *stream);
+int lpvmpc_solve_host(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LPVMPC_H */

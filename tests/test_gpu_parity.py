@@ -1,0 +1,140 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle on identical seeded inputs.
+
+Tolerances (BASELINE.json north_star):
+  * scheduling matrices: <= 4 ulp-ish (1e-14 relative) — CUDA sin/cos vs libm
+  * fixed-iteration, fixed-rho ADMM iterates: 1e-9 relative (inf-norm over the vector)
+  * converged mode: status, iteration count, active sets identical; controls/states within OSQP eps (1e-4 abs here,
+    the solutions are polished); objective within 1e-6 relative
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+import tests_common as tc
+
+pytestmark = pytest.mark.gpu
+
+lp = pytest.importorskip("lpvmpc_b200")
+W = lp.workloads if hasattr(lp, "workloads") else __import__("importlib").import_module("autonomous-racing-lpv-mpp-mpc_b200.workloads")
+
+
+def _relinf(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def _same_active_set(r, o, b):
+    """Active rows (the rows polish keeps) must be identical.  The lower/upper label must be identical too, except
+    on rows whose dual is zero up to round-off (|y_i| <= 1e-9 max|y|): there the label is the sign of noise — e.g. the
+    dynamics rows of the unweighted state `s` (Q[4,4] = 0, controllerMain.py:139,146) — and even the oracle's own
+    LDL' and LU back-ends disagree on it (tests/test_oracle_solver.py::test_degenerate_dual_labels)."""
+    if o["status"] != 1:
+        return
+    act_g = (r.active_lo[b] | r.active_up[b]).astype(bool)
+    act_o = (o["active_lo"] | o["active_up"]).astype(bool)
+    ys = np.abs(o["ys"])
+    firm = ys > 1e-9 * max(ys.max(), 1e-300)
+    assert np.array_equal(act_g[firm], act_o[firm]), b
+    assert np.array_equal(r.active_lo[b][firm], o["active_lo"][firm]), b
+    assert np.array_equal(r.active_up[b][firm], o["active_up"][firm]), b
+    # a round-off dual can only flip lower<->upper (or drop out if exactly 0.0); it never adds a firm row
+    assert act_g[~firm].sum() <= (~firm).sum()
+
+
+@pytest.fixture(scope="module")
+def track():
+    return lp.Map("L_shape").PointAndTangent
+
+
+def _oracle_ctrl(cfg, st, w, b, **kw):
+    return oracle.ctrl_solve(cfg, st, w["x0"][b], mode=1, x_sched=w["x0"][b], u_prev=w["u_prev"][b], vel_ref=w["vel_ref"][b],
+                             curv_ref=w["curv_ref"][b], lap=int(w["lap"][b]), old_steering=[w["u_old"][b, 0]],
+                             old_accel=float(w["u_old"][b, 1]), **kw)
+
+
+def test_schedule_matches_oracle(track):
+    N, B = 8, 64
+    w = W.controller_batch(B, N, seed=5)
+    s = lp.BatchSolver("controller", N, W.CTRL_DT, track=track, max_batch=B, **W.CTRL_TT)
+    cfg = oracle.make_cfg("controller", N, W.CTRL_DT, W.CTRL_TT["Q"], W.CTRL_TT["R"], W.CTRL_TT["dR"], track)
+    for lap in (0, 1):
+        lapv = np.full(B, lap, dtype=np.int32)
+        r = s.schedule(x0=w["x0"], u_prev=w["u_prev"], vel_ref=w["vel_ref"], curv_ref=w["curv_ref"], lap=lapv)
+        for b in range(B):
+            st, A, Bm, C, err = oracle.ctrl_predict(cfg, w["x0"][b], w["u_prev"][b], w["vel_ref"][b], w["curv_ref"][b], 60.0, lap)
+            assert err == int(r.sched_err[b]) == 0
+            np.testing.assert_allclose(r.A_out[b], A, rtol=1e-14, atol=1e-16)
+            np.testing.assert_allclose(r.B_out[b], Bm, rtol=1e-14, atol=1e-16)
+            np.testing.assert_allclose(r.states_out[b], st, rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("iters", [1, 7, 50, 200])
+def test_controller_fixed_iteration_iterates(track, iters):
+    N, B = 8, 48
+    w = W.controller_batch(B, N, seed=11)
+    fixed = dict(max_iter=iters, check_termination=0, adaptive_rho=0, polish=0)
+    s = lp.BatchSolver("controller", N, W.CTRL_DT, track=track, max_batch=B, **W.CTRL_TT, **fixed)
+    r = s.solve(w["x0"], extra_outputs=("xs", "zs", "ys"), **{k: w[k] for k in ("u_prev", "vel_ref", "curv_ref", "lap", "u_old")})
+    cfg = oracle.make_cfg("controller", N, W.CTRL_DT, W.CTRL_TT["Q"], W.CTRL_TT["R"], W.CTRL_TT["dR"], track)
+    st = oracle.default_settings(**fixed)
+    worst = 0.0
+    for b in range(B):
+        o = _oracle_ctrl(cfg, st, w, b)
+        assert int(r.status[b]) == o["status"] and int(r.iters[b]) == o["iter"] == iters
+        for k in ("xs", "zs", "ys"):
+            worst = max(worst, _relinf(r[k][b], o[k]))
+    assert worst < 1e-9, worst
+
+
+def test_controller_converged_matches_oracle(track):
+    N, B = 8, 256
+    w = W.controller_batch(B, N, seed=0)
+    s = lp.BatchSolver("controller", N, W.CTRL_DT, track=track, max_batch=B, **W.CTRL_TT)
+    r = s.solve(w["x0"], extra_outputs=("active_lo", "active_up"), **{k: w[k] for k in ("u_prev", "vel_ref", "curv_ref", "lap", "u_old")})
+    cfg = oracle.make_cfg("controller", N, W.CTRL_DT, W.CTRL_TT["Q"], W.CTRL_TT["R"], W.CTRL_TT["dR"], track)
+    st = oracle.default_settings(polish=1)
+    for b in range(B):
+        o = _oracle_ctrl(cfg, st, w, b)
+        assert int(r.status[b]) == o["status"], (b, r.status[b], o["status"])
+        assert int(r.iters[b]) == o["iter"], (b, r.iters[b], o["iter"])
+        assert int(r.rho_updates[b]) == o["rho_updates"]
+        assert int(r.polish_status[b]) == o["status_polish"], b
+        _same_active_set(r, o, b)
+        np.testing.assert_allclose(r.u_pred[b], o["uPred"], rtol=0, atol=1e-4)
+        np.testing.assert_allclose(r.x_pred[b], o["xPred"], rtol=0, atol=1e-4)
+        assert abs(r.obj[b] - o["obj_val"]) <= 1e-6 * abs(o["obj_val"]), (b, r.obj[b], o["obj_val"])
+
+
+def test_planner_fixed_and_converged(track):
+    N, B = 40, 24
+    w = W.planner_batch(B, N, seed=1)
+    cfg = oracle.make_cfg("planner", N, W.PLAN_DT, W.PLAN["Q"], W.PLAN["R"], W.PLAN["dR"], track, L_cf=W.PLAN["L_cf"])
+    keys = ("SS", "u_prev", "u_old", "max_ey", "ey_lo", "ey_hi")
+    fixed = dict(max_iter=100, check_termination=0, adaptive_rho=0, polish=0)
+    s = lp.BatchSolver("planner", N, W.PLAN_DT, track=track, max_batch=B, **W.PLAN, **fixed)
+    r = s.solve(w["x0"], extra_outputs=("xs", "zs", "ys"), **{k: w[k] for k in keys})
+    st = oracle.default_settings(**fixed)
+    worst = 0.0
+    for b in range(B):
+        o = oracle.plan_solve(cfg, st, w["x0"][b], mode=1, x_sched=w["x0"][b], SS=w["SS"][b], u_prev=w["u_prev"][b],
+                              u_old=w["u_old"][b], max_ey=float(w["max_ey"][b]), ey_lo=w["ey_lo"][b], ey_hi=w["ey_hi"][b])
+        for k in ("xs", "zs", "ys"):
+            worst = max(worst, _relinf(r[k][b], o[k]))
+    assert worst < 1e-9, worst
+    s.update_settings(**{k: getattr(oracle.default_settings(polish=1), k) for k in ("max_iter", "check_termination", "adaptive_rho", "polish")})
+    r = s.solve(w["x0"], extra_outputs=("active_lo", "active_up"), **{k: w[k] for k in keys})
+    st = oracle.default_settings(polish=1)
+    for b in range(B):
+        o = oracle.plan_solve(cfg, st, w["x0"][b], mode=1, x_sched=w["x0"][b], SS=w["SS"][b], u_prev=w["u_prev"][b],
+                              u_old=w["u_old"][b], max_ey=float(w["max_ey"][b]), ey_lo=w["ey_lo"][b], ey_hi=w["ey_hi"][b])
+        assert int(r.status[b]) == o["status"], (b, r.status[b], o["status"])
+        assert int(r.iters[b]) == o["iter"], (b, r.iters[b], o["iter"])
+        assert int(r.polish_status[b]) == o["status_polish"], b
+        if o["status"] in (1, 2, -2):
+            _same_active_set(r, o, b)
+            np.testing.assert_allclose(r.u_pred[b], o["uPred"], rtol=0, atol=1e-4)
+            np.testing.assert_allclose(r.x_pred[b], o["xPred"], rtol=0, atol=1e-4)
+            assert abs(r.obj[b] - o["obj_val"]) <= 1e-6 * abs(o["obj_val"])
+        else:
+            assert np.isnan(r.x_pred[b]).all()
