@@ -12,6 +12,7 @@
 #include "lpvmpc.h"
 #include "lpv_model.cuh"
 #include "lpv_qp.cuh"
+#include "lpv_t8.cuh"
 
 namespace lpv {
 
@@ -261,6 +262,9 @@ struct lpvmpc_handle {
   size_t ws_bytes;
   double *d_track = nullptr;
   double *d_gws = nullptr;
+  int variant = 1;           // 1: generic warp-per-QP kernel, 2: T8 register/shared-resident kernel
+  unsigned *d_queue = nullptr;  // work-queue counter of the persistent T8 kernel
+  double *d_cold = nullptr;     // T8 scratch slab (scalings, P) per resident lane
   // staging for the host API
   char *d_stage = nullptr, *h_stage = nullptr;
   size_t stage_bytes = 0;
@@ -310,8 +314,22 @@ int validate_args(lpvmpc_handle *h, int B, const lpvmpc_args *a, bool solve) {
   return LPVMPC_OK;
 }
 
+constexpr int kT8N = 8;
+
+int launch_t8(lpvmpc_handle *h, const Params &p, cudaStream_t s) {
+  if (p.B == 0) return LPVMPC_OK;
+  const int warps = (p.B + 3) / 4;
+  const int grid = warps < h->grid_cap ? warps : h->grid_cap;
+  CUDA_TRY(h, cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned), s));
+  lpv::t8::lpv_solve_t8_kernel<kT8N><<<grid, 32, h->ws_bytes, s>>>(p, h->d_queue, h->d_cold);
+  ++h->launches;
+  CUDA_TRY(h, cudaGetLastError());
+  return LPVMPC_OK;
+}
+
 template <int KIND>
 int launch_solve(lpvmpc_handle *h, const Params &p, cudaStream_t s) {
+  if (h->variant == 2) return launch_t8(h, p, s);
   const int grid = p.B < h->grid_cap ? p.B : h->grid_cap;
   if (grid == 0) return LPVMPC_OK;
   if (h->smem_mode) lpv::lpv_solve_kernel<KIND, true><<<grid, 32, h->ws_bytes, s>>>(p);
@@ -407,9 +425,27 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
   if (prop.major < 10) { h->err = "built for sm_100a (B200); device is older"; return bail(LPVMPC_E_UNSUPPORTED); }
   h->sm_count = prop.multiProcessorCount;
   h->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  {
+    // T8 kernel: controller, N = 8, no steering delay, diagonal Q and R
+    bool diag = true;
+    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) if (i != j && cfg->Q[i * 6 + j] != 0.0) diag = false;
+    if (cfg->R[1] != 0.0 || cfg->R[2] != 0.0) diag = false;
+    const bool eligible = cfg->kind == LPVMPC_CONTROLLER && cfg->N == kT8N && cfg->steering_delay == 0 && diag;
+    if (cfg->variant == 2 && !eligible) { h->err = "variant 2 (T8) needs controller, N=8, steering_delay=0, diagonal Q and R"; return bail(LPVMPC_E_UNSUPPORTED); }
+    h->variant = (cfg->variant == 1 || !eligible) ? 1 : 2;
+  }
   h->ws_bytes = (size_t)h->L.total * sizeof(double);
   h->smem_mode = h->ws_bytes <= (size_t)h->smem_optin;
-  if (h->smem_mode) {
+  if (h->variant == 2) {
+    h->ws_bytes = (size_t)4 * lpv::t8::Reg<kT8N>::TOTAL * sizeof(double);
+    h->smem_mode = true;
+    int per_sm = (int)(prop.sharedMemPerMultiprocessor / (h->ws_bytes + 1024));
+    if (per_sm < 1) per_sm = 1;
+    h->grid_cap = h->sm_count * per_sm;
+    CTRY(cudaFuncSetAttribute(lpv::t8::lpv_solve_t8_kernel<kT8N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ws_bytes));
+    CTRY(cudaMalloc(&h->d_queue, sizeof(unsigned)));
+    CTRY(cudaMalloc(&h->d_cold, sizeof(double) * (size_t)h->grid_cap * 32 * lpv::t8::Cold<kT8N>::TOTAL));
+  } else if (h->smem_mode) {
     int per_sm = (int)(prop.sharedMemPerMultiprocessor / (h->ws_bytes + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 32) per_sm = 32;
@@ -448,7 +484,7 @@ void lpvmpc_destroy(lpvmpc_handle *h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamDestroy(h->stream);
-  cudaFree(h->d_track); cudaFree(h->d_gws); cudaFree(h->d_stage);
+  cudaFree(h->d_track); cudaFree(h->d_gws); cudaFree(h->d_stage); cudaFree(h->d_queue); cudaFree(h->d_cold);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   delete h;
 }
@@ -456,9 +492,9 @@ void lpvmpc_destroy(lpvmpc_handle *h) {
 int lpvmpc_get_info(const lpvmpc_handle *h, lpvmpc_info *info) {
   if (!h || !info) return LPVMPC_E_ARG;
   info->n = h->n; info->d = h->d; info->N = h->L.N; info->nz = h->L.nz; info->m = h->L.m;
-  info->variant = 1;
+  info->variant = h->variant;
   info->workspace_in_smem = h->smem_mode ? 1 : 0;
-  info->smem_bytes_per_qp = h->smem_mode ? (int)h->ws_bytes : 0;
+  info->smem_bytes_per_qp = h->smem_mode ? (int)(h->variant == 2 ? h->ws_bytes / 4 : h->ws_bytes) : 0;
   info->workspace_bytes = (long long)(h->stage_bytes + (h->smem_mode ? 0 : h->ws_bytes * (size_t)h->grid_cap));
   info->kernel_launches = h->launches;
   return LPVMPC_OK;

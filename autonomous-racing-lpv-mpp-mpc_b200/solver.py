@@ -25,7 +25,7 @@ class BatchSolver(object):
     """One handle = one problem family (kind, horizon, weights, bounds, track, OSQP settings) on one GPU."""
 
     def __init__(self, kind, N, dt, Q, R, dR, track, L_cf=None, vehicle=None, max_vel=5.0, min_vel=0.9,
-                 steering_delay=0, max_batch=4096, device=0, settings=None, **osqp_settings):
+                 steering_delay=0, max_batch=4096, device=0, settings=None, variant=0, **osqp_settings):
         self.kind = nat.CONTROLLER if kind in ("controller", nat.CONTROLLER) else nat.PLANNER
         self.n = 6 if self.kind == nat.CONTROLLER else 5
         self.d = 2
@@ -60,7 +60,7 @@ class BatchSolver(object):
         cfg.track = self._track.ctypes.data_as(nat.c_double_p)
         cfg.max_batch = int(max_batch)
         cfg.device = int(device)
-        cfg.variant = 0
+        cfg.variant = int(variant)  # 0 auto, 1 generic warp-per-QP kernel, 2 T8 kernel (controller, N=8)
         cfg.settings = settings if settings is not None else nat.default_settings(**osqp_settings)
         self.steering_delay = int(steering_delay)
         self.max_batch = int(max_batch)
