@@ -11,4 +11,6 @@ from .track import Map, curvature
 __all__ = ["BatchSolver", "BatchResult", "PathFollowingLPV_MPC", "LPV_MPC_Planner", "Map", "curvature", "build",
            "default_settings", "NativeError", "STATUS_NAMES", "SCHED_GIVEN", "SCHED_PREDICT", "SCHED_ESTIMATE",
            "_native"]
-import importlib; workloads = importlib.import_module(__name__ + '.workloads')
+import importlib
+workloads = importlib.import_module(__name__ + '.workloads')
+sharding = importlib.import_module(__name__ + '.sharding')

@@ -220,7 +220,7 @@ def run_ours(args):
 
     spec, track, w, tune, dt, keys = make_workload(args.workload, rank)
     B = spec["B"]
-    solver = lp.BatchSolver(spec["kind"], spec["N"], dt, track=track.PointAndTangent, max_batch=B, device=local, **tune)
+    solver = lp.BatchSolver(spec["kind"], spec["N"], dt, track=track.PointAndTangent, max_batch=B, device=local, variant=args.variant, **tune)
     info0 = solver.info()
 
     def barrier():
@@ -345,6 +345,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="ctrl4096", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", type=int, default=0, help="kernel variant (0 = auto)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
