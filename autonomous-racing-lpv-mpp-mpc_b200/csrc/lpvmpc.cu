@@ -13,6 +13,7 @@
 #include "lpv_model.cuh"
 #include "lpv_qp.cuh"
 #include "lpv_t8.cuh"
+#include "lpv_g8.cuh"
 
 namespace lpv {
 
@@ -247,6 +248,22 @@ Layout make_layout(int kind, int N, int delay) {
   return L;
 }
 
+lpv::g8::Lay make_g8_layout(int kind, int N) {
+  const int NX = kind == LPVMPC_CONTROLLER ? 6 : 5;
+  lpv::g8::Lay L;
+  std::memset(&L, 0, sizeof(L));
+  L.N = N; L.gs = NX * 8;
+  int o = 0;
+  auto take = [&](int n) { const int r = o; o += n; return r; };
+  L.T = take((N + 1) * 64); L.K = take(N * 64); L.G = take(N * L.gs);
+  const int v = (N + 1) * 8;
+  L.X = take(v); L.Q = take(v); L.B = take(v); L.YD = take(v); L.BE = take(v); L.ED = take(v);
+  L.ZI = take(v); L.YI = take(v); L.SI = take(v); L.UI = take(v); L.LI = take(v);
+  L.total = o;
+  L.cold_total = lpv::g8::C_COUNT * v;
+  return L;
+}
+
 }  // namespace
 
 struct lpvmpc_handle {
@@ -262,7 +279,9 @@ struct lpvmpc_handle {
   size_t ws_bytes;
   double *d_track = nullptr;
   double *d_gws = nullptr;
-  int variant = 1;           // 1: generic warp-per-QP kernel, 2: T8 register/shared-resident kernel
+  int variant = 1;           // 1: generic warp-per-QP kernel, 2: T8 register/shared-resident kernel, 3: G8 compact kernel
+  lpv::g8::Lay GL;           // G8 shared-memory layout
+  int qpw = 4;               // G8: QPs per warp
   unsigned *d_queue = nullptr;  // work-queue counter of the persistent T8 kernel
   double *d_cold = nullptr;     // T8 scratch slab (scalings, P) per resident lane
   // staging for the host API
@@ -327,9 +346,35 @@ int launch_t8(lpvmpc_handle *h, const Params &p, cudaStream_t s) {
   return LPVMPC_OK;
 }
 
+template <int KIND, int QPW>
+void g8_launch(int grid, size_t smem, cudaStream_t s, const lpv::g8::G8Params &gp) {
+  lpv::g8::lpv_solve_g8_kernel<KIND, QPW><<<grid, 32, smem, s>>>(gp);
+}
+template <int KIND, int QPW>
+cudaError_t g8_attr(size_t smem) {
+  return cudaFuncSetAttribute(lpv::g8::lpv_solve_g8_kernel<KIND, QPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+template <int KIND>
+int launch_g8(lpvmpc_handle *h, const Params &p, cudaStream_t s) {
+  if (p.B == 0) return LPVMPC_OK;
+  lpv::g8::G8Params gp;
+  gp.L = h->GL; gp.M = p.M; gp.S = p.S; gp.a = p.a; gp.B = p.B; gp.queue = h->d_queue; gp.cold = h->d_cold;
+  const int warps = (p.B + h->qpw - 1) / h->qpw;
+  const int grid = warps < h->grid_cap ? warps : h->grid_cap;
+  CUDA_TRY(h, cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned), s));
+  if (h->qpw == 4) g8_launch<KIND, 4>(grid, h->ws_bytes, s, gp);
+  else if (h->qpw == 2) g8_launch<KIND, 2>(grid, h->ws_bytes, s, gp);
+  else g8_launch<KIND, 1>(grid, h->ws_bytes, s, gp);
+  ++h->launches;
+  CUDA_TRY(h, cudaGetLastError());
+  return LPVMPC_OK;
+}
+
 template <int KIND>
 int launch_solve(lpvmpc_handle *h, const Params &p, cudaStream_t s) {
   if (h->variant == 2) return launch_t8(h, p, s);
+  if (h->variant == 3) return launch_g8<KIND>(h, p, s);
   const int grid = p.B < h->grid_cap ? p.B : h->grid_cap;
   if (grid == 0) return LPVMPC_OK;
   if (h->smem_mode) lpv::lpv_solve_kernel<KIND, true><<<grid, 32, h->ws_bytes, s>>>(p);
@@ -433,10 +478,36 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
     const bool eligible = cfg->kind == LPVMPC_CONTROLLER && cfg->N == kT8N && cfg->steering_delay == 0 && diag;
     if (cfg->variant == 2 && !eligible) { h->err = "variant 2 (T8) needs controller, N=8, steering_delay=0, diagonal Q and R"; return bail(LPVMPC_E_UNSUPPORTED); }
     h->variant = (cfg->variant == 1 || !eligible) ? 1 : 2;
+    // G8 kernel: diagonal Q and R, no steering delay, per-QP state fits shared memory; planner rows use 64-bit stage masks
+    bool pdiag = true;
+    const int nxk = cfg->kind == LPVMPC_CONTROLLER ? 6 : 5;
+    for (int i = 0; i < nxk; ++i) for (int j = 0; j < nxk; ++j) if (i != j && cfg->Q[i * nxk + j] != 0.0) pdiag = false;
+    if (cfg->R[1] != 0.0 || cfg->R[2] != 0.0) pdiag = false;
+    h->GL = make_g8_layout(cfg->kind, cfg->N);
+    const size_t per_qp = (size_t)h->GL.total * sizeof(double);
+    const bool g8_ok = pdiag && cfg->steering_delay == 0 && per_qp <= (size_t)h->smem_optin &&
+                       (cfg->kind == LPVMPC_CONTROLLER || cfg->N <= 63);
+    if (cfg->variant == 3 && !g8_ok) { h->err = "variant 3 (G8) needs diagonal Q and R, steering_delay=0, planner N<=63 and a per-QP state that fits shared memory"; return bail(LPVMPC_E_UNSUPPORTED); }
+    if (cfg->variant == 3) h->variant = 3;
   }
   h->ws_bytes = (size_t)h->L.total * sizeof(double);
   h->smem_mode = h->ws_bytes <= (size_t)h->smem_optin;
-  if (h->variant == 2) {
+  if (h->variant == 3) {
+    const size_t per_qp = (size_t)h->GL.total * sizeof(double);
+    h->qpw = (4 * per_qp <= (size_t)h->smem_optin) ? 4 : ((2 * per_qp <= (size_t)h->smem_optin) ? 2 : 1);
+    h->ws_bytes = per_qp * h->qpw;
+    h->smem_mode = true;
+    int per_sm = (int)(prop.sharedMemPerMultiprocessor / (h->ws_bytes + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 16) per_sm = 16;
+    h->grid_cap = h->sm_count * per_sm;
+    const bool ctrl = cfg->kind == LPVMPC_CONTROLLER;
+    if (h->qpw == 4) CTRY(ctrl ? (g8_attr<LPVMPC_CONTROLLER, 4>(h->ws_bytes)) : (g8_attr<LPVMPC_PLANNER, 4>(h->ws_bytes)));
+    else if (h->qpw == 2) CTRY(ctrl ? (g8_attr<LPVMPC_CONTROLLER, 2>(h->ws_bytes)) : (g8_attr<LPVMPC_PLANNER, 2>(h->ws_bytes)));
+    else CTRY(ctrl ? (g8_attr<LPVMPC_CONTROLLER, 1>(h->ws_bytes)) : (g8_attr<LPVMPC_PLANNER, 1>(h->ws_bytes)));
+    CTRY(cudaMalloc(&h->d_queue, sizeof(unsigned)));
+    CTRY(cudaMalloc(&h->d_cold, sizeof(double) * (size_t)h->grid_cap * h->qpw * h->GL.cold_total));
+  } else if (h->variant == 2) {
     h->ws_bytes = (size_t)4 * lpv::t8::Reg<kT8N>::TOTAL * sizeof(double);
     h->smem_mode = true;
     int per_sm = (int)(prop.sharedMemPerMultiprocessor / (h->ws_bytes + 1024));
@@ -494,7 +565,7 @@ int lpvmpc_get_info(const lpvmpc_handle *h, lpvmpc_info *info) {
   info->n = h->n; info->d = h->d; info->N = h->L.N; info->nz = h->L.nz; info->m = h->L.m;
   info->variant = h->variant;
   info->workspace_in_smem = h->smem_mode ? 1 : 0;
-  info->smem_bytes_per_qp = h->smem_mode ? (int)(h->variant == 2 ? h->ws_bytes / 4 : h->ws_bytes) : 0;
+  info->smem_bytes_per_qp = h->smem_mode ? (int)(h->variant == 2 ? h->ws_bytes / 4 : (h->variant == 3 ? h->ws_bytes / h->qpw : h->ws_bytes)) : 0;
   info->workspace_bytes = (long long)(h->stage_bytes + (h->smem_mode ? 0 : h->ws_bytes * (size_t)h->grid_cap));
   info->kernel_launches = h->launches;
   return LPVMPC_OK;

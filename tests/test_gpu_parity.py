@@ -69,7 +69,7 @@ def test_schedule_matches_oracle(track):
             np.testing.assert_allclose(r.states_out[b], st, rtol=1e-12, atol=1e-14)
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("iters", [1, 7, 50, 200])
 def test_controller_fixed_iteration_iterates(track, iters, variant):
     N, B = 8, 48
@@ -89,7 +89,7 @@ def test_controller_fixed_iteration_iterates(track, iters, variant):
     assert worst < 1e-9, worst
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 def test_controller_converged_matches_oracle(track, variant):
     N, B = 8, 254  # not a multiple of 4: exercises the idle-group path of the T8 kernel
     w = W.controller_batch(B, N, seed=0)
@@ -109,13 +109,15 @@ def test_controller_converged_matches_oracle(track, variant):
         assert abs(r.obj[b] - o["obj_val"]) <= 1e-6 * abs(o["obj_val"]), (b, r.obj[b], o["obj_val"])
 
 
-def test_planner_fixed_and_converged(track):
+@pytest.mark.parametrize("variant", [1, 3])
+def test_planner_fixed_and_converged(track, variant):
     N, B = 40, 24
     w = W.planner_batch(B, N, seed=1)
     cfg = oracle.make_cfg("planner", N, W.PLAN_DT, W.PLAN["Q"], W.PLAN["R"], W.PLAN["dR"], track, L_cf=W.PLAN["L_cf"])
     keys = ("SS", "u_prev", "u_old", "max_ey", "ey_lo", "ey_hi")
     fixed = dict(max_iter=100, check_termination=0, adaptive_rho=0, polish=0)
-    s = lp.BatchSolver("planner", N, W.PLAN_DT, track=track, max_batch=B, **W.PLAN, **fixed)
+    s = lp.BatchSolver("planner", N, W.PLAN_DT, track=track, max_batch=B, variant=variant, **W.PLAN, **fixed)
+    assert s.info()["variant"] == variant
     r = s.solve(w["x0"], extra_outputs=("xs", "zs", "ys"), **{k: w[k] for k in keys})
     st = oracle.default_settings(**fixed)
     worst = 0.0
