@@ -29,7 +29,8 @@ struct Reg {  // shared-memory region of one QP, offsets in doubles
   static constexpr int ED = G + N * NB * NX;         // scaled identity entry of dynamics row (k, r)
   static constexpr int SI = ED + (N + 1) * NX;       // inequality coefficients (k, slot, t)
   static constexpr int UI = SI + N * 6;              // inequality upper bounds (scaled)
-  static constexpr int TOTAL = (UI + N * 6 + 1) & ~1;
+  static constexpr int EX = (UI + N * 6 + 1) & ~1;   // 2 x 8 doubles: ping-pong exchange buffer of the 8-lane all-gather
+  static constexpr int TOTAL = EX + 16;
 };
 // cold per-lane data in the global scratch slab (doubles per lane)
 template <int N>
@@ -55,6 +56,19 @@ __device__ __forceinline__ double gsum(double v) {
 __device__ __forceinline__ int gany(int v) {  // any lane of my 8-lane group
   const unsigned m = __ballot_sync(kFull, v);
   return ((m >> ((threadIdx.x & 31) & ~7)) & 0xffu) != 0;
+}
+
+// 8-lane all-gather through shared memory: 1 STS.64 + 4 broadcast LDS.128 instead of 16 SHFL.32 (+ the register moves
+// that re-pair the halves).  Same bytes through the shared-memory crossbar, a third of the instructions — the unrolled
+// hot loop is bound by instruction fetch.  PAR alternates so a slow lane never sees the next round's values.
+template <int PAR>
+__device__ __forceinline__ void gather_smem(double *ex, int r, double v, double (&g)[8]) {
+  double *b = ex + PAR * 8;
+  b[r] = v;
+  __syncwarp();
+  const double2 a0 = *reinterpret_cast<const double2 *>(b), a1 = *reinterpret_cast<const double2 *>(b + 2),
+                a2 = *reinterpret_cast<const double2 *>(b + 4), a3 = *reinterpret_cast<const double2 *>(b + 6);
+  g[0] = a0.x; g[1] = a0.y; g[2] = a1.x; g[3] = a1.y; g[4] = a2.x; g[5] = a2.y; g[6] = a3.x; g[7] = a3.y;
 }
 
 template <int N>
@@ -205,8 +219,7 @@ __device__ __forceinline__ void solve(const Ctx<N> &c, const double (&b)[N + 1],
   for (int k = 0; k <= N; ++k) {
     const int nbk = (k < N) ? NB : NX;
     double gv[NB];
-#pragma unroll
-    for (int cc = 0; cc < NB; ++cc) gv[cc] = (cc < nbk) ? gshfl(v, cc) : 0.0;
+    if (k & 1) gather_smem<1>(c.S + Reg<N>::EX, r, v, gv); else gather_smem<0>(c.S + Reg<N>::EX, r, v, gv);
     const double *Tk = c.Tb(k) + r * LDB;
     double a0 = 0.0, a1 = 0.0;
 #pragma unroll
@@ -228,8 +241,7 @@ __device__ __forceinline__ void solve(const Ctx<N> &c, const double (&b)[N + 1],
   for (int k = N - 1; k >= 0; --k) {
     const int nbn = (k + 1 < N) ? NB : NX;
     double gx[NB];
-#pragma unroll
-    for (int rr = 0; rr < NB; ++rr) gx[rr] = (rr < nbn) ? gshfl(x[k + 1], rr) : 0.0;
+    if ((N + k) & 1) gather_smem<1>(c.S + Reg<N>::EX, r, x[k + 1], gx); else gather_smem<0>(c.S + Reg<N>::EX, r, x[k + 1], gx);
     const double *Kn = c.Kb(k + 1);
     double c0 = 0.0, c1 = 0.0;
 #pragma unroll
@@ -249,8 +261,7 @@ __device__ __forceinline__ void solve(const Ctx<N> &c, const double (&b)[N + 1],
   }
   {
     double gx[NB];
-#pragma unroll
-    for (int rr = 0; rr < NB; ++rr) gx[rr] = gshfl(x[0], rr);
+    if ((N + 1) & 1) gather_smem<0>(c.S + Reg<N>::EX, r, x[0], gx); else gather_smem<1>(c.S + Reg<N>::EX, r, x[0], gx);
     const double *g = c.Gt(0);
     double a0 = c.ed(1) * x[1], a1 = 0.0;
 #pragma unroll
@@ -287,10 +298,12 @@ __device__ __forceinline__ void colsA(const Ctx<N> &c, const double (&td)[N + 1]
     if (k < N) {
       const double *g = c.Gt(k) + r * NX;
       double a1 = 0.0;
+      double gt[NB];
+      if (k & 1) gather_smem<1>(c.S + Reg<N>::EX, r, td[k + 1], gt); else gather_smem<0>(c.S + Reg<N>::EX, r, td[k + 1], gt);
 #pragma unroll
       for (int rr = 0; rr < NX; rr += 2) {
-        acc = fma(g[rr], gshfl(td[k + 1], rr), acc);
-        a1 = fma(g[rr + 1], gshfl(td[k + 1], rr + 1), a1);
+        acc = fma(g[rr], gt[rr], acc);
+        a1 = fma(g[rr + 1], gt[rr + 1], a1);
       }
       acc += a1;
       if (c.il) { acc = fma(c.si(k, 0), ti[k][0], acc); acc = fma(c.si(k, 1), ti[k][1], acc); }
@@ -907,14 +920,19 @@ __device__ __forceinline__ void admm_step(const Ctx<N> &c, Lane<N> &L, const dou
 }
 
 // ---------------------------------------------------------------- one persistent warp = 4 QPs at a time
-template <int N>
-__global__ void __launch_bounds__(32, 4) lpv_solve_t8_kernel(const __grid_constant__ Params p, unsigned *queue, double *cold_slab) {
+// QPW = QPs per warp (4 or 2).  With QPW = 2 the upper half-warp mirrors the lower one (same problems, same shared
+// and scratch regions, same values written by the same instruction) and 8 warps instead of 4 fit an SM: the unrolled
+// code is bound by instruction fetch per warp (profiles/r1_icache_probe.jsonl), so two half-empty warps per SM
+// sub-partition issue about twice as fast as one full warp.
+template <int N, int QPW>
+__global__ void __launch_bounds__(32, 16 / QPW) lpv_solve_t8_kernel(const __grid_constant__ Params p, unsigned *queue, double *cold_slab) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x;
   const int g = lane >> 3, r = lane & 7;
+  const int gg = g % QPW;
   Ctx<N> c;
-  c.S = smem + g * Reg<N>::TOTAL;
-  c.cold = cold_slab + ((size_t)(blockIdx.x * 4 + g) * 8 + r) * Cold<N>::TOTAL;
+  c.S = smem + gg * Reg<N>::TOTAL;
+  c.cold = cold_slab + ((size_t)(blockIdx.x * QPW + gg) * 8 + r) * Cold<N>::TOTAL;
   c.r = r; c.xl = r < NX; c.il = (r == 0) || (r >= NX); c.slot = (r == 0) ? 0 : ((r >= NX) ? r - 5 : 0);
   const lpvmpc_args &a = p.a;
   const lpvmpc_settings &S = p.S;
@@ -923,11 +941,11 @@ __global__ void __launch_bounds__(32, 4) lpv_solve_t8_kernel(const __grid_consta
 
   for (;;) {
     unsigned base = 0;
-    if (lane == 0) base = atomicAdd(queue, 4u);
+    if (lane == 0) base = atomicAdd(queue, (unsigned)QPW);
     base = __shfl_sync(kFull, base, 0);
     if ((int)base >= p.B) break;
-    const bool valid = (int)(base + g) < p.B;
-    const int b = valid ? (int)(base + g) : (int)base;  // idle groups shadow group 0 and never write
+    const bool valid = (g < QPW) && ((int)(base + gg) < p.B);
+    const int b = ((int)(base + gg) < p.B) ? (int)(base + gg) : (int)base;  // idle groups shadow another group and never write results
 
     Lane<N> L;
     Info I;

@@ -337,10 +337,11 @@ constexpr int kT8N = 8;
 
 int launch_t8(lpvmpc_handle *h, const Params &p, cudaStream_t s) {
   if (p.B == 0) return LPVMPC_OK;
-  const int warps = (p.B + 3) / 4;
+  const int warps = (p.B + h->qpw - 1) / h->qpw;
   const int grid = warps < h->grid_cap ? warps : h->grid_cap;
   CUDA_TRY(h, cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned), s));
-  lpv::t8::lpv_solve_t8_kernel<kT8N><<<grid, 32, h->ws_bytes, s>>>(p, h->d_queue, h->d_cold);
+  if (h->qpw == 2) lpv::t8::lpv_solve_t8_kernel<kT8N, 2><<<grid, 32, h->ws_bytes, s>>>(p, h->d_queue, h->d_cold);
+  else lpv::t8::lpv_solve_t8_kernel<kT8N, 4><<<grid, 32, h->ws_bytes, s>>>(p, h->d_queue, h->d_cold);
   ++h->launches;
   CUDA_TRY(h, cudaGetLastError());
   return LPVMPC_OK;
@@ -476,8 +477,9 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
     for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) if (i != j && cfg->Q[i * 6 + j] != 0.0) diag = false;
     if (cfg->R[1] != 0.0 || cfg->R[2] != 0.0) diag = false;
     const bool eligible = cfg->kind == LPVMPC_CONTROLLER && cfg->N == kT8N && cfg->steering_delay == 0 && diag;
-    if (cfg->variant == 2 && !eligible) { h->err = "variant 2 (T8) needs controller, N=8, steering_delay=0, diagonal Q and R"; return bail(LPVMPC_E_UNSUPPORTED); }
+    if ((cfg->variant == 2 || cfg->variant == 4) && !eligible) { h->err = "variants 2/4 (T8) need controller, N=8, steering_delay=0, diagonal Q and R"; return bail(LPVMPC_E_UNSUPPORTED); }
     h->variant = (cfg->variant == 1 || !eligible) ? 1 : 2;
+    h->qpw = (cfg->variant == 4) ? 2 : 4;
     // G8 kernel: diagonal Q and R, no steering delay, per-QP state fits shared memory; planner rows use 64-bit stage masks
     bool pdiag = true;
     const int nxk = cfg->kind == LPVMPC_CONTROLLER ? 6 : 5;
@@ -508,12 +510,15 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
     CTRY(cudaMalloc(&h->d_queue, sizeof(unsigned)));
     CTRY(cudaMalloc(&h->d_cold, sizeof(double) * (size_t)h->grid_cap * h->qpw * h->GL.cold_total));
   } else if (h->variant == 2) {
-    h->ws_bytes = (size_t)4 * lpv::t8::Reg<kT8N>::TOTAL * sizeof(double);
+    // variant 4 = experiment: 2 QPs per warp, 8 warps / SM (slower: the fetch limit is per SM sub-partition)
+    h->ws_bytes = (size_t)h->qpw * lpv::t8::Reg<kT8N>::TOTAL * sizeof(double);
     h->smem_mode = true;
     int per_sm = (int)(prop.sharedMemPerMultiprocessor / (h->ws_bytes + 1024));
     if (per_sm < 1) per_sm = 1;
+    if (per_sm > 16 / h->qpw) per_sm = 16 / h->qpw;
     h->grid_cap = h->sm_count * per_sm;
-    CTRY(cudaFuncSetAttribute(lpv::t8::lpv_solve_t8_kernel<kT8N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ws_bytes));
+    if (h->qpw == 2) CTRY((cudaFuncSetAttribute(lpv::t8::lpv_solve_t8_kernel<kT8N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ws_bytes)));
+    else CTRY((cudaFuncSetAttribute(lpv::t8::lpv_solve_t8_kernel<kT8N, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ws_bytes)));
     CTRY(cudaMalloc(&h->d_queue, sizeof(unsigned)));
     CTRY(cudaMalloc(&h->d_cold, sizeof(double) * (size_t)h->grid_cap * 32 * lpv::t8::Cold<kT8N>::TOTAL));
   } else if (h->smem_mode) {
@@ -565,7 +570,7 @@ int lpvmpc_get_info(const lpvmpc_handle *h, lpvmpc_info *info) {
   info->n = h->n; info->d = h->d; info->N = h->L.N; info->nz = h->L.nz; info->m = h->L.m;
   info->variant = h->variant;
   info->workspace_in_smem = h->smem_mode ? 1 : 0;
-  info->smem_bytes_per_qp = h->smem_mode ? (int)(h->variant == 2 ? h->ws_bytes / 4 : (h->variant == 3 ? h->ws_bytes / h->qpw : h->ws_bytes)) : 0;
+  info->smem_bytes_per_qp = h->smem_mode ? (int)(h->variant == 2 ? h->ws_bytes / h->qpw : (h->variant == 3 ? h->ws_bytes / h->qpw : h->ws_bytes)) : 0;
   info->workspace_bytes = (long long)(h->stage_bytes + (h->smem_mode ? 0 : h->ws_bytes * (size_t)h->grid_cap));
   info->kernel_launches = h->launches;
   return LPVMPC_OK;
