@@ -1,0 +1,1516 @@
+// "H8" kernel: 8 lanes per QP, QPW QPs per warp, compact code, hot state in shared memory, cold state in an L2 slab.
+//
+// Same algorithm as lpv_qp.cuh / lpv_g8.cuh / oracle/osqp_ref.c (OSQP 0.6: Ruiz scaling, rho vector, relaxed ADMM,
+// termination + infeasibility certificates every check_termination iterations, adaptive rho, polish), restricted to
+// diagonal Q and R (the reference's tunings, controllerMain.py:139-148, plannerMain.py:96-99) and steering_delay = 0.
+//
+// What is different from G8 (profiles/r1b_*: G8 issues 4 000 instructions per ADMM step and keeps 18 KB per QP):
+//
+//  * The dynamics rows are equalities, so their z is pinned to the right-hand side `be` after the first step and their
+//    dual only enters the next right-hand side through r = A_dyn'(rho_eq z_dyn - y_dyn).  With S x~ = rhs solved,
+//        rho_eq A_dyn'A_dyn x~ = rhs - (P + sigma I + A_in' rho A_in) x~  =: rhs - M x~      (M: diagonal + slew coupling)
+//    so r is advanced by an element-wise recursion,
+//        r <- r - alpha (rhs - M x~) + c CR,     CR = rho_eq A_dyn' be,   c = 2 on the first step, alpha afterwards,
+//    and the ADMM step needs NO product with A_k / B_k at all: forward sweep, backward sweep, element-wise update.
+//    The explicit dual y_dyn is recovered when somebody needs it (termination check, certificates, polish, output) from
+//    the running sum XS of x~:  y_dyn += rho_eq (alpha A_dyn XS - (alpha n + (1 - alpha) [first step inside]) be).
+//  * A_k / B_k (G), the scalings, q, be, y_dyn and every polish vector live in a per-slot global slab that stays in L2;
+//    shared memory holds the block factor (T, K), 6 stage vectors and the single-variable rows: 14.0 KB per controller
+//    QP at N = 8 -> 16 QPs per SM.
+//  * Hot loops use per-lane base pointers and immediate offsets (the row swizzle is applied to the gather, not to the
+//    matrix reads) and explicit fma().
+//
+// Lane r of a group owns component r of every stage variable w_k = [x_k; u_k], the dynamics row (k, r) and the
+// single-variable rows on its variable.  8x8 blocks of T and K are stored row-major with the 16-byte chunks of row rr
+// XOR-swizzled by (rr >> 1): row reads (LDS.128) and column reads (LDS.64) are bank-conflict free without padding.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "lpv_qp.cuh"
+
+namespace lpv {
+namespace h8 {
+
+struct Lay {  // per-QP offsets (doubles); computed on the host (lpvmpc.cu: make_h8_layout)
+  int N, nsl;                  // horizon; single-variable-row slots per stage in shared memory (6 controller, 7 planner)
+  int T, K;                    // (N+1) x 64, N x 64 (K_k at k-1)
+  int X, B, R, CR, XS, DG;     // (N+1) x 8: iterate x, rhs / sweep vector, r - q, CR, sum of x~, diag(M)
+  int ZI, YI, SI, UI, LI;      // (N+1) x nsl: single-variable rows (z, y, coefficient, bounds; LI planner only)
+  int PO;                      // (N+2) x 2, zero padded: PO[(i+1)*2 + c] couples u_i[c] and u_{i+1}[c]
+  int total;                   // doubles per QP in shared memory (== 8 mod 16: groups land on different bank halves)
+  int cold_total;              // doubles per QP slot in the global slab
+  int cG;                      // offset of G (N x NX x 8, row-major rows of -[A_k B_k], scaled) inside the slot
+};
+enum { C_D = 0, C_DINV, C_E, C_EINV, C_PD, C_PO, C_EI, C_EIINV, C_Q, C_BE, C_ED, C_YD, C_PVX, C_PVYI, C_DYD, C_PX, C_PYD,
+       C_PYI, C_R2D, C_R2I, C_ACTD, C_ACTI, C_ZT, C_COUNT };
+
+struct H8Params {
+  Lay L;
+  Model M;
+  lpvmpc_settings S;
+  lpvmpc_args a;
+  int B;
+  unsigned *queue;
+  double *cold;
+};
+
+template <int KIND> struct Dims;
+template <> struct Dims<LPVMPC_CONTROLLER> { static constexpr int NX = 6, NT = 2, NSL = 6; };
+template <> struct Dims<LPVMPC_PLANNER> { static constexpr int NX = 5, NT = 1, NSL = 7; };
+
+__device__ __forceinline__ double gshfl(double v, int src) { return __shfl_sync(kFull, v, src, 8); }
+__device__ __forceinline__ double gmax(double v) {
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) { const double w = __shfl_xor_sync(kFull, v, o, 8); v = (w > v) ? w : v; }
+  return v;
+}
+__device__ __forceinline__ double gsum(double v) {
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o, 8);
+  return v;
+}
+__device__ __forceinline__ int gany(int v) {
+  const unsigned m = __ballot_sync(kFull, v);
+  return ((m >> ((threadIdx.x & 31) & ~7)) & 0xffu) != 0;
+}
+__device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+__device__ __forceinline__ void st2(double *p, double a, double b) { *reinterpret_cast<double2 *>(p) = make_double2(a, b); }
+__device__ __forceinline__ int swz(int rr) { return (rr >> 1) & 3; }
+// offset of logical 16-byte chunk j of row rr inside a swizzled 8-wide block
+__device__ __forceinline__ int chunk(int rr, int j) { return rr * 8 + ((j ^ swz(rr)) << 1); }
+
+template <int KIND>
+struct Ctx {
+  static constexpr int NX = Dims<KIND>::NX, NB = NX + 2, NT = Dims<KIND>::NT, NSL = Dims<KIND>::NSL;
+  double *S;     // my QP's shared region
+  double *cold;  // my QP slot in the global slab
+  const Lay *L;
+  int N, r;
+  int ro[4];     // my row of a swizzled block: offset of logical chunk j
+  int co[4];     // my column of a swizzled block: offset inside row rr is co[rr >> 1]
+  bool xl, ul;   // state lane / input lane (neither: idle lane)
+  int islot;     // first single-variable-row slot of my variable inside a stage (t adds 1)
+  uint64_t eqm, loosem;  // planner: bit k = my box row at stage k is an equality / both bounds infinite
+
+  __device__ __forceinline__ bool var_live(int k) const { return xl || (ul && k < N); }
+  __device__ __forceinline__ bool has_in(int k) const {
+    if (KIND == LPVMPC_CONTROLLER) return (r == 0 || ul) && k < N;
+    return xl || (ul && k < N);
+  }
+  __device__ __forceinline__ double *cd(int arr) const { return cold + arr * (N + 1) * 8; }
+  __device__ __forceinline__ double *Tb(int k) const { return S + L->T + k * 64; }
+  __device__ __forceinline__ double *Kb(int k) const { return S + L->K + (k - 1) * 64; }
+  __device__ __forceinline__ const double *Gb(int k) const { return cold + L->cG + k * (NX * 8); }
+  __device__ __forceinline__ int si(int k, int t) const { return k * NSL + islot + t; }   // shared-memory slot
+  __device__ __forceinline__ int ci(int k, int t) const { return k * 8 + islot + t; }     // slab slot
+  // row-weight classes of my single-variable row (planner); controller rows are always plain inequalities
+  __device__ __forceinline__ double rho_of(int k, double rho, double rho_eq) const {
+    if (KIND == LPVMPC_CONTROLLER) return rho;
+    return ((eqm >> k) & 1ull) ? rho_eq : (((loosem >> k) & 1ull) ? kRhoMin : rho);
+  }
+};
+
+// dot product of my row of a swizzled block with a vector gathered in logical order
+__device__ __forceinline__ double rowdot(const double *blk, const int (&ro)[4], const double (&g)[8]) {
+  const double2 t0 = ld2(blk + ro[0]), t1 = ld2(blk + ro[1]), t2 = ld2(blk + ro[2]), t3 = ld2(blk + ro[3]);
+  double a0 = t0.x * g[0], a1 = t1.x * g[2], a2 = t2.x * g[4], a3 = t3.x * g[6];
+  a0 = fma(t0.y, g[1], a0); a1 = fma(t1.y, g[3], a1); a2 = fma(t2.y, g[5], a2); a3 = fma(t3.y, g[7], a3);
+  return (a0 + a1) + (a2 + a3);
+}
+// my row / my column of a plain row-major 8-wide block (G in the slab, or in shared memory during setup)
+__device__ __forceinline__ double prowdot(const double *blk, int r, const double (&g)[8]) {
+  const double2 t0 = ld2(blk + r * 8), t1 = ld2(blk + r * 8 + 2), t2 = ld2(blk + r * 8 + 4), t3 = ld2(blk + r * 8 + 6);
+  double a0 = t0.x * g[0], a1 = t1.x * g[2], a2 = t2.x * g[4], a3 = t3.x * g[6];
+  a0 = fma(t0.y, g[1], a0); a1 = fma(t1.y, g[3], a1); a2 = fma(t2.y, g[5], a2); a3 = fma(t3.y, g[7], a3);
+  return (a0 + a1) + (a2 + a3);
+}
+template <int NR>
+__device__ __forceinline__ double pcoldot(const double *blk, int r, const double (&g)[8]) {
+  double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+  for (int rr = 0; rr < NR; rr += 2) {
+    a0 = fma(blk[rr * 8 + r], g[rr], a0);
+    if (rr + 1 < NR) a1 = fma(blk[(rr + 1) * 8 + r], g[rr + 1], a1);
+  }
+  return a0 + a1;
+}
+__device__ __forceinline__ void gather8(double v, double (&g)[8]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) g[c] = gshfl(v, c);
+}
+
+// ---------------------------------------------------------------- block factorisation (cold)
+// Row weights: ADMM -> rho_eq on the dynamics rows, rho / rho_eq / rho_min on the single-variable rows;
+// polish -> 1/delta on the active rows (C_ACTD / C_ACTI), 0 elsewhere.  In ADMM mode also stores diag(M) in DG.
+struct FW { int polish; double rho, rho_eq, idel; };
+
+template <int KIND>
+__device__ __noinline__ void factor(const Ctx<KIND> c, const FW fw, const double sigma) {
+  constexpr int NX = Ctx<KIND>::NX, NB = Ctx<KIND>::NB, NT = Ctx<KIND>::NT;
+  const int N = c.N, r = c.r;
+  const Lay &L = *c.L;
+  const double *PD = c.cd(C_PD), *PO = c.cd(C_PO), *ACTD = c.cd(C_ACTD), *ACTI = c.cd(C_ACTI), *ED = c.cd(C_ED);
+  const double *SI = c.S + L.SI;
+  double *DG = c.S + L.DG;
+  auto wd = [&](int k) -> double {  // weight of my dynamics row (k, r)
+    if (!c.xl) return 0.0;
+    return fw.polish ? ((ACTD[k * 8 + r] != 0.0) ? fw.idel : 0.0) : fw.rho_eq;
+  };
+#pragma unroll 1
+  for (int k = 0; k <= N; ++k) {
+    const int nbk = (k < N) ? NB : NX;
+    const bool rowlive = r < nbk;
+    double s[8], so[8];
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) { s[cc] = 0.0; so[cc] = 0.0; }
+    const double wdk = wd(k);
+    const double edk = c.xl ? ED[k * 8 + r] : 0.0;
+    {
+      double d = PD[k * 8 + r] + sigma;
+      if (c.has_in(k)) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const double a = SI[c.si(k, t)];
+          const double w = fw.polish ? ((ACTI[c.ci(k, t)] != 0.0) ? fw.idel : 0.0) : c.rho_of(k, fw.rho, fw.rho_eq);
+          d = fma(w * a, a, d);
+        }
+      }
+      if (!fw.polish) DG[k * 8 + r] = rowlive ? d : 1.0;
+      if (c.xl) d = fma(wdk * edk, edk, d);
+      if (!rowlive) d = 1.0;
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) if (cc == r) s[cc] = d;
+    }
+    if (k < N) {  // next-stage dynamics rows: sum_rr w(k+1, rr) G[rr][r] G[rr][cc]
+      const double *g = c.Gb(k);
+      const double wn = wd(k + 1);
+#pragma unroll
+      for (int rr = 0; rr < NX; ++rr) {
+        const double col = gshfl(wn, rr) * g[rr * 8 + r];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const double2 e = ld2(g + rr * 8 + 2 * j);
+          s[2 * j] = fma(col, e.x, s[2 * j]);
+          s[2 * j + 1] = fma(col, e.y, s[2 * j + 1]);
+        }
+      }
+    }
+    if (k > 0) {
+      if (c.xl) {  // my row of S_{k,k-1}
+        const double f = wdk * edk;
+        const double *gp = c.Gb(k - 1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const double2 e = ld2(gp + r * 8 + 2 * j); so[2 * j] = f * e.x; so[2 * j + 1] = f * e.y; }
+      } else if (c.ul && k < N) {
+#pragma unroll
+        for (int cc = NX; cc < NB; ++cc) if (cc == r) so[cc] = PO[(k - 1) * 8 + r];
+      }
+      double *Kk = c.Kb(k);
+      const double *Tp = c.Tb(k - 1);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) st2(Kk + c.ro[j], so[2 * j], so[2 * j + 1]);  // park S_{k,k-1} in K_k's slot
+      __syncwarp();
+      double kr[8];
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) kr[cc] = 0.0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double2 e = ld2(Tp + chunk(j, q));
+          kr[2 * q] = fma(so[j], e.x, kr[2 * q]);
+          kr[2 * q + 1] = fma(so[j], e.y, kr[2 * q + 1]);
+        }
+      }
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) {
+        double acc = s[cc];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double2 e = ld2(Kk + chunk(cc, q));  // S_{k,k-1}[cc][2q..2q+1]
+          acc = fma(-kr[2 * q], e.x, acc);
+          acc = fma(-kr[2 * q + 1], e.y, acc);
+        }
+        s[cc] = acc;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) st2(Kk + c.ro[j], kr[2 * j], kr[2 * j + 1]);
+    }
+    if (!rowlive) {
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) s[cc] = (cc == r) ? 1.0 : 0.0;
+    }
+    // Gauss-Jordan inverse of the pivot block, rows across lanes (no pivoting: the block is SPD)
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      if (p < nbk) {
+        double pr[8];
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) pr[cc] = gshfl(s[cc], p);
+        const double piv = 1.0 / pr[p];
+        if (r == p) {
+#pragma unroll
+          for (int cc = 0; cc < 8; ++cc) s[cc] = (cc == p) ? piv : s[cc] * piv;
+        } else {
+          const double fp = s[p] * piv;
+#pragma unroll
+          for (int cc = 0; cc < 8; ++cc) s[cc] = (cc == p) ? -fp : fma(-fp, pr[cc], s[cc]);
+        }
+      }
+    }
+    double *Tk = c.Tb(k);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) st2(Tk + c.ro[j], s[2 * j], s[2 * j + 1]);
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------- hot loop
+// Per-lane pointers into the QP's shared region (computed once per QP).
+template <int KIND>
+struct Hot {
+  double *B;               // + r
+  const double *Tr, *Kr;   // my row of block 0 (physical chunk order: immediate offsets 0, 2, 4, 6)
+  const double *Kc[4];     // my column of block 0, rows 2q and 2q+1 at +0 and +8
+  int go[4];               // gather offsets (doubles) that bring the vector into my row's physical chunk order
+  double *X, *R, *XS;      // + r
+  const double *CR, *DG;   // + r
+  double *ZI, *YI;         // + islot
+  const double *SI, *UI, *LI;
+  const double *PO;        // + (ul ? r - NX : 0)
+  int pstride;             // 2 for input lanes, 0 otherwise (state lanes keep reading the zero pad)
+};
+
+// forward sweep: B holds the right-hand side on entry, W_k = T_k v_k on exit
+template <int KIND>
+__device__ __forceinline__ void sweep_fwd(const Hot<KIND> &h, const int N) {
+  double *Bk = h.B;                         // B + k*8 + r
+  double *Bg = h.B - ((threadIdx.x & 7));   // B + k*8
+  const double *Tk = h.Tr, *Kk = h.Kr;
+  double v = *Bk;
+#pragma unroll 1
+  for (int k = 0; k <= N; ++k) {
+    *Bk = v;
+    __syncwarp();
+    const double2 g0 = ld2(Bg + h.go[0]), g1 = ld2(Bg + h.go[1]), g2 = ld2(Bg + h.go[2]), g3 = ld2(Bg + h.go[3]);
+    const double2 t0 = ld2(Tk), t1 = ld2(Tk + 2), t2 = ld2(Tk + 4), t3 = ld2(Tk + 6);
+    double w0 = t0.x * g0.x, w1 = t1.x * g1.x, w2 = t2.x * g2.x, w3 = t3.x * g3.x;
+    w0 = fma(t0.y, g0.y, w0); w1 = fma(t1.y, g1.y, w1); w2 = fma(t2.y, g2.y, w2); w3 = fma(t3.y, g3.y, w3);
+    if (k < N) {
+      const double2 k0 = ld2(Kk), k1 = ld2(Kk + 2), k2 = ld2(Kk + 4), k3 = ld2(Kk + 6);
+      const double bn = Bk[8];
+      double a0 = fma(-k0.x, g0.x, bn), a1 = -(k1.x * g1.x), a2 = -(k2.x * g2.x), a3 = -(k3.x * g3.x);
+      a0 = fma(-k0.y, g0.y, a0); a1 = fma(-k1.y, g1.y, a1); a2 = fma(-k2.y, g2.y, a2); a3 = fma(-k3.y, g3.y, a3);
+      v = (a0 + a1) + (a2 + a3);
+    }
+    __syncwarp();
+    *Bk = (w0 + w1) + (w2 + w3);
+    Bk += 8; Bg += 8; Tk += 64; Kk += 64;
+  }
+}
+
+// backward sweep only (polish): x_k = W_k - K_{k+1}' x_{k+1}, written back into B
+template <int KIND>
+__device__ __forceinline__ void sweep_bwd_plain(const Hot<KIND> &h, const int N) {
+  double gn[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) gn[q] = 0.0;
+#pragma unroll 1
+  for (int k = N; k >= 0; --k) {
+    double *Bk = h.B + k * 8;
+    double x = *Bk;
+    if (k < N) {
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double *p = h.Kc[q] + k * 64;
+        a0 = fma(p[0], gn[2 * q], a0);
+        a1 = fma(p[8], gn[2 * q + 1], a1);
+      }
+      x -= a0 + a1;
+    }
+    *Bk = x;
+    __syncwarp();
+    const double *Bg = Bk - (threadIdx.x & 7);
+    const double2 g0 = ld2(Bg), g1 = ld2(Bg + 2), g2 = ld2(Bg + 4), g3 = ld2(Bg + 6);
+    gn[0] = g0.x; gn[1] = g0.y; gn[2] = g1.x; gn[3] = g1.y; gn[4] = g2.x; gn[5] = g2.y; gn[6] = g3.x; gn[7] = g3.y;
+  }
+  __syncwarp();
+}
+
+// Element-wise ADMM update of my variable at stage j given x~_j (x1), x~_{j-1} (xm) and x~_{j+1} (xp):
+// r recursion, z / y of my single-variable rows, relaxed x, next right-hand side, running sum of x~.
+template <int KIND>
+struct Upd {
+  double rho, rho_eq, rinv, rinv_eq, sigma, alpha, oma, cc;
+  uint64_t eqm, loosem;
+  bool live, xl, ul;
+  int N;
+};
+template <int KIND>
+__device__ __forceinline__ void update_stage(const Hot<KIND> &h, const Upd<KIND> &u, const int j, const double x1, const double xm,
+                                             const double xp) {
+  constexpr int NT = Dims<KIND>::NT, NSL = Dims<KIND>::NSL;
+  const int o = j * 8;
+  const bool vlive = u.xl || (u.ul && j < u.N);
+  if (!vlive) return;
+  const double xo = h.X[o], rr = h.R[o], dg = h.DG[o], cr = h.CR[o], xs = h.XS[o];
+  const double pm = h.PO[j * h.pstride], pp = h.PO[(j + 1) * h.pstride];
+  double m = dg * x1;
+  m = fma(pm, xm, m);
+  m = fma(pp, xp, m);
+  double sold = 0.0, snew = 0.0;
+  bool has_in;
+  if (KIND == LPVMPC_CONTROLLER) has_in = ((threadIdx.x & 7) == 0 || u.ul) && j < u.N;
+  else has_in = true;
+  if (has_in) {
+    double rt = u.rho, ri = u.rinv;
+    if (KIND == LPVMPC_PLANNER) {
+      if ((u.eqm >> j) & 1ull) { rt = u.rho_eq; ri = u.rinv_eq; }
+      else if ((u.loosem >> j) & 1ull) { rt = kRhoMin; ri = 1.0 / kRhoMin; }
+    }
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const int oi = j * NSL + t;
+      const double si = h.SI[oi], zi = h.ZI[oi], yi = h.YI[oi], ui = h.UI[oi];
+      sold = fma(si, fma(rt, zi, -yi), sold);
+      const double zr = fma(u.alpha, si * x1, u.oma * zi);
+      double zn = fma(ri, yi, zr);
+      if (KIND == LPVMPC_PLANNER) { const double li = h.LI[oi]; zn = (zn > li) ? zn : li; }
+      // controller rows: the lower bound is -OSQP_INFTY (times the row scaling): below any iterate, no clamp needed
+      zn = (zn < ui) ? zn : ui;
+      const double yn = fma(rt, zr - zn, yi);
+      if (u.live) { h.ZI[oi] = zn; h.YI[oi] = yn; }
+      snew = fma(si, fma(rt, zn, -yn), snew);
+    }
+  }
+  const double hh = fma(u.sigma, xo, rr) + sold;            // the right-hand side this x~ was solved for
+  const double rn = fma(-u.alpha, hh - m, fma(u.cc, cr, rr));
+  const double xn = fma(u.alpha, x1, u.oma * xo);
+  if (u.live) h.X[o] = xn;
+  h.R[o] = rn;
+  h.XS[o] = xs + x1;
+  h.B[o] = fma(u.sigma, xn, rn) + snew;
+}
+
+// backward sweep fused with the element-wise update of stage k+1 (hot)
+template <int KIND>
+__device__ __forceinline__ void sweep_bwd_admm(const Hot<KIND> &h, const Upd<KIND> &u) {
+  const int N = u.N;
+  double gn[8];
+  double x1, x2 = 0.0;
+  {  // stage N: x~_N = W_N
+    double *Bk = h.B + N * 8;
+    x1 = *Bk;
+    __syncwarp();
+    const double *Bg = Bk - (threadIdx.x & 7);
+    const double2 g0 = ld2(Bg), g1 = ld2(Bg + 2), g2 = ld2(Bg + 4), g3 = ld2(Bg + 6);
+    gn[0] = g0.x; gn[1] = g0.y; gn[2] = g1.x; gn[3] = g1.y; gn[4] = g2.x; gn[5] = g2.y; gn[6] = g3.x; gn[7] = g3.y;
+  }
+#pragma unroll 1
+  for (int k = N - 1; k >= 0; --k) {
+    double *Bk = h.B + k * 8;
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const double *p = h.Kc[q] + k * 64;
+      a0 = fma(p[0], gn[2 * q], a0);
+      a1 = fma(p[8], gn[2 * q + 1], a1);
+    }
+    const double xt = *Bk - (a0 + a1);
+    *Bk = xt;
+    __syncwarp();
+    const double *Bg = Bk - (threadIdx.x & 7);
+    const double2 g0 = ld2(Bg), g1 = ld2(Bg + 2), g2 = ld2(Bg + 4), g3 = ld2(Bg + 6);
+    gn[0] = g0.x; gn[1] = g0.y; gn[2] = g1.x; gn[3] = g1.y; gn[4] = g2.x; gn[5] = g2.y; gn[6] = g3.x; gn[7] = g3.y;
+    update_stage<KIND>(h, u, k + 1, x1, xt, x2);   // overwrites B[k+1] (everybody has read it: the __syncwarp above)
+    x2 = x1; x1 = xt;
+  }
+  __syncwarp();
+  update_stage<KIND>(h, u, 0, x1, 0.0, x2);
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------- per-QP scalars shared by the cold routines
+struct Info {
+  double pri_res, dua_res, obj;
+  double n_rp, n_z, n_Ax, n_rd, n_q, n_Aty, n_Px;  // scaled-space inf-norms of the last update_info
+  double u_z, u_Ax, u_q, u_Aty, u_Px;              // the same, unscaled (termination)
+  double csc, cinv;
+  int status, unscale;
+};
+
+// (P v)_(k, r) for a vector stored [k*8 + r] (diagonal Q, R and the slew-rate coupling of the inputs)
+template <int KIND>
+__device__ __forceinline__ double rowP(const Ctx<KIND> &c, const double *PD, const double *PO, const double *v, int k) {
+  const int N = c.N, o = k * 8 + c.r;
+  double acc = PD[o] * v[o];
+  if (c.ul) {
+    if (k > 0 && k < N) acc = fma(PO[o - 8], v[o - 8], acc);
+    if (k < N - 1) acc = fma(PO[o], v[o + 8], acc);
+    if (k == N) acc = 0.0;
+  }
+  return acc;
+}
+// (A v) on my dynamics row (k, r): v stored [k*8 + r]
+template <int KIND>
+__device__ __forceinline__ double rowA_dyn(const Ctx<KIND> &c, const double *ED, const double *v, int k) {
+  double acc = ED[k * 8 + c.r] * v[k * 8 + c.r];
+  if (k > 0) {
+    double g[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) g[q] = v[(k - 1) * 8 + q];
+    acc += prowdot(c.Gb(k - 1), c.r, g);
+  }
+  return acc;
+}
+// (A' t)_(k, r): td on the dynamics rows [k*8 + rr], ti on the single-variable rows [k*8 + slot] (slab indexing)
+template <int KIND>
+__device__ __forceinline__ double colA(const Ctx<KIND> &c, const double *ED, const double *td, const double *ti, int k) {
+  constexpr int NX = Ctx<KIND>::NX, NT = Ctx<KIND>::NT;
+  const double *SI = c.S + c.L->SI;
+  const int o = k * 8 + c.r;
+  double acc = c.xl ? ED[o] * td[o] : 0.0;
+  if (k < c.N) {
+    double g[8];
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) g[rr] = (rr < NX) ? td[(k + 1) * 8 + rr] : 0.0;
+    acc += pcoldot<NX>(c.Gb(k), c.r, g);
+  }
+  if (c.has_in(k)) {
+#pragma unroll
+    for (int t = 0; t < NT; ++t) acc = fma(SI[c.si(k, t)], ti[c.ci(k, t)], acc);
+  }
+  return acc;
+}
+// the same with the single-variable part taken from a shared-memory array (NSL indexing)
+template <int KIND>
+__device__ __forceinline__ double colA_s(const Ctx<KIND> &c, const double *ED, const double *td, const double *tis, int k) {
+  constexpr int NX = Ctx<KIND>::NX, NT = Ctx<KIND>::NT;
+  const double *SI = c.S + c.L->SI;
+  const int o = k * 8 + c.r;
+  double acc = c.xl ? ED[o] * td[o] : 0.0;
+  if (k < c.N) {
+    double g[8];
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) g[rr] = (rr < NX) ? td[(k + 1) * 8 + rr] : 0.0;
+    acc += pcoldot<NX>(c.Gb(k), c.r, g);
+  }
+  if (c.has_in(k)) {
+#pragma unroll
+    for (int t = 0; t < NT; ++t) acc = fma(SI[c.si(k, t)], tis[c.si(k, t)], acc);
+  }
+  return acc;
+}
+
+// y_dyn <- y_dyn + rho_eq (alpha A_dyn XS - (alpha n + (1 - alpha) first) be);  XS <- 0     (see the header)
+template <int KIND>
+__device__ __noinline__ void sync_yd(const Ctx<KIND> c, const bool live, const double rho_eq, const double alpha, const int n,
+                                    const int first) {
+  const int N = c.N, r = c.r;
+  double *XS = c.S + c.L->XS;
+  double *YD = c.cd(C_YD);
+  const double *BE = c.cd(C_BE), *ED = c.cd(C_ED);
+  const double cb = alpha * n + (first ? (1.0 - alpha) : 0.0);
+  if (n > 0) {
+#pragma unroll 1
+    for (int k = 0; k <= N; ++k) {
+      if (c.xl) {
+        const int o = k * 8 + r;
+        const double ax = rowA_dyn<KIND>(c, ED, XS, k);
+        if (live) YD[o] = YD[o] + rho_eq * (alpha * ax - cb * BE[o]);
+      }
+    }
+  }
+  __syncwarp();
+#pragma unroll 1
+  for (int k = 0; k <= N; ++k) XS[k * 8 + r] = 0.0;
+  __syncwarp();
+}
+
+// CR = rho_eq A_dyn' be (start, and after a rho update by rescaling), R = zsel CR - A_dyn' y_dyn - q,
+// B = sigma x + R + A_in'(rho z - y).  `doit` guards the groups that keep their state.
+template <int KIND>
+__device__ __noinline__ void rhs_init(const Ctx<KIND> c, const bool doit, const double rho, const double rho_eq, const double sigma,
+                                     const double zsel) {
+  constexpr int NT = Ctx<KIND>::NT;
+  const int N = c.N, r = c.r;
+  const Lay &L = *c.L;
+  double *S = c.S;
+  double *BV = S + L.B, *R = S + L.R, *CR = S + L.CR;
+  const double *X = S + L.X, *ZI = S + L.ZI, *YI = S + L.YI, *SI = S + L.SI;
+  const double *YD = c.cd(C_YD), *BE = c.cd(C_BE), *ED = c.cd(C_ED), *QV = c.cd(C_Q);
+  double *TD = c.cd(C_R2D);  // scratch
+#pragma unroll 1
+  for (int k = 0; k <= N; ++k) TD[k * 8 + r] = 0.0;
+  __syncwarp();
+#pragma unroll 1
+  for (int k = 0; k <= N; ++k) {
+    const int o = k * 8 + r;
+    if (c.var_live(k)) {
+      const double cr = rho_eq * colA<KIND>(c, ED, BE, TD, k);   // TD == 0: dynamics part only
+      const double aty = colA<KIND>(c, ED, YD, TD, k);
+      double sin = 0.0;
+      if (c.has_in(k)) {
+        const double rt = c.rho_of(k, rho, rho_eq);
+#pragma unroll
+        for (int t = 0; t < NT; ++t) sin = fma(SI[c.si(k, t)], rt * ZI[c.si(k, t)] - YI[c.si(k, t)], sin);
+      }
+      if (doit) {
+        const double rr = (zsel * cr - aty) - QV[o];
+        CR[o] = cr; R[o] = rr;
+        BV[o] = fma(sigma, X[o], rr) + sin;
+      }
+    } else if (doit) { CR[o] = 0.0; R[o] = 0.0; BV[o] = 0.0; }
+  }
+  __syncwarp();
+}
+
+// residual norms at the current iterate (update_info); y_dyn must be in sync
+template <int KIND>
+__device__ __noinline__ void update_info(const Ctx<KIND> c, Info *ip, const double zsel) {
+  constexpr int NT = Ctx<KIND>::NT;
+  Info &I = *ip;
+  const int N = c.N, r = c.r;
+  const Lay &L = *c.L;
+  const double *S = c.S;
+  const double *X = S + L.X, *ZI = S + L.ZI, *YI = S + L.YI, *SI = S + L.SI;
+  const double *YD = c.cd(C_YD), *BE = c.cd(C_BE), *ED = c.cd(C_ED), *QV = c.cd(C_Q);
+  const double *EINV = c.cd(C_EINV), *EIINV = c.cd(C_EIINV), *DINV = c.cd(C_DINV), *PD = c.cd(C_PD), *PO = c.cd(C_PO);
+  double a_rp = 0, a_z = 0, a_Ax = 0, b_rp = 0, b_z = 0, b_Ax = 0;
+  double a_rd = 0, a_q = 0, a_Aty = 0, a_Px = 0, b_rd = 0, b_q = 0, b_Aty = 0, b_Px = 0;
+#pragma unroll 1
+  for (int k = 0; k <= N; ++k) {
+    const int o = k * 8 + r;
+    if (c.xl) {
+      const double Ax = rowA_dyn<KIND>(c, ED, X, k), z = zsel * BE[o], rr = Ax - z, ei = EINV[o];
+      a_rp = absmax(a_rp, rr); a_z = absmax(a_z, z); a_Ax = absmax(a_Ax, Ax);
+      b_rp = absmax(b_rp, ei * rr); b_z = absmax(b_z, ei * z); b_Ax = absmax(b_Ax, ei * Ax);
+    }
+    if (c.has_in(k)) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const int oi = c.si(k, t);
+        const double ax = SI[oi] * X[o], z = ZI[oi], rr = ax - z, ei = EIINV[c.ci(k, t)];
+        a_rp = absmax(a_rp, rr); a_z = absmax(a_z, z); a_Ax = absmax(a_Ax, ax);
+        b_rp = absmax(b_rp, ei * rr); b_z = absmax(b_z, ei * z); b_Ax = absmax(b_Ax, ei * ax);
+      }
+    }
+    if (c.var_live(k)) {
+      const double Px = rowP<KIND>(c, PD, PO, X, k), Aty = colA_s<KIND>(c, ED, YD, YI, k);
+      const double rr = (QV[o] + Px) + Aty, di = DINV[o];
+      a_rd = absmax(a_rd, rr); a_q = absmax(a_q, QV[o]); a_Aty = absmax(a_Aty, Aty); a_Px = absmax(a_Px, Px);
+      b_rd = absmax(b_rd, di * rr); b_q = absmax(b_q, di * QV[o]); b_Aty = absmax(b_Aty, di * Aty); b_Px = absmax(b_Px, di * Px);
+    }
+  }
+  I.n_rp = gmax(a_rp); I.n_z = gmax(a_z); I.n_Ax = gmax(a_Ax); I.n_rd = gmax(a_rd); I.n_q = gmax(a_q); I.n_Aty = gmax(a_Aty); I.n_Px = gmax(a_Px);
+  if (I.unscale) {
+    I.pri_res = gmax(b_rp); I.u_z = gmax(b_z); I.u_Ax = gmax(b_Ax);
+    I.dua_res = I.cinv * gmax(b_rd); I.u_q = gmax(b_q); I.u_Aty = gmax(b_Aty); I.u_Px = gmax(b_Px);
+  } else {
+    I.pri_res = I.n_rp; I.u_z = I.n_z; I.u_Ax = I.n_Ax; I.dua_res = I.n_rd; I.u_q = I.n_q; I.u_Aty = I.n_Aty; I.u_Px = I.n_Px;
+  }
+}
+
+// ---------------------------------------------------------------- infeasibility certificates (rare)
+// delta_y / delta_x of the last ADMM step against the iterate saved before it (C_PVX, C_PVYI).  The dynamics part of
+// delta_y is rho_eq (alpha A_dyn x~ - c be) with x~ = (x - (1 - alpha) x_prev) / alpha of that step (c = 1 on the very
+// first step, alpha afterwards).  The projected delta_y goes to C_DYD / C_PYI (free while ADMM runs).
+template <int KIND>
+__device__ __noinline__ bool primal_infeasible(const Ctx<KIND> c, const Info *ip, const double eps, const double rho_eq,
+                                              const double alpha, const int last_was_first) {
+  constexpr int NT = Ctx<KIND>::NT;
+  const bool unscale = ip->unscale;
+  const int N = c.N, r = c.r;
+  const Lay &L = *c.L;
+  const double *S = c.S;
+  const double *X = S + L.X, *YI = S + L.YI, *UI = S + L.UI, *LI = S + L.LI;
+  const double *BE = c.cd(C_BE), *ED = c.cd(C_ED), *PVX = c.cd(C_PVX);
+  const double *PVYI = c.cd(C_PVYI), *E = c.cd(C_E), *EI = c.cd(C_EI), *DINV = c.cd(C_DINV);
+  double *DYD = c.cd(C_DYD), *DYI = c.cd(C_PYI), *XT = c.cd(C_ZT);
+  const double ia = 1.0 / alpha, oma = 1.0 - alpha, cb = last_was_first ? 1.0 : alpha;
+#pragma unroll 1
+  for (int k = 0; k <= N; ++k) { const int o = k * 8 + r; XT[o] = c.var_live(k) ? (X[o] - oma * PVX[o]) * ia : 0.0; }
+  __syncwarp();
+  double nrm = 0.0, lhs = 0.0;
+#pragma unroll 1
+  for (int k = 0; k <= N; ++k) {
+    const int o = k * 8 + r;
+    double d = 0.0;
+    if (c.xl) d = rho_eq * (alpha * rowA_dyn<KIND>(c, ED, XT, k) - cb * BE[o]);  // equality rows: no projection
+    DYD[o] = d;
+    if (c.xl) {
+      nrm = absmax(nrm, unscale ? E[o] * d : d);
+      lhs += BE[o] * ((d > 0) ? d : 0) + BE[o] * ((d < 0) ? d : 0);
+    }
+    if (c.has_in(k)) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const int oi = c.si(k, t), oc = c.ci(k, t);
+        double di = YI[oi] - PVYI[oc];
+        const double lo = (KIND == LPVMPC_PLANNER) ? LI[oi] : -kInfty, up = UI[oi];
+        if (up > kInfty * kMinScaling) {
+          if (lo < -kInfty * kMinScaling) di = 0.0;
+          else di = (di < 0.0) ? di : 0.0;
+        } else if (lo < -kInfty * kMinScaling) di = (di > 0.0) ? di : 0.0;
+        DYI[oc] = di;
+        nrm = absmax(nrm, unscale ? EI[oc] * di : di);
+        lhs += up * ((di > 0) ? di : 0) + lo * ((di < 0) ? di : 0);
+      }
+    }
+  }
+  nrm = gmax(nrm);
+  lhs = gsum(lhs);
+  __syncwarp();
+  double mx = 0.0;
+#pragma unroll 1
+  for (int k = 0; k <= N; ++k) {
+    if (c.var_live(k)) {
+      const double at = colA<KIND>(c, ED, DYD, DYI, k);
+      mx = absmax(mx, unscale ? DINV[k * 8 + r] * at : at);
+    }
+  }
+  mx = gmax(mx);
+  return (nrm > eps) && (lhs < -eps * nrm) && (mx < eps * nrm);
+}
+
+template <int KIND>
+__device__ __noinline__ bool dual_infeasible(const Ctx<KIND> c, const Info *ip, const double eps) {
+  constexpr int NT = Ctx<KIND>::NT;
+  const bool unscale = ip->unscale;
+  const int N = c.N, r = c.r;
+  const Lay &L = *c.L;
+  const double *S = c.S;
+  const double *X = S + L.X, *SI = S + L.SI, *UI = S + L.UI, *LI = S + L.LI;
+  const double *QV = c.cd(C_Q), *ED = c.cd(C_ED);
+  const double *PVX = c.cd(C_PVX), *D = c.cd(C_D), *DINV = c.cd(C_DINV), *EINV = c.cd(C_EINV), *EIINV = c.cd(C_EIINV);
+  const double *PD = c.cd(C_PD), *PO = c.cd(C_PO);
+  double *DX = c.cd(C_PX);
+  double nrm = 0.0, qdx = 0.0;
+#pragma unroll 1
+  for (int k = 0; k <= N; ++k) {
+    const int o = k * 8 + r;
+    const double dx = c.var_live(k) ? X[o] - PVX[o] : 0.0;
+    DX[o] = dx;
+    nrm = absmax(nrm, unscale ? D[o] * dx : dx);
+    qdx += QV[o] * dx;
+  }
+  nrm = gmax(nrm); qdx = gsum(qdx);
+  __syncwarp();
+  const double cs = unscale ? ip->csc : 1.0;
+  double mx = 0.0;
+  int viol = 0;
+#pragma unroll 1
+  for (int k = 0; k <= N; ++k) {
+    const int o = k * 8 + r;
+    if (c.var_live(k)) {
+      const double Pdx = rowP<KIND>(c, PD, PO, DX, k);
+      mx = absmax(mx, unscale ? DINV[o] * Pdx : Pdx);
+    }
+    if (c.xl) {
+      double v = rowA_dyn<KIND>(c, ED, DX, k);
+      if (unscale) v = EINV[o] * v;
+      if (v > eps * nrm || v < -eps * nrm) viol = 1;
+    }
+    if (c.has_in(k)) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const int oi = c.si(k, t);
+        double v = SI[oi] * DX[o];
+        if (unscale) v = EIINV[c.ci(k, t)] * v;
+        const double lo = (KIND == LPVMPC_PLANNER) ? LI[oi] : -kInfty;
+        if (((UI[oi] < kInfty * kMinScaling) && (v > eps * nrm)) || ((lo > -kInfty * kMinScaling) && (v < -eps * nrm))) viol = 1;
+      }
+    }
+  }
+  mx = gmax(mx);
+  viol = gany(viol);
+  return (nrm > eps) && (qdx < -cs * eps * nrm) && (mx < cs * eps * nrm) && !viol;
+}
+
+// returns 1 when a termination status was set for my group (check_termination)
+template <int KIND>
+__device__ __noinline__ int check_termination(const Ctx<KIND> c, const lpvmpc_settings &S, Info *ip, const bool live, const int approximate,
+                                             const double rho_eq, const int last_was_first, const bool have_prev) {
+  Info &I = *ip;
+  double eps_abs = S.eps_abs, eps_rel = S.eps_rel, eps_pi = S.eps_prim_inf, eps_di = S.eps_dual_inf;
+  const bool ncvx = (I.pri_res > kInfty) || (I.dua_res > kInfty);
+  if (approximate) { eps_abs *= 10; eps_rel *= 10; eps_pi *= 10; eps_di *= 10; }
+  const double eps_prim = eps_abs + eps_rel * (I.u_z > I.u_Ax ? I.u_z : I.u_Ax);
+  const bool prim_ok = I.pri_res < eps_prim;
+  double mr = I.u_q; mr = (I.u_Aty > mr) ? I.u_Aty : mr; mr = (I.u_Px > mr) ? I.u_Px : mr;
+  if (I.unscale) mr *= I.cinv;
+  const double eps_dual = eps_abs + eps_rel * mr;
+  const bool dual_ok = I.dua_res < eps_dual;
+  bool prim_inf = false, dual_inf = false;
+  if (have_prev) {
+    if (__any_sync(kFull, live && !ncvx && !prim_ok)) prim_inf = primal_infeasible<KIND>(c, ip, eps_pi, rho_eq, S.alpha, last_was_first) && !prim_ok;
+    if (__any_sync(kFull, live && !ncvx && !dual_ok)) dual_inf = dual_infeasible<KIND>(c, ip, eps_di) && !dual_ok;
+  }
+  if (!live) return 0;
+  if (ncvx) { I.status = LPVMPC_NON_CVX; I.obj = nan(""); return 1; }
+  if (prim_ok && dual_ok) { I.status = approximate ? LPVMPC_SOLVED_INACCURATE : LPVMPC_SOLVED; return 1; }
+  if (prim_inf) { I.status = approximate ? LPVMPC_PRIMAL_INFEASIBLE_INACCURATE : LPVMPC_PRIMAL_INFEASIBLE; I.obj = kInfty; return 1; }
+  if (dual_inf) { I.status = approximate ? LPVMPC_DUAL_INFEASIBLE_INACCURATE : LPVMPC_DUAL_INFEASIBLE; I.obj = -kInfty; return 1; }
+  return 0;
+}
+
+template <int KIND>
+__device__ __noinline__ double objective(const Ctx<KIND> c, const double *xv, const double scale) {
+  const double *PD = c.cd(C_PD), *PO = c.cd(C_PO), *QV = c.cd(C_Q);
+  double acc = 0.0;
+#pragma unroll 1
+  for (int k = 0; k <= c.N; ++k)
+    if (c.var_live(k)) acc += (0.5 * rowP<KIND>(c, PD, PO, xv, k) + QV[k * 8 + c.r]) * xv[k * 8 + c.r];
+  return gsum(acc) * scale;
+}
+
+// ---------------------------------------------------------------- setup: schedule + build + Ruiz (cold, once per QP)
+// Works in shared memory (scratch in the factor area and in the R / CR / XS vectors), then moves the cold data to the
+// slab.  Returns flags: bit 0 = Curvature() failed, bit 1 = l > u somewhere.
+template <int KIND>
+__device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const int b, const bool valid, double *csc_out,
+                                 uint64_t *eqm_out, uint64_t *loosem_out) {
+  constexpr int NX = Ctx<KIND>::NX, NB = Ctx<KIND>::NB, NT = Ctx<KIND>::NT, GS = NX * 8;
+  const int N = c.N, r = c.r;
+  const Lay &L = *c.L;
+  const Model &M = p.M;
+  const lpvmpc_args &a = p.a;
+  const lpvmpc_settings &St = p.S;
+  double *S = c.S;
+  const int nx = NX * (N + 1), nz = nx + 2 * N, NS8 = (N + 1) * 8;
+  const int ucomp = r - NX;
+  int sched_err = 0, data_err = 0;
+  double x0r = 0.0;
+  double *Gs = S + L.K;            // N x GS, plain row-major rows (scratch home of G during setup)
+  double *scr = Gs + N * GS;       // nz doubles (N*16 >= nz)
+  // ---- schedule: G_k = -[A_k B_k] (unscaled), my row
+  if (a.sched_mode == LPVMPC_SCHED_GIVEN) {
+#pragma unroll 1
+    for (int k = 0; k < N; ++k) {
+      if (c.xl) {
+        const double *Ar = a.A + ((size_t)b * N + k) * NX * NX + r * NX, *Br = a.Bm + ((size_t)b * N + k) * NX * 2 + r * 2;
+        double row[8];
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) row[cc] = (cc < NX) ? -Ar[cc < NX ? cc : 0] : ((cc < NB) ? -Br[cc - NX < 2 ? cc - NX : 0] : 0.0);
+        double *gk = Gs + k * GS + r * 8;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) st2(gk + 2 * j, row[2 * j], row[2 * j + 1]);
+      }
+    }
+    x0r = c.xl ? a.x0[(size_t)b * NX + r] : 0.0;
+  } else {
+    const bool predict = a.sched_mode == LPVMPC_SCHED_PREDICT;
+    double st[NX];
+    const double *xs = (predict && a.x_sched) ? a.x_sched + (size_t)b * NX : a.x0 + (size_t)b * NX;
+#pragma unroll
+    for (int q = 0; q < NX; ++q) st[q] = predict ? xs[q] : 0.0;
+    const double *up = a.u_prev + (size_t)b * N * 2;
+    const int lap = a.lap ? a.lap[b] : a.lap_all;
+    x0r = c.xl ? a.x0[(size_t)b * NX + r] : 0.0;
+#pragma unroll 1
+    for (int k = 0; k < N; ++k) {
+      const double delta = up[k * 2];
+      double Ai[NX * NX], Bi[NX * 2];
+      if (KIND == LPVMPC_CONTROLLER) {
+        double vx, vy, epsi, ey, cur, Cf, Cr;
+        if (predict) {
+          vy = st[1]; epsi = st[3]; ey = st[NX - 1];
+          cur = (lap == 0) ? curvature(M.track, M.nseg, st[4], sched_err) : a.curv_ref[(size_t)b * N + k];
+          vx = a.vel_ref[(size_t)b * (N + 1) + k];
+          Cf = a.Cf_new; Cr = a.Cf_new;
+        } else {
+          const double *t = a.traj + ((size_t)b * N + k) * 6;
+          vx = t[0]; vy = t[1]; epsi = t[3]; ey = t[5];
+          cur = curvature(M.track, M.nseg, t[4], sched_err);
+          Cf = M.Cf; Cr = M.Cr;
+        }
+        ctrl_stage(M, Cf, Cr, vx, vy, epsi, ey, cur, delta, Ai, Bi);
+      } else {
+        if (predict) {
+          const double cur = curvature(M.track, M.nseg, a.SS[(size_t)b * (N + 1) + k], sched_err);
+          plan_stage(M, st[0], st[1], st[3], st[4], cur, delta, Ai, Bi);
+        } else {
+          const double *t = a.traj + ((size_t)b * N + k) * 6;
+          const double cur = curvature(M.track, M.nseg, t[5], sched_err);
+          plan_stage(M, t[0], t[1], t[3], t[4], cur, delta, Ai, Bi);
+        }
+      }
+      double row[8];  // my row of [A B], selected without dynamic register indexing
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) {
+        double v = 0.0;
+        if (cc < NB) {
+#pragma unroll
+          for (int rr = 0; rr < NX; ++rr) {
+            const double e = (cc < NX) ? Ai[rr * NX + (cc < NX ? cc : 0)] : Bi[rr * 2 + (cc - NX < 2 ? cc - NX : 0)];
+            v = (r == rr) ? e : v;
+          }
+        }
+        row[cc] = v;
+      }
+      if (c.xl) {
+        double *gk = Gs + k * GS + r * 8;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) st2(gk + 2 * j, -row[2 * j], -row[2 * j + 1]);
+        if (valid && a.A_out) {
+#pragma unroll
+          for (int cc = 0; cc < NX; ++cc) a.A_out[((size_t)b * N + k) * NX * NX + r * NX + cc] = row[cc];
+        }
+        if (valid && a.B_out) { a.B_out[((size_t)b * N + k) * NX * 2 + r * 2] = row[NX]; a.B_out[((size_t)b * N + k) * NX * 2 + r * 2 + 1] = row[NX + 1]; }
+      }
+      if (predict) {
+        propagate<NX>(Ai, Bi, up + k * 2, st);
+        if (c.xl) {
+          double mine = 0.0;
+#pragma unroll
+          for (int rr = 0; rr < NX; ++rr) mine = (r == rr) ? st[rr] : mine;
+          if (valid && a.states_out) a.states_out[((size_t)b * N + k) * NX + r] = mine;
+          if (k == 0 && a.x0_from_prediction) x0r = mine;
+        }
+      }
+    }
+  }
+  __syncwarp();
+  sched_err = gany(sched_err);
+
+  // ---- build (PathFollowingLPVMPC.py:334-348, 397-464; LPV_MPC_Planner.py:145-181)
+  double *X = S + L.X, *BV = S + L.B, *QV = S + L.R, *BE = S + L.CR, *ED = S + L.XS;   // q, be, ed: scratch homes
+  double *ZI = S + L.ZI, *YI = S + L.YI, *SI = S + L.SI, *UI = S + L.UI, *LI = S + L.LI;
+  double *sD = S + L.T, *sE = sD + NS8, *sEI = sE + NS8, *sDt = sEI + NS8, *sEt = sDt + NS8, *sEti = sEt + NS8;
+  double *sPD = sEti + NS8, *sPO = sPD + NS8;  // 8 arrays of NS8 doubles == (N+1)*64
+  double *sLI = S + L.DG;                       // controller: scratch home of the (never active) lower bounds
+  {
+    const double Qrr = c.xl ? M.Q[r * NX + r] : 0.0;
+    const double Q0r = c.xl ? M.Q[r] : 0.0;
+    const double Rcc = c.ul ? M.R[ucomp * 2 + ucomp] : 0.0;
+    const double dRc = c.ul ? M.dR[ucomp] : 0.0;
+    const double uold = (c.ul && a.u_old) ? a.u_old[(size_t)b * 2 + ucomp] : 0.0;
+    const double mey = (KIND == LPVMPC_PLANNER) ? a.max_ey[b] : 0.0;
+#pragma unroll 1
+    for (int k = 0; k <= N; ++k) {
+      const int o = k * 8 + r;
+      double pd = 0.0, po = 0.0, q = 0.0, be = 0.0, ed = 0.0;
+      if (c.xl) {
+        pd = 2 * Qrr;
+        if (KIND == LPVMPC_CONTROLLER) q = -2 * (a.vel_ref[(size_t)b * (N + 1) + k] * Q0r);
+        else q = M.L_cf[r];
+        be = (k == 0) ? (x0r + 0.0) : (0.0 + (a.C ? a.C[((size_t)b * N + (k - 1)) * NX + r] : 0.0));
+        ed = 1.0;
+      } else if (c.ul) {
+        double v = Rcc + 2 * dRc;
+        if (k == N - 1) v = v - dRc;
+        pd = (k < N) ? 2 * v : 0.0;
+        if (KIND == LPVMPC_CONTROLLER) q = (k == 0) ? -2 * (uold * dRc) : -2 * 0.0;
+        else q = (k == 0) ? -2 * (uold * dRc) : 0.0;
+        po = (k < N - 1) ? 2 * (-dRc) : 0.0;
+      }
+      sPD[o] = pd; sPO[o] = po; QV[o] = q; BE[o] = be; ED[o] = ed;
+      sD[o] = 1.0; sE[o] = 1.0; sEI[o] = 1.0; sEti[o] = 1.0;
+      X[o] = 0.0; BV[o] = 0.0;
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int k = 0; k <= N; ++k) {
+      if (c.has_in(k)) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const int oi = c.si(k, t);
+          double si, lo, up;
+          if (KIND == LPVMPC_CONTROLLER) {
+            lo = -kInfty;
+            if (r == 0) { si = t ? 1.0 : -1.0; up = t ? M.max_vel : -0.01; }
+            else if (r == NX) { si = t ? -1.0 : 1.0; up = 0.249; }
+            else { si = t ? -1.0 : 1.0; up = t ? 1.0 : 4.0; }
+          } else {
+            si = 1.0;
+            if (c.xl) {
+              lo = (r == 0) ? M.min_vel : (r == 1 ? -1.0 : (r == 2 ? -2.0 : (r == 3 ? -mey : -0.8)));
+              up = (r == 0) ? M.max_vel : (r == 1 ? 1.0 : (r == 2 ? 2.0 : (r == 3 ? mey : 0.8)));
+              if (r == 3 && a.ey_lo) lo = a.ey_lo[(size_t)b * (N + 1) + k];
+              if (r == 3 && a.ey_hi) up = a.ey_hi[(size_t)b * (N + 1) + k];
+            } else { lo = ucomp ? -0.7 : -0.249; up = ucomp ? 2.0 : 0.249; }
+          }
+          lo = (lo > -kInfty) ? lo : -kInfty;  // python wrapper: l = max(l, -OSQP_INFTY), u = min(u, OSQP_INFTY)
+          up = (up < kInfty) ? up : kInfty;
+          if (lo > up) data_err = 1;
+          SI[oi] = si; UI[oi] = up; ZI[oi] = 0.0; YI[oi] = 0.0;
+          if (KIND == LPVMPC_PLANNER) LI[oi] = lo;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  data_err = gany(data_err);
+  (void)sLI;
+
+  // ---- Ruiz equilibration (OSQP scale_data)
+  double csc = 1.0;
+#pragma unroll 1
+  for (int it = 0; it < St.scaling; ++it) {
+#pragma unroll 1
+    for (int k = 0; k <= N; ++k) {
+      const int o = k * 8 + r;
+      double pa = fabs(sPD[o]);
+      if (c.ul) {
+        if (k < N - 1) pa = absmax(pa, sPO[o]);
+        if (k > 0 && k < N) pa = absmax(pa, sPO[o - 8]);
+      }
+      double qa = c.xl ? fabs(ED[o]) : 0.0;
+      if (k < N) {
+        const double *gk = Gs + k * GS;
+#pragma unroll
+        for (int rr = 0; rr < NX; ++rr) qa = absmax(qa, gk[rr * 8 + r]);
+      }
+      if (c.has_in(k)) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          qa = absmax(qa, SI[c.si(k, t)]);
+          sEti[c.ci(k, t)] = 1.0 / sqrt(limit_scaling(fabs(SI[c.si(k, t)])));
+        }
+      }
+      sDt[o] = 1.0 / sqrt(limit_scaling(pa > qa ? pa : qa));
+      double ea = c.xl ? fabs(ED[o]) : 0.0;
+      if (k > 0 && c.xl) {
+        const double *gp = Gs + (k - 1) * GS + r * 8;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const double2 e = ld2(gp + 2 * j); ea = absmax(ea, e.x); ea = absmax(ea, e.y); }
+      }
+      sEt[o] = 1.0 / sqrt(limit_scaling(ea));
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int k = 0; k <= N; ++k) {
+      const int o = k * 8 + r;
+      const double dt = sDt[o];
+      if (k < N) {
+        double *gk = Gs + k * GS;
+#pragma unroll
+        for (int rr = 0; rr < NX; ++rr) { double *e = gk + rr * 8 + r; *e = (*e * sEt[(k + 1) * 8 + rr]) * dt; }
+        if (k < N - 1 && c.ul) sPO[o] = (sPO[o] * dt) * sDt[o + 8];
+      }
+      if (c.has_in(k)) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const int oi = c.si(k, t), oc = c.ci(k, t);
+          SI[oi] = (SI[oi] * sEti[oc]) * dt;
+          sEI[oc] = sEI[oc] * sEti[oc];
+        }
+      }
+      if (c.xl) ED[o] = (ED[o] * sEt[o]) * dt;
+      sPD[o] = (sPD[o] * dt) * dt;
+      QV[o] = dt * QV[o];
+      sD[o] = sD[o] * dt;
+      sE[o] = sE[o] * sEt[o];
+    }
+    __syncwarp();
+    // cost scaling: mean of the column norms of P in the reference variable order
+    double qn = 0.0;
+#pragma unroll 1
+    for (int k = 0; k <= N; ++k) {
+      const int o = k * 8 + r;
+      double pa = fabs(sPD[o]);
+      if (c.ul) {
+        if (k < N - 1) pa = absmax(pa, sPO[o]);
+        if (k > 0 && k < N) pa = absmax(pa, sPO[o - 8]);
+      }
+      if (c.xl) scr[k * NX + r] = pa;
+      else if (c.ul && k < N) scr[nx + k * 2 + ucomp] = pa;
+      if (c.var_live(k)) qn = absmax(qn, QV[o]);
+    }
+    qn = gmax(qn);
+    __syncwarp();
+    double ct = 0.0;
+#pragma unroll 2
+    for (int j = 0; j < nz; ++j) ct += scr[j];
+    ct = ct / nz;
+    qn = limit_scaling(qn);
+    ct = ct > qn ? ct : qn;
+    ct = limit_scaling(ct);
+    ct = 1.0 / ct;
+#pragma unroll 1
+    for (int k = 0; k <= N; ++k) { const int o = k * 8 + r; sPD[o] *= ct; QV[o] *= ct; sPO[o] *= ct; }
+    csc *= ct;
+    __syncwarp();
+  }
+  *csc_out = csc;
+  // ---- scaled bounds, constraint classes, cold data to the slab, G to the slab
+  {
+    double *cD = c.cd(C_D), *cDI = c.cd(C_DINV), *cE = c.cd(C_E), *cEI = c.cd(C_EINV), *cPD = c.cd(C_PD), *cPO = c.cd(C_PO);
+    double *cEi = c.cd(C_EI), *cEiI = c.cd(C_EIINV), *cQ = c.cd(C_Q), *cBE = c.cd(C_BE), *cED = c.cd(C_ED), *cYD = c.cd(C_YD);
+    double *POs = S + L.PO;
+    uint64_t eqm = 0, loosem = 0;
+#pragma unroll 1
+    for (int k = 0; k <= N; ++k) {
+      const int o = k * 8 + r;
+      cD[o] = sD[o]; cDI[o] = 1.0 / sD[o]; cE[o] = sE[o]; cEI[o] = 1.0 / sE[o]; cPD[o] = sPD[o]; cPO[o] = sPO[o];
+      cEi[o] = sEI[o]; cEiI[o] = 1.0 / sEI[o];
+      cQ[o] = c.var_live(k) ? QV[o] : 0.0; cBE[o] = sE[o] * BE[o]; cED[o] = ED[o]; cYD[o] = 0.0;
+      if (c.ul) POs[(k + 1) * 2 + ucomp] = (k < N - 1) ? sPO[o] : 0.0;
+    }
+    if (c.ul) { POs[ucomp] = 0.0; }
+    double *Gd = c.cold + L.cG;
+#pragma unroll 1
+    for (int k = 0; k < N; ++k) {
+      if (c.xl) {
+        const double *gs = Gs + k * GS + r * 8;
+        double *gd = Gd + k * GS + r * 8;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const double2 e = ld2(gs + 2 * j); st2(gd + 2 * j, e.x, e.y); }
+      }
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int k = 0; k <= N; ++k) {
+      if (c.has_in(k)) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const int oi = c.si(k, t), oc = c.ci(k, t);
+          const double up = sEI[oc] * UI[oi];
+          UI[oi] = up;
+          if (KIND == LPVMPC_PLANNER) {
+            const double lo = sEI[oc] * LI[oi];
+            LI[oi] = lo;
+            if ((lo < -kInfty * kMinScaling) && (up > kInfty * kMinScaling)) loosem |= 1ull << k;
+            else if (up - lo < kRhoTol) eqm |= 1ull << k;
+          }
+        }
+      }
+    }
+    *eqm_out = eqm; *loosem_out = loosem;
+    __syncwarp();
+    // the scratch homes become hot vectors: XS = 0 (R, CR are set by rhs_init, DG by factor)
+#pragma unroll 1
+    for (int k = 0; k <= N; ++k) (S + L.XS)[k * 8 + r] = 0.0;
+    __threadfence_block();
+    __syncwarp();
+  }
+  return (sched_err ? 1 : 0) | (data_err ? 2 : 0);
+}
+
+// ---------------------------------------------------------------- polish (cold, once per QP)
+// Works on the slab (C_PX, C_PYD, C_PYI); on success the polished (x, z, y) replace the iterate.
+template <int KIND>
+__device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const lpvmpc_settings &St, Info *ip, const bool do_pol) {
+  constexpr int NT = Ctx<KIND>::NT, NX = Ctx<KIND>::NX;
+  Info &I = *ip;
+  const bool unscale = I.unscale;
+  const int N = c.N, r = c.r;
+  const Lay &L = *c.L;
+  double *S = c.S;
+  double *X = S + L.X, *ZI = S + L.ZI, *YI = S + L.YI, *BV = S + L.B;
+  const double *SI = S + L.SI, *UI = S + L.UI, *LI = S + L.LI;
+  double *YD = c.cd(C_YD);
+  const double *BE = c.cd(C_BE), *ED = c.cd(C_ED), *QV = c.cd(C_Q);
+  double *PX = c.cd(C_PX), *PYD = c.cd(C_PYD), *PYI = c.cd(C_PYI), *R2D = c.cd(C_R2D), *R2I = c.cd(C_R2I);
+  double *ACTD = c.cd(C_ACTD), *ACTI = c.cd(C_ACTI), *ZT = c.cd(C_ZT);
+  const double *PD = c.cd(C_PD), *PO = c.cd(C_PO), *EINV = c.cd(C_EINV), *EIINV = c.cd(C_EIINV), *DINV = c.cd(C_DINV);
+  const double delta = St.delta, idel = 1.0 / St.delta;
+  auto lo_of = [&](int oi) { return (KIND == LPVMPC_PLANNER) ? LI[oi] : -kInfty; };
+  // active-set guess (form_Ared): 1 = lower, 2 = upper, 3 = both
+#pragma unroll 1
+  for (int k = 0; k <= N; ++k) {
+    const int o = k * 8 + r;
+    double ad = 0.0;
+    if (c.xl && do_pol) { if (0.0 < -YD[o]) ad += 1.0; if (0.0 < YD[o]) ad += 2.0; }  // equality row: z == l == u
+    ACTD[o] = ad;
+    if (c.has_in(k)) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const int oi = c.si(k, t);
+        double ai = 0.0;
+        if (do_pol) { if (ZI[oi] - lo_of(oi) < -YI[oi]) ai += 1.0; if (UI[oi] - ZI[oi] < YI[oi]) ai += 2.0; }
+        ACTI[c.ci(k, t)] = ai;
+      }
+    }
+  }
+  __syncwarp();
+  FW fw; fw.polish = 1; fw.rho = 0.0; fw.rho_eq = 0.0; fw.idel = idel;
+  factor<KIND>(c, fw, delta);
+  auto bred_i = [&](int k, int t) { const double a = ACTI[c.ci(k, t)]; return (a == 1.0 || a == 3.0) ? lo_of(c.si(k, t)) : UI[c.si(k, t)]; };
+  // first solve: rhs = -q + A_red'(b_red / delta); targets go through R2D / R2I
+#pragma unroll 1
+  for (int k = 0; k <= N; ++k) {
+    const int o = k * 8 + r;
+    R2D[o] = (c.xl && ACTD[o] != 0.0) ? idel * BE[o] : 0.0;
+    if (c.has_in(k)) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) R2I[c.ci(k, t)] = (ACTI[c.ci(k, t)] != 0.0) ? idel * bred_i(k, t) : 0.0;
+    }
+  }
+  __syncwarp();
+#pragma unroll 1
+  for (int k = 0; k <= N; ++k) { const int o = k * 8 + r; BV[o] = c.var_live(k) ? (-QV[o] + colA<KIND>(c, ED, R2D, R2I, k)) : 0.0; }
+  __syncwarp();
+  sweep_fwd<KIND>(h, N);
+  __syncwarp();
+  sweep_bwd_plain<KIND>(h, N);
+#pragma unroll 1
+  for (int k = 0; k <= N; ++k) {
+    const int o = k * 8 + r;
+    PX[o] = BV[o];
+    PYD[o] = (c.xl && ACTD[o] != 0.0) ? (rowA_dyn<KIND>(c, ED, BV, k) - BE[o]) * idel : 0.0;
+    if (c.has_in(k)) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) PYI[c.ci(k, t)] = (ACTI[c.ci(k, t)] != 0.0) ? (SI[c.si(k, t)] * BV[o] - bred_i(k, t)) * idel : 0.0;
+    }
+  }
+  __syncwarp();
+#pragma unroll 1
+  for (int it = 0; it < St.polish_refine_iter + kPolishExtraRefine; ++it) {
+    // residual of the un-regularised reduced KKT: r2 on the active rows
+#pragma unroll 1
+    for (int k = 0; k <= N; ++k) {
+      const int o = k * 8 + r;
+      R2D[o] = (c.xl && ACTD[o] != 0.0) ? (BE[o] - rowA_dyn<KIND>(c, ED, PX, k)) : 0.0;
+      if (c.has_in(k)) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) R2I[c.ci(k, t)] = (ACTI[c.ci(k, t)] != 0.0) ? (bred_i(k, t) - SI[c.si(k, t)] * PX[o]) : 0.0;
+      }
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int k = 0; k <= N; ++k) {
+      const int o = k * 8 + r;
+      double b = 0.0;
+      if (c.var_live(k)) {
+        const double Px = rowP<KIND>(c, PD, PO, PX, k), Aty = colA<KIND>(c, ED, PYD, PYI, k);
+        // A'(r2 / delta): same column product on scaled entries
+        double at = c.xl ? ED[o] * (idel * R2D[o]) : 0.0;
+        if (k < N) {
+          double g[8];
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) g[rr] = (rr < NX) ? idel * R2D[(k + 1) * 8 + rr] : 0.0;
+          at += pcoldot<NX>(c.Gb(k), r, g);
+        }
+        if (c.has_in(k)) {
+#pragma unroll
+          for (int t = 0; t < NT; ++t) at = fma(SI[c.si(k, t)], idel * R2I[c.ci(k, t)], at);
+        }
+        b = ((-QV[o] - Px) - Aty) + at;
+      }
+      BV[o] = b;
+    }
+    __syncwarp();
+    sweep_fwd<KIND>(h, N);
+    __syncwarp();
+    sweep_bwd_plain<KIND>(h, N);
+#pragma unroll 1
+    for (int k = 0; k <= N; ++k) { if (c.xl) ZT[k * 8 + r] = rowA_dyn<KIND>(c, ED, BV, k); }   // z~ = A_dyn dx
+    __syncwarp();
+#pragma unroll 1
+    for (int k = 0; k <= N; ++k) {
+      const int o = k * 8 + r;
+      if (c.xl && ACTD[o] != 0.0) PYD[o] += (ZT[o] - R2D[o]) * idel;
+      if (c.has_in(k)) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) { const int oc = c.ci(k, t); if (ACTI[oc] != 0.0) PYI[oc] += (SI[c.si(k, t)] * BV[o] - R2I[oc]) * idel; }
+      }
+      PX[o] += BV[o];
+    }
+    __syncwarp();
+  }
+  // pol z = A x, normal-cone projection, residuals, acceptance.  Polished z of the single-variable rows -> R2I.
+  double a_rp = 0, a_rd = 0;
+#pragma unroll 1
+  for (int k = 0; k <= N; ++k) {
+    const int o = k * 8 + r;
+    if (c.xl) {
+      const double Ax = rowA_dyn<KIND>(c, ED, PX, k), t = Ax + PYD[o];
+      PYD[o] = t - BE[o];
+      const double rr = Ax - BE[o];
+      a_rp = absmax(a_rp, unscale ? EINV[o] * rr : rr);
+    } else PYD[o] = 0.0;
+    if (c.has_in(k)) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const int oi = c.si(k, t), oc = c.ci(k, t);
+        const double ax = SI[oi] * PX[o], tt = ax + PYI[oc];
+        const double zc = clampd(tt, lo_of(oi), UI[oi]);
+        R2I[oc] = zc; PYI[oc] = tt - zc;
+        const double rr = ax - zc;
+        a_rp = absmax(a_rp, unscale ? EIINV[oc] * rr : rr);
+      }
+    }
+  }
+  __syncwarp();
+#pragma unroll 1
+  for (int k = 0; k <= N; ++k) {
+    const int o = k * 8 + r;
+    if (c.var_live(k)) {
+      const double rr = (QV[o] + rowP<KIND>(c, PD, PO, PX, k)) + colA<KIND>(c, ED, PYD, PYI, k);
+      a_rd = absmax(a_rd, unscale ? DINV[o] * rr : rr);
+    }
+  }
+  const double pol_pri = gmax(a_rp), pol_dua = (unscale ? I.cinv : 1.0) * gmax(a_rd);
+  const double pol_obj = objective<KIND>(c, PX, St.scaling ? I.cinv : 1.0);
+  const bool ok = (pol_pri < I.pri_res && pol_dua < I.dua_res) || (pol_pri < I.pri_res && I.dua_res < 1e-10) ||
+                  (pol_dua < I.dua_res && I.pri_res < 1e-10);
+  if (!do_pol) return 0;
+  if (!ok) return -1;
+  I.obj = pol_obj; I.pri_res = pol_pri; I.dua_res = pol_dua;
+#pragma unroll 1
+  for (int k = 0; k <= N; ++k) {
+    const int o = k * 8 + r;
+    X[o] = PX[o]; YD[o] = PYD[o];
+    if (c.has_in(k)) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) { ZI[c.si(k, t)] = R2I[c.ci(k, t)]; YI[c.si(k, t)] = PYI[c.ci(k, t)]; }
+    }
+  }
+  return 1;
+}
+
+// ---------------------------------------------------------------- persistent warps, QPW QPs at a time each
+constexpr int kSyncEvery = 25;  // y_dyn is brought up to date at least every kSyncEvery steps (keeps XS small)
+
+template <int KIND, int QPW>
+__global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant__ H8Params p) {
+  extern __shared__ double smem[];
+  constexpr int NX = Ctx<KIND>::NX, NB = Ctx<KIND>::NB, NT = Ctx<KIND>::NT, NSL = Ctx<KIND>::NSL;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  const int g = lane >> 3, r = lane & 7;
+  const Lay &L = p.L;
+  const int N = L.N;
+  Ctx<KIND> c;
+  c.S = smem; c.cold = p.cold;
+  c.L = &L; c.N = N; c.r = r;
+  c.xl = r < NX; c.ul = (r >= NX) && (r < NB);
+  if (KIND == LPVMPC_CONTROLLER) c.islot = (r == 0) ? 0 : ((r >= NX) ? (r - NX + 1) * 2 : 0);
+  else c.islot = r;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { c.ro[j] = chunk(r, j); c.co[j] = (((r >> 1) ^ j) << 1) | (r & 1); }
+  c.eqm = 0; c.loosem = 0;
+  const lpvmpc_args &a = p.a;
+  const lpvmpc_settings &S = p.S;
+  const int nx = NX * (N + 1), nz = nx + 2 * N;
+  const int m = (KIND == LPVMPC_CONTROLLER) ? (6 * N + nx) : (nx + nz);
+  const int ucomp = r - NX;
+  double *wsm = smem + (size_t)warp * QPW * L.total;
+  const size_t wslot = (size_t)(blockIdx.x * wpc + warp) * QPW;
+
+  for (;;) {
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(p.queue, (unsigned)QPW);
+    base = __shfl_sync(kFull, base, 0);
+    if ((int)base >= p.B) break;
+    // Groups without a problem of their own (batch tail, or g >= QPW) mirror group 0 exactly: same problem, same
+    // shared / scratch region, same values written by the same instruction; only user-visible outputs are guarded.
+    const bool valid = (g < QPW) && ((int)(base + g) < p.B);
+    const int gq = valid ? g : 0;
+    const int b = (int)base + gq;
+    c.S = wsm + gq * L.total;
+    c.cold = p.cold + (wslot + gq) * L.cold_total;
+
+    Hot<KIND> h;
+    {
+      double *Sq = c.S;
+      h.B = Sq + L.B + r;
+      h.Tr = Sq + L.T + r * 8; h.Kr = Sq + L.K + r * 8;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { h.Kc[q] = Sq + L.K + (2 * q) * 8 + c.co[q]; h.go[q] = (q ^ swz(r)) << 1; }
+      h.X = Sq + L.X + r; h.R = Sq + L.R + r; h.XS = Sq + L.XS + r; h.CR = Sq + L.CR + r; h.DG = Sq + L.DG + r;
+      h.ZI = Sq + L.ZI + c.islot; h.YI = Sq + L.YI + c.islot; h.SI = Sq + L.SI + c.islot; h.UI = Sq + L.UI + c.islot;
+      h.LI = Sq + L.LI + c.islot;
+      h.PO = Sq + L.PO + (c.ul ? ucomp : 0); h.pstride = c.ul ? 2 : 0;
+    }
+
+    Info I;
+    double csc = 1.0;
+    int flags = 0;
+    {
+      uint64_t eqm = 0, loosem = 0;
+      flags = setup<KIND>(c, p, b, valid, &csc, &eqm, &loosem);
+      c.eqm = eqm; c.loosem = loosem;
+    }
+    I.csc = csc; I.cinv = 1.0 / csc;
+    I.unscale = (S.scaling && !S.scaled_termination) ? 1 : 0;
+    I.pri_res = 0.0; I.dua_res = 0.0; I.obj = nan("");
+    I.n_rp = I.n_z = I.n_Ax = I.n_rd = I.n_q = I.n_Aty = I.n_Px = 0.0;
+    I.u_z = I.u_Ax = I.u_q = I.u_Aty = I.u_Px = 0.0;
+    I.status = (flags & 1) ? LPVMPC_SCHEDULE_ERROR : ((flags & 2) ? LPVMPC_DATA_ERROR : LPVMPC_UNSOLVED);
+
+    const double sigma = S.sigma, alpha = S.alpha;
+    double rho = fmin(fmax(S.rho, kRhoMin), kRhoMax);
+    double rho_eq = kRhoEqOverIneq * rho;
+    {
+      FW fw; fw.polish = 0; fw.rho = rho; fw.rho_eq = rho_eq; fw.idel = 0.0;
+      factor<KIND>(c, fw, sigma);
+    }
+    rhs_init<KIND>(c, true, rho, rho_eq, sigma, 0.0);
+    bool live = (flags == 0);
+    const bool failed = flags != 0;
+    int iter_done = 0, rho_updates = 0;
+    int adapt_interval = S.adaptive_rho_interval;
+    if (S.adaptive_rho && !adapt_interval) adapt_interval = S.check_termination ? 4 * S.check_termination : 100;
+    const int ct = S.check_termination, ai = S.adaptive_rho ? adapt_interval : 0;
+
+    Upd<KIND> u;
+    u.sigma = sigma; u.alpha = alpha; u.oma = 1.0 - alpha; u.eqm = c.eqm; u.loosem = c.loosem; u.xl = c.xl; u.ul = c.ul; u.N = N;
+    int iter = 0, nsync = 0, first_in = 0;   // steps since the last y_dyn sync; whether step 0 is among them
+    double rho_eq_last = rho_eq;             // rho_eq of the last executed step (delta_y of the certificates)
+    bool checked_last = false;
+    double zsel = 0.0;
+    while (iter < S.max_iter && __any_sync(kFull, live)) {
+      int stop = S.max_iter;
+      if (ct) { const int nxt = (iter / ct + 1) * ct; stop = nxt < stop ? nxt : stop; }
+      if (ai) { const int nxt = (iter / ai + 1) * ai; stop = nxt < stop ? nxt : stop; }
+      { const int nxt = iter + kSyncEvery; stop = nxt < stop ? nxt : stop; }
+      u.rho = rho; u.rho_eq = rho_eq; u.rinv = 1.0 / rho; u.rinv_eq = 1.0 / rho_eq; u.live = live;
+#pragma unroll 1
+      for (; iter < stop; ++iter) {
+        if (iter == stop - 1 && live) {  // keep the iterate before the last step of the chunk: delta_x, delta_y
+          double *PVX = c.cd(C_PVX), *PVYI = c.cd(C_PVYI);
+          const double *X = c.S + L.X, *YI = c.S + L.YI;
+#pragma unroll 1
+          for (int k = 0; k <= N; ++k) {
+            PVX[k * 8 + r] = X[k * 8 + r];
+            if (c.has_in(k)) {
+#pragma unroll
+              for (int t = 0; t < NT; ++t) PVYI[c.ci(k, t)] = YI[c.si(k, t)];
+            }
+          }
+        }
+        u.cc = (iter == 0) ? 2.0 : alpha;
+        sweep_fwd<KIND>(h, N);
+        sweep_bwd_admm<KIND>(h, u);
+        if (iter == 0) first_in = 1;
+        ++nsync;
+        zsel = 1.0;
+      }
+      __syncwarp();
+      const int last_was_first = (iter == 1);
+      rho_eq_last = rho_eq;
+      sync_yd<KIND>(c, live, rho_eq, alpha, nsync, first_in);
+      nsync = 0; first_in = 0;
+      const bool can_check = ct && (iter % ct == 0);
+      const bool can_adapt = ai && (iter % ai == 0);
+      checked_last = can_check;
+      if (can_check || can_adapt) {
+        Info J = I;
+        update_info<KIND>(c, &J, zsel);
+        if (live) { I = J; iter_done = iter; }
+        if (can_check) {
+          if (check_termination<KIND>(c, S, &I, live, 0, rho_eq_last, last_was_first, true)) live = false;  // frozen: stores are predicated on `live`
+        }
+        if (can_adapt) {
+          const double pr = I.n_rp / ((I.n_z > I.n_Ax ? I.n_z : I.n_Ax) + 1e-10);
+          double dn = I.n_q; dn = (I.n_Aty > dn) ? I.n_Aty : dn; dn = (I.n_Px > dn) ? I.n_Px : dn;
+          const double dr = I.n_rd / (dn + 1e-10);
+          double rho_new = rho * sqrt(pr / (dr + 1e-10));
+          rho_new = fmin(fmax(rho_new, kRhoMin), kRhoMax);
+          const bool upd = live && ((rho_new > rho * S.adaptive_rho_tolerance) || (rho_new < rho / S.adaptive_rho_tolerance));
+          if (__any_sync(kFull, upd)) {
+            // groups that do not update must keep their factor: re-factorising with unchanged rho reproduces it
+            if (upd) { rho = rho_new; rho_eq = kRhoEqOverIneq * rho; ++rho_updates; }
+            FW fw; fw.polish = 0; fw.rho = rho; fw.rho_eq = rho_eq; fw.idel = 0.0;
+            __syncwarp();
+            factor<KIND>(c, fw, sigma);
+            rhs_init<KIND>(c, upd, rho, rho_eq, sigma, zsel);  // the pending right-hand side was built with the old rho
+          }
+        }
+      }
+    }
+    if (!checked_last && __any_sync(kFull, live)) {
+      Info J = I;
+      update_info<KIND>(c, &J, zsel);
+      if (live) { I = J; iter_done = iter; }
+      if (check_termination<KIND>(c, S, &I, live, 0, rho_eq_last, iter == 1, iter > 0)) live = false;
+    }
+    {
+      const bool unsolved = (I.status == LPVMPC_UNSOLVED);
+      if (__any_sync(kFull, unsolved)) {
+        if (!check_termination<KIND>(c, S, &I, unsolved, 1, rho_eq_last, iter == 1, iter > 0) && unsolved) I.status = LPVMPC_MAX_ITER_REACHED;
+      }
+    }
+    const int status = I.status;
+    const bool has_sol = !(status == LPVMPC_PRIMAL_INFEASIBLE || status == LPVMPC_PRIMAL_INFEASIBLE_INACCURATE ||
+                           status == LPVMPC_DUAL_INFEASIBLE || status == LPVMPC_DUAL_INFEASIBLE_INACCURATE ||
+                           status == LPVMPC_NON_CVX || status == LPVMPC_SCHEDULE_ERROR || status == LPVMPC_DATA_ERROR);
+    {
+      const double o = objective<KIND>(c, c.S + L.X, S.scaling ? I.cinv : 1.0);
+      if (has_sol) I.obj = o;
+    }
+    // row / variable indices in the reference order
+    auto ref_dyn = [&](int k) { return (KIND == LPVMPC_CONTROLLER) ? (6 * N + k * NX + r) : (k * NX + r); };
+    auto ref_in = [&](int k, int t) {
+      if (KIND == LPVMPC_CONTROLLER) return (r == 0) ? (2 * k + t) : (2 * N + 4 * k + 2 * ucomp + t);
+      return nx + (c.xl ? (k * NX + r) : (nx + k * 2 + ucomp));
+    };
+    auto ref_var = [&](int k) { return c.xl ? (k * NX + r) : (nx + k * 2 + ucomp); };
+    if (valid && (a.xs || a.zs || a.ys)) {
+      const double *X = c.S + L.X, *ZI = c.S + L.ZI, *YI = c.S + L.YI;
+      const double *YD = c.cd(C_YD), *BE = c.cd(C_BE);
+#pragma unroll 1
+      for (int k = 0; k <= N; ++k) {
+        const int o = k * 8 + r;
+        if (c.var_live(k) && a.xs) a.xs[(size_t)b * nz + ref_var(k)] = X[o];
+        if (c.xl) {
+          if (a.zs) a.zs[(size_t)b * m + ref_dyn(k)] = (iter > 0 && !failed) ? BE[o] : 0.0;
+          if (a.ys) a.ys[(size_t)b * m + ref_dyn(k)] = YD[o];
+        }
+        if (c.has_in(k)) {
+#pragma unroll
+          for (int t = 0; t < NT; ++t) {
+            if (a.zs) a.zs[(size_t)b * m + ref_in(k, t)] = ZI[c.si(k, t)];
+            if (a.ys) a.ys[(size_t)b * m + ref_in(k, t)] = YI[c.si(k, t)];
+          }
+        }
+      }
+    }
+    int polish_status = 0;
+    const bool do_pol = S.polish && status == LPVMPC_SOLVED;
+    bool polished_sets = false;
+    if (__any_sync(kFull, do_pol)) {
+      polish_status = polish<KIND>(c, h, S, &I, do_pol);
+      polished_sets = do_pol;
+    }
+    // ---- outputs
+    if (valid) {
+      const double *X = c.S + L.X, *YI = c.S + L.YI;
+      const double *YD = c.cd(C_YD), *D = c.cd(C_D), *E = c.cd(C_E), *EI = c.cd(C_EI), *ACTD = c.cd(C_ACTD), *ACTI = c.cd(C_ACTI);
+#pragma unroll 1
+      for (int k = 0; k <= N; ++k) {
+        const int o = k * 8 + r;
+        const double v = has_sol ? D[o] * X[o] : nan("");
+        if (c.xl) a.x_pred[(size_t)b * nx + k * NX + r] = v;
+        else if (c.ul && k < N) a.u_pred[(size_t)b * 2 * N + k * 2 + ucomp] = v;
+        if (c.xl) {
+          const size_t q = (size_t)b * m + ref_dyn(k);
+          const int act = polished_sets ? (int)ACTD[o] : 0;
+          if (a.y) a.y[q] = has_sol ? I.cinv * (E[o] * YD[o]) : nan("");
+          if (a.active_lo) a.active_lo[q] = act & 1;
+          if (a.active_up) a.active_up[q] = (act >> 1) & 1;
+        }
+        if (c.has_in(k)) {
+#pragma unroll
+          for (int t = 0; t < NT; ++t) {
+            const int oc = c.ci(k, t);
+            const size_t q = (size_t)b * m + ref_in(k, t);
+            const int act = polished_sets ? (int)ACTI[oc] : 0;
+            if (a.y) a.y[q] = has_sol ? I.cinv * (EI[oc] * YI[c.si(k, t)]) : nan("");
+            if (a.active_lo) a.active_lo[q] = act & 1;
+            if (a.active_up) a.active_up[q] = (act >> 1) & 1;
+          }
+        }
+      }
+      if (r == 0) {
+        a.status[b] = status;
+        if (a.iters) a.iters[b] = iter_done;
+        if (a.rho_updates) a.rho_updates[b] = rho_updates;
+        if (a.polish_status) a.polish_status[b] = polish_status;
+        if (a.obj) a.obj[b] = I.obj;
+        if (a.pri_res) a.pri_res[b] = failed ? nan("") : I.pri_res;
+        if (a.dua_res) a.dua_res[b] = failed ? nan("") : I.dua_res;
+      }
+    }
+    __syncwarp();
+  }
+  (void)NSL;
+}
+
+}  // namespace h8
+}  // namespace lpv

@@ -14,6 +14,7 @@
 #include "lpv_qp.cuh"
 #include "lpv_t8.cuh"
 #include "lpv_g8.cuh"
+#include "lpv_h8.cuh"
 
 namespace lpv {
 
@@ -264,6 +265,26 @@ lpv::g8::Lay make_g8_layout(int kind, int N) {
   return L;
 }
 
+lpv::h8::Lay make_h8_layout(int kind, int N) {
+  const int NX = kind == LPVMPC_CONTROLLER ? 6 : 5;
+  lpv::h8::Lay L;
+  std::memset(&L, 0, sizeof(L));
+  L.N = N; L.nsl = kind == LPVMPC_CONTROLLER ? 6 : 7;
+  int o = 0;
+  auto take = [&](int n) { const int r = o; o += (n + 1) & ~1; return r; };
+  L.T = take((N + 1) * 64); L.K = take(N * 64);
+  const int v = (N + 1) * 8, w = (N + 1) * L.nsl;
+  L.X = take(v); L.B = take(v); L.R = take(v); L.CR = take(v); L.XS = take(v); L.DG = take(v);
+  L.ZI = take(w); L.YI = take(w); L.SI = take(w); L.UI = take(w);
+  L.LI = kind == LPVMPC_CONTROLLER ? L.UI : take(w);
+  L.PO = take((N + 2) * 2);
+  while (o % 16 != 8) o += 2;  // groups of a warp land on different bank halves
+  L.total = o;
+  L.cG = lpv::h8::C_COUNT * v;
+  L.cold_total = L.cG + N * NX * 8;
+  return L;
+}
+
 }  // namespace
 
 struct lpvmpc_handle {
@@ -281,7 +302,9 @@ struct lpvmpc_handle {
   double *d_gws = nullptr;
   int variant = 1;           // 1: generic warp-per-QP kernel, 2: T8 register/shared-resident kernel, 3: G8 compact kernel
   lpv::g8::Lay GL;           // G8 shared-memory layout
-  int qpw = 4;               // G8: QPs per warp
+  lpv::h8::Lay HL;           // H8 layout (shared memory + slab)
+  int wpc = 1;               // H8: warps per CTA
+  int qpw = 4;               // T8 / G8 / H8: QPs per warp
   unsigned *d_queue = nullptr;  // work-queue counter of the persistent T8 kernel
   double *d_cold = nullptr;     // T8 scratch slab (scalings, P) per resident lane
   // staging for the host API
@@ -372,10 +395,37 @@ int launch_g8(lpvmpc_handle *h, const Params &p, cudaStream_t s) {
   return LPVMPC_OK;
 }
 
+template <int KIND, int QPW>
+void h8_launch(int grid, int threads, size_t smem, cudaStream_t s, const lpv::h8::H8Params &hp) {
+  lpv::h8::lpv_solve_h8_kernel<KIND, QPW><<<grid, threads, smem, s>>>(hp);
+}
+template <int KIND, int QPW>
+cudaError_t h8_attr(size_t smem) {
+  return cudaFuncSetAttribute(lpv::h8::lpv_solve_h8_kernel<KIND, QPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+template <int KIND>
+int launch_h8(lpvmpc_handle *h, const Params &p, cudaStream_t s) {
+  if (p.B == 0) return LPVMPC_OK;
+  lpv::h8::H8Params hp;
+  hp.L = h->HL; hp.M = p.M; hp.S = p.S; hp.a = p.a; hp.B = p.B; hp.queue = h->d_queue; hp.cold = h->d_cold;
+  const int per_cta = h->qpw * h->wpc;
+  const int ctas = (p.B + per_cta - 1) / per_cta;
+  const int grid = ctas < h->grid_cap ? ctas : h->grid_cap;
+  CUDA_TRY(h, cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned), s));
+  if (h->qpw == 4) h8_launch<KIND, 4>(grid, 32 * h->wpc, h->ws_bytes, s, hp);
+  else if (h->qpw == 2) h8_launch<KIND, 2>(grid, 32 * h->wpc, h->ws_bytes, s, hp);
+  else h8_launch<KIND, 1>(grid, 32 * h->wpc, h->ws_bytes, s, hp);
+  ++h->launches;
+  CUDA_TRY(h, cudaGetLastError());
+  return LPVMPC_OK;
+}
+
 template <int KIND>
 int launch_solve(lpvmpc_handle *h, const Params &p, cudaStream_t s) {
   if (h->variant == 2) return launch_t8(h, p, s);
   if (h->variant == 3) return launch_g8<KIND>(h, p, s);
+  if (h->variant == 5) return launch_h8<KIND>(h, p, s);
   const int grid = p.B < h->grid_cap ? p.B : h->grid_cap;
   if (grid == 0) return LPVMPC_OK;
   if (h->smem_mode) lpv::lpv_solve_kernel<KIND, true><<<grid, 32, h->ws_bytes, s>>>(p);
@@ -491,10 +541,40 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
                        (cfg->kind == LPVMPC_CONTROLLER || cfg->N <= 63);
     if (cfg->variant == 3 && !g8_ok) { h->err = "variant 3 (G8) needs diagonal Q and R, steering_delay=0, planner N<=63 and a per-QP state that fits shared memory"; return bail(LPVMPC_E_UNSUPPORTED); }
     if (cfg->variant == 3) h->variant = 3;
+    // H8 kernel: same restrictions as G8, smaller shared-memory footprint (cold data in an L2 slab)
+    h->HL = make_h8_layout(cfg->kind, cfg->N);
+    const bool h8_ok = pdiag && cfg->steering_delay == 0 && (size_t)h->HL.total * sizeof(double) + 1024 <= (size_t)h->smem_optin &&
+                       (cfg->kind == LPVMPC_CONTROLLER || cfg->N <= 63);
+    if (cfg->variant == 5 && !h8_ok) { h->err = "variant 5 (H8) needs diagonal Q and R, steering_delay=0, planner N<=63 and a per-QP state that fits shared memory"; return bail(LPVMPC_E_UNSUPPORTED); }
+    if (cfg->variant == 5 || (cfg->variant == 0 && h8_ok)) h->variant = 5;
   }
   h->ws_bytes = (size_t)h->L.total * sizeof(double);
   h->smem_mode = h->ws_bytes <= (size_t)h->smem_optin;
-  if (h->variant == 3) {
+  if (h->variant == 5) {
+    // pick (QPs per warp, warps per CTA) that keeps the most QPs resident per SM
+    const size_t per_qp = (size_t)h->HL.total * sizeof(double);
+    const size_t sm_bytes = prop.sharedMemPerMultiprocessor;
+    int best_q = 0, best_qpw = 1, best_wpc = 1, best_ctas = 1;
+    const int qs[3] = {4, 2, 1};
+    for (int qi = 0; qi < 3; ++qi) for (int w = 2; w >= 1; --w) {
+      const size_t cta = per_qp * qs[qi] * w;
+      if (cta > (size_t)h->smem_optin) continue;
+      int ctas = (int)(sm_bytes / (cta + 1024));
+      if (ctas > 32) ctas = 32;
+      const int q = ctas * qs[qi] * w;
+      if (q > best_q) { best_q = q; best_qpw = qs[qi]; best_wpc = w; best_ctas = ctas; }
+    }
+    h->qpw = best_qpw; h->wpc = best_wpc;
+    h->ws_bytes = per_qp * h->qpw * h->wpc;
+    h->smem_mode = true;
+    h->grid_cap = h->sm_count * best_ctas;
+    const bool ctrl = cfg->kind == LPVMPC_CONTROLLER;
+    if (h->qpw == 4) CTRY(ctrl ? (h8_attr<LPVMPC_CONTROLLER, 4>(h->ws_bytes)) : (h8_attr<LPVMPC_PLANNER, 4>(h->ws_bytes)));
+    else if (h->qpw == 2) CTRY(ctrl ? (h8_attr<LPVMPC_CONTROLLER, 2>(h->ws_bytes)) : (h8_attr<LPVMPC_PLANNER, 2>(h->ws_bytes)));
+    else CTRY(ctrl ? (h8_attr<LPVMPC_CONTROLLER, 1>(h->ws_bytes)) : (h8_attr<LPVMPC_PLANNER, 1>(h->ws_bytes)));
+    CTRY(cudaMalloc(&h->d_queue, sizeof(unsigned)));
+    CTRY(cudaMalloc(&h->d_cold, sizeof(double) * (size_t)h->grid_cap * h->wpc * h->qpw * h->HL.cold_total));
+  } else if (h->variant == 3) {
     const size_t per_qp = (size_t)h->GL.total * sizeof(double);
     h->qpw = (4 * per_qp <= (size_t)h->smem_optin) ? 4 : ((2 * per_qp <= (size_t)h->smem_optin) ? 2 : 1);
     h->ws_bytes = per_qp * h->qpw;
@@ -570,7 +650,7 @@ int lpvmpc_get_info(const lpvmpc_handle *h, lpvmpc_info *info) {
   info->n = h->n; info->d = h->d; info->N = h->L.N; info->nz = h->L.nz; info->m = h->L.m;
   info->variant = h->variant;
   info->workspace_in_smem = h->smem_mode ? 1 : 0;
-  info->smem_bytes_per_qp = h->smem_mode ? (int)(h->variant == 2 ? h->ws_bytes / h->qpw : (h->variant == 3 ? h->ws_bytes / h->qpw : h->ws_bytes)) : 0;
+  info->smem_bytes_per_qp = h->smem_mode ? (int)(h->variant == 5 ? h->ws_bytes / (h->qpw * h->wpc) : ((h->variant == 2 || h->variant == 3) ? h->ws_bytes / h->qpw : h->ws_bytes)) : 0;
   info->workspace_bytes = (long long)(h->stage_bytes + (h->smem_mode ? 0 : h->ws_bytes * (size_t)h->grid_cap));
   info->kernel_launches = h->launches;
   return LPVMPC_OK;
