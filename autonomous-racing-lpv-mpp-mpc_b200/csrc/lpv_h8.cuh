@@ -4,25 +4,34 @@
 // termination + infeasibility certificates every check_termination iterations, adaptive rho, polish), restricted to
 // diagonal Q and R (the reference's tunings, controllerMain.py:139-148, plannerMain.py:96-99) and steering_delay = 0.
 //
-// What is different from G8 (profiles/r1b_*: G8 issues 4 000 instructions per ADMM step and keeps 18 KB per QP):
+// Measurements that shaped it (profiles/r1b_*, r1c_*; tools/fp64_latency.cu, tools/smem_probe.cu):
+//  * the solve is SHARED-MEMORY-BANDWIDTH bound: one wavefront (<= 128 B of distinct banks) per cycle per SM, and every
+//    FMA of a block mat-vec needs one fp64 operand from shared memory.  A 4-way bank conflict on an LDS.128 costs 16
+//    cycles, a broadcast LDS.128 (8 lanes of a group read the same 16 B) costs 1 cycle when the four groups of the warp
+//    hit different banks, an 8-lanes-consecutive LDS.64 costs 2 cycles when neighbouring groups are 64 B apart mod 128.
+//  * G8 issues 4 000 instructions and 18 KB of state per QP.
 //
+// What H8 does about it:
 //  * The dynamics rows are equalities, so their z is pinned to the right-hand side `be` after the first step and their
 //    dual only enters the next right-hand side through r = A_dyn'(rho_eq z_dyn - y_dyn).  With S x~ = rhs solved,
 //        rho_eq A_dyn'A_dyn x~ = rhs - (P + sigma I + A_in' rho A_in) x~  =: rhs - M x~      (M: diagonal + slew coupling)
 //    so r is advanced by an element-wise recursion,
 //        r <- r - alpha (rhs - M x~) + c CR,     CR = rho_eq A_dyn' be,   c = 2 on the first step, alpha afterwards,
 //    and the ADMM step needs NO product with A_k / B_k at all: forward sweep, backward sweep, element-wise update.
-//    The explicit dual y_dyn is recovered when somebody needs it (termination check, certificates, polish, output) from
-//    the running sum XS of x~:  y_dyn += rho_eq (alpha A_dyn XS - (alpha n + (1 - alpha) [first step inside]) be).
+//    The explicit dual y_dyn is recovered every kSyncEvery steps from the running sum XS of x~,
+//        y_dyn += rho_eq (alpha A_dyn XS - (alpha n + (1 - alpha) [first step inside]) be),
+//    and r is re-projected from it (r = CR - A_dyn' y_dyn - q): the recursion integrates the residual of the block solve
+//    (1e-11 relative per step), whose component outside range(A_dyn') nothing else would remove.
 //  * A_k / B_k (G), the scalings, q, be, y_dyn and every polish vector live in a per-slot global slab that stays in L2;
 //    shared memory holds the block factor (T, K), 6 stage vectors and the single-variable rows: 14.0 KB per controller
 //    QP at N = 8 -> 16 QPs per SM.
-//  * Hot loops use per-lane base pointers and immediate offsets (the row swizzle is applied to the gather, not to the
-//    matrix reads) and explicit fma().
+//  * Layout for the wavefront rules above: T_k / K_{k+1} interleaved per stage with XOR-swizzled rows (row and column
+//    reads conflict free), one pointer per logical 16-byte chunk; the 8-lane all-gather goes through a per-warp
+//    double-buffered 256-byte buffer laid out [chunk][group] so that a gather is 4 single-wavefront LDS.128; stage
+//    vectors interleaved per stage [B X R XS DG CR]; single-variable rows as {z,y} / {s,u} pairs.
 //
 // Lane r of a group owns component r of every stage variable w_k = [x_k; u_k], the dynamics row (k, r) and the
-// single-variable rows on its variable.  8x8 blocks of T and K are stored row-major with the 16-byte chunks of row rr
-// XOR-swizzled by (rr >> 1): row reads (LDS.128) and column reads (LDS.64) are bank-conflict free without padding.
+// single-variable rows on its variable.
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -33,13 +42,15 @@
 namespace lpv {
 namespace h8 {
 
+constexpr int TKS = 128;  // doubles per stage of the factor: T_k (64) then K_{k+1} (64)
+constexpr int VS = 48;    // doubles per stage of the stage vectors
+enum { V_B = 0, V_X = 8, V_R = 16, V_XS = 24, V_DG = 32, V_CR = 40 };
+
 struct Lay {  // per-QP offsets (doubles); computed on the host (lpvmpc.cu: make_h8_layout)
-  int N, nsl;                  // horizon; single-variable-row slots per stage in shared memory (6 controller, 7 planner)
-  int T, K;                    // (N+1) x 64, N x 64 (K_k at k-1)
-  int X, B, R, CR, XS, DG;     // (N+1) x 8: iterate x, rhs / sweep vector, r - q, CR, sum of x~, diag(M)
-  int ZI, YI, SI, UI, LI;      // (N+1) x nsl: single-variable rows (z, y, coefficient, bounds; LI planner only)
-  int PO;                      // (N+2) x 2, zero padded: PO[(i+1)*2 + c] couples u_i[c] and u_{i+1}[c]
-  int total;                   // doubles per QP in shared memory (== 8 mod 16: groups land on different bank halves)
+  int N, nsl;                  // horizon; single-variable-row slots per stage (6 controller, 7 planner)
+  int is;                      // doubles per stage of the single-variable-row block: {z,y} x nsl, {s,u} x nsl, [l x nsl], pm x 2
+  int TK, V, I;                // (N+1) x TKS - 64, (N+1) x VS, (N+1) x is
+  int total;                   // doubles per QP in shared memory (== 8 mod 16: neighbouring groups 64 B apart mod 128)
   int cold_total;              // doubles per QP slot in the global slab
   int cG;                      // offset of G (N x NX x 8, row-major rows of -[A_k B_k], scaled) inside the slot
 };
@@ -57,8 +68,8 @@ struct H8Params {
 };
 
 template <int KIND> struct Dims;
-template <> struct Dims<LPVMPC_CONTROLLER> { static constexpr int NX = 6, NT = 2, NSL = 6; };
-template <> struct Dims<LPVMPC_PLANNER> { static constexpr int NX = 5, NT = 1, NSL = 7; };
+template <> struct Dims<LPVMPC_CONTROLLER> { static constexpr int NX = 6, NT = 2, NSL = 6, OLI = 24, OPM = 24, IS = 26; };
+template <> struct Dims<LPVMPC_PLANNER> { static constexpr int NX = 5, NT = 1, NSL = 7, OLI = 28, OPM = 36, IS = 38; };
 
 __device__ __forceinline__ double gshfl(double v, int src) { return __shfl_sync(kFull, v, src, 8); }
 __device__ __forceinline__ double gmax(double v) {
@@ -84,6 +95,7 @@ __device__ __forceinline__ int chunk(int rr, int j) { return rr * 8 + ((j ^ swz(
 template <int KIND>
 struct Ctx {
   static constexpr int NX = Dims<KIND>::NX, NB = NX + 2, NT = Dims<KIND>::NT, NSL = Dims<KIND>::NSL;
+  static constexpr int OLI = Dims<KIND>::OLI, OPM = Dims<KIND>::OPM, IS = Dims<KIND>::IS;
   double *S;     // my QP's shared region
   double *cold;  // my QP slot in the global slab
   const Lay *L;
@@ -100,11 +112,20 @@ struct Ctx {
     return xl || (ul && k < N);
   }
   __device__ __forceinline__ double *cd(int arr) const { return cold + arr * (N + 1) * 8; }
-  __device__ __forceinline__ double *Tb(int k) const { return S + L->T + k * 64; }
-  __device__ __forceinline__ double *Kb(int k) const { return S + L->K + (k - 1) * 64; }
+  __device__ __forceinline__ double *Tb(int k) const { return S + L->TK + k * TKS; }
+  __device__ __forceinline__ double *Kb(int k) const { return S + L->TK + (k - 1) * TKS + 64; }
   __device__ __forceinline__ const double *Gb(int k) const { return cold + L->cG + k * (NX * 8); }
-  __device__ __forceinline__ int si(int k, int t) const { return k * NSL + islot + t; }   // shared-memory slot
-  __device__ __forceinline__ int ci(int k, int t) const { return k * 8 + islot + t; }     // slab slot
+  __device__ __forceinline__ double *V(int arr) const { return S + L->V + arr; }          // element (k, q) at [k*VS + q]
+  // single-variable rows in shared memory: z, y, coefficient, upper (and lower: planner) bound of my row t at stage k
+  __device__ __forceinline__ double *Ib(int k) const { return S + L->I + k * IS; }
+  __device__ __forceinline__ double &zi(int k, int t) const { return Ib(k)[(islot + t) * 2]; }
+  __device__ __forceinline__ double &yi(int k, int t) const { return Ib(k)[(islot + t) * 2 + 1]; }
+  __device__ __forceinline__ double &si(int k, int t) const { return Ib(k)[NSL * 2 + (islot + t) * 2]; }
+  __device__ __forceinline__ double &ui(int k, int t) const { return Ib(k)[NSL * 2 + (islot + t) * 2 + 1]; }
+  __device__ __forceinline__ double &li(int k, int t) const { return Ib(k)[OLI + islot + t]; }   // planner only
+  __device__ __forceinline__ double lo_of(int k, int t) const { return (KIND == LPVMPC_PLANNER) ? li(k, t) : -kInfty; }
+  __device__ __forceinline__ double &pm(int k, int cu) const { return Ib(k)[OPM + cu]; }        // couples u_{k-1}[cu], u_k[cu]
+  __device__ __forceinline__ int ci(int k, int t) const { return k * 8 + islot + t; }           // slab slot of my row
   // row-weight classes of my single-variable row (planner); controller rows are always plain inequalities
   __device__ __forceinline__ double rho_of(int k, double rho, double rho_eq) const {
     if (KIND == LPVMPC_CONTROLLER) return rho;
@@ -112,13 +133,6 @@ struct Ctx {
   }
 };
 
-// dot product of my row of a swizzled block with a vector gathered in logical order
-__device__ __forceinline__ double rowdot(const double *blk, const int (&ro)[4], const double (&g)[8]) {
-  const double2 t0 = ld2(blk + ro[0]), t1 = ld2(blk + ro[1]), t2 = ld2(blk + ro[2]), t3 = ld2(blk + ro[3]);
-  double a0 = t0.x * g[0], a1 = t1.x * g[2], a2 = t2.x * g[4], a3 = t3.x * g[6];
-  a0 = fma(t0.y, g[1], a0); a1 = fma(t1.y, g[3], a1); a2 = fma(t2.y, g[5], a2); a3 = fma(t3.y, g[7], a3);
-  return (a0 + a1) + (a2 + a3);
-}
 // my row / my column of a plain row-major 8-wide block (G in the slab, or in shared memory during setup)
 __device__ __forceinline__ double prowdot(const double *blk, int r, const double (&g)[8]) {
   const double2 t0 = ld2(blk + r * 8), t1 = ld2(blk + r * 8 + 2), t2 = ld2(blk + r * 8 + 4), t3 = ld2(blk + r * 8 + 6);
@@ -136,10 +150,6 @@ __device__ __forceinline__ double pcoldot(const double *blk, int r, const double
   }
   return a0 + a1;
 }
-__device__ __forceinline__ void gather8(double v, double (&g)[8]) {
-#pragma unroll
-  for (int c = 0; c < 8; ++c) g[c] = gshfl(v, c);
-}
 
 // ---------------------------------------------------------------- block factorisation (cold)
 // Row weights: ADMM -> rho_eq on the dynamics rows, rho / rho_eq / rho_min on the single-variable rows;
@@ -150,10 +160,8 @@ template <int KIND>
 __device__ __noinline__ void factor(const Ctx<KIND> c, const FW fw, const double sigma) {
   constexpr int NX = Ctx<KIND>::NX, NB = Ctx<KIND>::NB, NT = Ctx<KIND>::NT;
   const int N = c.N, r = c.r;
-  const Lay &L = *c.L;
   const double *PD = c.cd(C_PD), *PO = c.cd(C_PO), *ACTD = c.cd(C_ACTD), *ACTI = c.cd(C_ACTI), *ED = c.cd(C_ED);
-  const double *SI = c.S + L.SI;
-  double *DG = c.S + L.DG;
+  double *DG = c.V(V_DG);
   auto wd = [&](int k) -> double {  // weight of my dynamics row (k, r)
     if (!c.xl) return 0.0;
     return fw.polish ? ((ACTD[k * 8 + r] != 0.0) ? fw.idel : 0.0) : fw.rho_eq;
@@ -172,12 +180,12 @@ __device__ __noinline__ void factor(const Ctx<KIND> c, const FW fw, const double
       if (c.has_in(k)) {
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
-          const double a = SI[c.si(k, t)];
+          const double a = c.si(k, t);
           const double w = fw.polish ? ((ACTI[c.ci(k, t)] != 0.0) ? fw.idel : 0.0) : c.rho_of(k, fw.rho, fw.rho_eq);
           d = fma(w * a, a, d);
         }
       }
-      if (!fw.polish) DG[k * 8 + r] = rowlive ? d : 1.0;
+      if (!fw.polish) DG[k * VS + r] = rowlive ? d : 1.0;
       if (c.xl) d = fma(wdk * edk, edk, d);
       if (!rowlive) d = 1.0;
 #pragma unroll
@@ -269,74 +277,120 @@ __device__ __noinline__ void factor(const Ctx<KIND> c, const FW fw, const double
 }
 
 // ---------------------------------------------------------------- hot loop
-// Per-lane pointers into the QP's shared region (computed once per QP).
+// Explicit shared-space accesses (32-bit byte addresses, immediate offsets); every access is a volatile asm with a
+// memory clobber, so the compiler keeps them in program order with respect to each other and to the plain accesses of
+// the cold code.
+template <int OFF = 0>
+__device__ __forceinline__ double lds(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(a), "n"(OFF) : "memory");
+  return v;
+}
+template <int OFF = 0>
+__device__ __forceinline__ double2 lds2(uint32_t a) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(a), "n"(OFF) : "memory");
+  return v;
+}
+template <int OFF = 0>
+__device__ __forceinline__ void sts(uint32_t a, double v) {
+  asm volatile("st.shared.f64 [%0+%1], %2;" ::"r"(a), "n"(OFF), "d"(v) : "memory");
+}
+template <int OFF = 0>
+__device__ __forceinline__ void sts2(uint32_t a, double x, double y) {
+  asm volatile("st.shared.v2.f64 [%0+%1], {%2, %3};" ::"r"(a), "n"(OFF), "d"(x), "d"(y) : "memory");
+}
+
+constexpr int TKB = TKS * 8, VB = VS * 8;  // bytes per stage
+
+// Per-lane shared-space addresses of stage 0 (computed once per QP).
 template <int KIND>
 struct Hot {
-  double *B;               // + r
-  const double *Tr, *Kr;   // my row of block 0 (physical chunk order: immediate offsets 0, 2, 4, 6)
-  const double *Kc[4];     // my column of block 0, rows 2q and 2q+1 at +0 and +8
-  int go[4];               // gather offsets (doubles) that bring the vector into my row's physical chunk order
-  double *X, *R, *XS;      // + r
-  const double *CR, *DG;   // + r
-  double *ZI, *YI;         // + islot
-  const double *SI, *UI, *LI;
-  const double *PO;        // + (ul ? r - NX : 0)
-  int pstride;             // 2 for input lanes, 0 otherwise (state lanes keep reading the zero pad)
+  uint32_t tk[4];   // logical 16-byte chunk j of my row of T_0 (the same chunk of K_1 at +512)
+  uint32_t kc[4];   // my column of K_1 in row 2q (row 2q+1 at +64)
+  uint32_t v;       // my element of the stage vectors: B +0, X +64, R +128, XS +192, DG +256, CR +320
+  uint32_t ib;      // my first single-variable row: {z,y} of row t at +16t, {s,u} at +NSL*16 + 16t
+  uint32_t il;      // planner: lower bound of my row
+  uint32_t pm;      // input lanes: slew coupling with the previous stage (next stage's at +IS*8)
+  uint32_t gpub, ggat;  // all-gather buffer 0 (buffer 1 at ^256): where I publish, where my group's 64 bytes start
 };
 
-// forward sweep: B holds the right-hand side on entry, W_k = T_k v_k on exit
+__device__ __forceinline__ double dot8(const double2 &a0, const double2 &a1, const double2 &a2, const double2 &a3, const double2 &g0,
+                                      const double2 &g1, const double2 &g2, const double2 &g3) {
+  double w0 = a0.x * g0.x, w1 = a1.x * g1.x, w2 = a2.x * g2.x, w3 = a3.x * g3.x;
+  w0 = fma(a0.y, g0.y, w0); w1 = fma(a1.y, g1.y, w1); w2 = fma(a2.y, g2.y, w2); w3 = fma(a3.y, g3.y, w3);
+  return (w0 + w1) + (w2 + w3);
+}
+
+// forward sweep: B holds the right-hand side on entry, W_k = T_k v_k on exit.  `gsel` toggles the gather buffer.
 template <int KIND>
-__device__ __forceinline__ void sweep_fwd(const Hot<KIND> &h, const int N) {
-  double *Bk = h.B;                         // B + k*8 + r
-  double *Bg = h.B - ((threadIdx.x & 7));   // B + k*8
-  const double *Tk = h.Tr, *Kk = h.Kr;
-  double v = *Bk;
+__device__ __forceinline__ void sweep_fwd(const Hot<KIND> &h, const int N, uint32_t &gsel) {
+  uint32_t t0 = h.tk[0], t1 = h.tk[1], t2 = h.tk[2], t3 = h.tk[3], vb = h.v;
+  double v = lds(vb);
 #pragma unroll 1
-  for (int k = 0; k <= N; ++k) {
-    *Bk = v;
+  for (int k = 0; k < N; ++k) {
+    sts(h.gpub ^ gsel, v);
+    const double2 a0 = lds2(t0), a1 = lds2(t1), a2 = lds2(t2), a3 = lds2(t3);
+    const double2 b0 = lds2<512>(t0), b1 = lds2<512>(t1), b2 = lds2<512>(t2), b3 = lds2<512>(t3);
+    const double bn = lds<VB>(vb);
     __syncwarp();
-    const double2 g0 = ld2(Bg + h.go[0]), g1 = ld2(Bg + h.go[1]), g2 = ld2(Bg + h.go[2]), g3 = ld2(Bg + h.go[3]);
-    const double2 t0 = ld2(Tk), t1 = ld2(Tk + 2), t2 = ld2(Tk + 4), t3 = ld2(Tk + 6);
-    double w0 = t0.x * g0.x, w1 = t1.x * g1.x, w2 = t2.x * g2.x, w3 = t3.x * g3.x;
-    w0 = fma(t0.y, g0.y, w0); w1 = fma(t1.y, g1.y, w1); w2 = fma(t2.y, g2.y, w2); w3 = fma(t3.y, g3.y, w3);
-    if (k < N) {
-      const double2 k0 = ld2(Kk), k1 = ld2(Kk + 2), k2 = ld2(Kk + 4), k3 = ld2(Kk + 6);
-      const double bn = Bk[8];
-      double a0 = fma(-k0.x, g0.x, bn), a1 = -(k1.x * g1.x), a2 = -(k2.x * g2.x), a3 = -(k3.x * g3.x);
-      a0 = fma(-k0.y, g0.y, a0); a1 = fma(-k1.y, g1.y, a1); a2 = fma(-k2.y, g2.y, a2); a3 = fma(-k3.y, g3.y, a3);
-      v = (a0 + a1) + (a2 + a3);
-    }
-    __syncwarp();
-    *Bk = (w0 + w1) + (w2 + w3);
-    Bk += 8; Bg += 8; Tk += 64; Kk += 64;
+    const uint32_t gg = h.ggat ^ gsel;
+    const double2 g0 = lds2(gg), g1 = lds2<64>(gg), g2 = lds2<128>(gg), g3 = lds2<192>(gg);
+    double c0 = fma(-b0.x, g0.x, bn), c1 = -(b1.x * g1.x), c2 = -(b2.x * g2.x), c3 = -(b3.x * g3.x);
+    c0 = fma(-b0.y, g0.y, c0); c1 = fma(-b1.y, g1.y, c1); c2 = fma(-b2.y, g2.y, c2); c3 = fma(-b3.y, g3.y, c3);
+    v = (c0 + c1) + (c2 + c3);
+    sts(vb, dot8(a0, a1, a2, a3, g0, g1, g2, g3));
+    t0 += TKB; t1 += TKB; t2 += TKB; t3 += TKB; vb += VB; gsel ^= 256u;
   }
+  {  // stage N: no K
+    sts(h.gpub ^ gsel, v);
+    const double2 a0 = lds2(t0), a1 = lds2(t1), a2 = lds2(t2), a3 = lds2(t3);
+    __syncwarp();
+    const uint32_t gg = h.ggat ^ gsel;
+    const double2 g0 = lds2(gg), g1 = lds2<64>(gg), g2 = lds2<128>(gg), g3 = lds2<192>(gg);
+    sts(vb, dot8(a0, a1, a2, a3, g0, g1, g2, g3));
+    gsel ^= 256u;
+  }
+}
+
+// x~_k = W_k - K_{k+1}' x~_{k+1} for one stage: returns my component, refreshes gn with the gathered x~_k
+__device__ __forceinline__ double bwd_step(const uint32_t k0, const uint32_t k1, const uint32_t k2, const uint32_t k3, const uint32_t vb,
+                                          const uint32_t gpub, const uint32_t ggat, uint32_t &gsel, double (&gn)[8]) {
+  const double e0 = lds(k0), e1 = lds<64>(k0), e2 = lds(k1), e3 = lds<64>(k1), e4 = lds(k2), e5 = lds<64>(k2), e6 = lds(k3), e7 = lds<64>(k3);
+  const double w = lds(vb);
+  double a0 = fma(-e0, gn[0], w), a1 = -(e1 * gn[1]);
+  a0 = fma(-e2, gn[2], a0); a1 = fma(-e3, gn[3], a1);
+  a0 = fma(-e4, gn[4], a0); a1 = fma(-e5, gn[5], a1);
+  a0 = fma(-e6, gn[6], a0); a1 = fma(-e7, gn[7], a1);
+  const double xt = a0 + a1;
+  sts(gpub ^ gsel, xt);
+  return xt;
+}
+__device__ __forceinline__ void gather_in(const uint32_t ggat, uint32_t &gsel, double (&gn)[8]) {
+  __syncwarp();
+  const uint32_t gg = ggat ^ gsel;
+  const double2 g0 = lds2(gg), g1 = lds2<64>(gg), g2 = lds2<128>(gg), g3 = lds2<192>(gg);
+  gn[0] = g0.x; gn[1] = g0.y; gn[2] = g1.x; gn[3] = g1.y; gn[4] = g2.x; gn[5] = g2.y; gn[6] = g3.x; gn[7] = g3.y;
+  gsel ^= 256u;
 }
 
 // backward sweep only (polish): x_k = W_k - K_{k+1}' x_{k+1}, written back into B
 template <int KIND>
-__device__ __forceinline__ void sweep_bwd_plain(const Hot<KIND> &h, const int N) {
+__device__ __forceinline__ void sweep_bwd_plain(const Hot<KIND> &h, const int N, uint32_t &gsel) {
   double gn[8];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) gn[q] = 0.0;
+  uint32_t vb = h.v + N * VB;
+  uint32_t k0 = h.kc[0] + N * TKB, k1 = h.kc[1] + N * TKB, k2 = h.kc[2] + N * TKB, k3 = h.kc[3] + N * TKB;
+  {
+    const double x = lds(vb);
+    sts(h.gpub ^ gsel, x);
+    gather_in(h.ggat, gsel, gn);
+  }
 #pragma unroll 1
-  for (int k = N; k >= 0; --k) {
-    double *Bk = h.B + k * 8;
-    double x = *Bk;
-    if (k < N) {
-      double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const double *p = h.Kc[q] + k * 64;
-        a0 = fma(p[0], gn[2 * q], a0);
-        a1 = fma(p[8], gn[2 * q + 1], a1);
-      }
-      x -= a0 + a1;
-    }
-    *Bk = x;
-    __syncwarp();
-    const double *Bg = Bk - (threadIdx.x & 7);
-    const double2 g0 = ld2(Bg), g1 = ld2(Bg + 2), g2 = ld2(Bg + 4), g3 = ld2(Bg + 6);
-    gn[0] = g0.x; gn[1] = g0.y; gn[2] = g1.x; gn[3] = g1.y; gn[4] = g2.x; gn[5] = g2.y; gn[6] = g3.x; gn[7] = g3.y;
+  for (int k = N - 1; k >= 0; --k) {
+    vb -= VB; k0 -= TKB; k1 -= TKB; k2 -= TKB; k3 -= TKB;
+    const double xt = bwd_step(k0, k1, k2, k3, vb, h.gpub, h.ggat, gsel, gn);
+    sts(vb, xt);
+    gather_in(h.ggat, gsel, gn);
   }
   __syncwarp();
 }
@@ -347,90 +401,83 @@ template <int KIND>
 struct Upd {
   double rho, rho_eq, rinv, rinv_eq, sigma, alpha, oma, cc;
   uint64_t eqm, loosem;
-  bool live, xl, ul;
+  bool live, xl, ul, inl;   // inl: my variable has single-variable rows (at stages < N for the controller)
   int N;
 };
 template <int KIND>
-__device__ __forceinline__ void update_stage(const Hot<KIND> &h, const Upd<KIND> &u, const int j, const double x1, const double xm,
-                                             const double xp) {
-  constexpr int NT = Dims<KIND>::NT, NSL = Dims<KIND>::NSL;
-  const int o = j * 8;
+__device__ __forceinline__ void update_stage(const Upd<KIND> &u, const int j, const uint32_t vj, const uint32_t ij, const uint32_t lj,
+                                             const uint32_t pj, const double x1, const double xm, const double xp) {
+  constexpr int NT = Dims<KIND>::NT, NSL = Dims<KIND>::NSL, IS = Dims<KIND>::IS;
   const bool vlive = u.xl || (u.ul && j < u.N);
-  if (!vlive) return;
-  const double xo = h.X[o], rr = h.R[o], dg = h.DG[o], cr = h.CR[o], xs = h.XS[o];
-  const double pm = h.PO[j * h.pstride], pp = h.PO[(j + 1) * h.pstride];
-  double m = dg * x1;
-  m = fma(pm, xm, m);
-  m = fma(pp, xp, m);
-  double sold = 0.0, snew = 0.0;
-  bool has_in;
-  if (KIND == LPVMPC_CONTROLLER) has_in = ((threadIdx.x & 7) == 0 || u.ul) && j < u.N;
-  else has_in = true;
-  if (has_in) {
-    double rt = u.rho, ri = u.rinv;
-    if (KIND == LPVMPC_PLANNER) {
-      if ((u.eqm >> j) & 1ull) { rt = u.rho_eq; ri = u.rinv_eq; }
-      else if ((u.loosem >> j) & 1ull) { rt = kRhoMin; ri = 1.0 / kRhoMin; }
+  if (vlive) {
+    const double xo = lds<64>(vj), rr = lds<128>(vj), xs = lds<192>(vj), dg = lds<256>(vj), cr = lds<320>(vj);
+    double m = dg * x1;
+    if (u.ul) {
+      const double pm = lds(pj), pp = lds<IS * 8>(pj);
+      m = fma(pm, xm, m);
+      m = fma(pp, xp, m);
     }
-#pragma unroll
-    for (int t = 0; t < NT; ++t) {
-      const int oi = j * NSL + t;
-      const double si = h.SI[oi], zi = h.ZI[oi], yi = h.YI[oi], ui = h.UI[oi];
-      sold = fma(si, fma(rt, zi, -yi), sold);
-      const double zr = fma(u.alpha, si * x1, u.oma * zi);
-      double zn = fma(ri, yi, zr);
-      if (KIND == LPVMPC_PLANNER) { const double li = h.LI[oi]; zn = (zn > li) ? zn : li; }
-      // controller rows: the lower bound is -OSQP_INFTY (times the row scaling): below any iterate, no clamp needed
-      zn = (zn < ui) ? zn : ui;
-      const double yn = fma(rt, zr - zn, yi);
-      if (u.live) { h.ZI[oi] = zn; h.YI[oi] = yn; }
-      snew = fma(si, fma(rt, zn, -yn), snew);
+    double sold = 0.0, snew = 0.0;
+    if (u.inl && (KIND == LPVMPC_PLANNER || j < u.N)) {
+      double rt = u.rho, ri = u.rinv;
+      if (KIND == LPVMPC_PLANNER) {
+        if ((u.eqm >> j) & 1ull) { rt = u.rho_eq; ri = u.rinv_eq; }
+        else if ((u.loosem >> j) & 1ull) { rt = kRhoMin; ri = 1.0 / kRhoMin; }
+      }
+      {
+        const double2 zy = lds2(ij), su = lds2<NSL * 16>(ij);
+        sold = fma(su.x, fma(rt, zy.x, -zy.y), sold);
+        const double zr = fma(u.alpha, su.x * x1, u.oma * zy.x);
+        double zn = fma(ri, zy.y, zr);
+        if (KIND == LPVMPC_PLANNER) { const double li = lds(lj); zn = (zn > li) ? zn : li; }
+        // controller rows: the lower bound is -OSQP_INFTY (times the row scaling): below any iterate, no clamp needed
+        zn = (zn < su.y) ? zn : su.y;
+        const double yn = fma(rt, zr - zn, zy.y);
+        if (u.live) sts2(ij, zn, yn);
+        snew = fma(su.x, fma(rt, zn, -yn), snew);
+      }
+      if (NT > 1) {
+        const double2 zy = lds2<16>(ij), su = lds2<NSL * 16 + 16>(ij);
+        sold = fma(su.x, fma(rt, zy.x, -zy.y), sold);
+        const double zr = fma(u.alpha, su.x * x1, u.oma * zy.x);
+        double zn = fma(ri, zy.y, zr);
+        zn = (zn < su.y) ? zn : su.y;
+        const double yn = fma(rt, zr - zn, zy.y);
+        if (u.live) sts2<16>(ij, zn, yn);
+        snew = fma(su.x, fma(rt, zn, -yn), snew);
+      }
     }
+    const double hh = fma(u.sigma, xo, rr) + sold;            // the right-hand side this x~ was solved for
+    const double rn = fma(-u.alpha, hh - m, fma(u.cc, cr, rr));
+    const double xn = fma(u.alpha, x1, u.oma * xo);
+    if (u.live) sts<64>(vj, xn);
+    sts<128>(vj, rn);
+    sts<192>(vj, xs + x1);
+    sts(vj, fma(u.sigma, xn, rn) + snew);
   }
-  const double hh = fma(u.sigma, xo, rr) + sold;            // the right-hand side this x~ was solved for
-  const double rn = fma(-u.alpha, hh - m, fma(u.cc, cr, rr));
-  const double xn = fma(u.alpha, x1, u.oma * xo);
-  if (u.live) h.X[o] = xn;
-  h.R[o] = rn;
-  h.XS[o] = xs + x1;
-  h.B[o] = fma(u.sigma, xn, rn) + snew;
 }
 
 // backward sweep fused with the element-wise update of stage k+1 (hot)
 template <int KIND>
-__device__ __forceinline__ void sweep_bwd_admm(const Hot<KIND> &h, const Upd<KIND> &u) {
+__device__ __forceinline__ void sweep_bwd_admm(const Hot<KIND> &h, const Upd<KIND> &u, uint32_t &gsel) {
+  constexpr int ISB = Dims<KIND>::IS * 8;
   const int N = u.N;
   double gn[8];
-  double x1, x2 = 0.0;
-  {  // stage N: x~_N = W_N
-    double *Bk = h.B + N * 8;
-    x1 = *Bk;
-    __syncwarp();
-    const double *Bg = Bk - (threadIdx.x & 7);
-    const double2 g0 = ld2(Bg), g1 = ld2(Bg + 2), g2 = ld2(Bg + 4), g3 = ld2(Bg + 6);
-    gn[0] = g0.x; gn[1] = g0.y; gn[2] = g1.x; gn[3] = g1.y; gn[4] = g2.x; gn[5] = g2.y; gn[6] = g3.x; gn[7] = g3.y;
-  }
+  uint32_t vb = h.v + N * VB, ib = h.ib + N * ISB, il = h.il + N * ISB, pb = h.pm + N * ISB;
+  uint32_t k0 = h.kc[0] + N * TKB, k1 = h.kc[1] + N * TKB, k2 = h.kc[2] + N * TKB, k3 = h.kc[3] + N * TKB;
+  double x1 = lds(vb), x2 = 0.0;   // stage N: x~_N = W_N
+  sts(h.gpub ^ gsel, x1);
+  gather_in(h.ggat, gsel, gn);
 #pragma unroll 1
   for (int k = N - 1; k >= 0; --k) {
-    double *Bk = h.B + k * 8;
-    double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const double *p = h.Kc[q] + k * 64;
-      a0 = fma(p[0], gn[2 * q], a0);
-      a1 = fma(p[8], gn[2 * q + 1], a1);
-    }
-    const double xt = *Bk - (a0 + a1);
-    *Bk = xt;
-    __syncwarp();
-    const double *Bg = Bk - (threadIdx.x & 7);
-    const double2 g0 = ld2(Bg), g1 = ld2(Bg + 2), g2 = ld2(Bg + 4), g3 = ld2(Bg + 6);
-    gn[0] = g0.x; gn[1] = g0.y; gn[2] = g1.x; gn[3] = g1.y; gn[4] = g2.x; gn[5] = g2.y; gn[6] = g3.x; gn[7] = g3.y;
-    update_stage<KIND>(h, u, k + 1, x1, xt, x2);   // overwrites B[k+1] (everybody has read it: the __syncwarp above)
+    k0 -= TKB; k1 -= TKB; k2 -= TKB; k3 -= TKB;
+    const double xt = bwd_step(k0, k1, k2, k3, vb - VB, h.gpub, h.ggat, gsel, gn);
+    update_stage<KIND>(u, k + 1, vb, ib, il, pb, x1, xt, x2);   // stage k+1: independent of the chain, fills its latency
+    gather_in(h.ggat, gsel, gn);
+    vb -= VB; ib -= ISB; il -= ISB; pb -= ISB;
     x2 = x1; x1 = xt;
   }
-  __syncwarp();
-  update_stage<KIND>(h, u, 0, x1, 0.0, x2);
+  update_stage<KIND>(u, 0, vb, ib, il, pb, x1, 0.0, x2);
   __syncwarp();
 }
 
@@ -443,35 +490,35 @@ struct Info {
   int status, unscale;
 };
 
-// (P v)_(k, r) for a vector stored [k*8 + r] (diagonal Q, R and the slew-rate coupling of the inputs)
+// (P v)_(k, r) for a vector stored [k*vs + r] (diagonal Q, R and the slew-rate coupling of the inputs)
 template <int KIND>
-__device__ __forceinline__ double rowP(const Ctx<KIND> &c, const double *PD, const double *PO, const double *v, int k) {
-  const int N = c.N, o = k * 8 + c.r;
-  double acc = PD[o] * v[o];
+__device__ __forceinline__ double rowP(const Ctx<KIND> &c, const double *PD, const double *PO, const double *v, int vs, int k) {
+  const int N = c.N, o = k * 8 + c.r, ov = k * vs + c.r;
+  double acc = PD[o] * v[ov];
   if (c.ul) {
-    if (k > 0 && k < N) acc = fma(PO[o - 8], v[o - 8], acc);
-    if (k < N - 1) acc = fma(PO[o], v[o + 8], acc);
+    if (k > 0 && k < N) acc = fma(PO[o - 8], v[ov - vs], acc);
+    if (k < N - 1) acc = fma(PO[o], v[ov + vs], acc);
     if (k == N) acc = 0.0;
   }
   return acc;
 }
-// (A v) on my dynamics row (k, r): v stored [k*8 + r]
+// (A v) on my dynamics row (k, r): v stored [k*vs + r]
 template <int KIND>
-__device__ __forceinline__ double rowA_dyn(const Ctx<KIND> &c, const double *ED, const double *v, int k) {
-  double acc = ED[k * 8 + c.r] * v[k * 8 + c.r];
+__device__ __forceinline__ double rowA_dyn(const Ctx<KIND> &c, const double *ED, const double *v, int vs, int k) {
+  double acc = ED[k * 8 + c.r] * v[k * vs + c.r];
   if (k > 0) {
     double g[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) g[q] = v[(k - 1) * 8 + q];
+    for (int q = 0; q < 8; ++q) g[q] = v[(k - 1) * vs + q];
     acc += prowdot(c.Gb(k - 1), c.r, g);
   }
   return acc;
 }
-// (A' t)_(k, r): td on the dynamics rows [k*8 + rr], ti on the single-variable rows [k*8 + slot] (slab indexing)
+// (A' t)_(k, r): td on the dynamics rows [k*8 + rr] (slab), ti on the single-variable rows: slab array [k*8 + slot] when
+// `tis` is false, the shared-memory duals y when true
 template <int KIND>
-__device__ __forceinline__ double colA(const Ctx<KIND> &c, const double *ED, const double *td, const double *ti, int k) {
+__device__ __forceinline__ double colA(const Ctx<KIND> &c, const double *ED, const double *td, const double *ti, bool tis, int k) {
   constexpr int NX = Ctx<KIND>::NX, NT = Ctx<KIND>::NT;
-  const double *SI = c.S + c.L->SI;
   const int o = k * 8 + c.r;
   double acc = c.xl ? ED[o] * td[o] : 0.0;
   if (k < c.N) {
@@ -482,36 +529,18 @@ __device__ __forceinline__ double colA(const Ctx<KIND> &c, const double *ED, con
   }
   if (c.has_in(k)) {
 #pragma unroll
-    for (int t = 0; t < NT; ++t) acc = fma(SI[c.si(k, t)], ti[c.ci(k, t)], acc);
-  }
-  return acc;
-}
-// the same with the single-variable part taken from a shared-memory array (NSL indexing)
-template <int KIND>
-__device__ __forceinline__ double colA_s(const Ctx<KIND> &c, const double *ED, const double *td, const double *tis, int k) {
-  constexpr int NX = Ctx<KIND>::NX, NT = Ctx<KIND>::NT;
-  const double *SI = c.S + c.L->SI;
-  const int o = k * 8 + c.r;
-  double acc = c.xl ? ED[o] * td[o] : 0.0;
-  if (k < c.N) {
-    double g[8];
-#pragma unroll
-    for (int rr = 0; rr < 8; ++rr) g[rr] = (rr < NX) ? td[(k + 1) * 8 + rr] : 0.0;
-    acc += pcoldot<NX>(c.Gb(k), c.r, g);
-  }
-  if (c.has_in(k)) {
-#pragma unroll
-    for (int t = 0; t < NT; ++t) acc = fma(SI[c.si(k, t)], tis[c.si(k, t)], acc);
+    for (int t = 0; t < NT; ++t) acc = fma(c.si(k, t), tis ? c.yi(k, t) : ti[c.ci(k, t)], acc);
   }
   return acc;
 }
 
-// y_dyn <- y_dyn + rho_eq (alpha A_dyn XS - (alpha n + (1 - alpha) first) be);  XS <- 0     (see the header)
+// Brings the explicit dynamics dual up to date from the running sum of x~ (see the header):
+//   y_dyn <- y_dyn + rho_eq (alpha A_dyn XS - (alpha n + (1 - alpha) first) be);  XS <- 0
 template <int KIND>
 __device__ __noinline__ void sync_yd(const Ctx<KIND> c, const bool live, const double rho_eq, const double alpha, const int n,
                                     const int first) {
   const int N = c.N, r = c.r;
-  double *XS = c.S + c.L->XS;
+  double *XS = c.V(V_XS);
   double *YD = c.cd(C_YD);
   const double *BE = c.cd(C_BE), *ED = c.cd(C_ED);
   const double cb = alpha * n + (first ? (1.0 - alpha) : 0.0);
@@ -520,51 +549,63 @@ __device__ __noinline__ void sync_yd(const Ctx<KIND> c, const bool live, const d
     for (int k = 0; k <= N; ++k) {
       if (c.xl) {
         const int o = k * 8 + r;
-        const double ax = rowA_dyn<KIND>(c, ED, XS, k);
+        const double ax = rowA_dyn<KIND>(c, ED, XS, VS, k);
         if (live) YD[o] = YD[o] + rho_eq * (alpha * ax - cb * BE[o]);
       }
     }
-  }
-  __syncwarp();
+    __syncwarp();
 #pragma unroll 1
-  for (int k = 0; k <= N; ++k) XS[k * 8 + r] = 0.0;
+    for (int k = 0; k <= N; ++k) XS[k * VS + r] = 0.0;
+  }
   __syncwarp();
 }
 
-// CR = rho_eq A_dyn' be (start, and after a rho update by rescaling), R = zsel CR - A_dyn' y_dyn - q,
-// B = sigma x + R + A_in'(rho z - y).  `doit` guards the groups that keep their state.
+// Re-projects the recursion state from the explicit iterate:
+//   CR = rho_eq A_dyn' be (when `new_cr`);  R = zsel CR - A_dyn' y_dyn - q;  B = sigma x + R + A_in'(rho z - y)
+// `doit` guards the groups that keep their state.
 template <int KIND>
-__device__ __noinline__ void rhs_init(const Ctx<KIND> c, const bool doit, const double rho, const double rho_eq, const double sigma,
-                                     const double zsel) {
-  constexpr int NT = Ctx<KIND>::NT;
+__device__ __noinline__ void reproject(const Ctx<KIND> c, const bool doit, const double rho, const double rho_eq, const double sigma,
+                                      const double zsel, const bool new_cr) {
+  constexpr int NT = Ctx<KIND>::NT, NX = Ctx<KIND>::NX;
   const int N = c.N, r = c.r;
-  const Lay &L = *c.L;
-  double *S = c.S;
-  double *BV = S + L.B, *R = S + L.R, *CR = S + L.CR;
-  const double *X = S + L.X, *ZI = S + L.ZI, *YI = S + L.YI, *SI = S + L.SI;
+  double *BV = c.V(V_B), *R = c.V(V_R), *CR = c.V(V_CR);
+  const double *X = c.V(V_X);
   const double *YD = c.cd(C_YD), *BE = c.cd(C_BE), *ED = c.cd(C_ED), *QV = c.cd(C_Q);
-  double *TD = c.cd(C_R2D);  // scratch
-#pragma unroll 1
-  for (int k = 0; k <= N; ++k) TD[k * 8 + r] = 0.0;
-  __syncwarp();
 #pragma unroll 1
   for (int k = 0; k <= N; ++k) {
-    const int o = k * 8 + r;
+    const int o = k * 8 + r, ov = k * VS + r;
     if (c.var_live(k)) {
-      const double cr = rho_eq * colA<KIND>(c, ED, BE, TD, k);   // TD == 0: dynamics part only
-      const double aty = colA<KIND>(c, ED, YD, TD, k);
+      const double *gk = c.Gb(k);
+      double crd = CR[ov];
+      if (new_cr) {
+        double acc = c.xl ? ED[o] * BE[o] : 0.0;
+        if (k < N) {
+          double g[8];
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) g[rr] = (rr < NX) ? BE[(k + 1) * 8 + rr] : 0.0;
+          acc += pcoldot<NX>(gk, r, g);
+        }
+        crd = rho_eq * acc;
+      }
+      double aty = c.xl ? ED[o] * YD[o] : 0.0;
+      if (k < N) {
+        double g[8];
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) g[rr] = (rr < NX) ? YD[(k + 1) * 8 + rr] : 0.0;
+        aty += pcoldot<NX>(gk, r, g);
+      }
       double sin = 0.0;
       if (c.has_in(k)) {
         const double rt = c.rho_of(k, rho, rho_eq);
 #pragma unroll
-        for (int t = 0; t < NT; ++t) sin = fma(SI[c.si(k, t)], rt * ZI[c.si(k, t)] - YI[c.si(k, t)], sin);
+        for (int t = 0; t < NT; ++t) sin = fma(c.si(k, t), rt * c.zi(k, t) - c.yi(k, t), sin);
       }
       if (doit) {
-        const double rr = (zsel * cr - aty) - QV[o];
-        CR[o] = cr; R[o] = rr;
-        BV[o] = fma(sigma, X[o], rr) + sin;
+        const double rr = (zsel * crd - aty) - QV[o];
+        CR[ov] = crd; R[ov] = rr;
+        BV[ov] = fma(sigma, X[ov], rr) + sin;
       }
-    } else if (doit) { CR[o] = 0.0; R[o] = 0.0; BV[o] = 0.0; }
+    } else if (doit) { CR[ov] = 0.0; R[ov] = 0.0; BV[ov] = 0.0; }
   }
   __syncwarp();
 }
@@ -575,9 +616,7 @@ __device__ __noinline__ void update_info(const Ctx<KIND> c, Info *ip, const doub
   constexpr int NT = Ctx<KIND>::NT;
   Info &I = *ip;
   const int N = c.N, r = c.r;
-  const Lay &L = *c.L;
-  const double *S = c.S;
-  const double *X = S + L.X, *ZI = S + L.ZI, *YI = S + L.YI, *SI = S + L.SI;
+  const double *X = c.V(V_X);
   const double *YD = c.cd(C_YD), *BE = c.cd(C_BE), *ED = c.cd(C_ED), *QV = c.cd(C_Q);
   const double *EINV = c.cd(C_EINV), *EIINV = c.cd(C_EIINV), *DINV = c.cd(C_DINV), *PD = c.cd(C_PD), *PO = c.cd(C_PO);
   double a_rp = 0, a_z = 0, a_Ax = 0, b_rp = 0, b_z = 0, b_Ax = 0;
@@ -586,21 +625,20 @@ __device__ __noinline__ void update_info(const Ctx<KIND> c, Info *ip, const doub
   for (int k = 0; k <= N; ++k) {
     const int o = k * 8 + r;
     if (c.xl) {
-      const double Ax = rowA_dyn<KIND>(c, ED, X, k), z = zsel * BE[o], rr = Ax - z, ei = EINV[o];
+      const double Ax = rowA_dyn<KIND>(c, ED, X, VS, k), z = zsel * BE[o], rr = Ax - z, ei = EINV[o];
       a_rp = absmax(a_rp, rr); a_z = absmax(a_z, z); a_Ax = absmax(a_Ax, Ax);
       b_rp = absmax(b_rp, ei * rr); b_z = absmax(b_z, ei * z); b_Ax = absmax(b_Ax, ei * Ax);
     }
     if (c.has_in(k)) {
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
-        const int oi = c.si(k, t);
-        const double ax = SI[oi] * X[o], z = ZI[oi], rr = ax - z, ei = EIINV[c.ci(k, t)];
+        const double ax = c.si(k, t) * X[k * VS + r], z = c.zi(k, t), rr = ax - z, ei = EIINV[c.ci(k, t)];
         a_rp = absmax(a_rp, rr); a_z = absmax(a_z, z); a_Ax = absmax(a_Ax, ax);
         b_rp = absmax(b_rp, ei * rr); b_z = absmax(b_z, ei * z); b_Ax = absmax(b_Ax, ei * ax);
       }
     }
     if (c.var_live(k)) {
-      const double Px = rowP<KIND>(c, PD, PO, X, k), Aty = colA_s<KIND>(c, ED, YD, YI, k);
+      const double Px = rowP<KIND>(c, PD, PO, X, VS, k), Aty = colA<KIND>(c, ED, YD, nullptr, true, k);
       const double rr = (QV[o] + Px) + Aty, di = DINV[o];
       a_rd = absmax(a_rd, rr); a_q = absmax(a_q, QV[o]); a_Aty = absmax(a_Aty, Aty); a_Px = absmax(a_Px, Px);
       b_rd = absmax(b_rd, di * rr); b_q = absmax(b_q, di * QV[o]); b_Aty = absmax(b_Aty, di * Aty); b_Px = absmax(b_Px, di * Px);
@@ -625,22 +663,20 @@ __device__ __noinline__ bool primal_infeasible(const Ctx<KIND> c, const Info *ip
   constexpr int NT = Ctx<KIND>::NT;
   const bool unscale = ip->unscale;
   const int N = c.N, r = c.r;
-  const Lay &L = *c.L;
-  const double *S = c.S;
-  const double *X = S + L.X, *YI = S + L.YI, *UI = S + L.UI, *LI = S + L.LI;
+  const double *X = c.V(V_X);
   const double *BE = c.cd(C_BE), *ED = c.cd(C_ED), *PVX = c.cd(C_PVX);
   const double *PVYI = c.cd(C_PVYI), *E = c.cd(C_E), *EI = c.cd(C_EI), *DINV = c.cd(C_DINV);
   double *DYD = c.cd(C_DYD), *DYI = c.cd(C_PYI), *XT = c.cd(C_ZT);
   const double ia = 1.0 / alpha, oma = 1.0 - alpha, cb = last_was_first ? 1.0 : alpha;
 #pragma unroll 1
-  for (int k = 0; k <= N; ++k) { const int o = k * 8 + r; XT[o] = c.var_live(k) ? (X[o] - oma * PVX[o]) * ia : 0.0; }
+  for (int k = 0; k <= N; ++k) { const int o = k * 8 + r; XT[o] = c.var_live(k) ? (X[k * VS + r] - oma * PVX[o]) * ia : 0.0; }
   __syncwarp();
   double nrm = 0.0, lhs = 0.0;
 #pragma unroll 1
   for (int k = 0; k <= N; ++k) {
     const int o = k * 8 + r;
     double d = 0.0;
-    if (c.xl) d = rho_eq * (alpha * rowA_dyn<KIND>(c, ED, XT, k) - cb * BE[o]);  // equality rows: no projection
+    if (c.xl) d = rho_eq * (alpha * rowA_dyn<KIND>(c, ED, XT, 8, k) - cb * BE[o]);  // equality rows: no projection
     DYD[o] = d;
     if (c.xl) {
       nrm = absmax(nrm, unscale ? E[o] * d : d);
@@ -649,9 +685,9 @@ __device__ __noinline__ bool primal_infeasible(const Ctx<KIND> c, const Info *ip
     if (c.has_in(k)) {
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
-        const int oi = c.si(k, t), oc = c.ci(k, t);
-        double di = YI[oi] - PVYI[oc];
-        const double lo = (KIND == LPVMPC_PLANNER) ? LI[oi] : -kInfty, up = UI[oi];
+        const int oc = c.ci(k, t);
+        double di = c.yi(k, t) - PVYI[oc];
+        const double lo = c.lo_of(k, t), up = c.ui(k, t);
         if (up > kInfty * kMinScaling) {
           if (lo < -kInfty * kMinScaling) di = 0.0;
           else di = (di < 0.0) ? di : 0.0;
@@ -669,7 +705,7 @@ __device__ __noinline__ bool primal_infeasible(const Ctx<KIND> c, const Info *ip
 #pragma unroll 1
   for (int k = 0; k <= N; ++k) {
     if (c.var_live(k)) {
-      const double at = colA<KIND>(c, ED, DYD, DYI, k);
+      const double at = colA<KIND>(c, ED, DYD, DYI, false, k);
       mx = absmax(mx, unscale ? DINV[k * 8 + r] * at : at);
     }
   }
@@ -682,9 +718,7 @@ __device__ __noinline__ bool dual_infeasible(const Ctx<KIND> c, const Info *ip, 
   constexpr int NT = Ctx<KIND>::NT;
   const bool unscale = ip->unscale;
   const int N = c.N, r = c.r;
-  const Lay &L = *c.L;
-  const double *S = c.S;
-  const double *X = S + L.X, *SI = S + L.SI, *UI = S + L.UI, *LI = S + L.LI;
+  const double *X = c.V(V_X);
   const double *QV = c.cd(C_Q), *ED = c.cd(C_ED);
   const double *PVX = c.cd(C_PVX), *D = c.cd(C_D), *DINV = c.cd(C_DINV), *EINV = c.cd(C_EINV), *EIINV = c.cd(C_EIINV);
   const double *PD = c.cd(C_PD), *PO = c.cd(C_PO);
@@ -693,7 +727,7 @@ __device__ __noinline__ bool dual_infeasible(const Ctx<KIND> c, const Info *ip, 
 #pragma unroll 1
   for (int k = 0; k <= N; ++k) {
     const int o = k * 8 + r;
-    const double dx = c.var_live(k) ? X[o] - PVX[o] : 0.0;
+    const double dx = c.var_live(k) ? X[k * VS + r] - PVX[o] : 0.0;
     DX[o] = dx;
     nrm = absmax(nrm, unscale ? D[o] * dx : dx);
     qdx += QV[o] * dx;
@@ -707,22 +741,20 @@ __device__ __noinline__ bool dual_infeasible(const Ctx<KIND> c, const Info *ip, 
   for (int k = 0; k <= N; ++k) {
     const int o = k * 8 + r;
     if (c.var_live(k)) {
-      const double Pdx = rowP<KIND>(c, PD, PO, DX, k);
+      const double Pdx = rowP<KIND>(c, PD, PO, DX, 8, k);
       mx = absmax(mx, unscale ? DINV[o] * Pdx : Pdx);
     }
     if (c.xl) {
-      double v = rowA_dyn<KIND>(c, ED, DX, k);
+      double v = rowA_dyn<KIND>(c, ED, DX, 8, k);
       if (unscale) v = EINV[o] * v;
       if (v > eps * nrm || v < -eps * nrm) viol = 1;
     }
     if (c.has_in(k)) {
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
-        const int oi = c.si(k, t);
-        double v = SI[oi] * DX[o];
+        double v = c.si(k, t) * DX[o];
         if (unscale) v = EIINV[c.ci(k, t)] * v;
-        const double lo = (KIND == LPVMPC_PLANNER) ? LI[oi] : -kInfty;
-        if (((UI[oi] < kInfty * kMinScaling) && (v > eps * nrm)) || ((lo > -kInfty * kMinScaling) && (v < -eps * nrm))) viol = 1;
+        if (((c.ui(k, t) < kInfty * kMinScaling) && (v > eps * nrm)) || ((c.lo_of(k, t) > -kInfty * kMinScaling) && (v < -eps * nrm))) viol = 1;
       }
     }
   }
@@ -759,12 +791,12 @@ __device__ __noinline__ int check_termination(const Ctx<KIND> c, const lpvmpc_se
 }
 
 template <int KIND>
-__device__ __noinline__ double objective(const Ctx<KIND> c, const double *xv, const double scale) {
+__device__ __noinline__ double objective(const Ctx<KIND> c, const double *xv, const int vs, const double scale) {
   const double *PD = c.cd(C_PD), *PO = c.cd(C_PO), *QV = c.cd(C_Q);
   double acc = 0.0;
 #pragma unroll 1
   for (int k = 0; k <= c.N; ++k)
-    if (c.var_live(k)) acc += (0.5 * rowP<KIND>(c, PD, PO, xv, k) + QV[k * 8 + c.r]) * xv[k * 8 + c.r];
+    if (c.var_live(k)) acc += (0.5 * rowP<KIND>(c, PD, PO, xv, vs, k) + QV[k * 8 + c.r]) * xv[k * vs + c.r];
   return gsum(acc) * scale;
 }
 
@@ -785,8 +817,11 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
   const int ucomp = r - NX;
   int sched_err = 0, data_err = 0;
   double x0r = 0.0;
-  double *Gs = S + L.K;            // N x GS, plain row-major rows (scratch home of G during setup)
-  double *scr = Gs + N * GS;       // nz doubles (N*16 >= nz)
+  // scratch in the factor area ((N+1)*128 - 64 doubles): 8 arrays of NS8, then G (N x GS, plain rows), then nz doubles
+  double *sD = S + L.TK, *sE = sD + NS8, *sEI = sE + NS8, *sDt = sEI + NS8, *sEt = sDt + NS8, *sEti = sEt + NS8;
+  double *sPD = sEti + NS8, *sPO = sPD + NS8;
+  double *Gs = sPO + NS8;
+  double *scr = Gs + N * GS;
   // ---- schedule: G_k = -[A_k B_k] (unscaled), my row
   if (a.sched_mode == LPVMPC_SCHED_GIVEN) {
 #pragma unroll 1
@@ -878,11 +913,7 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
   sched_err = gany(sched_err);
 
   // ---- build (PathFollowingLPVMPC.py:334-348, 397-464; LPV_MPC_Planner.py:145-181)
-  double *X = S + L.X, *BV = S + L.B, *QV = S + L.R, *BE = S + L.CR, *ED = S + L.XS;   // q, be, ed: scratch homes
-  double *ZI = S + L.ZI, *YI = S + L.YI, *SI = S + L.SI, *UI = S + L.UI, *LI = S + L.LI;
-  double *sD = S + L.T, *sE = sD + NS8, *sEI = sE + NS8, *sDt = sEI + NS8, *sEt = sDt + NS8, *sEti = sEt + NS8;
-  double *sPD = sEti + NS8, *sPO = sPD + NS8;  // 8 arrays of NS8 doubles == (N+1)*64
-  double *sLI = S + L.DG;                       // controller: scratch home of the (never active) lower bounds
+  double *X = c.V(V_X), *BV = c.V(V_B), *QV = c.V(V_R), *BE = c.V(V_CR), *ED = c.V(V_XS);   // q, be, ed: scratch homes [k*VS + r]
   {
     const double Qrr = c.xl ? M.Q[r * NX + r] : 0.0;
     const double Q0r = c.xl ? M.Q[r] : 0.0;
@@ -892,7 +923,7 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
     const double mey = (KIND == LPVMPC_PLANNER) ? a.max_ey[b] : 0.0;
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
-      const int o = k * 8 + r;
+      const int o = k * 8 + r, ov = k * VS + r;
       double pd = 0.0, po = 0.0, q = 0.0, be = 0.0, ed = 0.0;
       if (c.xl) {
         pd = 2 * Qrr;
@@ -908,9 +939,9 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
         else q = (k == 0) ? -2 * (uold * dRc) : 0.0;
         po = (k < N - 1) ? 2 * (-dRc) : 0.0;
       }
-      sPD[o] = pd; sPO[o] = po; QV[o] = q; BE[o] = be; ED[o] = ed;
+      sPD[o] = pd; sPO[o] = po; QV[ov] = q; BE[ov] = be; ED[ov] = ed;
       sD[o] = 1.0; sE[o] = 1.0; sEI[o] = 1.0; sEti[o] = 1.0;
-      X[o] = 0.0; BV[o] = 0.0;
+      X[ov] = 0.0; BV[ov] = 0.0;
     }
     __syncwarp();
 #pragma unroll 1
@@ -918,7 +949,6 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
       if (c.has_in(k)) {
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
-          const int oi = c.si(k, t);
           double si, lo, up;
           if (KIND == LPVMPC_CONTROLLER) {
             lo = -kInfty;
@@ -937,15 +967,14 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
           lo = (lo > -kInfty) ? lo : -kInfty;  // python wrapper: l = max(l, -OSQP_INFTY), u = min(u, OSQP_INFTY)
           up = (up < kInfty) ? up : kInfty;
           if (lo > up) data_err = 1;
-          SI[oi] = si; UI[oi] = up; ZI[oi] = 0.0; YI[oi] = 0.0;
-          if (KIND == LPVMPC_PLANNER) LI[oi] = lo;
+          c.si(k, t) = si; c.ui(k, t) = up; c.zi(k, t) = 0.0; c.yi(k, t) = 0.0;
+          if (KIND == LPVMPC_PLANNER) c.li(k, t) = lo;
         }
       }
     }
     __syncwarp();
   }
   data_err = gany(data_err);
-  (void)sLI;
 
   // ---- Ruiz equilibration (OSQP scale_data)
   double csc = 1.0;
@@ -953,13 +982,13 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
   for (int it = 0; it < St.scaling; ++it) {
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
-      const int o = k * 8 + r;
+      const int o = k * 8 + r, ov = k * VS + r;
       double pa = fabs(sPD[o]);
       if (c.ul) {
         if (k < N - 1) pa = absmax(pa, sPO[o]);
         if (k > 0 && k < N) pa = absmax(pa, sPO[o - 8]);
       }
-      double qa = c.xl ? fabs(ED[o]) : 0.0;
+      double qa = c.xl ? fabs(ED[ov]) : 0.0;
       if (k < N) {
         const double *gk = Gs + k * GS;
 #pragma unroll
@@ -968,12 +997,12 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
       if (c.has_in(k)) {
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
-          qa = absmax(qa, SI[c.si(k, t)]);
-          sEti[c.ci(k, t)] = 1.0 / sqrt(limit_scaling(fabs(SI[c.si(k, t)])));
+          qa = absmax(qa, c.si(k, t));
+          sEti[c.ci(k, t)] = 1.0 / sqrt(limit_scaling(fabs(c.si(k, t))));
         }
       }
       sDt[o] = 1.0 / sqrt(limit_scaling(pa > qa ? pa : qa));
-      double ea = c.xl ? fabs(ED[o]) : 0.0;
+      double ea = c.xl ? fabs(ED[ov]) : 0.0;
       if (k > 0 && c.xl) {
         const double *gp = Gs + (k - 1) * GS + r * 8;
 #pragma unroll
@@ -984,7 +1013,7 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
     __syncwarp();
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
-      const int o = k * 8 + r;
+      const int o = k * 8 + r, ov = k * VS + r;
       const double dt = sDt[o];
       if (k < N) {
         double *gk = Gs + k * GS;
@@ -995,14 +1024,14 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
       if (c.has_in(k)) {
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
-          const int oi = c.si(k, t), oc = c.ci(k, t);
-          SI[oi] = (SI[oi] * sEti[oc]) * dt;
+          const int oc = c.ci(k, t);
+          c.si(k, t) = (c.si(k, t) * sEti[oc]) * dt;
           sEI[oc] = sEI[oc] * sEti[oc];
         }
       }
-      if (c.xl) ED[o] = (ED[o] * sEt[o]) * dt;
+      if (c.xl) ED[ov] = (ED[ov] * sEt[o]) * dt;
       sPD[o] = (sPD[o] * dt) * dt;
-      QV[o] = dt * QV[o];
+      QV[ov] = dt * QV[ov];
       sD[o] = sD[o] * dt;
       sE[o] = sE[o] * sEt[o];
     }
@@ -1019,7 +1048,7 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
       }
       if (c.xl) scr[k * NX + r] = pa;
       else if (c.ul && k < N) scr[nx + k * 2 + ucomp] = pa;
-      if (c.var_live(k)) qn = absmax(qn, QV[o]);
+      if (c.var_live(k)) qn = absmax(qn, QV[k * VS + r]);
     }
     qn = gmax(qn);
     __syncwarp();
@@ -1032,7 +1061,7 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
     ct = limit_scaling(ct);
     ct = 1.0 / ct;
 #pragma unroll 1
-    for (int k = 0; k <= N; ++k) { const int o = k * 8 + r; sPD[o] *= ct; QV[o] *= ct; sPO[o] *= ct; }
+    for (int k = 0; k <= N; ++k) { const int o = k * 8 + r; sPD[o] *= ct; QV[k * VS + r] *= ct; sPO[o] *= ct; }
     csc *= ct;
     __syncwarp();
   }
@@ -1041,17 +1070,15 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
   {
     double *cD = c.cd(C_D), *cDI = c.cd(C_DINV), *cE = c.cd(C_E), *cEI = c.cd(C_EINV), *cPD = c.cd(C_PD), *cPO = c.cd(C_PO);
     double *cEi = c.cd(C_EI), *cEiI = c.cd(C_EIINV), *cQ = c.cd(C_Q), *cBE = c.cd(C_BE), *cED = c.cd(C_ED), *cYD = c.cd(C_YD);
-    double *POs = S + L.PO;
     uint64_t eqm = 0, loosem = 0;
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
-      const int o = k * 8 + r;
+      const int o = k * 8 + r, ov = k * VS + r;
       cD[o] = sD[o]; cDI[o] = 1.0 / sD[o]; cE[o] = sE[o]; cEI[o] = 1.0 / sE[o]; cPD[o] = sPD[o]; cPO[o] = sPO[o];
       cEi[o] = sEI[o]; cEiI[o] = 1.0 / sEI[o];
-      cQ[o] = c.var_live(k) ? QV[o] : 0.0; cBE[o] = sE[o] * BE[o]; cED[o] = ED[o]; cYD[o] = 0.0;
-      if (c.ul) POs[(k + 1) * 2 + ucomp] = (k < N - 1) ? sPO[o] : 0.0;
+      cQ[o] = c.var_live(k) ? QV[ov] : 0.0; cBE[o] = sE[o] * BE[ov]; cED[o] = ED[ov]; cYD[o] = 0.0;
+      if (c.ul) c.pm(k, ucomp) = (k > 0 && k < N) ? sPO[o - 8] : 0.0;   // couples u_{k-1}, u_k
     }
-    if (c.ul) { POs[ucomp] = 0.0; }
     double *Gd = c.cold + L.cG;
 #pragma unroll 1
     for (int k = 0; k < N; ++k) {
@@ -1068,12 +1095,12 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
       if (c.has_in(k)) {
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
-          const int oi = c.si(k, t), oc = c.ci(k, t);
-          const double up = sEI[oc] * UI[oi];
-          UI[oi] = up;
+          const int oc = c.ci(k, t);
+          const double up = sEI[oc] * c.ui(k, t);
+          c.ui(k, t) = up;
           if (KIND == LPVMPC_PLANNER) {
-            const double lo = sEI[oc] * LI[oi];
-            LI[oi] = lo;
+            const double lo = sEI[oc] * c.li(k, t);
+            c.li(k, t) = lo;
             if ((lo < -kInfty * kMinScaling) && (up > kInfty * kMinScaling)) loosem |= 1ull << k;
             else if (up - lo < kRhoTol) eqm |= 1ull << k;
           }
@@ -1082,10 +1109,9 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
     }
     *eqm_out = eqm; *loosem_out = loosem;
     __syncwarp();
-    // the scratch homes become hot vectors: XS = 0 (R, CR are set by rhs_init, DG by factor)
+    // the scratch homes become hot vectors: XS = 0 (R, CR, B are set by refresh, DG by factor)
 #pragma unroll 1
-    for (int k = 0; k <= N; ++k) (S + L.XS)[k * 8 + r] = 0.0;
-    __threadfence_block();
+    for (int k = 0; k <= N; ++k) c.V(V_XS)[k * VS + r] = 0.0;
     __syncwarp();
   }
   return (sched_err ? 1 : 0) | (data_err ? 2 : 0);
@@ -1094,35 +1120,33 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
 // ---------------------------------------------------------------- polish (cold, once per QP)
 // Works on the slab (C_PX, C_PYD, C_PYI); on success the polished (x, z, y) replace the iterate.
 template <int KIND>
-__device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const lpvmpc_settings &St, Info *ip, const bool do_pol) {
+__device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const lpvmpc_settings &St, Info *ip, const bool do_pol, uint32_t gsel) {
   constexpr int NT = Ctx<KIND>::NT, NX = Ctx<KIND>::NX;
   Info &I = *ip;
   const bool unscale = I.unscale;
   const int N = c.N, r = c.r;
-  const Lay &L = *c.L;
-  double *S = c.S;
-  double *X = S + L.X, *ZI = S + L.ZI, *YI = S + L.YI, *BV = S + L.B;
-  const double *SI = S + L.SI, *UI = S + L.UI, *LI = S + L.LI;
+  double *X = c.V(V_X), *BV = c.V(V_B);
   double *YD = c.cd(C_YD);
   const double *BE = c.cd(C_BE), *ED = c.cd(C_ED), *QV = c.cd(C_Q);
   double *PX = c.cd(C_PX), *PYD = c.cd(C_PYD), *PYI = c.cd(C_PYI), *R2D = c.cd(C_R2D), *R2I = c.cd(C_R2I);
   double *ACTD = c.cd(C_ACTD), *ACTI = c.cd(C_ACTI), *ZT = c.cd(C_ZT);
   const double *PD = c.cd(C_PD), *PO = c.cd(C_PO), *EINV = c.cd(C_EINV), *EIINV = c.cd(C_EIINV), *DINV = c.cd(C_DINV);
   const double delta = St.delta, idel = 1.0 / St.delta;
-  auto lo_of = [&](int oi) { return (KIND == LPVMPC_PLANNER) ? LI[oi] : -kInfty; };
   // active-set guess (form_Ared): 1 = lower, 2 = upper, 3 = both
 #pragma unroll 1
   for (int k = 0; k <= N; ++k) {
     const int o = k * 8 + r;
     double ad = 0.0;
-    if (c.xl && do_pol) { if (0.0 < -YD[o]) ad += 1.0; if (0.0 < YD[o]) ad += 2.0; }  // equality row: z == l == u
+    // equality row (z == l == u): lower / upper by the sign of the dual.  Upstream drops the row when the dual is exactly
+    // 0.0; round-off makes that impossible there, but y_dyn recovered from the running sum can be exactly 0.0 on the rows
+    // of the unweighted state `s`, and the polish system needs every dynamics row: keep it (as "lower").
+    if (c.xl && do_pol) ad = (0.0 < YD[o]) ? 2.0 : 1.0;
     ACTD[o] = ad;
     if (c.has_in(k)) {
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
-        const int oi = c.si(k, t);
         double ai = 0.0;
-        if (do_pol) { if (ZI[oi] - lo_of(oi) < -YI[oi]) ai += 1.0; if (UI[oi] - ZI[oi] < YI[oi]) ai += 2.0; }
+        if (do_pol) { if (c.zi(k, t) - c.lo_of(k, t) < -c.yi(k, t)) ai += 1.0; if (c.ui(k, t) - c.zi(k, t) < c.yi(k, t)) ai += 2.0; }
         ACTI[c.ci(k, t)] = ai;
       }
     }
@@ -1130,7 +1154,7 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
   __syncwarp();
   FW fw; fw.polish = 1; fw.rho = 0.0; fw.rho_eq = 0.0; fw.idel = idel;
   factor<KIND>(c, fw, delta);
-  auto bred_i = [&](int k, int t) { const double a = ACTI[c.ci(k, t)]; return (a == 1.0 || a == 3.0) ? lo_of(c.si(k, t)) : UI[c.si(k, t)]; };
+  auto bred_i = [&](int k, int t) { const double a = ACTI[c.ci(k, t)]; return (a == 1.0 || a == 3.0) ? c.lo_of(k, t) : c.ui(k, t); };
   // first solve: rhs = -q + A_red'(b_red / delta); targets go through R2D / R2I
 #pragma unroll 1
   for (int k = 0; k <= N; ++k) {
@@ -1143,19 +1167,19 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
   }
   __syncwarp();
 #pragma unroll 1
-  for (int k = 0; k <= N; ++k) { const int o = k * 8 + r; BV[o] = c.var_live(k) ? (-QV[o] + colA<KIND>(c, ED, R2D, R2I, k)) : 0.0; }
+  for (int k = 0; k <= N; ++k) BV[k * VS + r] = c.var_live(k) ? (-QV[k * 8 + r] + colA<KIND>(c, ED, R2D, R2I, false, k)) : 0.0;
   __syncwarp();
-  sweep_fwd<KIND>(h, N);
-  __syncwarp();
-  sweep_bwd_plain<KIND>(h, N);
+  sweep_fwd<KIND>(h, N, gsel);
+  sweep_bwd_plain<KIND>(h, N, gsel);
 #pragma unroll 1
   for (int k = 0; k <= N; ++k) {
     const int o = k * 8 + r;
-    PX[o] = BV[o];
-    PYD[o] = (c.xl && ACTD[o] != 0.0) ? (rowA_dyn<KIND>(c, ED, BV, k) - BE[o]) * idel : 0.0;
+    const double xk = BV[k * VS + r];
+    PX[o] = xk;
+    PYD[o] = (c.xl && ACTD[o] != 0.0) ? (rowA_dyn<KIND>(c, ED, BV, VS, k) - BE[o]) * idel : 0.0;
     if (c.has_in(k)) {
 #pragma unroll
-      for (int t = 0; t < NT; ++t) PYI[c.ci(k, t)] = (ACTI[c.ci(k, t)] != 0.0) ? (SI[c.si(k, t)] * BV[o] - bred_i(k, t)) * idel : 0.0;
+      for (int t = 0; t < NT; ++t) PYI[c.ci(k, t)] = (ACTI[c.ci(k, t)] != 0.0) ? (c.si(k, t) * xk - bred_i(k, t)) * idel : 0.0;
     }
   }
   __syncwarp();
@@ -1165,10 +1189,10 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
       const int o = k * 8 + r;
-      R2D[o] = (c.xl && ACTD[o] != 0.0) ? (BE[o] - rowA_dyn<KIND>(c, ED, PX, k)) : 0.0;
+      R2D[o] = (c.xl && ACTD[o] != 0.0) ? (BE[o] - rowA_dyn<KIND>(c, ED, PX, 8, k)) : 0.0;
       if (c.has_in(k)) {
 #pragma unroll
-        for (int t = 0; t < NT; ++t) R2I[c.ci(k, t)] = (ACTI[c.ci(k, t)] != 0.0) ? (bred_i(k, t) - SI[c.si(k, t)] * PX[o]) : 0.0;
+        for (int t = 0; t < NT; ++t) R2I[c.ci(k, t)] = (ACTI[c.ci(k, t)] != 0.0) ? (bred_i(k, t) - c.si(k, t) * PX[o]) : 0.0;
       }
     }
     __syncwarp();
@@ -1177,7 +1201,7 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
       const int o = k * 8 + r;
       double b = 0.0;
       if (c.var_live(k)) {
-        const double Px = rowP<KIND>(c, PD, PO, PX, k), Aty = colA<KIND>(c, ED, PYD, PYI, k);
+        const double Px = rowP<KIND>(c, PD, PO, PX, 8, k), Aty = colA<KIND>(c, ED, PYD, PYI, false, k);
         // A'(r2 / delta): same column product on scaled entries
         double at = c.xl ? ED[o] * (idel * R2D[o]) : 0.0;
         if (k < N) {
@@ -1188,28 +1212,28 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
         }
         if (c.has_in(k)) {
 #pragma unroll
-          for (int t = 0; t < NT; ++t) at = fma(SI[c.si(k, t)], idel * R2I[c.ci(k, t)], at);
+          for (int t = 0; t < NT; ++t) at = fma(c.si(k, t), idel * R2I[c.ci(k, t)], at);
         }
         b = ((-QV[o] - Px) - Aty) + at;
       }
-      BV[o] = b;
+      BV[k * VS + r] = b;
     }
     __syncwarp();
-    sweep_fwd<KIND>(h, N);
-    __syncwarp();
-    sweep_bwd_plain<KIND>(h, N);
+    sweep_fwd<KIND>(h, N, gsel);
+    sweep_bwd_plain<KIND>(h, N, gsel);
 #pragma unroll 1
-    for (int k = 0; k <= N; ++k) { if (c.xl) ZT[k * 8 + r] = rowA_dyn<KIND>(c, ED, BV, k); }   // z~ = A_dyn dx
+    for (int k = 0; k <= N; ++k) { if (c.xl) ZT[k * 8 + r] = rowA_dyn<KIND>(c, ED, BV, VS, k); }   // z~ = A_dyn dx
     __syncwarp();
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
       const int o = k * 8 + r;
+      const double dx = BV[k * VS + r];
       if (c.xl && ACTD[o] != 0.0) PYD[o] += (ZT[o] - R2D[o]) * idel;
       if (c.has_in(k)) {
 #pragma unroll
-        for (int t = 0; t < NT; ++t) { const int oc = c.ci(k, t); if (ACTI[oc] != 0.0) PYI[oc] += (SI[c.si(k, t)] * BV[o] - R2I[oc]) * idel; }
+        for (int t = 0; t < NT; ++t) { const int oc = c.ci(k, t); if (ACTI[oc] != 0.0) PYI[oc] += (c.si(k, t) * dx - R2I[oc]) * idel; }
       }
-      PX[o] += BV[o];
+      PX[o] += dx;
     }
     __syncwarp();
   }
@@ -1219,7 +1243,7 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
   for (int k = 0; k <= N; ++k) {
     const int o = k * 8 + r;
     if (c.xl) {
-      const double Ax = rowA_dyn<KIND>(c, ED, PX, k), t = Ax + PYD[o];
+      const double Ax = rowA_dyn<KIND>(c, ED, PX, 8, k), t = Ax + PYD[o];
       PYD[o] = t - BE[o];
       const double rr = Ax - BE[o];
       a_rp = absmax(a_rp, unscale ? EINV[o] * rr : rr);
@@ -1227,9 +1251,9 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
     if (c.has_in(k)) {
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
-        const int oi = c.si(k, t), oc = c.ci(k, t);
-        const double ax = SI[oi] * PX[o], tt = ax + PYI[oc];
-        const double zc = clampd(tt, lo_of(oi), UI[oi]);
+        const int oc = c.ci(k, t);
+        const double ax = c.si(k, t) * PX[o], tt = ax + PYI[oc];
+        const double zc = clampd(tt, c.lo_of(k, t), c.ui(k, t));
         R2I[oc] = zc; PYI[oc] = tt - zc;
         const double rr = ax - zc;
         a_rp = absmax(a_rp, unscale ? EIINV[oc] * rr : rr);
@@ -1241,12 +1265,12 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
   for (int k = 0; k <= N; ++k) {
     const int o = k * 8 + r;
     if (c.var_live(k)) {
-      const double rr = (QV[o] + rowP<KIND>(c, PD, PO, PX, k)) + colA<KIND>(c, ED, PYD, PYI, k);
+      const double rr = (QV[o] + rowP<KIND>(c, PD, PO, PX, 8, k)) + colA<KIND>(c, ED, PYD, PYI, false, k);
       a_rd = absmax(a_rd, unscale ? DINV[o] * rr : rr);
     }
   }
   const double pol_pri = gmax(a_rp), pol_dua = (unscale ? I.cinv : 1.0) * gmax(a_rd);
-  const double pol_obj = objective<KIND>(c, PX, St.scaling ? I.cinv : 1.0);
+  const double pol_obj = objective<KIND>(c, PX, 8, St.scaling ? I.cinv : 1.0);
   const bool ok = (pol_pri < I.pri_res && pol_dua < I.dua_res) || (pol_pri < I.pri_res && I.dua_res < 1e-10) ||
                   (pol_dua < I.dua_res && I.pri_res < 1e-10);
   if (!do_pol) return 0;
@@ -1255,22 +1279,23 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
 #pragma unroll 1
   for (int k = 0; k <= N; ++k) {
     const int o = k * 8 + r;
-    X[o] = PX[o]; YD[o] = PYD[o];
+    X[k * VS + r] = PX[o]; YD[o] = PYD[o];
     if (c.has_in(k)) {
 #pragma unroll
-      for (int t = 0; t < NT; ++t) { ZI[c.si(k, t)] = R2I[c.ci(k, t)]; YI[c.si(k, t)] = PYI[c.ci(k, t)]; }
+      for (int t = 0; t < NT; ++t) { c.zi(k, t) = R2I[c.ci(k, t)]; c.yi(k, t) = PYI[c.ci(k, t)]; }
     }
   }
   return 1;
 }
 
 // ---------------------------------------------------------------- persistent warps, QPW QPs at a time each
-constexpr int kSyncEvery = 25;  // y_dyn is brought up to date at least every kSyncEvery steps (keeps XS small)
+constexpr int kSyncEvery = 25;  // y_dyn is brought up to date and r re-projected at least every kSyncEvery steps
 
 template <int KIND, int QPW>
 __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant__ H8Params p) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   constexpr int NX = Ctx<KIND>::NX, NB = Ctx<KIND>::NB, NT = Ctx<KIND>::NT, NSL = Ctx<KIND>::NSL;
+  constexpr int OLI = Ctx<KIND>::OLI, OPM = Ctx<KIND>::OPM;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
   const int g = lane >> 3, r = lane & 7;
   const Lay &L = p.L;
@@ -1291,6 +1316,10 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
   const int ucomp = r - NX;
   double *wsm = smem + (size_t)warp * QPW * L.total;
   const size_t wslot = (size_t)(blockIdx.x * wpc + warp) * QPW;
+  // all-gather buffers: two 256-byte buffers per warp, 512-byte aligned, after the QP regions
+  const uint32_t smem_a = (uint32_t)__cvta_generic_to_shared(smem);
+  const uint32_t gbuf = ((smem_a + (uint32_t)(wpc * QPW * L.total * 8) + 511u) & ~511u) + (uint32_t)warp * 512u;
+  uint32_t gsel = 0;
 
   for (;;) {
     unsigned base = 0;
@@ -1307,15 +1336,18 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
 
     Hot<KIND> h;
     {
-      double *Sq = c.S;
-      h.B = Sq + L.B + r;
-      h.Tr = Sq + L.T + r * 8; h.Kr = Sq + L.K + r * 8;
+      const uint32_t sq = smem_a + (uint32_t)((warp * QPW + gq) * L.total) * 8u;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { h.Kc[q] = Sq + L.K + (2 * q) * 8 + c.co[q]; h.go[q] = (q ^ swz(r)) << 1; }
-      h.X = Sq + L.X + r; h.R = Sq + L.R + r; h.XS = Sq + L.XS + r; h.CR = Sq + L.CR + r; h.DG = Sq + L.DG + r;
-      h.ZI = Sq + L.ZI + c.islot; h.YI = Sq + L.YI + c.islot; h.SI = Sq + L.SI + c.islot; h.UI = Sq + L.UI + c.islot;
-      h.LI = Sq + L.LI + c.islot;
-      h.PO = Sq + L.PO + (c.ul ? ucomp : 0); h.pstride = c.ul ? 2 : 0;
+      for (int q = 0; q < 4; ++q) {
+        h.tk[q] = sq + (uint32_t)(L.TK + c.ro[q]) * 8u;
+        h.kc[q] = sq + (uint32_t)(L.TK + 64 + (2 * q) * 8 + c.co[q]) * 8u;
+      }
+      h.v = sq + (uint32_t)(L.V + r) * 8u;
+      h.ib = sq + (uint32_t)(L.I + c.islot * 2) * 8u;
+      h.il = sq + (uint32_t)(L.I + OLI + c.islot) * 8u;
+      h.pm = sq + (uint32_t)(L.I + OPM + (c.ul ? ucomp : 0)) * 8u;
+      h.gpub = gbuf + (uint32_t)(64 * (r >> 1) + 16 * g + 8 * (r & 1));
+      h.ggat = gbuf + (uint32_t)(16 * g);
     }
 
     Info I;
@@ -1340,7 +1372,7 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
       FW fw; fw.polish = 0; fw.rho = rho; fw.rho_eq = rho_eq; fw.idel = 0.0;
       factor<KIND>(c, fw, sigma);
     }
-    rhs_init<KIND>(c, true, rho, rho_eq, sigma, 0.0);
+    reproject<KIND>(c, true, rho, rho_eq, sigma, 0.0, true);
     bool live = (flags == 0);
     const bool failed = flags != 0;
     int iter_done = 0, rho_updates = 0;
@@ -1350,6 +1382,7 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
 
     Upd<KIND> u;
     u.sigma = sigma; u.alpha = alpha; u.oma = 1.0 - alpha; u.eqm = c.eqm; u.loosem = c.loosem; u.xl = c.xl; u.ul = c.ul; u.N = N;
+    u.inl = (KIND == LPVMPC_CONTROLLER) ? (r == 0 || c.ul) : (c.xl || c.ul);
     int iter = 0, nsync = 0, first_in = 0;   // steps since the last y_dyn sync; whether step 0 is among them
     double rho_eq_last = rho_eq;             // rho_eq of the last executed step (delta_y of the certificates)
     bool checked_last = false;
@@ -1364,19 +1397,19 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
       for (; iter < stop; ++iter) {
         if (iter == stop - 1 && live) {  // keep the iterate before the last step of the chunk: delta_x, delta_y
           double *PVX = c.cd(C_PVX), *PVYI = c.cd(C_PVYI);
-          const double *X = c.S + L.X, *YI = c.S + L.YI;
+          const double *X = c.V(V_X);
 #pragma unroll 1
           for (int k = 0; k <= N; ++k) {
-            PVX[k * 8 + r] = X[k * 8 + r];
+            PVX[k * 8 + r] = X[k * VS + r];
             if (c.has_in(k)) {
 #pragma unroll
-              for (int t = 0; t < NT; ++t) PVYI[c.ci(k, t)] = YI[c.si(k, t)];
+              for (int t = 0; t < NT; ++t) PVYI[c.ci(k, t)] = c.yi(k, t);
             }
           }
         }
         u.cc = (iter == 0) ? 2.0 : alpha;
-        sweep_fwd<KIND>(h, N);
-        sweep_bwd_admm<KIND>(h, u);
+        sweep_fwd<KIND>(h, N, gsel);
+        sweep_bwd_admm<KIND>(h, u, gsel);
         if (iter == 0) first_in = 1;
         ++nsync;
         zsel = 1.0;
@@ -1388,6 +1421,7 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
       nsync = 0; first_in = 0;
       const bool can_check = ct && (iter % ct == 0);
       const bool can_adapt = ai && (iter % ai == 0);
+      bool new_cr = false;
       checked_last = can_check;
       if (can_check || can_adapt) {
         Info J = I;
@@ -1409,10 +1443,12 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
             FW fw; fw.polish = 0; fw.rho = rho; fw.rho_eq = rho_eq; fw.idel = 0.0;
             __syncwarp();
             factor<KIND>(c, fw, sigma);
-            rhs_init<KIND>(c, upd, rho, rho_eq, sigma, zsel);  // the pending right-hand side was built with the old rho
+            new_cr = true;
           }
         }
       }
+      // re-project r (and the pending right-hand side) from the explicit iterate: removes the drift of the recursion
+      if (iter < S.max_iter && __any_sync(kFull, live)) reproject<KIND>(c, live, rho, rho_eq, sigma, zsel, new_cr);
     }
     if (!checked_last && __any_sync(kFull, live)) {
       Info J = I;
@@ -1431,7 +1467,7 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
                            status == LPVMPC_DUAL_INFEASIBLE || status == LPVMPC_DUAL_INFEASIBLE_INACCURATE ||
                            status == LPVMPC_NON_CVX || status == LPVMPC_SCHEDULE_ERROR || status == LPVMPC_DATA_ERROR);
     {
-      const double o = objective<KIND>(c, c.S + L.X, S.scaling ? I.cinv : 1.0);
+      const double o = objective<KIND>(c, c.V(V_X), VS, S.scaling ? I.cinv : 1.0);
       if (has_sol) I.obj = o;
     }
     // row / variable indices in the reference order
@@ -1442,12 +1478,12 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
     };
     auto ref_var = [&](int k) { return c.xl ? (k * NX + r) : (nx + k * 2 + ucomp); };
     if (valid && (a.xs || a.zs || a.ys)) {
-      const double *X = c.S + L.X, *ZI = c.S + L.ZI, *YI = c.S + L.YI;
+      const double *X = c.V(V_X);
       const double *YD = c.cd(C_YD), *BE = c.cd(C_BE);
 #pragma unroll 1
       for (int k = 0; k <= N; ++k) {
         const int o = k * 8 + r;
-        if (c.var_live(k) && a.xs) a.xs[(size_t)b * nz + ref_var(k)] = X[o];
+        if (c.var_live(k) && a.xs) a.xs[(size_t)b * nz + ref_var(k)] = X[k * VS + r];
         if (c.xl) {
           if (a.zs) a.zs[(size_t)b * m + ref_dyn(k)] = (iter > 0 && !failed) ? BE[o] : 0.0;
           if (a.ys) a.ys[(size_t)b * m + ref_dyn(k)] = YD[o];
@@ -1455,8 +1491,8 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
         if (c.has_in(k)) {
 #pragma unroll
           for (int t = 0; t < NT; ++t) {
-            if (a.zs) a.zs[(size_t)b * m + ref_in(k, t)] = ZI[c.si(k, t)];
-            if (a.ys) a.ys[(size_t)b * m + ref_in(k, t)] = YI[c.si(k, t)];
+            if (a.zs) a.zs[(size_t)b * m + ref_in(k, t)] = c.zi(k, t);
+            if (a.ys) a.ys[(size_t)b * m + ref_in(k, t)] = c.yi(k, t);
           }
         }
       }
@@ -1465,17 +1501,17 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
     const bool do_pol = S.polish && status == LPVMPC_SOLVED;
     bool polished_sets = false;
     if (__any_sync(kFull, do_pol)) {
-      polish_status = polish<KIND>(c, h, S, &I, do_pol);
+      polish_status = polish<KIND>(c, h, S, &I, do_pol, gsel);
       polished_sets = do_pol;
     }
     // ---- outputs
     if (valid) {
-      const double *X = c.S + L.X, *YI = c.S + L.YI;
+      const double *X = c.V(V_X);
       const double *YD = c.cd(C_YD), *D = c.cd(C_D), *E = c.cd(C_E), *EI = c.cd(C_EI), *ACTD = c.cd(C_ACTD), *ACTI = c.cd(C_ACTI);
 #pragma unroll 1
       for (int k = 0; k <= N; ++k) {
         const int o = k * 8 + r;
-        const double v = has_sol ? D[o] * X[o] : nan("");
+        const double v = has_sol ? D[o] * X[k * VS + r] : nan("");
         if (c.xl) a.x_pred[(size_t)b * nx + k * NX + r] = v;
         else if (c.ul && k < N) a.u_pred[(size_t)b * 2 * N + k * 2 + ucomp] = v;
         if (c.xl) {
@@ -1491,7 +1527,7 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
             const int oc = c.ci(k, t);
             const size_t q = (size_t)b * m + ref_in(k, t);
             const int act = polished_sets ? (int)ACTI[oc] : 0;
-            if (a.y) a.y[q] = has_sol ? I.cinv * (EI[oc] * YI[c.si(k, t)]) : nan("");
+            if (a.y) a.y[q] = has_sol ? I.cinv * (EI[oc] * c.yi(k, t)) : nan("");
             if (a.active_lo) a.active_lo[q] = act & 1;
             if (a.active_up) a.active_up[q] = (act >> 1) & 1;
           }
@@ -1509,7 +1545,7 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
     }
     __syncwarp();
   }
-  (void)NSL;
+  (void)NSL; (void)NB;
 }
 
 }  // namespace h8

@@ -270,16 +270,15 @@ lpv::h8::Lay make_h8_layout(int kind, int N) {
   lpv::h8::Lay L;
   std::memset(&L, 0, sizeof(L));
   L.N = N; L.nsl = kind == LPVMPC_CONTROLLER ? 6 : 7;
+  L.is = kind == LPVMPC_CONTROLLER ? 26 : 38;
   int o = 0;
   auto take = [&](int n) { const int r = o; o += (n + 1) & ~1; return r; };
-  L.T = take((N + 1) * 64); L.K = take(N * 64);
-  const int v = (N + 1) * 8, w = (N + 1) * L.nsl;
-  L.X = take(v); L.B = take(v); L.R = take(v); L.CR = take(v); L.XS = take(v); L.DG = take(v);
-  L.ZI = take(w); L.YI = take(w); L.SI = take(w); L.UI = take(w);
-  L.LI = kind == LPVMPC_CONTROLLER ? L.UI : take(w);
-  L.PO = take((N + 2) * 2);
-  while (o % 16 != 8) o += 2;  // groups of a warp land on different bank halves
+  L.TK = take((N + 1) * lpv::h8::TKS - 64);
+  L.V = take((N + 1) * lpv::h8::VS);
+  L.I = take((N + 1) * L.is);
+  while (o % 16 != 8) o += 2;  // neighbouring groups of a warp 64 B apart mod 128
   L.total = o;
+  const int v = (N + 1) * 8;
   L.cG = lpv::h8::C_COUNT * v;
   L.cold_total = L.cG + N * NX * 8;
   return L;
@@ -557,7 +556,7 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
     int best_q = 0, best_qpw = 1, best_wpc = 1, best_ctas = 1;
     const int qs[3] = {4, 2, 1};
     for (int qi = 0; qi < 3; ++qi) for (int w = 2; w >= 1; --w) {
-      const size_t cta = per_qp * qs[qi] * w;
+      const size_t cta = per_qp * qs[qi] * w + 512 * (size_t)w + 512;
       if (cta > (size_t)h->smem_optin) continue;
       int ctas = (int)(sm_bytes / (cta + 1024));
       if (ctas > 32) ctas = 32;
@@ -565,7 +564,7 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
       if (q > best_q) { best_q = q; best_qpw = qs[qi]; best_wpc = w; best_ctas = ctas; }
     }
     h->qpw = best_qpw; h->wpc = best_wpc;
-    h->ws_bytes = per_qp * h->qpw * h->wpc;
+    h->ws_bytes = per_qp * h->qpw * h->wpc + 512 * (size_t)h->wpc + 512;
     h->smem_mode = true;
     h->grid_cap = h->sm_count * best_ctas;
     const bool ctrl = cfg->kind == LPVMPC_CONTROLLER;
@@ -650,7 +649,7 @@ int lpvmpc_get_info(const lpvmpc_handle *h, lpvmpc_info *info) {
   info->n = h->n; info->d = h->d; info->N = h->L.N; info->nz = h->L.nz; info->m = h->L.m;
   info->variant = h->variant;
   info->workspace_in_smem = h->smem_mode ? 1 : 0;
-  info->smem_bytes_per_qp = h->smem_mode ? (int)(h->variant == 5 ? h->ws_bytes / (h->qpw * h->wpc) : ((h->variant == 2 || h->variant == 3) ? h->ws_bytes / h->qpw : h->ws_bytes)) : 0;
+  info->smem_bytes_per_qp = h->smem_mode ? (int)(h->variant == 5 ? (size_t)h->HL.total * sizeof(double) : ((h->variant == 2 || h->variant == 3) ? h->ws_bytes / h->qpw : h->ws_bytes)) : 0;
   info->workspace_bytes = (long long)(h->stage_bytes + (h->smem_mode ? 0 : h->ws_bytes * (size_t)h->grid_cap));
   info->kernel_launches = h->launches;
   return LPVMPC_OK;
