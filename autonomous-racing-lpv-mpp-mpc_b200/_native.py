@@ -12,7 +12,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "liblpvmpc.so")
 _SRC_DIR = os.path.join(_PKG, "csrc")
-_SOURCES = [os.path.join(_SRC_DIR, f) for f in ("lpvmpc.cu", "lpv_qp.cuh", "lpv_t8.cuh", "lpv_g8.cuh", "lpv_h8.cuh", "lpv_model.cuh")] + \
+_SOURCES = [os.path.join(_SRC_DIR, f) for f in ("lpvmpc.cu", "lpv_qp.cuh", "lpv_t8.cuh", "lpv_g8.cuh", "lpv_h8.cuh", "lpv_h8t.cuh", "lpv_model.cuh")] + \
            [os.path.join(_ROOT, "include", "lpvmpc.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",

@@ -15,6 +15,7 @@
 #include "lpv_t8.cuh"
 #include "lpv_g8.cuh"
 #include "lpv_h8.cuh"
+#include "lpv_h8t.cuh"
 
 namespace lpv {
 
@@ -284,6 +285,25 @@ lpv::h8::Lay make_h8_layout(int kind, int N) {
   return L;
 }
 
+lpv::h8t::Lay make_h8t_layout(int kind, int N) {
+  const int NX = kind == LPVMPC_CONTROLLER ? 6 : 5;
+  lpv::h8t::Lay L;
+  std::memset(&L, 0, sizeof(L));
+  L.N = N; L.nsl = kind == LPVMPC_CONTROLLER ? 6 : 7;
+  L.is = kind == LPVMPC_CONTROLLER ? 26 : 38;
+  int o = 0;
+  auto take = [&](int n) { const int r = o; o += (n + 1) & ~1; return r; };
+  L.V = take((N + 1) * lpv::h8t::VS);
+  L.I = take((N + 1) * L.is);
+  L.G = take(N * NX * 8);
+  L.CS = take(lpv::h8t::C_NSMEM * (N + 1) * 8);
+  L.FS = take(128);
+  while (o % 16 != 8) o += 2;  // neighbouring groups of a warp 64 B apart mod 128
+  L.total = o;
+  L.cold_total = (lpv::h8t::C_COUNT - lpv::h8t::C_NSMEM) * (N + 1) * 8;
+  return L;
+}
+
 }  // namespace
 
 struct lpvmpc_handle {
@@ -302,6 +322,7 @@ struct lpvmpc_handle {
   int variant = 1;           // 1: generic warp-per-QP kernel, 2: T8 register/shared-resident kernel, 3: G8 compact kernel
   lpv::g8::Lay GL;           // G8 shared-memory layout
   lpv::h8::Lay HL;           // H8 layout (shared memory + slab)
+  lpv::h8t::Lay TL;          // H8T layout (tensor memory + shared memory + slab)
   int wpc = 1;               // H8: warps per CTA
   int qpw = 4;               // T8 / G8 / H8: QPs per warp
   unsigned *d_queue = nullptr;  // work-queue counter of the persistent T8 kernel
@@ -420,8 +441,22 @@ int launch_h8(lpvmpc_handle *h, const Params &p, cudaStream_t s) {
   return LPVMPC_OK;
 }
 
+int launch_h8t(lpvmpc_handle *h, const Params &p, cudaStream_t s) {
+  if (p.B == 0) return LPVMPC_OK;
+  lpv::h8t::H8Params hp;
+  hp.L = h->TL; hp.M = p.M; hp.S = p.S; hp.a = p.a; hp.B = p.B; hp.queue = h->d_queue; hp.cold = h->d_cold;
+  const int ctas = (p.B + 15) / 16;
+  const int grid = ctas < h->grid_cap ? ctas : h->grid_cap;
+  CUDA_TRY(h, cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned), s));
+  lpv::h8t::lpv_solve_h8t_kernel<LPVMPC_CONTROLLER, 4><<<grid, 128, h->ws_bytes, s>>>(hp);
+  ++h->launches;
+  CUDA_TRY(h, cudaGetLastError());
+  return LPVMPC_OK;
+}
+
 template <int KIND>
 int launch_solve(lpvmpc_handle *h, const Params &p, cudaStream_t s) {
+  if (h->variant == 6) return launch_h8t(h, p, s);
   if (h->variant == 2) return launch_t8(h, p, s);
   if (h->variant == 3) return launch_g8<KIND>(h, p, s);
   if (h->variant == 5) return launch_h8<KIND>(h, p, s);
@@ -546,10 +581,25 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
                        (cfg->kind == LPVMPC_CONTROLLER || cfg->N <= 63);
     if (cfg->variant == 5 && !h8_ok) { h->err = "variant 5 (H8) needs diagonal Q and R, steering_delay=0, planner N<=63 and a per-QP state that fits shared memory"; return bail(LPVMPC_E_UNSUPPORTED); }
     if (cfg->variant == 5 || (cfg->variant == 0 && h8_ok)) h->variant = 5;
+    // H8T kernel: controller, block factor in tensor memory (48 N + 16 columns of the SM's 512), 16 QPs per CTA, one CTA per SM
+    h->TL = make_h8t_layout(cfg->kind, cfg->N);
+    const size_t h8t_bytes = (size_t)h->TL.total * sizeof(double) * 16 + 4 * 512 + 512;
+    const bool h8t_ok = pdiag && cfg->steering_delay == 0 && cfg->kind == LPVMPC_CONTROLLER && 48 * cfg->N + 16 <= 512 &&
+                        h8t_bytes + 64 <= (size_t)h->smem_optin;
+    if (cfg->variant == 6 && !h8t_ok) { h->err = "variant 6 (H8T) needs controller, diagonal Q and R, steering_delay=0, N<=10"; return bail(LPVMPC_E_UNSUPPORTED); }
+    if (cfg->variant == 6) h->variant = 6;
   }
   h->ws_bytes = (size_t)h->L.total * sizeof(double);
   h->smem_mode = h->ws_bytes <= (size_t)h->smem_optin;
-  if (h->variant == 5) {
+  if (h->variant == 6) {
+    h->qpw = 4; h->wpc = 4;
+    h->ws_bytes = (size_t)h->TL.total * sizeof(double) * 16 + 4 * 512 + 512;
+    h->smem_mode = true;
+    h->grid_cap = h->sm_count;
+    CTRY((cudaFuncSetAttribute(lpv::h8t::lpv_solve_h8t_kernel<LPVMPC_CONTROLLER, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ws_bytes)));
+    CTRY(cudaMalloc(&h->d_queue, sizeof(unsigned)));
+    CTRY(cudaMalloc(&h->d_cold, sizeof(double) * (size_t)h->grid_cap * 16 * h->TL.cold_total));
+  } else if (h->variant == 5) {
     // pick (QPs per warp, warps per CTA) that keeps the most QPs resident per SM
     const size_t per_qp = (size_t)h->HL.total * sizeof(double);
     const size_t sm_bytes = prop.sharedMemPerMultiprocessor;
@@ -649,7 +699,7 @@ int lpvmpc_get_info(const lpvmpc_handle *h, lpvmpc_info *info) {
   info->n = h->n; info->d = h->d; info->N = h->L.N; info->nz = h->L.nz; info->m = h->L.m;
   info->variant = h->variant;
   info->workspace_in_smem = h->smem_mode ? 1 : 0;
-  info->smem_bytes_per_qp = h->smem_mode ? (int)(h->variant == 5 ? (size_t)h->HL.total * sizeof(double) : ((h->variant == 2 || h->variant == 3) ? h->ws_bytes / h->qpw : h->ws_bytes)) : 0;
+  info->smem_bytes_per_qp = h->smem_mode ? (int)(h->variant == 6 ? (size_t)h->TL.total * sizeof(double) : h->variant == 5 ? (size_t)h->HL.total * sizeof(double) : ((h->variant == 2 || h->variant == 3) ? h->ws_bytes / h->qpw : h->ws_bytes)) : 0;
   info->workspace_bytes = (long long)(h->stage_bytes + (h->smem_mode ? 0 : h->ws_bytes * (size_t)h->grid_cap));
   info->kernel_launches = h->launches;
   return LPVMPC_OK;
