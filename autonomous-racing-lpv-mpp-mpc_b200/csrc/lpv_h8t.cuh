@@ -32,7 +32,7 @@ enum { V_B = 0, V_X = 8, V_R = 16, V_XS = 24, V_DG = 32, V_CR = 40 };
 struct Lay {  // per-QP offsets (doubles); computed on the host (lpvmpc.cu: make_h8t_layout)
   int N, nsl;                  // horizon; single-variable-row slots per stage (6 controller, 7 planner)
   int is;                      // doubles per stage of the single-variable-row block: {z,y} x nsl, {s,u} x nsl, [l x nsl], pm x 2
-  int V, I;                    // (N+1) x VS, (N+1) x is
+  int V, I;                    // (N+1) x VS, (N+2) x is (block N+1: dummy rows {z = y = s = 0, u = +inf, l = -inf}, zero coupling)
   int G;                       // N x NX x 8: rows of -[A_k B_k] (scaled), chunks XOR-swizzled
   int CS;                      // C_NSMEM x (N+1) x 8: the cold vectors kept in shared memory
   int FS;                      // 128: factorisation scratch (previous pivot inverse, parked off-diagonal block)
@@ -70,6 +70,25 @@ __device__ __forceinline__ double gsum(double v) {
 __device__ __forceinline__ int gany(int v) {
   const unsigned m = __ballot_sync(kFull, v);
   return ((m >> ((threadIdx.x & 31) & ~7)) & 0xffu) != 0;
+}
+// Reciprocal and reciprocal square root from the hardware seed (2^-23) and three Newton steps: ~1 ulp, a dozen
+// instructions and half the latency of the IEEE division / sqrt sequences (70+ instructions each).
+__device__ __forceinline__ double frcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0); r = fma(r, e, r);
+  e = fma(-x, r, 1.0); r = fma(r, e, r);
+  e = fma(-x, r, 1.0); r = fma(r, e, r);
+  return r;
+}
+__device__ __forceinline__ double frsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  double e = fma(-hx * y, y, 0.5); y = fma(y, e, y);
+  e = fma(-hx * y, y, 0.5); y = fma(y, e, y);
+  e = fma(-hx * y, y, 0.5); y = fma(y, e, y);
+  return y;
 }
 __device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 __device__ __forceinline__ void st2(double *p, double a, double b) { *reinterpret_cast<double2 *>(p) = make_double2(a, b); }
@@ -280,7 +299,7 @@ __device__ __noinline__ void factor(const Ctx<KIND> c, const FW fw, const double
         double pr[8];
 #pragma unroll
         for (int cc = 0; cc < 8; ++cc) pr[cc] = gshfl(s[cc], p);
-        const double piv = 1.0 / pr[p];
+        const double piv = frcp(pr[p]);
         if (r == p) {
 #pragma unroll
           for (int cc = 0; cc < 8; ++cc) s[cc] = (cc == p) ? piv : s[cc] * piv;
@@ -334,7 +353,8 @@ struct Hot {
   uint32_t v;       // my element of the stage vectors: B +0, X +64, R +128, XS +192, DG +256, CR +320
   uint32_t ib;      // my first single-variable row: {z,y} of row t at +16t, {s,u} at +NSL*16 + 16t
   uint32_t il;      // planner: lower bound of my row
-  uint32_t pm;      // input lanes: slew coupling with the previous stage (next stage's at +IS*8)
+  uint32_t pm, pm2; // slew coupling with the previous / the next stage (state lanes: the zero pad, stride 0)
+  uint32_t istr, pstr;  // bytes per stage of my single-variable rows / my slew coupling (0: dummy row / zero pad)
   uint32_t gpub, ggat;  // all-gather buffer 0 (buffer 1 at ^256): where I publish, where my group's 64 bytes start
 };
 
@@ -424,75 +444,82 @@ __device__ __forceinline__ void sweep_bwd_plain(const Hot<KIND> &h, const int N,
   __syncwarp();
 }
 
-// Element-wise ADMM update of my variable at stage j given x~_j (x1), x~_{j-1} (xm) and x~_{j+1} (xp):
-// r recursion, z / y of my single-variable rows, relaxed x, next right-hand side, running sum of x~.
+// Element-wise ADMM update of my variable at stage j given x~_j (x1), x~_{j-1} (xm) and x~_{j+1} (xp): r recursion,
+// z / y of my single-variable rows, relaxed x, next right-hand side, running sum of x~.
+// BRANCH FREE: lanes without a live variable work on all-zero vector slots, lanes without single-variable rows (and
+// every lane at a stage without rows) on a dummy row {z = y = s = 0, u = +inf} that reproduces itself, state lanes read
+// a zero slew coupling.  Split in two parts so that the first fills the publish -> gather latency of the sweep.
 template <int KIND>
 struct Upd {
   double rho, rho_eq, rinv, rinv_eq, sigma, alpha, oma, cc;
   uint64_t eqm, loosem;
-  bool live, xl, ul, inl;   // inl: my variable has single-variable rows (at stages < N for the controller)
+  bool live;
   int N;
 };
+struct UpdMid { double xo, rr, xs, cr, m, sold, snew; };
+
 template <int KIND>
-__device__ __forceinline__ void update_stage(const Upd<KIND> &u, const int j, const uint32_t vj, const uint32_t ij, const uint32_t lj,
-                                             const uint32_t pj, const double x1, const double xm, const double xp) {
-  constexpr int NT = Dims<KIND>::NT, NSL = Dims<KIND>::NSL, IS = Dims<KIND>::IS;
-  const bool vlive = u.xl || (u.ul && j < u.N);
-  if (vlive) {
-    const double xo = lds<64>(vj), rr = lds<128>(vj), xs = lds<192>(vj), dg = lds<256>(vj), cr = lds<320>(vj);
-    double m = dg * x1;
-    if (u.ul) {
-      const double pm = lds(pj), pp = lds<IS * 8>(pj);
-      m = fma(pm, xm, m);
-      m = fma(pp, xp, m);
-    }
-    double sold = 0.0, snew = 0.0;
-    if (u.inl && (KIND == LPVMPC_PLANNER || j < u.N)) {
-      double rt = u.rho, ri = u.rinv;
-      if (KIND == LPVMPC_PLANNER) {
-        if ((u.eqm >> j) & 1ull) { rt = u.rho_eq; ri = u.rinv_eq; }
-        else if ((u.loosem >> j) & 1ull) { rt = kRhoMin; ri = 1.0 / kRhoMin; }
-      }
-      {
-        const double2 zy = lds2(ij), su = lds2<NSL * 16>(ij);
-        sold = fma(su.x, fma(rt, zy.x, -zy.y), sold);
-        const double zr = fma(u.alpha, su.x * x1, u.oma * zy.x);
-        double zn = fma(ri, zy.y, zr);
-        if (KIND == LPVMPC_PLANNER) { const double li = lds(lj); zn = (zn > li) ? zn : li; }
-        // controller rows: the lower bound is -OSQP_INFTY (times the row scaling): below any iterate, no clamp needed
-        zn = (zn < su.y) ? zn : su.y;
-        const double yn = fma(rt, zr - zn, zy.y);
-        if (u.live) sts2(ij, zn, yn);
-        snew = fma(su.x, fma(rt, zn, -yn), snew);
-      }
-      if (NT > 1) {
-        const double2 zy = lds2<16>(ij), su = lds2<NSL * 16 + 16>(ij);
-        sold = fma(su.x, fma(rt, zy.x, -zy.y), sold);
-        const double zr = fma(u.alpha, su.x * x1, u.oma * zy.x);
-        double zn = fma(ri, zy.y, zr);
-        zn = (zn < su.y) ? zn : su.y;
-        const double yn = fma(rt, zr - zn, zy.y);
-        if (u.live) sts2<16>(ij, zn, yn);
-        snew = fma(su.x, fma(rt, zn, -yn), snew);
-      }
-    }
-    const double hh = fma(u.sigma, xo, rr) + sold;            // the right-hand side this x~ was solved for
-    const double rn = fma(-u.alpha, hh - m, fma(u.cc, cr, rr));
-    const double xn = fma(u.alpha, x1, u.oma * xo);
-    if (u.live) sts<64>(vj, xn);
-    sts<128>(vj, rn);
-    sts<192>(vj, xs + x1);
-    sts(vj, fma(u.sigma, xn, rn) + snew);
+__device__ __forceinline__ void update_part1(const Upd<KIND> &u, const int j, const uint32_t vj, const uint32_t ij, const uint32_t lj,
+                                             const uint32_t pj, const uint32_t pj2, const double x1, const double xm, const double xp,
+                                             UpdMid &q) {
+  constexpr int NT = Dims<KIND>::NT, NSL = Dims<KIND>::NSL;
+  q.xo = lds<64>(vj); q.rr = lds<128>(vj); q.xs = lds<192>(vj); q.cr = lds<320>(vj);
+  const double dg = lds<256>(vj);
+  const double pm = lds(pj), pp = lds(pj2);
+  const double2 zy0 = lds2(ij), su0 = lds2<NSL * 16>(ij);
+  double2 zy1 = make_double2(0.0, 0.0), su1 = make_double2(0.0, 0.0);
+  if (NT > 1) { zy1 = lds2<16>(ij); su1 = lds2<NSL * 16 + 16>(ij); }
+  double li = 0.0;
+  if (KIND == LPVMPC_PLANNER) li = lds(lj);
+  double m = dg * x1;
+  m = fma(pm, xm, m);
+  q.m = fma(pp, xp, m);
+  double rt = u.rho, ri = u.rinv;
+  if (KIND == LPVMPC_PLANNER) {
+    const bool eq = (u.eqm >> j) & 1ull, lo = (u.loosem >> j) & 1ull;
+    rt = eq ? u.rho_eq : (lo ? kRhoMin : u.rho);
+    ri = eq ? u.rinv_eq : (lo ? 1.0 / kRhoMin : u.rinv);
   }
+  double sold, snew;
+  {
+    sold = su0.x * fma(rt, zy0.x, -zy0.y);
+    const double zr = fma(u.alpha, su0.x * x1, u.oma * zy0.x);
+    double zn = fma(ri, zy0.y, zr);
+    if (KIND == LPVMPC_PLANNER) zn = (zn > li) ? zn : li;
+    // controller rows: the lower bound is -OSQP_INFTY (times the row scaling): below any iterate, no clamp needed
+    zn = (zn < su0.y) ? zn : su0.y;
+    const double yn = fma(rt, zr - zn, zy0.y);
+    if (u.live) sts2(ij, zn, yn);
+    snew = su0.x * fma(rt, zn, -yn);
+  }
+  if (NT > 1) {
+    sold = fma(su1.x, fma(rt, zy1.x, -zy1.y), sold);
+    const double zr = fma(u.alpha, su1.x * x1, u.oma * zy1.x);
+    double zn = fma(ri, zy1.y, zr);
+    zn = (zn < su1.y) ? zn : su1.y;
+    const double yn = fma(rt, zr - zn, zy1.y);
+    if (u.live) sts2<16>(ij, zn, yn);
+    snew = fma(su1.x, fma(rt, zn, -yn), snew);
+  }
+  q.sold = sold; q.snew = snew;
+}
+template <int KIND>
+__device__ __forceinline__ void update_part2(const Upd<KIND> &u, const uint32_t vj, const double x1, const UpdMid &q) {
+  const double hh = fma(u.sigma, q.xo, q.rr) + q.sold;            // the right-hand side this x~ was solved for
+  const double rn = fma(-u.alpha, hh - q.m, fma(u.cc, q.cr, q.rr));
+  const double xn = fma(u.alpha, x1, u.oma * q.xo);
+  if (u.live) sts<64>(vj, xn);
+  sts<128>(vj, rn);
+  sts<192>(vj, q.xs + x1);
+  sts(vj, fma(u.sigma, xn, rn) + q.snew);
 }
 
 // backward sweep fused with the element-wise update of stage k+1 (hot)
 template <int KIND>
 __device__ __forceinline__ void sweep_bwd_admm(const Hot<KIND> &h, const Upd<KIND> &u, uint32_t &gsel) {
-  constexpr int ISB = Dims<KIND>::IS * 8;
   const int N = u.N;
   double gn[8];
-  uint32_t vb = h.v + N * VB, ib = h.ib + N * ISB, il = h.il + N * ISB, pb = h.pm + N * ISB;
+  uint32_t vb = h.v + N * VB, ib = h.ib + N * h.istr, il = h.il + N * h.istr, pb = h.pm + N * h.pstr, pb2 = h.pm2 + N * h.pstr;
   uint32_t tc = h.tKc + (uint32_t)((N - 1) * 16);
   TmRow e;
   tm_ld8(tc, e);
@@ -507,13 +534,19 @@ __device__ __forceinline__ void sweep_bwd_admm(const Hot<KIND> &h, const Upd<KIN
     sts(h.gpub ^ gsel, xt);
     tc -= 16;
     tm_ld8(k > 0 ? tc : h.tKc, e);   // column of K_k for the next stage (k = 0: dummy request, keeps the code converged)
-    update_stage<KIND>(u, k + 1, vb, ib, il, pb, x1, xt, x2);   // stage k+1: independent of the chain, fills its latency
+    UpdMid q;
+    update_part1<KIND>(u, k + 1, vb, ib, il, pb, pb2, x1, xt, x2, q);   // stage k+1: independent of the chain, fills its latency
     gather_in(h.ggat, gsel, gn);
-    vb -= VB; ib -= ISB; il -= ISB; pb -= ISB;
+    update_part2<KIND>(u, vb, x1, q);
+    vb -= VB; ib -= h.istr; il -= h.istr; pb -= h.pstr; pb2 -= h.pstr;
     x2 = x1; x1 = xt;
   }
   tm_wait_ld();
-  update_stage<KIND>(u, 0, vb, ib, il, pb, x1, 0.0, x2);
+  {
+    UpdMid q;
+    update_part1<KIND>(u, 0, vb, ib, il, pb, pb2, x1, 0.0, x2, q);
+    update_part2<KIND>(u, vb, x1, q);
+  }
   __syncwarp();
 }
 
@@ -850,6 +883,7 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
   const lpvmpc_settings &St = p.S;
   double *S = c.S;
   const int nx = NX * (N + 1), nz = nx + 2 * N, NS8 = (N + 1) * 8;
+  (void)nx;
   const int ucomp = r - NX;
   int sched_err = 0, data_err = 0;
   double x0r = 0.0;
@@ -858,7 +892,6 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
   double *sPD = c.cd(C_PD), *sPO = c.cd(C_PO), *sD = c.cd(C_Q), *sE = c.cd(C_BE), *sEI = c.cd(C_ED), *sDt = c.cd(C_YD);
   double *sEt = c.cd(C_DINV), *sEti = c.cd(C_EINV);
   double *Gs = S + L.G;
-  double *scr = S + L.FS;
   (void)NS8;
   // ---- schedule: G_k = -[A_k B_k] (unscaled), my row
   if (a.sched_mode == LPVMPC_SCHED_GIVEN) {
@@ -981,6 +1014,19 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
       sD[o] = 1.0; sE[o] = 1.0; sEI[o] = 1.0; sEti[o] = 1.0;
       X[ov] = 0.0; BV[ov] = 0.0;
     }
+    // every single-variable-row slot starts as a dummy row; block N+1 and the dummy area are all dummies
+    {
+      constexpr int NSLc = Ctx<KIND>::NSL, OLIc = Ctx<KIND>::OLI, OPMc = Ctx<KIND>::OPM;
+#pragma unroll 1
+      for (int k = 0; k <= N + 1; ++k) {
+        double *ibk = c.Ib(k);
+        if (r < NSLc) {
+          ibk[r * 2] = 0.0; ibk[r * 2 + 1] = 0.0; ibk[NSLc * 2 + r * 2] = 0.0; ibk[NSLc * 2 + r * 2 + 1] = kInfty * kInfty;
+          if (KIND == LPVMPC_PLANNER) ibk[OLIc + r] = -kInfty * kInfty;
+        }
+        if (r < 2) ibk[OPMc + r] = 0.0;
+      }
+    }
     __syncwarp();
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
@@ -1036,17 +1082,17 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
           qa = absmax(qa, c.si(k, t));
-          sEti[c.ci(k, t)] = 1.0 / sqrt(limit_scaling(fabs(c.si(k, t))));
+          sEti[c.ci(k, t)] = frsqrt(limit_scaling(fabs(c.si(k, t))));
         }
       }
-      sDt[o] = 1.0 / sqrt(limit_scaling(pa > qa ? pa : qa));
+      sDt[o] = frsqrt(limit_scaling(pa > qa ? pa : qa));
       double ea = c.xl ? fabs(ED[ov]) : 0.0;
       if (k > 0 && c.xl) {
         const double *gp = Gs + (k - 1) * GS;
 #pragma unroll
         for (int j = 0; j < 4; ++j) { const double2 e = ld2(gp + c.ro[j]); ea = absmax(ea, e.x); ea = absmax(ea, e.y); }
       }
-      sEt[o] = 1.0 / sqrt(limit_scaling(ea));
+      sEt[o] = frsqrt(limit_scaling(ea));
     }
     __syncwarp();
 #pragma unroll 1
@@ -1074,8 +1120,8 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
       sE[o] = sE[o] * sEt[o];
     }
     __syncwarp();
-    // cost scaling: mean of the column norms of P in the reference variable order
-    double qn = 0.0;
+    // cost scaling: mean of the column norms of P (summed per lane, then across the group)
+    double qn = 0.0, ct = 0.0;
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
       const int o = k * 8 + r;
@@ -1084,20 +1130,14 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
         if (k < N - 1) pa = absmax(pa, sPO[o]);
         if (k > 0 && k < N) pa = absmax(pa, sPO[o - 8]);
       }
-      if (c.xl) scr[k * NX + r] = pa;
-      else if (c.ul && k < N) scr[nx + k * 2 + ucomp] = pa;
-      if (c.var_live(k)) qn = absmax(qn, QV[k * VS + r]);
+      if (c.var_live(k)) { ct += pa; qn = absmax(qn, QV[k * VS + r]); }
     }
     qn = gmax(qn);
-    __syncwarp();
-    double ct = 0.0;
-#pragma unroll 2
-    for (int j = 0; j < nz; ++j) ct += scr[j];
-    ct = ct / nz;
+    ct = gsum(ct) / nz;
     qn = limit_scaling(qn);
     ct = ct > qn ? ct : qn;
     ct = limit_scaling(ct);
-    ct = 1.0 / ct;
+    ct = frcp(ct);
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) { const int o = k * 8 + r; sPD[o] *= ct; QV[k * VS + r] *= ct; sPO[o] *= ct; }
     csc *= ct;
@@ -1375,9 +1415,15 @@ __global__ void __launch_bounds__(128, 1) lpv_solve_h8t_kernel(const __grid_cons
       const uint32_t sq = smem_a + (uint32_t)((warp * QPW + gq) * L.total) * 8u;
       h.tT = c.tT(0); h.tKr = c.tKr(1); h.tKc = c.tKc(1);
       h.v = sq + (uint32_t)(L.V + r) * 8u;
-      h.ib = sq + (uint32_t)(L.I + c.islot * 2) * 8u;
-      h.il = sq + (uint32_t)(L.I + OLI + c.islot) * 8u;
-      h.pm = sq + (uint32_t)(L.I + OPM + (c.ul ? ucomp : 0)) * 8u;
+      constexpr int ISBk = Ctx<KIND>::IS * 8;
+      const bool rows = (KIND == LPVMPC_CONTROLLER) ? (r == 0 || c.ul) : (c.xl || c.ul);
+      const uint32_t dm = sq + (uint32_t)(L.I + (N + 1) * Ctx<KIND>::IS) * 8u;   // block N+1: dummy rows, zero coupling
+      h.ib = rows ? sq + (uint32_t)(L.I + c.islot * 2) * 8u : dm;
+      h.il = rows ? sq + (uint32_t)(L.I + OLI + c.islot) * 8u : dm + (uint32_t)OLI * 8u;
+      h.istr = rows ? (uint32_t)ISBk : 0u;
+      h.pm = c.ul ? sq + (uint32_t)(L.I + OPM + ucomp) * 8u : dm + (uint32_t)OPM * 8u;
+      h.pm2 = c.ul ? h.pm + (uint32_t)ISBk : h.pm;
+      h.pstr = c.ul ? (uint32_t)ISBk : 0u;
       h.gpub = gbuf + (uint32_t)(64 * (r >> 1) + 16 * g + 8 * (r & 1));
       h.ggat = gbuf + (uint32_t)(16 * g);
     }
@@ -1413,8 +1459,7 @@ __global__ void __launch_bounds__(128, 1) lpv_solve_h8t_kernel(const __grid_cons
     const int ct = S.check_termination, ai = S.adaptive_rho ? adapt_interval : 0;
 
     Upd<KIND> u;
-    u.sigma = sigma; u.alpha = alpha; u.oma = 1.0 - alpha; u.eqm = c.eqm; u.loosem = c.loosem; u.xl = c.xl; u.ul = c.ul; u.N = N;
-    u.inl = (KIND == LPVMPC_CONTROLLER) ? (r == 0 || c.ul) : (c.xl || c.ul);
+    u.sigma = sigma; u.alpha = alpha; u.oma = 1.0 - alpha; u.eqm = c.eqm; u.loosem = c.loosem; u.N = N;
     int iter = 0, nsync = 0, first_in = 0;   // steps since the last y_dyn sync; whether step 0 is among them
     double rho_eq_last = rho_eq;             // rho_eq of the last executed step (delta_y of the certificates)
     bool checked_last = false;

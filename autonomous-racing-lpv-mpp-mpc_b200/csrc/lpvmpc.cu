@@ -294,7 +294,7 @@ lpv::h8t::Lay make_h8t_layout(int kind, int N) {
   int o = 0;
   auto take = [&](int n) { const int r = o; o += (n + 1) & ~1; return r; };
   L.V = take((N + 1) * lpv::h8t::VS);
-  L.I = take((N + 1) * L.is);
+  L.I = take((N + 2) * L.is);
   L.G = take(N * NX * 8);
   L.CS = take(lpv::h8t::C_NSMEM * (N + 1) * 8);
   L.FS = take(128);
