@@ -587,7 +587,7 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
     const bool h8t_ok = pdiag && cfg->steering_delay == 0 && cfg->kind == LPVMPC_CONTROLLER && 48 * cfg->N + 16 <= 512 &&
                         h8t_bytes + 64 <= (size_t)h->smem_optin;
     if (cfg->variant == 6 && !h8t_ok) { h->err = "variant 6 (H8T) needs controller, diagonal Q and R, steering_delay=0, N<=10"; return bail(LPVMPC_E_UNSUPPORTED); }
-    if (cfg->variant == 6) h->variant = 6;
+    if (cfg->variant == 6 || (cfg->variant == 0 && h8t_ok)) h->variant = 6;
   }
   h->ws_bytes = (size_t)h->L.total * sizeof(double);
   h->smem_mode = h->ws_bytes <= (size_t)h->smem_optin;
