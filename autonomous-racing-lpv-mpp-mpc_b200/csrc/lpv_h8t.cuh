@@ -1184,7 +1184,11 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
 }
 
 // ---------------------------------------------------------------- polish (cold, once per QP)
-// Works on the slab (C_PX, C_PYD, C_PYI); on success the polished (x, z, y) replace the iterate.
+// Reduced KKT system of the active rows solved in condensed form (row weights 1/delta) with iterative refinement.
+// The work vectors sit in the stage vectors ADMM no longer needs (x -> R, y_dyn -> XS, r2_dyn -> DG); on success the
+// polished (x, z, y) replace the iterate.  Each refinement step is two passes over the stages around one solve:
+//   rhs = -q - P x - A_red'(y - r2 / delta)                                  (one product with the columns of G)
+//   dx  = S^-1 rhs;  A dx gives dy = (A dx - r2) / delta and r2 <- r2 - A dx   (one product with the rows of G)
 template <int KIND>
 __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const lpvmpc_settings &St, Info *ip, const bool do_pol, uint32_t gsel) {
   constexpr int NT = Ctx<KIND>::NT, NX = Ctx<KIND>::NX;
@@ -1192,10 +1196,10 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
   const bool unscale = I.unscale;
   const int N = c.N, r = c.r;
   double *X = c.V(V_X), *BV = c.V(V_B);
+  double *PX = c.V(V_R), *PYD = c.V(V_XS), *R2D = c.V(V_DG);       // [k*VS + q]
   double *YD = c.cd(C_YD);
   const double *BE = c.cd(C_BE), *ED = c.cd(C_ED), *QV = c.cd(C_Q);
-  double *PX = c.cd(C_PX), *PYD = c.cd(C_PYD), *PYI = c.cd(C_PYI), *R2D = c.cd(C_R2D), *R2I = c.cd(C_R2I);
-  double *ACTD = c.cd(C_ACTD), *ACTI = c.cd(C_ACTI), *ZT = c.cd(C_ZT);
+  double *PYI = c.cd(C_PYI), *R2I = c.cd(C_R2I), *ACTD = c.cd(C_ACTD), *ACTI = c.cd(C_ACTI);
   const double *PD = c.cd(C_PD), *PO = c.cd(C_PO), *EINV = c.cd(C_EINV), *EIINV = c.cd(C_EIINV), *DINV = c.cd(C_DINV);
   const double delta = St.delta, idel = 1.0 / St.delta;
   // active-set guess (form_Ared): 1 = lower, 2 = upper, 3 = both
@@ -1221,85 +1225,102 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
   FW fw; fw.polish = 1; fw.rho = 0.0; fw.rho_eq = 0.0; fw.idel = idel;
   factor<KIND>(c, fw, delta);
   auto bred_i = [&](int k, int t) { const double a = ACTI[c.ci(k, t)]; return (a == 1.0 || a == 3.0) ? c.lo_of(k, t) : c.ui(k, t); };
-  // first solve: rhs = -q + A_red'(b_red / delta); targets go through R2D / R2I
+  // first solve: rhs = -q + A_red'(b_red / delta); the targets go through R2D / R2I
 #pragma unroll 1
   for (int k = 0; k <= N; ++k) {
     const int o = k * 8 + r;
-    R2D[o] = (c.xl && ACTD[o] != 0.0) ? idel * BE[o] : 0.0;
+    R2D[k * VS + r] = (c.xl && ACTD[o] != 0.0) ? idel * BE[o] : 0.0;
     if (c.has_in(k)) {
 #pragma unroll
       for (int t = 0; t < NT; ++t) R2I[c.ci(k, t)] = (ACTI[c.ci(k, t)] != 0.0) ? idel * bred_i(k, t) : 0.0;
     }
   }
   __syncwarp();
+  // (A' t)_(k, r) with t_dyn = R2D-like array stored [k*VS + q] and t_in from the slab array ti
+  auto colAt = [&](const double *td, const double *ti, int k) {
+    double acc = c.xl ? ED[k * 8 + r] * td[k * VS + r] : 0.0;
+    if (k < N) {
+      double g[8];
+#pragma unroll
+      for (int rr = 0; rr < 8; ++rr) g[rr] = (rr < NX) ? td[(k + 1) * VS + rr] : 0.0;
+      acc += coldot<NX>(c.Gb(k), c.co, g);
+    }
+    if (c.has_in(k)) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) acc = fma(c.si(k, t), ti[c.ci(k, t)], acc);
+    }
+    return acc;
+  };
 #pragma unroll 1
-  for (int k = 0; k <= N; ++k) BV[k * VS + r] = c.var_live(k) ? (-QV[k * 8 + r] + colA<KIND>(c, ED, R2D, R2I, false, k)) : 0.0;
+  for (int k = 0; k <= N; ++k) BV[k * VS + r] = c.var_live(k) ? (-QV[k * 8 + r] + colAt(R2D, R2I, k)) : 0.0;
   __syncwarp();
   sweep_fwd<KIND>(h, N, gsel);
   sweep_bwd_plain<KIND>(h, N, gsel);
+  // x, y = (A x - b) / delta, r2 = b - A x on the active rows
 #pragma unroll 1
   for (int k = 0; k <= N; ++k) {
-    const int o = k * 8 + r;
-    const double xk = BV[k * VS + r];
-    PX[o] = xk;
-    PYD[o] = (c.xl && ACTD[o] != 0.0) ? (rowA_dyn<KIND>(c, ED, BV, VS, k) - BE[o]) * idel : 0.0;
+    const int o = k * 8 + r, ov = k * VS + r;
+    const double xk = BV[ov];
+    PX[ov] = xk;
+    const bool ad = c.xl && ACTD[o] != 0.0;
+    const double res = ad ? (BE[o] - rowA_dyn<KIND>(c, ED, BV, VS, k)) : 0.0;
+    R2D[ov] = res;
+    PYD[ov] = -res * idel;
     if (c.has_in(k)) {
 #pragma unroll
-      for (int t = 0; t < NT; ++t) PYI[c.ci(k, t)] = (ACTI[c.ci(k, t)] != 0.0) ? (c.si(k, t) * xk - bred_i(k, t)) * idel : 0.0;
+      for (int t = 0; t < NT; ++t) {
+        const int oc = c.ci(k, t);
+        const double ri = (ACTI[oc] != 0.0) ? (bred_i(k, t) - c.si(k, t) * xk) : 0.0;
+        R2I[oc] = ri; PYI[oc] = -ri * idel;
+      }
     }
   }
   __syncwarp();
 #pragma unroll 1
   for (int it = 0; it < St.polish_refine_iter + kPolishExtraRefine; ++it) {
-    // residual of the un-regularised reduced KKT: r2 on the active rows
+    // rhs = -q - P x - A'(y - r2 / delta)
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
-      const int o = k * 8 + r;
-      R2D[o] = (c.xl && ACTD[o] != 0.0) ? (BE[o] - rowA_dyn<KIND>(c, ED, PX, 8, k)) : 0.0;
-      if (c.has_in(k)) {
-#pragma unroll
-        for (int t = 0; t < NT; ++t) R2I[c.ci(k, t)] = (ACTI[c.ci(k, t)] != 0.0) ? (bred_i(k, t) - c.si(k, t) * PX[o]) : 0.0;
-      }
-    }
-    __syncwarp();
-#pragma unroll 1
-    for (int k = 0; k <= N; ++k) {
-      const int o = k * 8 + r;
+      const int o = k * 8 + r, ov = k * VS + r;
       double b = 0.0;
       if (c.var_live(k)) {
-        const double Px = rowP<KIND>(c, PD, PO, PX, 8, k), Aty = colA<KIND>(c, ED, PYD, PYI, false, k);
-        // A'(r2 / delta): same column product on scaled entries
-        double at = c.xl ? ED[o] * (idel * R2D[o]) : 0.0;
+        const double Px = rowP<KIND>(c, PD, PO, PX, VS, k);
+        double acc = c.xl ? ED[o] * fma(-idel, R2D[ov], PYD[ov]) : 0.0;
         if (k < N) {
           double g[8];
 #pragma unroll
-          for (int rr = 0; rr < 8; ++rr) g[rr] = (rr < NX) ? idel * R2D[(k + 1) * 8 + rr] : 0.0;
-          at += coldot<NX>(c.Gb(k), c.co, g);
+          for (int rr = 0; rr < 8; ++rr) g[rr] = (rr < NX) ? fma(-idel, R2D[(k + 1) * VS + rr], PYD[(k + 1) * VS + rr]) : 0.0;
+          acc += coldot<NX>(c.Gb(k), c.co, g);
         }
         if (c.has_in(k)) {
 #pragma unroll
-          for (int t = 0; t < NT; ++t) at = fma(c.si(k, t), idel * R2I[c.ci(k, t)], at);
+          for (int t = 0; t < NT; ++t) { const int oc = c.ci(k, t); acc = fma(c.si(k, t), fma(-idel, R2I[oc], PYI[oc]), acc); }
         }
-        b = ((-QV[o] - Px) - Aty) + at;
+        b = (-QV[o] - Px) - acc;
       }
-      BV[k * VS + r] = b;
+      BV[ov] = b;
     }
     __syncwarp();
     sweep_fwd<KIND>(h, N, gsel);
     sweep_bwd_plain<KIND>(h, N, gsel);
-#pragma unroll 1
-    for (int k = 0; k <= N; ++k) { if (c.xl) ZT[k * 8 + r] = rowA_dyn<KIND>(c, ED, BV, VS, k); }   // z~ = A_dyn dx
-    __syncwarp();
+    // dy = (A dx - r2) / delta, r2 <- r2 - A dx, x <- x + dx
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
-      const int o = k * 8 + r;
-      const double dx = BV[k * VS + r];
-      if (c.xl && ACTD[o] != 0.0) PYD[o] += (ZT[o] - R2D[o]) * idel;
+      const int o = k * 8 + r, ov = k * VS + r;
+      const double dx = BV[ov];
+      if (c.xl && ACTD[o] != 0.0) {
+        const double z = rowA_dyn<KIND>(c, ED, BV, VS, k), r2 = R2D[ov];
+        PYD[ov] += (z - r2) * idel;
+        R2D[ov] = r2 - z;
+      }
       if (c.has_in(k)) {
 #pragma unroll
-        for (int t = 0; t < NT; ++t) { const int oc = c.ci(k, t); if (ACTI[oc] != 0.0) PYI[oc] += (c.si(k, t) * dx - R2I[oc]) * idel; }
+        for (int t = 0; t < NT; ++t) {
+          const int oc = c.ci(k, t);
+          if (ACTI[oc] != 0.0) { const double z = c.si(k, t) * dx, r2 = R2I[oc]; PYI[oc] += (z - r2) * idel; R2I[oc] = r2 - z; }
+        }
       }
-      PX[o] += dx;
+      PX[ov] += dx;
     }
     __syncwarp();
   }
@@ -1307,18 +1328,18 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
   double a_rp = 0, a_rd = 0;
 #pragma unroll 1
   for (int k = 0; k <= N; ++k) {
-    const int o = k * 8 + r;
+    const int o = k * 8 + r, ov = k * VS + r;
     if (c.xl) {
-      const double Ax = rowA_dyn<KIND>(c, ED, PX, 8, k), t = Ax + PYD[o];
-      PYD[o] = t - BE[o];
+      const double Ax = rowA_dyn<KIND>(c, ED, PX, VS, k), t = Ax + PYD[ov];
+      PYD[ov] = t - BE[o];
       const double rr = Ax - BE[o];
       a_rp = absmax(a_rp, unscale ? EINV[o] * rr : rr);
-    } else PYD[o] = 0.0;
+    } else PYD[ov] = 0.0;
     if (c.has_in(k)) {
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
         const int oc = c.ci(k, t);
-        const double ax = c.si(k, t) * PX[o], tt = ax + PYI[oc];
+        const double ax = c.si(k, t) * PX[ov], tt = ax + PYI[oc];
         const double zc = clampd(tt, c.lo_of(k, t), c.ui(k, t));
         R2I[oc] = zc; PYI[oc] = tt - zc;
         const double rr = ax - zc;
@@ -1331,12 +1352,12 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
   for (int k = 0; k <= N; ++k) {
     const int o = k * 8 + r;
     if (c.var_live(k)) {
-      const double rr = (QV[o] + rowP<KIND>(c, PD, PO, PX, 8, k)) + colA<KIND>(c, ED, PYD, PYI, false, k);
+      const double rr = (QV[o] + rowP<KIND>(c, PD, PO, PX, VS, k)) + colAt(PYD, PYI, k);
       a_rd = absmax(a_rd, unscale ? DINV[o] * rr : rr);
     }
   }
   const double pol_pri = gmax(a_rp), pol_dua = (unscale ? I.cinv : 1.0) * gmax(a_rd);
-  const double pol_obj = objective<KIND>(c, PX, 8, St.scaling ? I.cinv : 1.0);
+  const double pol_obj = objective<KIND>(c, PX, VS, St.scaling ? I.cinv : 1.0);
   const bool ok = (pol_pri < I.pri_res && pol_dua < I.dua_res) || (pol_pri < I.pri_res && I.dua_res < 1e-10) ||
                   (pol_dua < I.dua_res && I.pri_res < 1e-10);
   if (!do_pol) return 0;
@@ -1344,8 +1365,8 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
   I.obj = pol_obj; I.pri_res = pol_pri; I.dua_res = pol_dua;
 #pragma unroll 1
   for (int k = 0; k <= N; ++k) {
-    const int o = k * 8 + r;
-    X[k * VS + r] = PX[o]; YD[o] = PYD[o];
+    const int o = k * 8 + r, ov = k * VS + r;
+    X[ov] = PX[ov]; YD[o] = PYD[ov];
     if (c.has_in(k)) {
 #pragma unroll
       for (int t = 0; t < NT; ++t) { c.zi(k, t) = R2I[c.ci(k, t)]; c.yi(k, t) = PYI[c.ci(k, t)]; }
