@@ -49,7 +49,7 @@ enum { V_B = 0, V_X = 8, V_R = 16, V_XS = 24, V_DG = 32, V_CR = 40 };
 struct Lay {  // per-QP offsets (doubles); computed on the host (lpvmpc.cu: make_h8_layout)
   int N, nsl;                  // horizon; single-variable-row slots per stage (6 controller, 7 planner)
   int is;                      // doubles per stage of the single-variable-row block: {z,y} x nsl, {s,u} x nsl, [l x nsl], pm x 2
-  int TK, V, I;                // (N+1) x TKS - 64, (N+1) x VS, (N+1) x is
+  int TK, V, I;                // (N+1) x TKS - 64, (N+1) x VS, (N+2) x is (block N+1: dummy rows, zero coupling)
   int total;                   // doubles per QP in shared memory (== 8 mod 16: neighbouring groups 64 B apart mod 128)
   int cold_total;              // doubles per QP slot in the global slab
   int cG;                      // offset of G (N x NX x 8, row-major rows of -[A_k B_k], scaled) inside the slot
@@ -85,6 +85,25 @@ __device__ __forceinline__ double gsum(double v) {
 __device__ __forceinline__ int gany(int v) {
   const unsigned m = __ballot_sync(kFull, v);
   return ((m >> ((threadIdx.x & 31) & ~7)) & 0xffu) != 0;
+}
+// Reciprocal and reciprocal square root from the hardware seed (2^-23) and three Newton steps: ~1 ulp, a dozen
+// instructions and half the latency of the IEEE division / sqrt sequences (70+ instructions each).
+__device__ __forceinline__ double frcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0); r = fma(r, e, r);
+  e = fma(-x, r, 1.0); r = fma(r, e, r);
+  e = fma(-x, r, 1.0); r = fma(r, e, r);
+  return r;
+}
+__device__ __forceinline__ double frsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  double e = fma(-hx * y, y, 0.5); y = fma(y, e, y);
+  e = fma(-hx * y, y, 0.5); y = fma(y, e, y);
+  e = fma(-hx * y, y, 0.5); y = fma(y, e, y);
+  return y;
 }
 __device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 __device__ __forceinline__ void st2(double *p, double a, double b) { *reinterpret_cast<double2 *>(p) = make_double2(a, b); }
@@ -258,7 +277,7 @@ __device__ __noinline__ void factor(const Ctx<KIND> c, const FW fw, const double
         double pr[8];
 #pragma unroll
         for (int cc = 0; cc < 8; ++cc) pr[cc] = gshfl(s[cc], p);
-        const double piv = 1.0 / pr[p];
+        const double piv = frcp(pr[p]);
         if (r == p) {
 #pragma unroll
           for (int cc = 0; cc < 8; ++cc) s[cc] = (cc == p) ? piv : s[cc] * piv;
@@ -311,7 +330,8 @@ struct Hot {
   uint32_t v;       // my element of the stage vectors: B +0, X +64, R +128, XS +192, DG +256, CR +320
   uint32_t ib;      // my first single-variable row: {z,y} of row t at +16t, {s,u} at +NSL*16 + 16t
   uint32_t il;      // planner: lower bound of my row
-  uint32_t pm;      // input lanes: slew coupling with the previous stage (next stage's at +IS*8)
+  uint32_t pm, pm2; // slew coupling with the previous / the next stage (state lanes: the zero pad, stride 0)
+  uint32_t istr, pstr;  // bytes per stage of my single-variable rows / my slew coupling (0: dummy row / zero pad)
   uint32_t gpub, ggat;  // all-gather buffer 0 (buffer 1 at ^256): where I publish, where my group's 64 bytes start
 };
 
@@ -395,89 +415,112 @@ __device__ __forceinline__ void sweep_bwd_plain(const Hot<KIND> &h, const int N,
   __syncwarp();
 }
 
-// Element-wise ADMM update of my variable at stage j given x~_j (x1), x~_{j-1} (xm) and x~_{j+1} (xp):
-// r recursion, z / y of my single-variable rows, relaxed x, next right-hand side, running sum of x~.
+// Element-wise ADMM update of my variable at stage j given x~_j (x1), x~_{j-1} (xm) and x~_{j+1} (xp): r recursion,
+// z / y of my single-variable rows, relaxed x, next right-hand side, running sum of x~.
+// BRANCH FREE: lanes without a live variable work on all-zero vector slots, lanes without single-variable rows (and
+// every lane at a stage without rows) on a dummy row {z = y = s = 0, u = +inf} that reproduces itself, state lanes read
+// a zero slew coupling.  Split in two parts so that the first fills the publish -> gather latency of the sweep.
 template <int KIND>
 struct Upd {
   double rho, rho_eq, rinv, rinv_eq, sigma, alpha, oma, cc;
   uint64_t eqm, loosem;
-  bool live, xl, ul, inl;   // inl: my variable has single-variable rows (at stages < N for the controller)
+  bool live;
   int N;
 };
+struct UpdMid { double xo, rr, xs, cr, m, sold, snew; };
+struct UpdIn { double xo, rr, xs, cr, dg, pm, pp, li; double2 zy0, su0, zy1, su1; };
+
+// operands of the update of stage j: issued ahead of the sweep's dependent chain so that they arrive behind it
 template <int KIND>
-__device__ __forceinline__ void update_stage(const Upd<KIND> &u, const int j, const uint32_t vj, const uint32_t ij, const uint32_t lj,
-                                             const uint32_t pj, const double x1, const double xm, const double xp) {
-  constexpr int NT = Dims<KIND>::NT, NSL = Dims<KIND>::NSL, IS = Dims<KIND>::IS;
-  const bool vlive = u.xl || (u.ul && j < u.N);
-  if (vlive) {
-    const double xo = lds<64>(vj), rr = lds<128>(vj), xs = lds<192>(vj), dg = lds<256>(vj), cr = lds<320>(vj);
-    double m = dg * x1;
-    if (u.ul) {
-      const double pm = lds(pj), pp = lds<IS * 8>(pj);
-      m = fma(pm, xm, m);
-      m = fma(pp, xp, m);
-    }
-    double sold = 0.0, snew = 0.0;
-    if (u.inl && (KIND == LPVMPC_PLANNER || j < u.N)) {
-      double rt = u.rho, ri = u.rinv;
-      if (KIND == LPVMPC_PLANNER) {
-        if ((u.eqm >> j) & 1ull) { rt = u.rho_eq; ri = u.rinv_eq; }
-        else if ((u.loosem >> j) & 1ull) { rt = kRhoMin; ri = 1.0 / kRhoMin; }
-      }
-      {
-        const double2 zy = lds2(ij), su = lds2<NSL * 16>(ij);
-        sold = fma(su.x, fma(rt, zy.x, -zy.y), sold);
-        const double zr = fma(u.alpha, su.x * x1, u.oma * zy.x);
-        double zn = fma(ri, zy.y, zr);
-        if (KIND == LPVMPC_PLANNER) { const double li = lds(lj); zn = (zn > li) ? zn : li; }
-        // controller rows: the lower bound is -OSQP_INFTY (times the row scaling): below any iterate, no clamp needed
-        zn = (zn < su.y) ? zn : su.y;
-        const double yn = fma(rt, zr - zn, zy.y);
-        if (u.live) sts2(ij, zn, yn);
-        snew = fma(su.x, fma(rt, zn, -yn), snew);
-      }
-      if (NT > 1) {
-        const double2 zy = lds2<16>(ij), su = lds2<NSL * 16 + 16>(ij);
-        sold = fma(su.x, fma(rt, zy.x, -zy.y), sold);
-        const double zr = fma(u.alpha, su.x * x1, u.oma * zy.x);
-        double zn = fma(ri, zy.y, zr);
-        zn = (zn < su.y) ? zn : su.y;
-        const double yn = fma(rt, zr - zn, zy.y);
-        if (u.live) sts2<16>(ij, zn, yn);
-        snew = fma(su.x, fma(rt, zn, -yn), snew);
-      }
-    }
-    const double hh = fma(u.sigma, xo, rr) + sold;            // the right-hand side this x~ was solved for
-    const double rn = fma(-u.alpha, hh - m, fma(u.cc, cr, rr));
-    const double xn = fma(u.alpha, x1, u.oma * xo);
-    if (u.live) sts<64>(vj, xn);
-    sts<128>(vj, rn);
-    sts<192>(vj, xs + x1);
-    sts(vj, fma(u.sigma, xn, rn) + snew);
+__device__ __forceinline__ void update_loads(const uint32_t vj, const uint32_t ij, const uint32_t lj, const uint32_t pj, const uint32_t pj2,
+                                             UpdIn &in) {
+  constexpr int NT = Dims<KIND>::NT, NSL = Dims<KIND>::NSL;
+  in.xo = lds<64>(vj); in.rr = lds<128>(vj); in.xs = lds<192>(vj); in.dg = lds<256>(vj); in.cr = lds<320>(vj);
+  in.pm = lds(pj); in.pp = lds(pj2);
+  in.zy0 = lds2(ij); in.su0 = lds2<NSL * 16>(ij);
+  in.zy1 = make_double2(0.0, 0.0); in.su1 = make_double2(0.0, 0.0);
+  if (NT > 1) { in.zy1 = lds2<16>(ij); in.su1 = lds2<NSL * 16 + 16>(ij); }
+  in.li = 0.0;
+  if (KIND == LPVMPC_PLANNER) in.li = lds(lj);
+}
+template <int KIND>
+__device__ __forceinline__ void update_part1(const Upd<KIND> &u, const int j, const uint32_t ij, const UpdIn &in, const double x1,
+                                             const double xm, const double xp, UpdMid &q) {
+  constexpr int NT = Dims<KIND>::NT;
+  q.xo = in.xo; q.rr = in.rr; q.xs = in.xs; q.cr = in.cr;
+  double m = in.dg * x1;
+  m = fma(in.pm, xm, m);
+  q.m = fma(in.pp, xp, m);
+  double rt = u.rho, ri = u.rinv;
+  if (KIND == LPVMPC_PLANNER) {
+    const bool eq = (u.eqm >> j) & 1ull, lo = (u.loosem >> j) & 1ull;
+    rt = eq ? u.rho_eq : (lo ? kRhoMin : u.rho);
+    ri = eq ? u.rinv_eq : (lo ? 1.0 / kRhoMin : u.rinv);
   }
+  double sold, snew;
+  {
+    sold = in.su0.x * fma(rt, in.zy0.x, -in.zy0.y);
+    const double zr = fma(u.alpha, in.su0.x * x1, u.oma * in.zy0.x);
+    double zn = fma(ri, in.zy0.y, zr);
+    if (KIND == LPVMPC_PLANNER) zn = (zn > in.li) ? zn : in.li;
+    // controller rows: the lower bound is -OSQP_INFTY (times the row scaling): below any iterate, no clamp needed
+    zn = (zn < in.su0.y) ? zn : in.su0.y;
+    const double yn = fma(rt, zr - zn, in.zy0.y);
+    if (u.live) sts2(ij, zn, yn);
+    snew = in.su0.x * fma(rt, zn, -yn);
+  }
+  if (NT > 1) {
+    sold = fma(in.su1.x, fma(rt, in.zy1.x, -in.zy1.y), sold);
+    const double zr = fma(u.alpha, in.su1.x * x1, u.oma * in.zy1.x);
+    double zn = fma(ri, in.zy1.y, zr);
+    zn = (zn < in.su1.y) ? zn : in.su1.y;
+    const double yn = fma(rt, zr - zn, in.zy1.y);
+    if (u.live) sts2<16>(ij, zn, yn);
+    snew = fma(in.su1.x, fma(rt, zn, -yn), snew);
+  }
+  q.sold = sold; q.snew = snew;
+}
+template <int KIND>
+__device__ __forceinline__ void update_part2(const Upd<KIND> &u, const uint32_t vj, const double x1, const UpdMid &q) {
+  const double hh = fma(u.sigma, q.xo, q.rr) + q.sold;            // the right-hand side this x~ was solved for
+  const double rn = fma(-u.alpha, hh - q.m, fma(u.cc, q.cr, q.rr));
+  const double xn = fma(u.alpha, x1, u.oma * q.xo);
+  if (u.live) sts<64>(vj, xn);
+  sts<128>(vj, rn);
+  sts<192>(vj, q.xs + x1);
+  sts(vj, fma(u.sigma, xn, rn) + q.snew);
 }
 
 // backward sweep fused with the element-wise update of stage k+1 (hot)
 template <int KIND>
 __device__ __forceinline__ void sweep_bwd_admm(const Hot<KIND> &h, const Upd<KIND> &u, uint32_t &gsel) {
-  constexpr int ISB = Dims<KIND>::IS * 8;
   const int N = u.N;
   double gn[8];
-  uint32_t vb = h.v + N * VB, ib = h.ib + N * ISB, il = h.il + N * ISB, pb = h.pm + N * ISB;
+  uint32_t vb = h.v + N * VB, ib = h.ib + N * h.istr, il = h.il + N * h.istr, pb = h.pm + N * h.pstr, pb2 = h.pm2 + N * h.pstr;
   uint32_t k0 = h.kc[0] + N * TKB, k1 = h.kc[1] + N * TKB, k2 = h.kc[2] + N * TKB, k3 = h.kc[3] + N * TKB;
   double x1 = lds(vb), x2 = 0.0;   // stage N: x~_N = W_N
   sts(h.gpub ^ gsel, x1);
   gather_in(h.ggat, gsel, gn);
 #pragma unroll 1
   for (int k = N - 1; k >= 0; --k) {
+    UpdIn in;
+    update_loads<KIND>(vb, ib, il, pb, pb2, in);   // stage k+1, independent of the chain below
     k0 -= TKB; k1 -= TKB; k2 -= TKB; k3 -= TKB;
     const double xt = bwd_step(k0, k1, k2, k3, vb - VB, h.gpub, h.ggat, gsel, gn);
-    update_stage<KIND>(u, k + 1, vb, ib, il, pb, x1, xt, x2);   // stage k+1: independent of the chain, fills its latency
+    UpdMid q;
+    update_part1<KIND>(u, k + 1, ib, in, x1, xt, x2, q);   // fills the publish -> gather latency
     gather_in(h.ggat, gsel, gn);
-    vb -= VB; ib -= ISB; il -= ISB; pb -= ISB;
+    update_part2<KIND>(u, vb, x1, q);
+    vb -= VB; ib -= h.istr; il -= h.istr; pb -= h.pstr; pb2 -= h.pstr;
     x2 = x1; x1 = xt;
   }
-  update_stage<KIND>(u, 0, vb, ib, il, pb, x1, 0.0, x2);
+  {
+    UpdIn in;
+    update_loads<KIND>(vb, ib, il, pb, pb2, in);
+    UpdMid q;
+    update_part1<KIND>(u, 0, ib, in, x1, 0.0, x2, q);
+    update_part2<KIND>(u, vb, x1, q);
+  }
   __syncwarp();
 }
 
@@ -701,6 +744,8 @@ __device__ __noinline__ bool primal_infeasible(const Ctx<KIND> c, const Info *ip
   nrm = gmax(nrm);
   lhs = gsum(lhs);
   __syncwarp();
+  // the product with A' is only needed when the first two conditions of the certificate hold for some group
+  if (!__any_sync(kFull, (nrm > eps) && (lhs < -eps * nrm))) return false;
   double mx = 0.0;
 #pragma unroll 1
   for (int k = 0; k <= N; ++k) {
@@ -735,6 +780,8 @@ __device__ __noinline__ bool dual_infeasible(const Ctx<KIND> c, const Info *ip, 
   nrm = gmax(nrm); qdx = gsum(qdx);
   __syncwarp();
   const double cs = unscale ? ip->csc : 1.0;
+  // the products with P and A are only needed when the first two conditions of the certificate hold for some group
+  if (!__any_sync(kFull, (nrm > eps) && (qdx < -cs * eps * nrm))) return false;
   double mx = 0.0;
   int viol = 0;
 #pragma unroll 1
@@ -814,6 +861,7 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
   const lpvmpc_settings &St = p.S;
   double *S = c.S;
   const int nx = NX * (N + 1), nz = nx + 2 * N, NS8 = (N + 1) * 8;
+  (void)nx;
   const int ucomp = r - NX;
   int sched_err = 0, data_err = 0;
   double x0r = 0.0;
@@ -821,7 +869,6 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
   double *sD = S + L.TK, *sE = sD + NS8, *sEI = sE + NS8, *sDt = sEI + NS8, *sEt = sDt + NS8, *sEti = sEt + NS8;
   double *sPD = sEti + NS8, *sPO = sPD + NS8;
   double *Gs = sPO + NS8;
-  double *scr = Gs + N * GS;
   // ---- schedule: G_k = -[A_k B_k] (unscaled), my row
   if (a.sched_mode == LPVMPC_SCHED_GIVEN) {
 #pragma unroll 1
@@ -943,6 +990,19 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
       sD[o] = 1.0; sE[o] = 1.0; sEI[o] = 1.0; sEti[o] = 1.0;
       X[ov] = 0.0; BV[ov] = 0.0;
     }
+    // every single-variable-row slot starts as a dummy row; block N+1 and the dummy area are all dummies
+    {
+      constexpr int NSLc = Ctx<KIND>::NSL, OLIc = Ctx<KIND>::OLI, OPMc = Ctx<KIND>::OPM;
+#pragma unroll 1
+      for (int k = 0; k <= N + 1; ++k) {
+        double *ibk = c.Ib(k);
+        if (r < NSLc) {
+          ibk[r * 2] = 0.0; ibk[r * 2 + 1] = 0.0; ibk[NSLc * 2 + r * 2] = 0.0; ibk[NSLc * 2 + r * 2 + 1] = kInfty * kInfty;
+          if (KIND == LPVMPC_PLANNER) ibk[OLIc + r] = -kInfty * kInfty;
+        }
+        if (r < 2) ibk[OPMc + r] = 0.0;
+      }
+    }
     __syncwarp();
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
@@ -998,17 +1058,17 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
           qa = absmax(qa, c.si(k, t));
-          sEti[c.ci(k, t)] = 1.0 / sqrt(limit_scaling(fabs(c.si(k, t))));
+          sEti[c.ci(k, t)] = frsqrt(limit_scaling(fabs(c.si(k, t))));
         }
       }
-      sDt[o] = 1.0 / sqrt(limit_scaling(pa > qa ? pa : qa));
+      sDt[o] = frsqrt(limit_scaling(pa > qa ? pa : qa));
       double ea = c.xl ? fabs(ED[ov]) : 0.0;
       if (k > 0 && c.xl) {
         const double *gp = Gs + (k - 1) * GS + r * 8;
 #pragma unroll
         for (int j = 0; j < 4; ++j) { const double2 e = ld2(gp + 2 * j); ea = absmax(ea, e.x); ea = absmax(ea, e.y); }
       }
-      sEt[o] = 1.0 / sqrt(limit_scaling(ea));
+      sEt[o] = frsqrt(limit_scaling(ea));
     }
     __syncwarp();
 #pragma unroll 1
@@ -1036,8 +1096,8 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
       sE[o] = sE[o] * sEt[o];
     }
     __syncwarp();
-    // cost scaling: mean of the column norms of P in the reference variable order
-    double qn = 0.0;
+    // cost scaling: mean of the column norms of P (summed per lane, then across the group)
+    double qn = 0.0, ct = 0.0;
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
       const int o = k * 8 + r;
@@ -1046,20 +1106,14 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
         if (k < N - 1) pa = absmax(pa, sPO[o]);
         if (k > 0 && k < N) pa = absmax(pa, sPO[o - 8]);
       }
-      if (c.xl) scr[k * NX + r] = pa;
-      else if (c.ul && k < N) scr[nx + k * 2 + ucomp] = pa;
-      if (c.var_live(k)) qn = absmax(qn, QV[k * VS + r]);
+      if (c.var_live(k)) { ct += pa; qn = absmax(qn, QV[k * VS + r]); }
     }
     qn = gmax(qn);
-    __syncwarp();
-    double ct = 0.0;
-#pragma unroll 2
-    for (int j = 0; j < nz; ++j) ct += scr[j];
-    ct = ct / nz;
+    ct = gsum(ct) / nz;
     qn = limit_scaling(qn);
     ct = ct > qn ? ct : qn;
     ct = limit_scaling(ct);
-    ct = 1.0 / ct;
+    ct = frcp(ct);
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) { const int o = k * 8 + r; sPD[o] *= ct; QV[k * VS + r] *= ct; sPO[o] *= ct; }
     csc *= ct;
@@ -1118,7 +1172,11 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
 }
 
 // ---------------------------------------------------------------- polish (cold, once per QP)
-// Works on the slab (C_PX, C_PYD, C_PYI); on success the polished (x, z, y) replace the iterate.
+// Reduced KKT system of the active rows solved in condensed form (row weights 1/delta) with iterative refinement.
+// The work vectors sit in the stage vectors ADMM no longer needs (x -> R, y_dyn -> XS, r2_dyn -> DG); on success the
+// polished (x, z, y) replace the iterate.  Each refinement step is two passes over the stages around one solve:
+//   rhs = -q - P x - A_red'(y - r2 / delta)                                  (one product with the columns of G)
+//   dx  = S^-1 rhs;  A dx gives dy = (A dx - r2) / delta and r2 <- r2 - A dx   (one product with the rows of G)
 template <int KIND>
 __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const lpvmpc_settings &St, Info *ip, const bool do_pol, uint32_t gsel) {
   constexpr int NT = Ctx<KIND>::NT, NX = Ctx<KIND>::NX;
@@ -1126,10 +1184,10 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
   const bool unscale = I.unscale;
   const int N = c.N, r = c.r;
   double *X = c.V(V_X), *BV = c.V(V_B);
+  double *PX = c.V(V_R), *PYD = c.V(V_XS), *R2D = c.V(V_DG);       // [k*VS + q]
   double *YD = c.cd(C_YD);
   const double *BE = c.cd(C_BE), *ED = c.cd(C_ED), *QV = c.cd(C_Q);
-  double *PX = c.cd(C_PX), *PYD = c.cd(C_PYD), *PYI = c.cd(C_PYI), *R2D = c.cd(C_R2D), *R2I = c.cd(C_R2I);
-  double *ACTD = c.cd(C_ACTD), *ACTI = c.cd(C_ACTI), *ZT = c.cd(C_ZT);
+  double *PYI = c.cd(C_PYI), *R2I = c.cd(C_R2I), *ACTD = c.cd(C_ACTD), *ACTI = c.cd(C_ACTI);
   const double *PD = c.cd(C_PD), *PO = c.cd(C_PO), *EINV = c.cd(C_EINV), *EIINV = c.cd(C_EIINV), *DINV = c.cd(C_DINV);
   const double delta = St.delta, idel = 1.0 / St.delta;
   // active-set guess (form_Ared): 1 = lower, 2 = upper, 3 = both
@@ -1155,85 +1213,102 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
   FW fw; fw.polish = 1; fw.rho = 0.0; fw.rho_eq = 0.0; fw.idel = idel;
   factor<KIND>(c, fw, delta);
   auto bred_i = [&](int k, int t) { const double a = ACTI[c.ci(k, t)]; return (a == 1.0 || a == 3.0) ? c.lo_of(k, t) : c.ui(k, t); };
-  // first solve: rhs = -q + A_red'(b_red / delta); targets go through R2D / R2I
+  // first solve: rhs = -q + A_red'(b_red / delta); the targets go through R2D / R2I
 #pragma unroll 1
   for (int k = 0; k <= N; ++k) {
     const int o = k * 8 + r;
-    R2D[o] = (c.xl && ACTD[o] != 0.0) ? idel * BE[o] : 0.0;
+    R2D[k * VS + r] = (c.xl && ACTD[o] != 0.0) ? idel * BE[o] : 0.0;
     if (c.has_in(k)) {
 #pragma unroll
       for (int t = 0; t < NT; ++t) R2I[c.ci(k, t)] = (ACTI[c.ci(k, t)] != 0.0) ? idel * bred_i(k, t) : 0.0;
     }
   }
   __syncwarp();
+  // (A' t)_(k, r) with t_dyn = R2D-like array stored [k*VS + q] and t_in from the slab array ti
+  auto colAt = [&](const double *td, const double *ti, int k) {
+    double acc = c.xl ? ED[k * 8 + r] * td[k * VS + r] : 0.0;
+    if (k < N) {
+      double g[8];
+#pragma unroll
+      for (int rr = 0; rr < 8; ++rr) g[rr] = (rr < NX) ? td[(k + 1) * VS + rr] : 0.0;
+      acc += pcoldot<NX>(c.Gb(k), r, g);
+    }
+    if (c.has_in(k)) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) acc = fma(c.si(k, t), ti[c.ci(k, t)], acc);
+    }
+    return acc;
+  };
 #pragma unroll 1
-  for (int k = 0; k <= N; ++k) BV[k * VS + r] = c.var_live(k) ? (-QV[k * 8 + r] + colA<KIND>(c, ED, R2D, R2I, false, k)) : 0.0;
+  for (int k = 0; k <= N; ++k) BV[k * VS + r] = c.var_live(k) ? (-QV[k * 8 + r] + colAt(R2D, R2I, k)) : 0.0;
   __syncwarp();
   sweep_fwd<KIND>(h, N, gsel);
   sweep_bwd_plain<KIND>(h, N, gsel);
+  // x, y = (A x - b) / delta, r2 = b - A x on the active rows
 #pragma unroll 1
   for (int k = 0; k <= N; ++k) {
-    const int o = k * 8 + r;
-    const double xk = BV[k * VS + r];
-    PX[o] = xk;
-    PYD[o] = (c.xl && ACTD[o] != 0.0) ? (rowA_dyn<KIND>(c, ED, BV, VS, k) - BE[o]) * idel : 0.0;
+    const int o = k * 8 + r, ov = k * VS + r;
+    const double xk = BV[ov];
+    PX[ov] = xk;
+    const bool ad = c.xl && ACTD[o] != 0.0;
+    const double res = ad ? (BE[o] - rowA_dyn<KIND>(c, ED, BV, VS, k)) : 0.0;
+    R2D[ov] = res;
+    PYD[ov] = -res * idel;
     if (c.has_in(k)) {
 #pragma unroll
-      for (int t = 0; t < NT; ++t) PYI[c.ci(k, t)] = (ACTI[c.ci(k, t)] != 0.0) ? (c.si(k, t) * xk - bred_i(k, t)) * idel : 0.0;
+      for (int t = 0; t < NT; ++t) {
+        const int oc = c.ci(k, t);
+        const double ri = (ACTI[oc] != 0.0) ? (bred_i(k, t) - c.si(k, t) * xk) : 0.0;
+        R2I[oc] = ri; PYI[oc] = -ri * idel;
+      }
     }
   }
   __syncwarp();
 #pragma unroll 1
   for (int it = 0; it < St.polish_refine_iter + kPolishExtraRefine; ++it) {
-    // residual of the un-regularised reduced KKT: r2 on the active rows
+    // rhs = -q - P x - A'(y - r2 / delta)
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
-      const int o = k * 8 + r;
-      R2D[o] = (c.xl && ACTD[o] != 0.0) ? (BE[o] - rowA_dyn<KIND>(c, ED, PX, 8, k)) : 0.0;
-      if (c.has_in(k)) {
-#pragma unroll
-        for (int t = 0; t < NT; ++t) R2I[c.ci(k, t)] = (ACTI[c.ci(k, t)] != 0.0) ? (bred_i(k, t) - c.si(k, t) * PX[o]) : 0.0;
-      }
-    }
-    __syncwarp();
-#pragma unroll 1
-    for (int k = 0; k <= N; ++k) {
-      const int o = k * 8 + r;
+      const int o = k * 8 + r, ov = k * VS + r;
       double b = 0.0;
       if (c.var_live(k)) {
-        const double Px = rowP<KIND>(c, PD, PO, PX, 8, k), Aty = colA<KIND>(c, ED, PYD, PYI, false, k);
-        // A'(r2 / delta): same column product on scaled entries
-        double at = c.xl ? ED[o] * (idel * R2D[o]) : 0.0;
+        const double Px = rowP<KIND>(c, PD, PO, PX, VS, k);
+        double acc = c.xl ? ED[o] * fma(-idel, R2D[ov], PYD[ov]) : 0.0;
         if (k < N) {
           double g[8];
 #pragma unroll
-          for (int rr = 0; rr < 8; ++rr) g[rr] = (rr < NX) ? idel * R2D[(k + 1) * 8 + rr] : 0.0;
-          at += pcoldot<NX>(c.Gb(k), r, g);
+          for (int rr = 0; rr < 8; ++rr) g[rr] = (rr < NX) ? fma(-idel, R2D[(k + 1) * VS + rr], PYD[(k + 1) * VS + rr]) : 0.0;
+          acc += pcoldot<NX>(c.Gb(k), r, g);
         }
         if (c.has_in(k)) {
 #pragma unroll
-          for (int t = 0; t < NT; ++t) at = fma(c.si(k, t), idel * R2I[c.ci(k, t)], at);
+          for (int t = 0; t < NT; ++t) { const int oc = c.ci(k, t); acc = fma(c.si(k, t), fma(-idel, R2I[oc], PYI[oc]), acc); }
         }
-        b = ((-QV[o] - Px) - Aty) + at;
+        b = (-QV[o] - Px) - acc;
       }
-      BV[k * VS + r] = b;
+      BV[ov] = b;
     }
     __syncwarp();
     sweep_fwd<KIND>(h, N, gsel);
     sweep_bwd_plain<KIND>(h, N, gsel);
-#pragma unroll 1
-    for (int k = 0; k <= N; ++k) { if (c.xl) ZT[k * 8 + r] = rowA_dyn<KIND>(c, ED, BV, VS, k); }   // z~ = A_dyn dx
-    __syncwarp();
+    // dy = (A dx - r2) / delta, r2 <- r2 - A dx, x <- x + dx
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
-      const int o = k * 8 + r;
-      const double dx = BV[k * VS + r];
-      if (c.xl && ACTD[o] != 0.0) PYD[o] += (ZT[o] - R2D[o]) * idel;
+      const int o = k * 8 + r, ov = k * VS + r;
+      const double dx = BV[ov];
+      if (c.xl && ACTD[o] != 0.0) {
+        const double z = rowA_dyn<KIND>(c, ED, BV, VS, k), r2 = R2D[ov];
+        PYD[ov] += (z - r2) * idel;
+        R2D[ov] = r2 - z;
+      }
       if (c.has_in(k)) {
 #pragma unroll
-        for (int t = 0; t < NT; ++t) { const int oc = c.ci(k, t); if (ACTI[oc] != 0.0) PYI[oc] += (c.si(k, t) * dx - R2I[oc]) * idel; }
+        for (int t = 0; t < NT; ++t) {
+          const int oc = c.ci(k, t);
+          if (ACTI[oc] != 0.0) { const double z = c.si(k, t) * dx, r2 = R2I[oc]; PYI[oc] += (z - r2) * idel; R2I[oc] = r2 - z; }
+        }
       }
-      PX[o] += dx;
+      PX[ov] += dx;
     }
     __syncwarp();
   }
@@ -1241,18 +1316,18 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
   double a_rp = 0, a_rd = 0;
 #pragma unroll 1
   for (int k = 0; k <= N; ++k) {
-    const int o = k * 8 + r;
+    const int o = k * 8 + r, ov = k * VS + r;
     if (c.xl) {
-      const double Ax = rowA_dyn<KIND>(c, ED, PX, 8, k), t = Ax + PYD[o];
-      PYD[o] = t - BE[o];
+      const double Ax = rowA_dyn<KIND>(c, ED, PX, VS, k), t = Ax + PYD[ov];
+      PYD[ov] = t - BE[o];
       const double rr = Ax - BE[o];
       a_rp = absmax(a_rp, unscale ? EINV[o] * rr : rr);
-    } else PYD[o] = 0.0;
+    } else PYD[ov] = 0.0;
     if (c.has_in(k)) {
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
         const int oc = c.ci(k, t);
-        const double ax = c.si(k, t) * PX[o], tt = ax + PYI[oc];
+        const double ax = c.si(k, t) * PX[ov], tt = ax + PYI[oc];
         const double zc = clampd(tt, c.lo_of(k, t), c.ui(k, t));
         R2I[oc] = zc; PYI[oc] = tt - zc;
         const double rr = ax - zc;
@@ -1265,12 +1340,12 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
   for (int k = 0; k <= N; ++k) {
     const int o = k * 8 + r;
     if (c.var_live(k)) {
-      const double rr = (QV[o] + rowP<KIND>(c, PD, PO, PX, 8, k)) + colA<KIND>(c, ED, PYD, PYI, false, k);
+      const double rr = (QV[o] + rowP<KIND>(c, PD, PO, PX, VS, k)) + colAt(PYD, PYI, k);
       a_rd = absmax(a_rd, unscale ? DINV[o] * rr : rr);
     }
   }
   const double pol_pri = gmax(a_rp), pol_dua = (unscale ? I.cinv : 1.0) * gmax(a_rd);
-  const double pol_obj = objective<KIND>(c, PX, 8, St.scaling ? I.cinv : 1.0);
+  const double pol_obj = objective<KIND>(c, PX, VS, St.scaling ? I.cinv : 1.0);
   const bool ok = (pol_pri < I.pri_res && pol_dua < I.dua_res) || (pol_pri < I.pri_res && I.dua_res < 1e-10) ||
                   (pol_dua < I.dua_res && I.pri_res < 1e-10);
   if (!do_pol) return 0;
@@ -1278,8 +1353,8 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
   I.obj = pol_obj; I.pri_res = pol_pri; I.dua_res = pol_dua;
 #pragma unroll 1
   for (int k = 0; k <= N; ++k) {
-    const int o = k * 8 + r;
-    X[k * VS + r] = PX[o]; YD[o] = PYD[o];
+    const int o = k * 8 + r, ov = k * VS + r;
+    X[ov] = PX[ov]; YD[o] = PYD[ov];
     if (c.has_in(k)) {
 #pragma unroll
       for (int t = 0; t < NT; ++t) { c.zi(k, t) = R2I[c.ci(k, t)]; c.yi(k, t) = PYI[c.ci(k, t)]; }
@@ -1343,9 +1418,15 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
         h.kc[q] = sq + (uint32_t)(L.TK + 64 + (2 * q) * 8 + c.co[q]) * 8u;
       }
       h.v = sq + (uint32_t)(L.V + r) * 8u;
-      h.ib = sq + (uint32_t)(L.I + c.islot * 2) * 8u;
-      h.il = sq + (uint32_t)(L.I + OLI + c.islot) * 8u;
-      h.pm = sq + (uint32_t)(L.I + OPM + (c.ul ? ucomp : 0)) * 8u;
+      constexpr int ISBk = Ctx<KIND>::IS * 8;
+      const bool rows = (KIND == LPVMPC_CONTROLLER) ? (r == 0 || c.ul) : (c.xl || c.ul);
+      const uint32_t dm = sq + (uint32_t)(L.I + (N + 1) * Ctx<KIND>::IS) * 8u;   // block N+1: dummy rows, zero coupling
+      h.ib = rows ? sq + (uint32_t)(L.I + c.islot * 2) * 8u : dm;
+      h.il = rows ? sq + (uint32_t)(L.I + OLI + c.islot) * 8u : dm + (uint32_t)OLI * 8u;
+      h.istr = rows ? (uint32_t)ISBk : 0u;
+      h.pm = c.ul ? sq + (uint32_t)(L.I + OPM + ucomp) * 8u : dm + (uint32_t)OPM * 8u;
+      h.pm2 = c.ul ? h.pm + (uint32_t)ISBk : h.pm;
+      h.pstr = c.ul ? (uint32_t)ISBk : 0u;
       h.gpub = gbuf + (uint32_t)(64 * (r >> 1) + 16 * g + 8 * (r & 1));
       h.ggat = gbuf + (uint32_t)(16 * g);
     }
@@ -1381,8 +1462,7 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
     const int ct = S.check_termination, ai = S.adaptive_rho ? adapt_interval : 0;
 
     Upd<KIND> u;
-    u.sigma = sigma; u.alpha = alpha; u.oma = 1.0 - alpha; u.eqm = c.eqm; u.loosem = c.loosem; u.xl = c.xl; u.ul = c.ul; u.N = N;
-    u.inl = (KIND == LPVMPC_CONTROLLER) ? (r == 0 || c.ul) : (c.xl || c.ul);
+    u.sigma = sigma; u.alpha = alpha; u.oma = 1.0 - alpha; u.eqm = c.eqm; u.loosem = c.loosem; u.N = N;
     int iter = 0, nsync = 0, first_in = 0;   // steps since the last y_dyn sync; whether step 0 is among them
     double rho_eq_last = rho_eq;             // rho_eq of the last executed step (delta_y of the certificates)
     bool checked_last = false;

@@ -457,23 +457,29 @@ struct Upd {
   int N;
 };
 struct UpdMid { double xo, rr, xs, cr, m, sold, snew; };
+struct UpdIn { double xo, rr, xs, cr, dg, pm, pp, li; double2 zy0, su0, zy1, su1; };
 
+// operands of the update of stage j: issued ahead of the sweep's dependent chain so that they arrive behind it
 template <int KIND>
-__device__ __forceinline__ void update_part1(const Upd<KIND> &u, const int j, const uint32_t vj, const uint32_t ij, const uint32_t lj,
-                                             const uint32_t pj, const uint32_t pj2, const double x1, const double xm, const double xp,
-                                             UpdMid &q) {
+__device__ __forceinline__ void update_loads(const uint32_t vj, const uint32_t ij, const uint32_t lj, const uint32_t pj, const uint32_t pj2,
+                                             UpdIn &in) {
   constexpr int NT = Dims<KIND>::NT, NSL = Dims<KIND>::NSL;
-  q.xo = lds<64>(vj); q.rr = lds<128>(vj); q.xs = lds<192>(vj); q.cr = lds<320>(vj);
-  const double dg = lds<256>(vj);
-  const double pm = lds(pj), pp = lds(pj2);
-  const double2 zy0 = lds2(ij), su0 = lds2<NSL * 16>(ij);
-  double2 zy1 = make_double2(0.0, 0.0), su1 = make_double2(0.0, 0.0);
-  if (NT > 1) { zy1 = lds2<16>(ij); su1 = lds2<NSL * 16 + 16>(ij); }
-  double li = 0.0;
-  if (KIND == LPVMPC_PLANNER) li = lds(lj);
-  double m = dg * x1;
-  m = fma(pm, xm, m);
-  q.m = fma(pp, xp, m);
+  in.xo = lds<64>(vj); in.rr = lds<128>(vj); in.xs = lds<192>(vj); in.dg = lds<256>(vj); in.cr = lds<320>(vj);
+  in.pm = lds(pj); in.pp = lds(pj2);
+  in.zy0 = lds2(ij); in.su0 = lds2<NSL * 16>(ij);
+  in.zy1 = make_double2(0.0, 0.0); in.su1 = make_double2(0.0, 0.0);
+  if (NT > 1) { in.zy1 = lds2<16>(ij); in.su1 = lds2<NSL * 16 + 16>(ij); }
+  in.li = 0.0;
+  if (KIND == LPVMPC_PLANNER) in.li = lds(lj);
+}
+template <int KIND>
+__device__ __forceinline__ void update_part1(const Upd<KIND> &u, const int j, const uint32_t ij, const UpdIn &in, const double x1,
+                                             const double xm, const double xp, UpdMid &q) {
+  constexpr int NT = Dims<KIND>::NT;
+  q.xo = in.xo; q.rr = in.rr; q.xs = in.xs; q.cr = in.cr;
+  double m = in.dg * x1;
+  m = fma(in.pm, xm, m);
+  q.m = fma(in.pp, xp, m);
   double rt = u.rho, ri = u.rinv;
   if (KIND == LPVMPC_PLANNER) {
     const bool eq = (u.eqm >> j) & 1ull, lo = (u.loosem >> j) & 1ull;
@@ -482,24 +488,24 @@ __device__ __forceinline__ void update_part1(const Upd<KIND> &u, const int j, co
   }
   double sold, snew;
   {
-    sold = su0.x * fma(rt, zy0.x, -zy0.y);
-    const double zr = fma(u.alpha, su0.x * x1, u.oma * zy0.x);
-    double zn = fma(ri, zy0.y, zr);
-    if (KIND == LPVMPC_PLANNER) zn = (zn > li) ? zn : li;
+    sold = in.su0.x * fma(rt, in.zy0.x, -in.zy0.y);
+    const double zr = fma(u.alpha, in.su0.x * x1, u.oma * in.zy0.x);
+    double zn = fma(ri, in.zy0.y, zr);
+    if (KIND == LPVMPC_PLANNER) zn = (zn > in.li) ? zn : in.li;
     // controller rows: the lower bound is -OSQP_INFTY (times the row scaling): below any iterate, no clamp needed
-    zn = (zn < su0.y) ? zn : su0.y;
-    const double yn = fma(rt, zr - zn, zy0.y);
+    zn = (zn < in.su0.y) ? zn : in.su0.y;
+    const double yn = fma(rt, zr - zn, in.zy0.y);
     if (u.live) sts2(ij, zn, yn);
-    snew = su0.x * fma(rt, zn, -yn);
+    snew = in.su0.x * fma(rt, zn, -yn);
   }
   if (NT > 1) {
-    sold = fma(su1.x, fma(rt, zy1.x, -zy1.y), sold);
-    const double zr = fma(u.alpha, su1.x * x1, u.oma * zy1.x);
-    double zn = fma(ri, zy1.y, zr);
-    zn = (zn < su1.y) ? zn : su1.y;
-    const double yn = fma(rt, zr - zn, zy1.y);
+    sold = fma(in.su1.x, fma(rt, in.zy1.x, -in.zy1.y), sold);
+    const double zr = fma(u.alpha, in.su1.x * x1, u.oma * in.zy1.x);
+    double zn = fma(ri, in.zy1.y, zr);
+    zn = (zn < in.su1.y) ? zn : in.su1.y;
+    const double yn = fma(rt, zr - zn, in.zy1.y);
     if (u.live) sts2<16>(ij, zn, yn);
-    snew = fma(su1.x, fma(rt, zn, -yn), snew);
+    snew = fma(in.su1.x, fma(rt, zn, -yn), snew);
   }
   q.sold = sold; q.snew = snew;
 }
@@ -528,6 +534,8 @@ __device__ __forceinline__ void sweep_bwd_admm(const Hot<KIND> &h, const Upd<KIN
   gather_in(h.ggat, gsel, gn);
 #pragma unroll 1
   for (int k = N - 1; k >= 0; --k) {
+    UpdIn in;
+    update_loads<KIND>(vb, ib, il, pb, pb2, in);   // stage k+1, independent of the chain below
     const double w = lds(vb - VB);
     tm_wait_ld();
     const double xt = bwd_step(e, w, gn);
@@ -535,7 +543,7 @@ __device__ __forceinline__ void sweep_bwd_admm(const Hot<KIND> &h, const Upd<KIN
     tc -= 16;
     tm_ld8(k > 0 ? tc : h.tKc, e);   // column of K_k for the next stage (k = 0: dummy request, keeps the code converged)
     UpdMid q;
-    update_part1<KIND>(u, k + 1, vb, ib, il, pb, pb2, x1, xt, x2, q);   // stage k+1: independent of the chain, fills its latency
+    update_part1<KIND>(u, k + 1, ib, in, x1, xt, x2, q);   // fills the publish -> gather latency
     gather_in(h.ggat, gsel, gn);
     update_part2<KIND>(u, vb, x1, q);
     vb -= VB; ib -= h.istr; il -= h.istr; pb -= h.pstr; pb2 -= h.pstr;
@@ -543,8 +551,10 @@ __device__ __forceinline__ void sweep_bwd_admm(const Hot<KIND> &h, const Upd<KIN
   }
   tm_wait_ld();
   {
+    UpdIn in;
+    update_loads<KIND>(vb, ib, il, pb, pb2, in);
     UpdMid q;
-    update_part1<KIND>(u, 0, vb, ib, il, pb, pb2, x1, 0.0, x2, q);
+    update_part1<KIND>(u, 0, ib, in, x1, 0.0, x2, q);
     update_part2<KIND>(u, vb, x1, q);
   }
   __syncwarp();
@@ -770,6 +780,8 @@ __device__ __noinline__ bool primal_infeasible(const Ctx<KIND> c, const Info *ip
   nrm = gmax(nrm);
   lhs = gsum(lhs);
   __syncwarp();
+  // the product with A' is only needed when the first two conditions of the certificate hold for some group
+  if (!__any_sync(kFull, (nrm > eps) && (lhs < -eps * nrm))) return false;
   double mx = 0.0;
 #pragma unroll 1
   for (int k = 0; k <= N; ++k) {
@@ -804,6 +816,8 @@ __device__ __noinline__ bool dual_infeasible(const Ctx<KIND> c, const Info *ip, 
   nrm = gmax(nrm); qdx = gsum(qdx);
   __syncwarp();
   const double cs = unscale ? ip->csc : 1.0;
+  // the products with P and A are only needed when the first two conditions of the certificate hold for some group
+  if (!__any_sync(kFull, (nrm > eps) && (qdx < -cs * eps * nrm))) return false;
   double mx = 0.0;
   int viol = 0;
 #pragma unroll 1

@@ -276,7 +276,7 @@ lpv::h8::Lay make_h8_layout(int kind, int N) {
   auto take = [&](int n) { const int r = o; o += (n + 1) & ~1; return r; };
   L.TK = take((N + 1) * lpv::h8::TKS - 64);
   L.V = take((N + 1) * lpv::h8::VS);
-  L.I = take((N + 1) * L.is);
+  L.I = take((N + 2) * L.is);
   while (o % 16 != 8) o += 2;  // neighbouring groups of a warp 64 B apart mod 128
   L.total = o;
   const int v = (N + 1) * 8;
