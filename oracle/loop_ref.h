@@ -1,0 +1,56 @@
+/* TEST INFRASTRUCTURE — CPU restatement of the closed-loop tick around the controller QP (see loop_ref.c).
+ * Never linked into the product library. */
+#ifndef LOOP_REF_H
+#define LOOP_REF_H
+
+#include "lpv_ref.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* status codes the loop adds to OSQP's */
+#define LOOP_REF_SCHEDULE_ERROR (-20)
+#define LOOP_REF_OFF_TRACK (-22)
+
+typedef struct {
+  double sim_dt;       /* simulator/dt, MAIN_LAUNCH.launch:60 */
+  int substeps;        /* Simulator.f steps per controller tick */
+  int warmup_ticks;    /* ticks linearised around predicted_vectors_generation (controllerMain.py:310-320) */
+  int swap_ey_epsi;    /* 1: controllerMain.py:188 slot assignment (ey -> epsi slot, epsi -> ey slot) */
+  int reserved;
+  double vel_ref;      /* controllerMain.py:326 */
+  double Cf_new;       /* controllerMain.py:77 */
+  double half_width;   /* Map.halfWidth */
+  double slack;        /* Map.slack */
+  double sim_mu;       /* simulator/mu, MAIN_LAUNCH.launch:72 */
+} loop_ref_cfg;
+
+/* vehicleSimulator.py:164-199.  st = [x y yaw vx vy psiDot ax ay]; u = [motor, servo] (vehicleSimulator.py:337). */
+void loop_ref_sim_f(double *st, const double *u, const lpv_ref_vehicle *v, double mu, double dt);
+
+/* trackInitialization.py:283-383.  out = [s ey epsi]; returns CompletedFlag (0: the 10000 sentinels). */
+int loop_ref_local_position(const double *track, int nseg, double half_width, double slack, double x, double y,
+                            double psi, double *out);
+
+/* trackInitialization.py:205-260.  out = [x y theta]; returns 1 when no unique segment holds s. */
+int loop_ref_global_position(const double *track, int nseg, double s, double ey, double *out);
+
+/* controllerMain.py:510-553, first N rows: xx [N,6], uu [N,2] */
+void loop_ref_guess(const double *local, int N, double *xx, double *uu);
+
+/* n_ticks closed-loop ticks for B vehicles (OpenMP over vehicles).  Per tick (controllerMain.py:177-454, lap 0):
+ * measure (true state, vx >= 0.01) -> getLocalPosition -> lap logic -> OldSteering/OldAccelera <- cmd ->
+ * warm-up (_EstimateABC around the guess) or LPVPrediction -> solve -> cmd = uPred[0] -> `substeps` x Simulator.f.
+ * Arrays (row-major, updated in place): sim [B,8], cmd [B,2], u_pred [B,N,2], local [B,6],
+ * ctr [B,8] ints = [first_it, lap, half_track, last_status, last_iters, fail_status (0 = alive), fail_tick, ticks_done],
+ * stat [B,4] doubles = [solved ticks, total ADMM iterations, max |ey| (true), tick of the first lap completion or -1].
+ * x_pred [B,N+1,6] optional (last tick).  Returns the number of SOLVED ticks. */
+long loop_ref_run(const lpv_ref_cfg *c, const osqp_ref_settings *st, const loop_ref_cfg *lc, int B, int n_ticks,
+                  double *sim, double *cmd, double *u_pred, double *local, int *ctr, double *stat, double *x_pred,
+                  int threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

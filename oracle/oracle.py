@@ -11,7 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liblpv_oracle.so")
-_SOURCES = ["lpv_ref.c", "osqp_ref.c", "lpv_ref.h", "osqp_ref.h", "Makefile"]
+_SOURCES = ["lpv_ref.c", "osqp_ref.c", "loop_ref.c", "lpv_ref.h", "osqp_ref.h", "loop_ref.h", "Makefile"]
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)
@@ -325,3 +325,72 @@ def plan_batch(cfg, settings, x0, SS, u_prev, u_old, max_ey, ey_lo=None, ey_hi=N
                                       _dp(u_old), _dp(max_ey), _dp(ey_lo), _dp(ey_hi), C.c_int(threads),
                                       _dp(xP), _dp(uP), _ip(status), _ip(iters))
     return dict(xPred=xP, uPred=uP, status=status, iters=iters, solved=solved)
+
+
+# ------------------------------------------------------------------------------------------------
+# closed-loop tick around the controller QP (oracle/loop_ref.c)
+class LoopCfg(C.Structure):
+    _fields_ = [("sim_dt", C.c_double), ("substeps", C.c_int), ("warmup_ticks", C.c_int), ("swap_ey_epsi", C.c_int),
+                ("reserved", C.c_int), ("vel_ref", C.c_double), ("Cf_new", C.c_double), ("half_width", C.c_double),
+                ("slack", C.c_double), ("sim_mu", C.c_double)]
+
+
+def loop_cfg(half_width=0.3, slack=0.45, substeps=7, swap_ey_epsi=1, sim_dt=0.005, warmup_ticks=9, vel_ref=1.0,
+             Cf_new=60.0, sim_mu=0.05):
+    """Launch values: MAIN_LAUNCH.launch:60,72 (simulator dt, mu), controllerMain.py:77,310,326; Map.halfWidth/.slack of
+    the L_shape track (trackInitialization.py:20,53-54)."""
+    lc = LoopCfg()
+    lc.sim_dt, lc.substeps, lc.warmup_ticks, lc.swap_ey_epsi = sim_dt, substeps, warmup_ticks, swap_ey_epsi
+    lc.vel_ref, lc.Cf_new, lc.half_width, lc.slack, lc.sim_mu = vel_ref, Cf_new, half_width, slack, sim_mu
+    return lc
+
+
+def sim_f(state, u, veh=None, mu=0.05, dt=0.005):
+    """One Simulator.f step; state = [x y yaw vx vy psiDot ax ay], u = [motor, servo].  Returns the new state."""
+    v = Vehicle()
+    d = dict(lf=0.125, lr=0.125, m=1.98, Iz=0.03, Cf=60.0, Cr=60.0, mu=0.05)
+    d.update(veh or {})
+    for k, val in d.items():
+        setattr(v, k, float(val))
+    st = _f64(state).copy()
+    uu = _f64(u)
+    lib().loop_ref_sim_f(_dp(st), _dp(uu), C.byref(v), C.c_double(mu), C.c_double(dt))
+    return st
+
+
+def local_position(track, half_width, slack, x, y, psi):
+    tr = _f64(track)
+    out = np.zeros(3)
+    flag = lib().loop_ref_local_position(_dp(tr), C.c_int(tr.shape[0]), C.c_double(half_width), C.c_double(slack),
+                                         C.c_double(x), C.c_double(y), C.c_double(psi), _dp(out))
+    return out[0], out[1], out[2], flag
+
+
+def global_position(track, s, ey):
+    tr = _f64(track)
+    out = np.zeros(3)
+    err = lib().loop_ref_global_position(_dp(tr), C.c_int(tr.shape[0]), C.c_double(s), C.c_double(ey), _dp(out))
+    if err:
+        raise TypeError("no unique track segment holds s")
+    return out[0], out[1], out[2]
+
+
+def loop_state(sim0, N):
+    """Fresh closed-loop state for vehicles with simulator states sim0 [B,8] = [x y yaw vx vy psiDot ax ay]."""
+    sim = _f64(sim0).copy()
+    B = sim.shape[0]
+    ctr = np.zeros((B, 8), dtype=np.int32)
+    ctr[:, 0] = 1                                  # first_it = 1 (controllerMain.py:87)
+    stat = np.zeros((B, 4))
+    stat[:, 3] = -1.0
+    return dict(sim=sim, cmd=np.zeros((B, 2)), u_pred=np.zeros((B, N, 2)), local=np.zeros((B, 6)), ctr=ctr, stat=stat,
+                x_pred=np.zeros((B, N + 1, 6)))
+
+
+def loop_run(cfg, settings, lc, state, n_ticks, threads=1):
+    """Advance `state` (from loop_state) by n_ticks closed-loop ticks in place; returns the number of SOLVED ticks."""
+    lib().loop_ref_run.restype = C.c_long
+    B = state["sim"].shape[0]
+    return lib().loop_ref_run(C.byref(cfg), C.byref(settings), C.byref(lc), C.c_int(B), C.c_int(n_ticks),
+                              _dp(state["sim"]), _dp(state["cmd"]), _dp(state["u_pred"]), _dp(state["local"]),
+                              _ip(state["ctr"]), _dp(state["stat"]), _dp(state["x_pred"]), C.c_int(threads))
