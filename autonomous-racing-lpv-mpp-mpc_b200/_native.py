@@ -12,7 +12,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "liblpvmpc.so")
 _SRC_DIR = os.path.join(_PKG, "csrc")
-_SOURCES = [os.path.join(_SRC_DIR, f) for f in ("lpvmpc.cu", "lpv_qp.cuh", "lpv_t8.cuh", "lpv_g8.cuh", "lpv_h8.cuh", "lpv_h8t.cuh", "lpv_model.cuh")] + \
+_SOURCES = [os.path.join(_SRC_DIR, f) for f in ("lpvmpc.cu", "lpv_qp.cuh", "lpv_t8.cuh", "lpv_g8.cuh", "lpv_h8.cuh", "lpv_h8t.cuh", "lpv_model.cuh", "lpv_loop.cuh")] + \
            [os.path.join(_ROOT, "include", "lpvmpc.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
@@ -25,7 +25,7 @@ SCHED_GIVEN, SCHED_PREDICT, SCHED_ESTIMATE = 0, 1, 2
 STATUS_NAMES = {1: "solved", 2: "solved inaccurate", 3: "primal infeasible inaccurate",
                 4: "dual infeasible inaccurate", -2: "maximum iterations reached", -3: "primal infeasible",
                 -4: "dual infeasible", -7: "problem non convex", -10: "unsolved",
-                -20: "schedule error (Curvature lookup failed)", -21: "data error (l > u)"}
+                -20: "schedule error (Curvature lookup failed)", -21: "data error (l > u)", -22: "off track"}
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -75,9 +75,21 @@ class Args(C.Structure):
                  ("ys", C.c_void_p)])
 
 
+class LoopCfg(C.Structure):
+    _fields_ = [("sim_dt", C.c_double), ("substeps", C.c_int32), ("warmup_ticks", C.c_int32),
+                ("swap_ey_epsi", C.c_int32), ("reserved", C.c_int32), ("vel_ref", C.c_double), ("Cf_new", C.c_double),
+                ("half_width", C.c_double), ("slack", C.c_double), ("sim_mu", C.c_double)]
+
+
+class LoopState(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("sim", "cmd", "u_pred", "x_pred", "local", "stat", "ctr")]
+
+
 EXPORTS = ["lpvmpc_abi_version", "lpvmpc_default_settings", "lpvmpc_device_count", "lpvmpc_create", "lpvmpc_destroy",
            "lpvmpc_last_error", "lpvmpc_get_info", "lpvmpc_update_settings", "lpvmpc_schedule_dev",
-           "lpvmpc_schedule_host", "lpvmpc_solve_dev", "lpvmpc_solve_host"]
+           "lpvmpc_schedule_host", "lpvmpc_solve_dev", "lpvmpc_solve_host", "lpvmpc_loop_default_cfg", "lpvmpc_loop_init_dev",
+           "lpvmpc_loop_init_host", "lpvmpc_loop_run_dev", "lpvmpc_loop_run_host", "lpvmpc_loop_view_dev",
+           "lpvmpc_loop_read_host"]
 
 _lib = None
 
@@ -132,6 +144,14 @@ def lib():
     L.lpvmpc_schedule_host.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Args), C.c_void_p]
     L.lpvmpc_solve_dev.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Args), C.c_void_p]
     L.lpvmpc_solve_host.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Args)]
+    L.lpvmpc_loop_default_cfg.argtypes = [C.POINTER(LoopCfg)]
+    L.lpvmpc_loop_default_cfg.restype = None
+    L.lpvmpc_loop_init_dev.argtypes = [C.c_void_p, C.c_int32, C.POINTER(LoopCfg), C.c_void_p, C.c_void_p]
+    L.lpvmpc_loop_init_host.argtypes = [C.c_void_p, C.c_int32, C.POINTER(LoopCfg), C.c_void_p]
+    L.lpvmpc_loop_run_dev.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    L.lpvmpc_loop_run_host.argtypes = [C.c_void_p, C.c_int32]
+    L.lpvmpc_loop_view_dev.argtypes = [C.c_void_p, C.POINTER(LoopState), C.POINTER(C.c_int32)]
+    L.lpvmpc_loop_read_host.argtypes = [C.c_void_p, C.POINTER(LoopState)]
     if L.lpvmpc_abi_version() != ABI_VERSION:
         raise RuntimeError("liblpvmpc.so ABI version mismatch; rebuild with _native.build(force=True)")
     _lib = L

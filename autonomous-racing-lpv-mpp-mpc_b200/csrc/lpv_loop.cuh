@@ -1,0 +1,228 @@
+// Closed-loop tick around the controller QP, on the device (BASELINE configs[3]: Monte-Carlo fleet).
+//
+// One thread per vehicle does everything of the controller main loop that is NOT the QP: apply the last command to
+// the simulator's vehicle model, localise the car on the track, lap bookkeeping, and write the inputs of the next
+// batched solve (lpv_solve_*_kernel) in the layout lpvmpc_args expects.  Nothing goes back to the host per tick.
+//
+// Mirrors (paths under /root/reference/workspace/src/barc/src):
+//   Simulator.f                   vehicleSimulator.py:164-199 (u = [motor, servo], :337)
+//   Map.getLocalPosition          Utilities/trackInitialization.py:283-383, computeAngle :388-410
+//   predicted_vectors_generation  controllerMain.py:510-553
+//   main loop, lap 0              controllerMain.py:177-192, 252-257, 289-298, 310-331, 381-383
+// Compiled with -fmad=false: every expression keeps the reference's operation order.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "lpvmpc.h"
+#include "lpv_model.cuh"
+
+namespace lpv {
+namespace loop {
+
+constexpr double kPi = 3.141592653589793;
+
+enum { C_FIRST_IT = 0, C_LAP, C_HALF, C_STATUS, C_ITERS, C_FAIL, C_FAIL_TICK, C_TICKS, C_COUNT };
+enum { S_SOLVED = 0, S_ITERS, S_MAX_EY, S_LAP_TICK, S_COUNT };
+
+struct LoopParams {
+  lpvmpc_loop_cfg lc;
+  double lf, lr, m, Iz;
+  const double *track;
+  int nseg;
+  int N, B;
+  // state
+  double *sim;      // [B,8]  x y yaw vx vy psiDot ax ay
+  double *cmd;      // [B,2]  delta a
+  double *u_pred;   // [B,N,2] written by the solve
+  double *local;    // [B,6]  measured state in the controller's slots
+  int *ctr;         // [B,8]
+  double *stat;     // [B,4]
+  const int *status, *iters;  // [B] of the last solve
+  // inputs of the next solve
+  double *x0;       // [B,6]
+  double *u_prev;   // [B,N,2]
+  double *traj;     // [B,N,6]
+  double *u_old;    // [B,2]
+};
+
+__device__ __forceinline__ void sim_f(double *st, double motor, double servo, const LoopParams &p) {
+  const double x = st[0], y = st[1], yaw = st[2], vx = st[3], vy = st[4], psiDot = st[5], ax = st[6], ay = st[7];
+  const double dt = p.lc.sim_dt;
+  double a_F = 0.0, a_R = 0.0;
+  if (fabs(vx) > 0.2) {
+    a_F = servo - atan((vy + p.lf * psiDot) / fabs(vx));
+    a_R = atan((-vy + p.lr * psiDot) / fabs(vx));
+  }
+  const double FyF = 60 * a_F, FyR = 60 * a_R;
+  double sy, cy, ss, cs;
+  sincos(yaw, &sy, &cy);
+  sincos(servo, &ss, &cs);
+  st[0] = x + dt * (cy * vx - sy * vy);
+  st[1] = y + dt * (sy * vx + cy * vy);
+  st[3] = fabs(vx + dt * (ax + psiDot * vy));
+  st[4] = vy + dt * (ay - psiDot * vx);
+  st[6] = motor - p.lc.sim_mu * vx - FyF / p.m * ss;
+  st[7] = 1.0 / p.m * (FyF * cs + FyR);
+  st[2] = yaw + dt * (psiDot);
+  st[5] = psiDot + dt * (1.0 / p.Iz * (p.lf * FyF * cs - p.lr * FyR));
+}
+
+__device__ __forceinline__ double compute_angle(double p1x, double p1y, double ox, double oy, double p2x, double p2y) {
+  const double v1x = p1x - ox, v1y = p1y - oy, v2x = p2x - ox, v2y = p2y - oy;
+  const double dot = v1x * v2x + v1y * v2y;
+  const double det = v1x * v2y - v1y * v2x;
+  return atan2(det, dot);
+}
+
+// np.unwrap([a, b])[1]
+__device__ __forceinline__ double unwrap_second(double a, double b) {
+  const double period = 2 * kPi, hi = kPi, lo = -kPi;
+  const double dd = b - a;
+  double md = fmod(dd - lo, period);
+  if (md != 0.0 && md < 0.0) md += period;
+  double ddmod = md + lo;
+  if (ddmod == lo && dd > 0) ddmod = hi;
+  double corr = ddmod - dd;
+  if (fabs(dd) < kPi) corr = 0.0;
+  return b + corr;
+}
+
+__device__ __forceinline__ double norm2(double dx, double dy) { return sqrt(dx * dx + dy * dy); }
+__device__ __forceinline__ double sgn0(double v) { return (double)((v > 0) - (v < 0)); }
+
+// out = [s ey epsi]; returns CompletedFlag
+__device__ __forceinline__ int local_position(const double *__restrict__ track, int nseg, double width, double x, double y,
+                                              double psi, double *out) {
+  int done = 0;
+  double s = 0, ey = 0, epsi = 0;
+  for (int i = 0; i < nseg && !done; ++i) {
+    const double *Pi = track + i * 6;
+    const double *Pm = track + ((i == 0) ? (nseg - 1) : (i - 1)) * 6;
+    const double xf = Pi[0], yf = Pi[1], xs = Pm[0], ys = Pm[1];
+    if (Pi[5] == 0.0) {
+      epsi = unwrap_second(Pm[2], psi) - Pm[2];
+      if (norm2(xs - x, ys - y) == 0) { s = Pi[3]; ey = 0; done = 1; }
+      else if (norm2(xf - x, yf - y) == 0) { s = Pi[3] + Pi[4]; ey = 0; done = 1; }
+      else if (fabs(compute_angle(x, y, xs, ys, xf, yf)) <= kPi / 2 && fabs(compute_angle(x, y, xf, yf, xs, ys)) <= kPi / 2) {
+        const double v1 = norm2(x - xs, y - ys);
+        const double angle = compute_angle(xf, yf, xs, ys, x, y);
+        double sa, ca;
+        sincos(angle, &sa, &ca);
+        s = v1 * ca + Pi[3];
+        ey = v1 * sa;
+        if (fabs(ey) <= width) done = 1;
+      }
+    } else {
+      const double r = 1 / Pi[5];
+      const double direction = (r >= 0) ? 1 : -1;
+      const double ang = Pm[2];
+      double sc, cc;
+      sincos(ang + direction * kPi / 2, &sc, &cc);
+      const double CenterX = xs + fabs(r) * cc;
+      const double CenterY = ys + fabs(r) * sc;
+      if (norm2(xs - x, ys - y) == 0) { ey = 0; epsi = unwrap_second(ang, psi) - ang; s = Pi[3]; done = 1; }
+      else if (norm2(xf - x, yf - y) == 0) { s = Pi[3] + Pi[4]; ey = 0; epsi = unwrap_second(Pi[2], psi) - Pi[2]; done = 1; }
+      else {
+        const double arc1 = Pi[4] * Pi[5];
+        const double arc2 = compute_angle(xs, ys, CenterX, CenterY, x, y);
+        if (sgn0(arc1) == sgn0(arc2) && fabs(arc1) >= fabs(arc2)) {
+          const double vn = norm2(x - CenterX, y - CenterY);
+          s = fabs(arc2) * fabs(r) + Pi[3];
+          ey = -sgn0(direction) * (vn - fabs(r));
+          epsi = unwrap_second(ang + arc2, psi) - (ang + arc2);
+          if (fabs(ey) <= width) done = 1;
+        }
+      }
+    }
+  }
+  if (!done) { s = 10000; ey = 10000; epsi = 10000; }
+  out[0] = s; out[1] = ey; out[2] = epsi;
+  return done;
+}
+
+__constant__ double kGuessDv[20] = {0.05, 0.2, 0.4, 0.6, 0.7, 0.8, 0.9, 0.9, 0.9, 0.9, 0.9, 0.9, 0.9, 0.9, 0.9, 0.9, 0.9, 0.9, 0.9, 0.9};
+__constant__ double kGuessDs[20] = {0, 0.01, 0.02, 0.04, 0.07, 0.1, 0.14, 0.18, 0.23, 0.55, 0.66, 0.77, 0.89, 1.00, 1.19, 1.39, 1.59, 1.79, 1.89, 1.999};
+__constant__ double kGuessUa[20] = {0.0, 0.3, 0.5, 0.7, 0.8, 0.9, 0.9, 0.9, 0.8, 0.7, 0.6, 0.5, 0.4, 0.30, 0.22, 0.18, 0.14, 0.1, 0.1, 0.1};
+
+__device__ __forceinline__ bool feasible(int status) {
+  return status == LPVMPC_SOLVED || status == LPVMPC_SOLVED_INACCURATE || status == LPVMPC_MAX_ITER_REACHED;
+}
+
+// do_apply: fold the last solve into the vehicle (status, command, `substeps` simulator steps).
+// do_measure: localise, lap logic, write the next solve's inputs (`warmup` selects the _EstimateABC guess path).
+__global__ void __launch_bounds__(128) lpv_loop_kernel(const __grid_constant__ LoopParams p, int do_apply, int do_measure,
+                                                       int warmup) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= p.B) return;
+  const int N = p.N;
+  int *ct = p.ctr + (size_t)b * C_COUNT;
+  double *sv = p.stat + (size_t)b * S_COUNT;
+  double *S = p.sim + (size_t)b * 8;
+  double *cm = p.cmd + (size_t)b * 2;
+  int fail = ct[C_FAIL];
+  if (do_apply && !fail) {
+    const int status = p.status[b], it = p.iters[b];
+    ct[C_STATUS] = status; ct[C_ITERS] = it;
+    if (!feasible(status)) { fail = status; ct[C_FAIL] = status; ct[C_FAIL_TICK] = ct[C_TICKS]; }
+    else {
+      if (status == LPVMPC_SOLVED) sv[S_SOLVED] += 1;
+      sv[S_ITERS] += it;
+      const double delta = p.u_pred[(size_t)b * N * 2 + 0], acc = p.u_pred[(size_t)b * N * 2 + 1];
+      cm[0] = delta; cm[1] = acc;
+      double st[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) st[e] = S[e];
+      for (int k = 0; k < p.lc.substeps; ++k) sim_f(st, acc, delta, p);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) S[e] = st[e];
+      ct[C_TICKS] += 1;
+    }
+  }
+  if (!do_measure) return;
+  double *x0 = p.x0 + (size_t)b * 6;
+  if (!fail) {
+    double loc[6], lp[3];
+    loc[0] = S[3] < 0.01 ? 0.01 : S[3]; loc[1] = S[4]; loc[2] = S[5];
+    const int ok = local_position(p.track, p.nseg, p.lc.half_width + p.lc.slack, S[0], S[1], S[2], lp);
+    loc[4] = lp[0];
+    if (p.lc.swap_ey_epsi) { loc[3] = lp[1]; loc[5] = lp[2]; } else { loc[3] = lp[2]; loc[5] = lp[1]; }
+#pragma unroll
+    for (int e = 0; e < 6; ++e) p.local[(size_t)b * 6 + e] = loc[e];
+    if (!ok) { fail = LPVMPC_OFF_TRACK; ct[C_FAIL] = fail; ct[C_FAIL_TICK] = ct[C_TICKS]; ct[C_STATUS] = fail; }
+    else {
+      if (fabs(lp[1]) > sv[S_MAX_EY]) sv[S_MAX_EY] = fabs(lp[1]);
+      const double TrackLength = p.track[(p.nseg - 1) * 6 + 3] + p.track[(p.nseg - 1) * 6 + 4];
+      if (loc[4] >= 3 * TrackLength / 4) ct[C_HALF] = 1;
+      if (ct[C_HALF] == 1 && loc[4] <= TrackLength / 4) {
+        ct[C_HALF] = 0; ct[C_LAP] += 1;
+        if (sv[S_LAP_TICK] < 0) sv[S_LAP_TICK] = ct[C_TICKS];
+      }
+      p.u_old[(size_t)b * 2 + 0] = cm[0]; p.u_old[(size_t)b * 2 + 1] = cm[1];
+#pragma unroll
+      for (int e = 0; e < 6; ++e) x0[e] = loc[e];
+      double *up = p.u_prev + (size_t)b * N * 2;
+      if (warmup) {
+        double *tr = p.traj + (size_t)b * N * 6;
+        for (int i = 0; i < N; ++i) {
+          tr[i * 6 + 0] = loc[0] + kGuessDv[i]; tr[i * 6 + 1] = loc[1]; tr[i * 6 + 2] = loc[2];
+          tr[i * 6 + 3] = 0.0001; tr[i * 6 + 4] = loc[4] + kGuessDs[i]; tr[i * 6 + 5] = 0.0001;
+          up[i * 2 + 0] = 0.; up[i * 2 + 1] = kGuessUa[i];
+        }
+        ct[C_FIRST_IT] += 1;
+      } else {
+        const double *us = p.u_pred + (size_t)b * N * 2;
+        for (int i = 0; i < 2 * N; ++i) up[i] = us[i];
+      }
+    }
+  }
+  if (fail) {  // retired vehicle: a NaN arc length makes the solve kernel leave at once with LPVMPC_SCHEDULE_ERROR
+    const double qnan = nan("");
+#pragma unroll
+    for (int e = 0; e < 6; ++e) x0[e] = qnan;
+    if (warmup) for (int i = 0; i < N; ++i) p.traj[((size_t)b * N + i) * 6 + 4] = qnan;
+  }
+}
+
+}  // namespace loop
+}  // namespace lpv

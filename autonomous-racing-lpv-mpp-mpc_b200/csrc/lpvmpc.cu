@@ -16,6 +16,7 @@
 #include "lpv_g8.cuh"
 #include "lpv_h8.cuh"
 #include "lpv_h8t.cuh"
+#include "lpv_loop.cuh"
 
 namespace lpv {
 
@@ -333,6 +334,15 @@ struct lpvmpc_handle {
   cudaStream_t stream = nullptr;
   long long launches = 0;
   std::string err;
+  // closed-loop fleet (lpvmpc_loop_*)
+  char *d_loop = nullptr;        // one allocation holding every array below
+  lpv::loop::LoopParams LP;
+  lpvmpc_args loop_args;         // device pointers of the per-tick solve
+  double *d_loop_xpred = nullptr, *d_loop_velref = nullptr;
+  int32_t *d_loop_status = nullptr, *d_loop_iters = nullptr;
+  int loop_B = 0;
+  long long loop_tick = 0;       // ticks since the last init (selects the warm-up path)
+  cudaEvent_t loop_ev = nullptr; // last lpvmpc_loop_run_dev on the caller's stream (lpvmpc_loop_read_host waits for it)
 };
 
 namespace {
@@ -690,6 +700,8 @@ void lpvmpc_destroy(lpvmpc_handle *h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamDestroy(h->stream);
   cudaFree(h->d_track); cudaFree(h->d_gws); cudaFree(h->d_stage); cudaFree(h->d_queue); cudaFree(h->d_cold);
+  cudaFree(h->d_loop);
+  if (h->loop_ev) cudaEventDestroy(h->loop_ev);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   delete h;
 }
@@ -781,6 +793,158 @@ static int run_host(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, int32_t *
 }
 
 int lpvmpc_solve_host(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a) { return run_host(h, B, a, nullptr, true); }
+
+// ------------------------------------------------------------------------------------------------
+// closed-loop fleet
+void lpvmpc_loop_default_cfg(lpvmpc_loop_cfg *c) {
+  if (!c) return;
+  c->sim_dt = 0.005; c->substeps = 7; c->warmup_ticks = 9; c->swap_ey_epsi = 1; c->reserved = 0;
+  c->vel_ref = 1.0; c->Cf_new = 60.0; c->half_width = 0.3; c->slack = 0.45; c->sim_mu = 0.05;
+}
+
+int lpvmpc_loop_init_dev(lpvmpc_handle *h, int32_t B, const lpvmpc_loop_cfg *c, const double *sim0, void *stream) {
+  if (!h || !c || !sim0) return fail(h, LPVMPC_E_ARG, "null handle/cfg/sim0");
+  if (h->cfg.kind != LPVMPC_CONTROLLER || h->cfg.steering_delay != 0 || h->L.N > 20)
+    return fail(h, LPVMPC_E_UNSUPPORTED, "the closed loop needs a controller handle with N <= 20 and steering_delay = 0");
+  if (B < 1 || B > h->cfg.max_batch) return fail(h, LPVMPC_E_ARG, "fleet size must be in [1, max_batch]");
+  if (c->substeps < 0 || c->warmup_ticks < 0 || !(c->sim_dt > 0)) return fail(h, LPVMPC_E_ARG, "bad loop cfg");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int N = h->L.N;
+  const size_t D = sizeof(double), mb = (size_t)h->cfg.max_batch;
+  if (!h->d_loop) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t r = off; off += align256(bytes * mb); return r; };
+    const size_t o_sim = take(8 * D), o_cmd = take(2 * D), o_up = take(2 * N * D), o_xp = take(6 * (N + 1) * D),
+                 o_loc = take(6 * D), o_stat = take(4 * D), o_ctr = take(8 * sizeof(int32_t)), o_x0 = take(6 * D),
+                 o_uprev = take(2 * N * D), o_traj = take(6 * N * D), o_uold = take(2 * D), o_vel = take((N + 1) * D),
+                 o_status = take(sizeof(int32_t)), o_iters = take(sizeof(int32_t));
+    CUDA_TRY(h, cudaMalloc(&h->d_loop, off));
+    char *base = h->d_loop;
+    lpv::loop::LoopParams &P = h->LP;
+    P.sim = (double *)(base + o_sim); P.cmd = (double *)(base + o_cmd); P.u_pred = (double *)(base + o_up);
+    h->d_loop_xpred = (double *)(base + o_xp); P.local = (double *)(base + o_loc); P.stat = (double *)(base + o_stat);
+    P.ctr = (int *)(base + o_ctr); P.x0 = (double *)(base + o_x0); P.u_prev = (double *)(base + o_uprev);
+    P.traj = (double *)(base + o_traj); P.u_old = (double *)(base + o_uold); h->d_loop_velref = (double *)(base + o_vel);
+    h->d_loop_status = (int32_t *)(base + o_status); h->d_loop_iters = (int32_t *)(base + o_iters);
+    P.status = h->d_loop_status; P.iters = h->d_loop_iters;
+  }
+  lpv::loop::LoopParams &P = h->LP;
+  P.lc = *c; P.lf = h->M.lf; P.lr = h->M.lr; P.m = h->M.m; P.Iz = h->M.Iz; P.track = h->d_track; P.nseg = h->M.nseg;
+  P.N = N; P.B = B;
+  h->loop_B = B; h->loop_tick = 0;
+  // state: sim <- sim0, everything else zero, first_it = 1, lap tick = -1, vel_ref = const
+  CUDA_TRY(h, cudaMemcpyAsync(P.sim, sim0, 8 * D * (size_t)B, cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(h, cudaMemsetAsync(P.cmd, 0, 2 * D * (size_t)B, s));
+  CUDA_TRY(h, cudaMemsetAsync(P.u_pred, 0, 2 * N * D * (size_t)B, s));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_loop_xpred, 0, 6 * (N + 1) * D * (size_t)B, s));
+  CUDA_TRY(h, cudaMemsetAsync(P.local, 0, 6 * D * (size_t)B, s));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_loop_status, 0, sizeof(int32_t) * (size_t)B, s));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_loop_iters, 0, sizeof(int32_t) * (size_t)B, s));
+  {
+    std::vector<int32_t> ctr((size_t)B * 8, 0);
+    std::vector<double> stat((size_t)B * 4, 0.0), vel((size_t)B * (N + 1), c->vel_ref);
+    for (int b = 0; b < B; ++b) { ctr[(size_t)b * 8] = 1; stat[(size_t)b * 4 + 3] = -1.0; }
+    // pageable sources: the copies are staged before the calls return
+    CUDA_TRY(h, cudaMemcpyAsync(P.ctr, ctr.data(), ctr.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(P.stat, stat.data(), stat.size() * D, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_loop_velref, vel.data(), vel.size() * D, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+  }
+  lpvmpc_args &a = h->loop_args;
+  std::memset(&a, 0, sizeof(a));
+  a.lap_all = 0; a.Cf_new = c->Cf_new;
+  a.x0 = P.x0; a.u_prev = P.u_prev; a.vel_ref = h->d_loop_velref; a.traj = P.traj; a.u_old = P.u_old;
+  a.x_pred = h->d_loop_xpred; a.u_pred = P.u_pred; a.status = h->d_loop_status; a.iters = h->d_loop_iters;
+  return LPVMPC_OK;
+}
+
+int lpvmpc_loop_run_dev(lpvmpc_handle *h, int32_t n_ticks, void *stream) {
+  if (!h) return LPVMPC_E_ARG;
+  if (!h->d_loop || h->loop_B < 1) return fail(h, LPVMPC_E_ARG, "lpvmpc_loop_init_* first");
+  if (n_ticks < 0) return fail(h, LPVMPC_E_ARG, "n_ticks < 0");
+  if (n_ticks == 0) return LPVMPC_OK;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int B = h->loop_B, grid = (B + 127) / 128;
+  for (int t = 0; t < n_ticks; ++t) {
+    const int warm = h->loop_tick < (long long)h->LP.lc.warmup_ticks ? 1 : 0;
+    lpv::loop::lpv_loop_kernel<<<grid, 128, 0, s>>>(h->LP, t > 0 ? 1 : 0, 1, warm);
+    ++h->launches;
+    CUDA_TRY(h, cudaGetLastError());
+    lpvmpc_args &a = h->loop_args;
+    a.sched_mode = warm ? LPVMPC_SCHED_ESTIMATE : LPVMPC_SCHED_PREDICT;
+    a.x0_from_prediction = warm ? 0 : 1;
+    const int rc = lpvmpc_solve_dev(h, B, &a, stream);
+    if (rc) return rc;
+    ++h->loop_tick;
+  }
+  lpv::loop::lpv_loop_kernel<<<grid, 128, 0, s>>>(h->LP, 1, 0, 0);
+  ++h->launches;
+  CUDA_TRY(h, cudaGetLastError());
+  if (!h->loop_ev) CUDA_TRY(h, cudaEventCreateWithFlags(&h->loop_ev, cudaEventDisableTiming));
+  CUDA_TRY(h, cudaEventRecord(h->loop_ev, s));
+  return LPVMPC_OK;
+}
+
+int lpvmpc_loop_init_host(lpvmpc_handle *h, int32_t B, const lpvmpc_loop_cfg *c, const double *sim0) {
+  if (!h || !sim0) return fail(h, LPVMPC_E_ARG, "null handle/sim0");
+  if (B < 1 || B > h->cfg.max_batch) return fail(h, LPVMPC_E_ARG, "fleet size must be in [1, max_batch]");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const size_t bytes = 8 * sizeof(double) * (size_t)B;
+  if (bytes > h->stage_bytes) return fail(h, LPVMPC_E_ARG, "staging overflow");
+  std::memcpy(h->h_stage, sim0, bytes);
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_stage, h->h_stage, bytes, cudaMemcpyHostToDevice, h->stream));
+  const int rc = lpvmpc_loop_init_dev(h, B, c, reinterpret_cast<const double *>(h->d_stage), h->stream);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return LPVMPC_OK;
+}
+
+int lpvmpc_loop_run_host(lpvmpc_handle *h, int32_t n_ticks) {
+  if (!h) return LPVMPC_E_ARG;
+  const int rc = lpvmpc_loop_run_dev(h, n_ticks, h->stream);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return LPVMPC_OK;
+}
+
+int lpvmpc_loop_view_dev(lpvmpc_handle *h, lpvmpc_loop_state *view, int32_t *B) {
+  if (!h || !view) return LPVMPC_E_ARG;
+  if (!h->d_loop || h->loop_B < 1) return fail(h, LPVMPC_E_ARG, "lpvmpc_loop_init_* first");
+  view->sim = h->LP.sim; view->cmd = h->LP.cmd; view->u_pred = h->LP.u_pred; view->x_pred = h->d_loop_xpred;
+  view->local = h->LP.local; view->stat = h->LP.stat; view->ctr = h->LP.ctr;
+  if (B) *B = h->loop_B;
+  return LPVMPC_OK;
+}
+
+int lpvmpc_loop_read_host(lpvmpc_handle *h, const lpvmpc_loop_state *dst) {
+  if (!h || !dst) return LPVMPC_E_ARG;
+  if (!h->d_loop || h->loop_B < 1) return fail(h, LPVMPC_E_ARG, "lpvmpc_loop_init_* first");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const size_t B = (size_t)h->loop_B, D = sizeof(double), N = (size_t)h->L.N;
+  struct Item { void *dst; const void *src; size_t bytes; };
+  const Item items[] = {{dst->sim, h->LP.sim, 8 * D * B}, {dst->cmd, h->LP.cmd, 2 * D * B}, {dst->u_pred, h->LP.u_pred, 2 * N * D * B},
+                        {dst->x_pred, h->d_loop_xpred, 6 * (N + 1) * D * B}, {dst->local, h->LP.local, 6 * D * B},
+                        {dst->stat, h->LP.stat, 4 * D * B}, {dst->ctr, h->LP.ctr, 8 * sizeof(int32_t) * B}};
+  // through the pinned arena: one D2H per member, one wait (after the last run, whichever stream it was on)
+  if (h->loop_ev) CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->loop_ev, 0));
+  size_t off = 0;
+  for (const Item &it : items) {
+    if (!it.dst) continue;
+    if (off + it.bytes > h->stage_bytes) return fail(h, LPVMPC_E_ARG, "staging overflow");
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_stage + off, it.src, it.bytes, cudaMemcpyDeviceToHost, h->stream));
+    off += align256(it.bytes);
+  }
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  off = 0;
+  for (const Item &it : items) {
+    if (!it.dst) continue;
+    std::memcpy(it.dst, h->h_stage + off, it.bytes);
+    off += align256(it.bytes);
+  }
+  return LPVMPC_OK;
+}
 
 int lpvmpc_schedule_host(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, int32_t *sched_err) {
   return run_host(h, B, a, sched_err, false);

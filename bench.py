@@ -8,6 +8,9 @@ synthetic problems.  Workloads:
     ctrl4096   4,096 controller QPs, N=8, trajectory-tracking tune, lap=1       (BASELINE configs[1], default)
     plan16384  16,384 planner QPs, N=40, lateral-box "obstacles"                 (configs[2])
     ctrl1024N100  1,024 controller QPs, N=100                                     (configs[4])
+    mc8192     Monte-Carlo closed loop, 8,192 vehicles per GPU (configs[3] is 65,536 over 8 GPUs): a step is
+               `--ticks-per-step` controller ticks of the whole fleet, each tick = simulate + localise + schedule +
+               build + solve on the device (lpvmpc_loop_*); 24 steps x 23 ticks = the 552-tick lap
 Multi-GPU: one process per GPU (torchrun), every rank solves its own batch of the same size (weak scaling, no
 collective on the data path); value = all ranks' QPs / max-over-ranks device time.
 
@@ -49,6 +52,7 @@ WORKLOADS = {
     # not a BASELINE config: the cfg-2 distribution at a batch that fills every QP slot of the GPU many times over
     # (what a Monte-Carlo tick of configs[3] looks like to the solver: 8,192 vehicles per GPU and more)
     "ctrl65536": dict(kind="controller", N=8, B=65536, seed=0),
+    "mc8192": dict(kind="fleet", N=8, B=8192, seed=2),
 }
 
 
@@ -190,10 +194,176 @@ def cpu_reference_rate(name, threads, repeats=1, sample=None):
     return B, times, solved
 
 
+def cpu_fleet_rate(threads, vehicles, ticks, seed=2):
+    """vehicle-ticks/s of the CPU oracle's closed loop (oracle/loop_ref.c) on `threads` host threads."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    import lpvmpc_b200 as lp
+    W = lp.workloads
+    m = lp.Map("L_shape")
+    cfg = oracle.make_cfg("controller", 8, W.CTRL_DT, W.CTRL_PT["Q"], W.CTRL_PT["R"], W.CTRL_PT["dR"], m.PointAndTangent)
+    st = oracle.default_settings(polish=1)
+    lc = oracle.loop_cfg(half_width=m.halfWidth, slack=m.slack)
+    state = oracle.loop_state(lp.fleet_start(vehicles, seed=seed, track_map=m), 8)
+    t0 = time.perf_counter()
+    solved = oracle.loop_run(cfg, st, lc, state, ticks, threads=threads)
+    dt = time.perf_counter() - t0
+    done = int(state["ctr"][:, 7].sum())
+    return done / dt, dt, solved / float(max(done, 1))
+
+
+def run_fleet_reference(args):
+    threads = os.cpu_count() or 1
+    vehicles, ticks = max(64, 8 * threads), args.ticks_per_step
+    for _ in range(max(1, args.warmup)):   # full-size untimed passes: the host's OpenMP threads take a while to spin up
+        cpu_fleet_rate(threads, vehicles, ticks)
+    rates, times = [], []
+    for _ in range(args.steps):
+        r, dt, sf = cpu_fleet_rate(threads, vehicles, ticks)
+        rates.append(r); times.append(dt)
+    value = vehicles * ticks * len(times) / float(np.sum(times))
+    line = {
+        "impl": "reference", "metric": "LPV-MPC QP solves/sec", "value": value, "unit": "QP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "kind": "fleet", "N": 8, "vehicles_per_step": vehicles, "ticks_per_step": ticks,
+                   "note": "CPU oracle port of the closed loop (controller main loop + Simulator.f + getLocalPosition + OSQP "
+                           "restatement), every step restarts the sample fleet from tick 0; the reference's Python overhead is NOT included"},
+        "cpu_baseline": {"value": value, "unit": "QP/s", "cores": threads, "kind": "port",
+                         "sample": "%d vehicles x %d ticks per step x %d steps" % (vehicles, ticks, len(times))},
+        "e2e": {"value": value, "unit": "QP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "solved_fraction": sf,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_fleet(args):
+    """configs[3]: the device-resident closed loop.  A step = args.ticks_per_step ticks of the whole fleet."""
+    import torch
+    import lpvmpc_b200 as lp
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+    spec = WORKLOADS[args.workload]
+    B, tps = spec["B"], args.ticks_per_step
+    m = lp.Map("L_shape")
+    sim0 = lp.fleet_start(B, seed=spec["seed"] + 1000 * rank, track_map=m)
+    fleet = lp.ClosedLoopFleet(m, N=spec["N"], max_fleet=B, device=local, variant=args.variant)
+    info0 = fleet.solver.info()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.current_stream(local).cuda_stream
+    t0 = torch.as_tensor(sim0).to(dev)
+    fleet.start(t0)
+    for _ in range(args.warmup):   # warm-up steps also carry the fleet past the 9 _EstimateABC ticks
+        fleet.run(tps, stream=stream)
+    barrier()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    sampler = ClockSampler(local)
+    launches0 = fleet.solver.info()["kernel_launches"]
+    before = fleet.read(("stat", "ctr"))
+    sampler.start()
+    barrier()
+    for i in range(args.steps):
+        starts[i].record()
+        fleet.run(tps, stream=stream)
+        ends[i].record()
+    barrier()
+    clocks = sampler.stop()
+    launches = fleet.solver.info()["kernel_launches"] - launches0
+    after = fleet.read(("stat", "ctr"))
+    step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, ends)])
+    total_ms = float(step_ms.sum())
+    ticks_done = float((after["ctr"][:, 7] - before["ctr"][:, 7]).sum())
+    solved = float((after["stat"][:, 0] - before["stat"][:, 0]).sum())
+    iters_sum = float((after["stat"][:, 1] - before["stat"][:, 1]).sum())
+    # algorithmic flops: every tick is one controller QP with the measured iteration count, 1 factorisation (+ polish)
+    F_scale, F_form, F_fac, F_solve, F_iter, F_check = FLOP_TABLE[("controller", spec["N"])]
+    flops = ticks_done * (F_scale + F_form + F_fac + (F_fac + 4 * F_solve)) + iters_sum * (F_iter + F_check / 25.0)
+
+    # end to end through the host API: numpy start states in, whole run, numpy fleet state out
+    barrier()
+    te = time.perf_counter()
+    fleet.start(sim0)
+    fleet.run(tps * args.steps)
+    out = fleet.read()
+    e2e_total = time.perf_counter() - te
+    barrier()
+    e2e_ticks = float(out["ctr"][:, 7].sum())
+    h2d = int(sim0.nbytes)
+    d2h = int(sum(v.nbytes for v in out.values()))
+
+    if dist is not None:
+        t = torch.tensor([total_ms, e2e_total, ticks_done, solved, e2e_ticks], dtype=torch.float64, device=dev)
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        total_ms, e2e_total = float(tmax[0]), float(tmax[1])
+        ticks_all, solved_all, e2e_ticks_all = float(tsum[2]), float(tsum[3]), float(tsum[4])
+    else:
+        ticks_all, solved_all, e2e_ticks_all = ticks_done, solved, e2e_ticks
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+    peak, peak_src = fp64_peak_tflops()
+    ms_per_step = total_ms / args.steps
+    achieved = flops / (total_ms * 1e-3) * 1e-12
+    line = {
+        "metric": "LPV-MPC QP solves/sec", "value": ticks_all / (total_ms * 1e-3), "unit": "QP/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "kind": "fleet (closed loop: Simulator.f x7 + getLocalPosition + LPVPrediction + build + OSQP + polish per tick)",
+                   "N": spec["N"], "vehicles_per_gpu": B, "ticks_per_step": tps, "tune": "path tracking (controllerMain.py:139-141)",
+                   "osqp": "defaults + polish", "l2": "fleet state + solver slab stay resident by design (closed loop); no flush",
+                   "kernel_variant": info0["variant"], "swap_ey_epsi": 1},
+        "e2e": {"value": e2e_ticks_all / e2e_total, "unit": "QP/s", "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
+                "ms_per_step": 1e3 * e2e_total / args.steps, "note": "start(host states) + run(steps x ticks) + read(): one H2D and one D2H per run, nothing per tick"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "fp64_fma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "kernel": KERNEL_NAMES.get(info0["variant"], "?") + " (one launch per tick) + lpv_loop_kernel",
+                     "algorithmic_flops_per_step": flops / args.steps},
+        "kernel_latency_ms": {"per_tick_p50": float(np.percentile(step_ms, 50)) / tps, "per_tick_p99": float(np.percentile(step_ms, 99)) / tps},
+        "solved_fraction": solved_all / max(ticks_all, 1.0),
+        "iters": {"mean": iters_sum / max(ticks_done, 1.0)},
+        "retired_vehicles": int((after["ctr"][:, 5] != 0).sum()),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        vehicles = max(64, 8 * threads)
+        cpu_fleet_rate(threads, vehicles, 4 * tps)
+        r, dt, _ = cpu_fleet_rate(threads, vehicles, 4 * tps)
+        line["cpu_baseline"] = {"value": r, "unit": "QP/s", "cores": threads, "kind": "port",
+                                "sample": "%d vehicles x %d ticks from the same start distribution, OpenMP over all host cores (%.1f s)" % (vehicles, 4 * tps, dt)}
+    print(json.dumps(line))
+    fleet.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    if WORKLOADS[args.workload]["kind"] == "fleet":
+        return run_fleet_reference(args)
     threads = os.cpu_count() or 1
     spec = WORKLOADS[args.workload]
     sample = spec["B"] if spec["kind"] == "controller" and spec["N"] <= 20 else max(64, threads * 8)
@@ -391,10 +561,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-saturated", action="store_true", help="skip the 65,536-QP secondary measurement of the ctrl4096 run")
     ap.add_argument("--variant", type=int, default=0, help="kernel variant (0 = auto)")
+    ap.add_argument("--ticks-per-step", type=int, default=23, help="mc8192: controller ticks per step (24 x 23 = one lap)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
+    if WORKLOADS[args.workload]["kind"] == "fleet":
+        return run_fleet(args)
     return run_ours(args)
 
 

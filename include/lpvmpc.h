@@ -16,6 +16,9 @@
  *   lpvmpc_solve_*           .solve + osqp_solve_qp          PathFollowingLPVMPC.py:89-162,273-325
  *                            .solve (OSQP().setup/.solve)    LPV_MPC_Planner.py:86-236
  *                            (OSQP itself: PyPI `osqp` 0.6.x, setup+solve+polish; not vendored)
+ *   lpvmpc_loop_*            the controller node's main loop + the simulator node, for a fleet (see below)
+ *                            controllerMain.py:177-454, vehicleSimulator.py:164-199,
+ *                            Utilities/trackInitialization.py:283-383
  *
  * Conventions: plain pointers and sizes only; every call returns 0 or a negative LPVMPC_E_* code and
  * never throws; lpvmpc_last_error() gives the message.  A handle is bound to one CUDA device and is not
@@ -65,7 +68,8 @@ enum {
   LPVMPC_NON_CVX = -7,
   LPVMPC_UNSOLVED = -10,
   LPVMPC_SCHEDULE_ERROR = -20, /* Curvature(s) had no (unique) segment: the reference raises (utilities.py:46) */
-  LPVMPC_DATA_ERROR = -21      /* l > u: upstream osqp.setup() refuses the problem */
+  LPVMPC_DATA_ERROR = -21,     /* l > u: upstream osqp.setup() refuses the problem */
+  LPVMPC_OFF_TRACK = -22       /* closed loop: getLocalPosition found no segment (the reference returns 10000 sentinels) */
 };
 
 /* scheduling modes of lpvmpc_solve_* */
@@ -178,6 +182,64 @@ int lpvmpc_schedule_host(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, int3
 /* schedule (per sched_mode) + build + OSQP solve (+ polish) + unpack */
 int lpvmpc_solve_dev(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, void *stream);
 int lpvmpc_solve_host(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a);
+
+/* ------------------------------------------------------------------------------------------------
+ * Closed-loop fleet (BASELINE configs[3], SURVEY 8b `lpvmpc_step_closed_loop`): B independent vehicles, each running the
+ * controller main loop of the reference in path-tracking mode (lap 0) against the reference simulator's vehicle
+ * model, entirely on the device.  One tick =
+ *     measure the true state, vx >= 0.01                       controllerMain.py:179-184
+ *     Map.getLocalPosition(x, y, psi) -> s, ey, epsi           controllerMain.py:188, trackInitialization.py:283-383
+ *     lap bookkeeping                                          controllerMain.py:190-192, 252-257
+ *     OldSteering / OldAccelera <- last command                controllerMain.py:289-298
+ *     warm-up ticks: _EstimateABC around the hard-coded guess  controllerMain.py:310-315, 510-553
+ *     later ticks : LPVPrediction, x0 = first predicted state  controllerMain.py:326-331
+ *     solve (schedule + build + OSQP + polish)                 = lpvmpc_solve_dev on the same handle
+ *     command = uPred[0]                                       controllerMain.py:381-383
+ *     `substeps` x Simulator.f(u = [motor, servo])             vehicleSimulator.py:164-199, 337
+ * Differences from the reference, on purpose: a vehicle whose QP is not feasible ({SOLVED, SOLVED_INACCURATE,
+ * MAX_ITER_REACHED}, PathFollowingLPVMPC.py:322-324) or that leaves the track is retired (ctr[5] = the status, its
+ * state frozen) instead of carrying on with res.x / the 10000 sentinels; the state estimator is bypassed (true-state
+ * feedback; its gain tables are not in the reference repository).  The handle must be a controller with N <= 20 and
+ * steering_delay = 0.
+ */
+typedef struct {
+  double sim_dt;          /* simulator/dt (MAIN_LAUNCH.launch:60): 0.005 */
+  int32_t substeps;       /* Simulator.f steps per controller tick (33 ms / 5 ms, rounded up: 7) */
+  int32_t warmup_ticks;   /* first_it < 10 (controllerMain.py:310): 9 */
+  int32_t swap_ey_epsi;   /* 1 = controllerMain.py:188 as written (ey lands in the epsi slot and vice versa); 0 = as its comment intends */
+  int32_t reserved;
+  double vel_ref;         /* controllerMain.py:326: 1.0 */
+  double Cf_new;          /* controllerMain.py:77: 60 */
+  double half_width;      /* Map.halfWidth (trackInitialization.py:20) */
+  double slack;           /* Map.slack (trackInitialization.py:30,45,54) */
+  double sim_mu;          /* simulator/mu (MAIN_LAUNCH.launch:72) */
+} lpvmpc_loop_cfg;
+
+/* Fleet state, row-major.  ctr = [first_it, lap, half_track, last_status, last_iters, fail_status (0 = running),
+ * fail_tick, ticks_done]; stat = [SOLVED ticks, total ADMM iterations, max |ey| (true), tick of the first lap
+ * completion or -1]. */
+typedef struct {
+  double *sim;      /* [B,8]     x y yaw vx vy psiDot ax ay */
+  double *cmd;      /* [B,2]     last command [delta a] */
+  double *u_pred;   /* [B,N,2]   last predicted inputs */
+  double *x_pred;   /* [B,N+1,6] last predicted states */
+  double *local;    /* [B,6]     last measured state in the controller's slots [vx vy wz epsi s ey] */
+  double *stat;     /* [B,4] */
+  int32_t *ctr;     /* [B,8] */
+} lpvmpc_loop_state;
+
+void lpvmpc_loop_default_cfg(lpvmpc_loop_cfg *c); /* launch-file values, L_shape track widths */
+/* (Re)start a fleet of B <= max_batch vehicles from simulator states sim0 [B,8] (first_it = 1, command 0). */
+int lpvmpc_loop_init_dev(lpvmpc_handle *h, int32_t B, const lpvmpc_loop_cfg *c, const double *sim0, void *stream);
+int lpvmpc_loop_init_host(lpvmpc_handle *h, int32_t B, const lpvmpc_loop_cfg *c, const double *sim0);
+/* Enqueue n_ticks ticks (2 kernels per tick + 1; nothing returns to the host).  _host runs on the handle's stream
+ * and waits. */
+int lpvmpc_loop_run_dev(lpvmpc_handle *h, int32_t n_ticks, void *stream);
+int lpvmpc_loop_run_host(lpvmpc_handle *h, int32_t n_ticks);
+/* Device pointers of the fleet state (owned by the handle, valid until the next init / destroy). */
+int lpvmpc_loop_view_dev(lpvmpc_handle *h, lpvmpc_loop_state *view, int32_t *B);
+/* Copy the non-NULL members of `dst` (HOST pointers) out of the device state. */
+int lpvmpc_loop_read_host(lpvmpc_handle *h, const lpvmpc_loop_state *dst);
 
 #ifdef __cplusplus
 }
