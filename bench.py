@@ -561,8 +561,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-saturated", action="store_true", help="skip the 65,536-QP secondary measurement of the ctrl4096 run")
     ap.add_argument("--variant", type=int, default=0, help="kernel variant (0 = auto)")
+    ap.add_argument("--batch", type=int, default=0, help="override the workload's batch per GPU (profiling runs; not a BASELINE config)")
     ap.add_argument("--ticks-per-step", type=int, default=23, help="mc8192: controller ticks per step (24 x 23 = one lap)")
     args = ap.parse_args()
+    if args.batch > 0:
+        WORKLOADS[args.workload] = dict(WORKLOADS[args.workload], B=args.batch)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
