@@ -53,6 +53,10 @@ struct Lay {  // per-QP offsets (doubles); computed on the host (lpvmpc.cu: make
   int total;                   // doubles per QP in shared memory (== 8 mod 16: neighbouring groups 64 B apart mod 128)
   int cold_total;              // doubles per QP slot in the global slab
   int cG;                      // offset of G (N x NX x 8, row-major rows of -[A_k B_k], scaled) inside the slot
+  // streamed factor ("H8S"): the block factor lives in the slab ((N+1) x TKS at cTK) and is staged through a ring of
+  // `ring` stage blocks (power of two; 0 = factor resident in shared memory) by 1 KB TMA bulk copies issued `pfd`
+  // stage steps ahead; setup's scratch then aliases the slab copy of the factor
+  int ring, pfd, cTK;
 };
 enum { C_D = 0, C_DINV, C_E, C_EINV, C_PD, C_PO, C_EI, C_EIINV, C_Q, C_BE, C_ED, C_YD, C_PVX, C_PVYI, C_DYD, C_PX, C_PYD,
        C_PYI, C_R2D, C_R2I, C_ACTD, C_ACTI, C_ZT, C_COUNT };
@@ -119,6 +123,7 @@ struct Ctx {
   double *cold;  // my QP slot in the global slab
   const Lay *L;
   int N, r;
+  int kmask;     // stage -> factor block slot: -1 (resident: slot k) or ring - 1
   int ro[4];     // my row of a swizzled block: offset of logical chunk j
   int co[4];     // my column of a swizzled block: offset inside row rr is co[rr >> 1]
   bool xl, ul;   // state lane / input lane (neither: idle lane)
@@ -131,8 +136,8 @@ struct Ctx {
     return xl || (ul && k < N);
   }
   __device__ __forceinline__ double *cd(int arr) const { return cold + arr * (N + 1) * 8; }
-  __device__ __forceinline__ double *Tb(int k) const { return S + L->TK + k * TKS; }
-  __device__ __forceinline__ double *Kb(int k) const { return S + L->TK + (k - 1) * TKS + 64; }
+  __device__ __forceinline__ double *Tb(int k) const { return S + L->TK + (k & kmask) * TKS; }
+  __device__ __forceinline__ double *Kb(int k) const { return S + L->TK + ((k - 1) & kmask) * TKS + 64; }
   __device__ __forceinline__ const double *Gb(int k) const { return cold + L->cG + k * (NX * 8); }
   __device__ __forceinline__ double *V(int arr) const { return S + L->V + arr; }          // element (k, q) at [k*VS + q]
   // single-variable rows in shared memory: z, y, coefficient, upper (and lower: planner) bound of my row t at stage k
@@ -292,6 +297,26 @@ __device__ __noinline__ void factor(const Ctx<KIND> c, const FW fw, const double
 #pragma unroll
     for (int j = 0; j < 4; ++j) st2(Tk + c.ro[j], s[2 * j], s[2 * j + 1]);
     __syncwarp();
+    if (c.L->ring) {  // streamed factor: block k-1 = [T_{k-1} | K_k] is final, block N = [T_N | -] after the last stage
+      double *dst = c.cold + c.L->cTK;
+      if (k > 0) {
+        const double *src = c.Tb(k - 1);
+        double *d = dst + (size_t)(k - 1) * TKS;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const double2 e = ld2(src + j * 16 + 2 * r); st2(d + j * 16 + 2 * r, e.x, e.y); }
+      }
+      if (k == N) {
+        const double *src = c.Tb(N);
+        double *d = dst + (size_t)N * TKS;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const double2 e = ld2(src + j * 16 + 2 * r); st2(d + j * 16 + 2 * r, e.x, e.y); }
+      }
+    }
+  }
+  if (c.L->ring) {  // the slab copy is read by the async proxy (TMA) from here on, and the ring is overwritten by it
+    __threadfence_block();
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncwarp();
   }
 }
 
@@ -322,9 +347,75 @@ __device__ __forceinline__ void sts2(uint32_t a, double x, double y) {
 
 constexpr int TKB = TKS * 8, VB = VS * 8;  // bytes per stage
 
+// ---- streamed factor: ring of stage blocks filled by TMA bulk copies (cp.async.bulk + mbarrier complete_tx)
+// The sweeps touch the factor in a fixed cycle of 2N+1 stage steps (fwd: blocks 0..N, bwd: blocks N-1..0), so the ring
+// is a plain FIFO: the load of step t goes to slot t mod ring and is issued D steps ahead; every load is consumed
+// exactly once (blocks around the turning points are simply fetched again from L2).
+struct Strm {        // per group, identical in every lane
+  uint32_t t;        // stage steps consumed so far (slot = t & mask, mbarrier phase parity = (t >> lg) & 1)
+  uint32_t ahead;    // loads in flight beyond step t: 0 (cold) or D
+};
+struct StrmC {
+  uint32_t ring;     // shared address of ring slot 0 of my QP
+  uint32_t mbar;     // shared address of my QP's mbarriers (8 bytes per slot)
+  const double *gsrc;// slab copy of the factor: block k at + k * TKS
+  uint32_t mask, lg; // ring - 1, log2(ring)
+  int D, N;          // prefetch distance in stage steps (<= ring - 1); horizon
+  bool on, issuer;   // streaming enabled; this lane issues the copies of its group
+};
+__device__ __forceinline__ void strm_wait(const StrmC &sc, const uint32_t t) {
+  const uint32_t bar = sc.mbar + 8u * (t & sc.mask), ph = (t >> sc.lg) & 1u;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar), "r"(ph) : "memory");
+}
+// request the factor block of cycle position `pos` (may run past 2N: wraps) for step t
+__device__ __forceinline__ void strm_issue(const StrmC &sc, const uint32_t t, int pos) {
+  if (sc.issuer) {
+    if (pos > 2 * sc.N) pos -= 2 * sc.N + 1;
+    const int blk = pos <= sc.N ? pos : 2 * sc.N - pos;
+    const uint32_t slot = t & sc.mask, bar = sc.mbar + 8u * slot, dst = sc.ring + slot * (uint32_t)(TKS * 8);
+    const double *src = sc.gsrc + (size_t)blk * TKS;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(TKS * 8) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(TKS * 8), "r"(bar)
+                 : "memory");
+  }
+}
+// entering the stage step at cycle position `pos`: returns the byte offset of its block inside the ring
+__device__ __forceinline__ uint32_t strm_step(const StrmC &sc, Strm &sm, const int pos) {
+  const uint32_t t = sm.t;
+  strm_wait(sc, t);
+  strm_issue(sc, t + (uint32_t)sc.D, pos + sc.D);
+  sm.t = t + 1u;
+  return (t & sc.mask) * (uint32_t)(TKS * 8);
+}
+// before the first stage step after a (re)factorisation: fill the pipeline for positions 0 .. D-1
+__device__ __forceinline__ void strm_warm(const StrmC &sc, Strm &sm) {
+  if (sc.on && sm.ahead == 0u) {
+    for (int d = 0; d < sc.D; ++d) strm_issue(sc, sm.t + (uint32_t)d, d);
+    sm.ahead = (uint32_t)sc.D;
+  }
+}
+// nothing in flight after this (the loads issued ahead are waited for and dropped)
+__device__ __forceinline__ void strm_drain(const StrmC &sc, Strm &sm) {
+  if (sc.on) {
+    for (uint32_t d = 0; d < sm.ahead; ++d) strm_wait(sc, sm.t + d);
+    sm.t += sm.ahead;
+    sm.ahead = 0u;
+  }
+}
+
 // Per-lane shared-space addresses of stage 0 (computed once per QP).
 template <int KIND>
 struct Hot {
+  StrmC sc;         // streamed factor (sc.on) or resident
   uint32_t tk[4];   // logical 16-byte chunk j of my row of T_0 (the same chunk of K_1 at +512)
   uint32_t kc[4];   // my column of K_1 in row 2q (row 2q+1 at +64)
   uint32_t v;       // my element of the stage vectors: B +0, X +64, R +128, XS +192, DG +256, CR +320
@@ -344,11 +435,14 @@ __device__ __forceinline__ double dot8(const double2 &a0, const double2 &a1, con
 
 // forward sweep: B holds the right-hand side on entry, W_k = T_k v_k on exit.  `gsel` toggles the gather buffer.
 template <int KIND>
-__device__ __forceinline__ void sweep_fwd(const Hot<KIND> &h, const int N, uint32_t &gsel) {
-  uint32_t t0 = h.tk[0], t1 = h.tk[1], t2 = h.tk[2], t3 = h.tk[3], vb = h.v;
+__device__ __forceinline__ void sweep_fwd(const Hot<KIND> &h, Strm &sm, const int N, uint32_t &gsel) {
+  uint32_t vb = h.v;
   double v = lds(vb);
+  strm_warm(h.sc, sm);
 #pragma unroll 1
   for (int k = 0; k < N; ++k) {
+    const uint32_t so = h.sc.on ? strm_step(h.sc, sm, k) : (uint32_t)k * (uint32_t)TKB;
+    const uint32_t t0 = h.tk[0] + so, t1 = h.tk[1] + so, t2 = h.tk[2] + so, t3 = h.tk[3] + so;
     sts(h.gpub ^ gsel, v);
     const double2 a0 = lds2(t0), a1 = lds2(t1), a2 = lds2(t2), a3 = lds2(t3);
     const double2 b0 = lds2<512>(t0), b1 = lds2<512>(t1), b2 = lds2<512>(t2), b3 = lds2<512>(t3);
@@ -360,9 +454,11 @@ __device__ __forceinline__ void sweep_fwd(const Hot<KIND> &h, const int N, uint3
     c0 = fma(-b0.y, g0.y, c0); c1 = fma(-b1.y, g1.y, c1); c2 = fma(-b2.y, g2.y, c2); c3 = fma(-b3.y, g3.y, c3);
     v = (c0 + c1) + (c2 + c3);
     sts(vb, dot8(a0, a1, a2, a3, g0, g1, g2, g3));
-    t0 += TKB; t1 += TKB; t2 += TKB; t3 += TKB; vb += VB; gsel ^= 256u;
+    vb += VB; gsel ^= 256u;
   }
   {  // stage N: no K
+    const uint32_t so = h.sc.on ? strm_step(h.sc, sm, N) : (uint32_t)N * (uint32_t)TKB;
+    const uint32_t t0 = h.tk[0] + so, t1 = h.tk[1] + so, t2 = h.tk[2] + so, t3 = h.tk[3] + so;
     sts(h.gpub ^ gsel, v);
     const double2 a0 = lds2(t0), a1 = lds2(t1), a2 = lds2(t2), a3 = lds2(t3);
     __syncwarp();
@@ -396,10 +492,9 @@ __device__ __forceinline__ void gather_in(const uint32_t ggat, uint32_t &gsel, d
 
 // backward sweep only (polish): x_k = W_k - K_{k+1}' x_{k+1}, written back into B
 template <int KIND>
-__device__ __forceinline__ void sweep_bwd_plain(const Hot<KIND> &h, const int N, uint32_t &gsel) {
+__device__ __forceinline__ void sweep_bwd_plain(const Hot<KIND> &h, Strm &sm, const int N, uint32_t &gsel) {
   double gn[8];
   uint32_t vb = h.v + N * VB;
-  uint32_t k0 = h.kc[0] + N * TKB, k1 = h.kc[1] + N * TKB, k2 = h.kc[2] + N * TKB, k3 = h.kc[3] + N * TKB;
   {
     const double x = lds(vb);
     sts(h.gpub ^ gsel, x);
@@ -407,8 +502,9 @@ __device__ __forceinline__ void sweep_bwd_plain(const Hot<KIND> &h, const int N,
   }
 #pragma unroll 1
   for (int k = N - 1; k >= 0; --k) {
-    vb -= VB; k0 -= TKB; k1 -= TKB; k2 -= TKB; k3 -= TKB;
-    const double xt = bwd_step(k0, k1, k2, k3, vb, h.gpub, h.ggat, gsel, gn);
+    const uint32_t so = h.sc.on ? strm_step(h.sc, sm, 2 * N - k) : (uint32_t)k * (uint32_t)TKB;
+    vb -= VB;
+    const double xt = bwd_step(h.kc[0] + so, h.kc[1] + so, h.kc[2] + so, h.kc[3] + so, vb, h.gpub, h.ggat, gsel, gn);
     sts(vb, xt);
     gather_in(h.ggat, gsel, gn);
   }
@@ -493,11 +589,10 @@ __device__ __forceinline__ void update_part2(const Upd<KIND> &u, const uint32_t 
 
 // backward sweep fused with the element-wise update of stage k+1 (hot)
 template <int KIND>
-__device__ __forceinline__ void sweep_bwd_admm(const Hot<KIND> &h, const Upd<KIND> &u, uint32_t &gsel) {
+__device__ __forceinline__ void sweep_bwd_admm(const Hot<KIND> &h, Strm &sm, const Upd<KIND> &u, uint32_t &gsel) {
   const int N = u.N;
   double gn[8];
   uint32_t vb = h.v + N * VB, ib = h.ib + N * h.istr, il = h.il + N * h.istr, pb = h.pm + N * h.pstr, pb2 = h.pm2 + N * h.pstr;
-  uint32_t k0 = h.kc[0] + N * TKB, k1 = h.kc[1] + N * TKB, k2 = h.kc[2] + N * TKB, k3 = h.kc[3] + N * TKB;
   double x1 = lds(vb), x2 = 0.0;   // stage N: x~_N = W_N
   sts(h.gpub ^ gsel, x1);
   gather_in(h.ggat, gsel, gn);
@@ -505,8 +600,8 @@ __device__ __forceinline__ void sweep_bwd_admm(const Hot<KIND> &h, const Upd<KIN
   for (int k = N - 1; k >= 0; --k) {
     UpdIn in;
     update_loads<KIND>(vb, ib, il, pb, pb2, in);   // stage k+1, independent of the chain below
-    k0 -= TKB; k1 -= TKB; k2 -= TKB; k3 -= TKB;
-    const double xt = bwd_step(k0, k1, k2, k3, vb - VB, h.gpub, h.ggat, gsel, gn);
+    const uint32_t so = h.sc.on ? strm_step(h.sc, sm, 2 * N - k) : (uint32_t)k * (uint32_t)TKB;
+    const double xt = bwd_step(h.kc[0] + so, h.kc[1] + so, h.kc[2] + so, h.kc[3] + so, vb - VB, h.gpub, h.ggat, gsel, gn);
     UpdMid q;
     update_part1<KIND>(u, k + 1, ib, in, x1, xt, x2, q);   // fills the publish -> gather latency
     gather_in(h.ggat, gsel, gn);
@@ -866,7 +961,7 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
   int sched_err = 0, data_err = 0;
   double x0r = 0.0;
   // scratch in the factor area ((N+1)*128 - 64 doubles): 8 arrays of NS8, then G (N x GS, plain rows), then nz doubles
-  double *sD = S + L.TK, *sE = sD + NS8, *sEI = sE + NS8, *sDt = sEI + NS8, *sEt = sDt + NS8, *sEti = sEt + NS8;
+  double *sD = L.ring ? c.cold + L.cTK : S + L.TK, *sE = sD + NS8, *sEI = sE + NS8, *sDt = sEI + NS8, *sEt = sDt + NS8, *sEti = sEt + NS8;
   double *sPD = sEti + NS8, *sPO = sPD + NS8;
   double *Gs = sPO + NS8;
   // ---- schedule: G_k = -[A_k B_k] (unscaled), my row
@@ -1178,7 +1273,8 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
 //   rhs = -q - P x - A_red'(y - r2 / delta)                                  (one product with the columns of G)
 //   dx  = S^-1 rhs;  A dx gives dy = (A dx - r2) / delta and r2 <- r2 - A dx   (one product with the rows of G)
 template <int KIND>
-__device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const lpvmpc_settings &St, Info *ip, const bool do_pol, uint32_t gsel) {
+__device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, Strm *smp, const lpvmpc_settings &St, Info *ip, const bool do_pol, uint32_t gsel) {
+  Strm &sm = *smp;
   constexpr int NT = Ctx<KIND>::NT, NX = Ctx<KIND>::NX;
   Info &I = *ip;
   const bool unscale = I.unscale;
@@ -1211,6 +1307,7 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
   }
   __syncwarp();
   FW fw; fw.polish = 1; fw.rho = 0.0; fw.rho_eq = 0.0; fw.idel = idel;
+  strm_drain(h.sc, sm);
   factor<KIND>(c, fw, delta);
   auto bred_i = [&](int k, int t) { const double a = ACTI[c.ci(k, t)]; return (a == 1.0 || a == 3.0) ? c.lo_of(k, t) : c.ui(k, t); };
   // first solve: rhs = -q + A_red'(b_red / delta); the targets go through R2D / R2I
@@ -1242,8 +1339,8 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
 #pragma unroll 1
   for (int k = 0; k <= N; ++k) BV[k * VS + r] = c.var_live(k) ? (-QV[k * 8 + r] + colAt(R2D, R2I, k)) : 0.0;
   __syncwarp();
-  sweep_fwd<KIND>(h, N, gsel);
-  sweep_bwd_plain<KIND>(h, N, gsel);
+  sweep_fwd<KIND>(h, sm, N, gsel);
+  sweep_bwd_plain<KIND>(h, sm, N, gsel);
   // x, y = (A x - b) / delta, r2 = b - A x on the active rows
 #pragma unroll 1
   for (int k = 0; k <= N; ++k) {
@@ -1289,8 +1386,8 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
       BV[ov] = b;
     }
     __syncwarp();
-    sweep_fwd<KIND>(h, N, gsel);
-    sweep_bwd_plain<KIND>(h, N, gsel);
+    sweep_fwd<KIND>(h, sm, N, gsel);
+    sweep_bwd_plain<KIND>(h, sm, N, gsel);
     // dy = (A dx - r2) / delta, r2 <- r2 - A dx, x <- x + dx
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
@@ -1378,6 +1475,7 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
   Ctx<KIND> c;
   c.S = smem; c.cold = p.cold;
   c.L = &L; c.N = N; c.r = r;
+  c.kmask = L.ring ? (L.ring - 1) : -1;
   c.xl = r < NX; c.ul = (r >= NX) && (r < NB);
   if (KIND == LPVMPC_CONTROLLER) c.islot = (r == 0) ? 0 : ((r >= NX) ? (r - NX + 1) * 2 : 0);
   else c.islot = r;
@@ -1391,10 +1489,20 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
   const int ucomp = r - NX;
   double *wsm = smem + (size_t)warp * QPW * L.total;
   const size_t wslot = (size_t)(blockIdx.x * wpc + warp) * QPW;
-  // all-gather buffers: two 256-byte buffers per warp, 512-byte aligned, after the QP regions
+  // all-gather buffers: two 256-byte buffers per warp, 512-byte aligned, after the QP regions; then 8 mbarriers per QP
   const uint32_t smem_a = (uint32_t)__cvta_generic_to_shared(smem);
-  const uint32_t gbuf = ((smem_a + (uint32_t)(wpc * QPW * L.total * 8) + 511u) & ~511u) + (uint32_t)warp * 512u;
+  const uint32_t gbuf0 = (smem_a + (uint32_t)(wpc * QPW * L.total * 8) + 511u) & ~511u;
+  const uint32_t gbuf = gbuf0 + (uint32_t)warp * 512u;
+  const uint32_t mbar0 = gbuf0 + (uint32_t)wpc * 512u + (uint32_t)(warp * QPW) * 64u;
   uint32_t gsel = 0;
+  Strm sm;
+  sm.t = 0u; sm.ahead = 0u;
+  if (L.ring) {  // this warp's mbarriers (one arrival: the issuing lane's expect_tx)
+    if (lane < QPW * 8) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar0 + 8u * (uint32_t)lane) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncwarp();
+  }
 
   for (;;) {
     unsigned base = 0;
@@ -1409,9 +1517,18 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
     c.S = wsm + gq * L.total;
     c.cold = p.cold + (wslot + gq) * L.cold_total;
 
+    {  // groups that mirror group 0 wait on its mbarriers: take over its phase parities (only happens for g >= QPW,
+       // always, and for the groups of the batch tail, which never own a QP again)
+      const uint32_t t0 = __shfl_sync(kFull, sm.t, 0);
+      if (!valid) sm.t = t0;
+    }
     Hot<KIND> h;
     {
       const uint32_t sq = smem_a + (uint32_t)((warp * QPW + gq) * L.total) * 8u;
+      h.sc.on = L.ring != 0; h.sc.issuer = valid && r == 0 && L.ring != 0;
+      h.sc.ring = sq + (uint32_t)L.TK * 8u; h.sc.mbar = mbar0 + (uint32_t)gq * 64u;
+      h.sc.gsrc = c.cold + L.cTK; h.sc.mask = L.ring ? (uint32_t)(L.ring - 1) : 0u; h.sc.lg = (L.ring == 8) ? 3u : 2u;
+      h.sc.D = L.pfd; h.sc.N = N;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         h.tk[q] = sq + (uint32_t)(L.TK + c.ro[q]) * 8u;
@@ -1488,8 +1605,8 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
           }
         }
         u.cc = (iter == 0) ? 2.0 : alpha;
-        sweep_fwd<KIND>(h, N, gsel);
-        sweep_bwd_admm<KIND>(h, u, gsel);
+        sweep_fwd<KIND>(h, sm, N, gsel);
+        sweep_bwd_admm<KIND>(h, sm, u, gsel);
         if (iter == 0) first_in = 1;
         ++nsync;
         zsel = 1.0;
@@ -1522,6 +1639,7 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
             if (upd) { rho = rho_new; rho_eq = kRhoEqOverIneq * rho; ++rho_updates; }
             FW fw; fw.polish = 0; fw.rho = rho; fw.rho_eq = rho_eq; fw.idel = 0.0;
             __syncwarp();
+            strm_drain(h.sc, sm);
             factor<KIND>(c, fw, sigma);
             new_cr = true;
           }
@@ -1581,7 +1699,7 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
     const bool do_pol = S.polish && status == LPVMPC_SOLVED;
     bool polished_sets = false;
     if (__any_sync(kFull, do_pol)) {
-      polish_status = polish<KIND>(c, h, S, &I, do_pol, gsel);
+      polish_status = polish<KIND>(c, h, &sm, S, &I, do_pol, gsel);
       polished_sets = do_pol;
     }
     // ---- outputs
@@ -1623,6 +1741,7 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
         if (a.dua_res) a.dua_res[b] = failed ? nan("") : I.dua_res;
       }
     }
+    strm_drain(h.sc, sm);   // nothing may be in flight into the ring when the next QP's setup / factor starts
     __syncwarp();
   }
   (void)NSL; (void)NB;

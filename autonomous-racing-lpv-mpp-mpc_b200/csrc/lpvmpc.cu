@@ -267,15 +267,18 @@ lpv::g8::Lay make_g8_layout(int kind, int N) {
   return L;
 }
 
-lpv::h8::Lay make_h8_layout(int kind, int N) {
+// ring = 0: block factor resident in shared memory; ring = 4 / 8: factor in the slab, staged through a ring of `ring`
+// stage blocks by TMA bulk copies (prefetch distance ring - 2)
+lpv::h8::Lay make_h8_layout(int kind, int N, int ring) {
   const int NX = kind == LPVMPC_CONTROLLER ? 6 : 5;
   lpv::h8::Lay L;
   std::memset(&L, 0, sizeof(L));
   L.N = N; L.nsl = kind == LPVMPC_CONTROLLER ? 6 : 7;
   L.is = kind == LPVMPC_CONTROLLER ? 26 : 38;
+  L.ring = ring; L.pfd = ring ? ring - 2 : 0;
   int o = 0;
   auto take = [&](int n) { const int r = o; o += (n + 1) & ~1; return r; };
-  L.TK = take((N + 1) * lpv::h8::TKS - 64);
+  L.TK = take(ring ? ring * lpv::h8::TKS : (N + 1) * lpv::h8::TKS - 64);
   L.V = take((N + 1) * lpv::h8::VS);
   L.I = take((N + 2) * L.is);
   while (o % 16 != 8) o += 2;  // neighbouring groups of a warp 64 B apart mod 128
@@ -283,6 +286,8 @@ lpv::h8::Lay make_h8_layout(int kind, int N) {
   const int v = (N + 1) * 8;
   L.cG = lpv::h8::C_COUNT * v;
   L.cold_total = L.cG + N * NX * 8;
+  L.cTK = L.cold_total;
+  if (ring) L.cold_total += (N + 1) * lpv::h8::TKS;   // also setup's scratch (8 (N+1) 8 + N NX 8 + nz doubles fit)
   return L;
 }
 
@@ -586,11 +591,19 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
     if (cfg->variant == 3 && !g8_ok) { h->err = "variant 3 (G8) needs diagonal Q and R, steering_delay=0, planner N<=63 and a per-QP state that fits shared memory"; return bail(LPVMPC_E_UNSUPPORTED); }
     if (cfg->variant == 3) h->variant = 3;
     // H8 kernel: same restrictions as G8, smaller shared-memory footprint (cold data in an L2 slab)
-    h->HL = make_h8_layout(cfg->kind, cfg->N);
+    h->HL = make_h8_layout(cfg->kind, cfg->N, 0);
     const bool h8_ok = pdiag && cfg->steering_delay == 0 && (size_t)h->HL.total * sizeof(double) + 1024 <= (size_t)h->smem_optin &&
                        (cfg->kind == LPVMPC_CONTROLLER || cfg->N <= 63);
     if (cfg->variant == 5 && !h8_ok) { h->err = "variant 5 (H8) needs diagonal Q and R, steering_delay=0, planner N<=63 and a per-QP state that fits shared memory"; return bail(LPVMPC_E_UNSUPPORTED); }
     if (cfg->variant == 5 || (cfg->variant == 0 && h8_ok)) h->variant = 5;
+    // H8S = H8 with the factor streamed from the slab (variants 7: ring of 4 blocks, 8: ring of 8): N <= 254, stage vectors
+    // and single-variable rows must still fit shared memory
+    const lpv::h8::Lay SL4 = make_h8_layout(cfg->kind, cfg->N, 4);
+    const bool h8s_ok = pdiag && cfg->steering_delay == 0 && cfg->N <= 254 && (size_t)SL4.total * sizeof(double) + 2048 <= (size_t)h->smem_optin &&
+                        (cfg->kind == LPVMPC_CONTROLLER || cfg->N <= 63);
+    if ((cfg->variant == 7 || cfg->variant == 8) && !h8s_ok) { h->err = "variants 7/8 (H8S) need diagonal Q and R, steering_delay=0, planner N<=63, N<=254"; return bail(LPVMPC_E_UNSUPPORTED); }
+    if (cfg->variant == 7 || cfg->variant == 8) { h->variant = 5; h->HL = make_h8_layout(cfg->kind, cfg->N, cfg->variant == 7 ? 4 : 8); }
+    else if (cfg->variant == 0 && h8s_ok && (!h8_ok || 2 * (size_t)SL4.total <= (size_t)h->HL.total)) { h->variant = 5; h->HL = SL4; }   // streaming at least doubles the resident QPs
     // H8T kernel: controller, block factor in tensor memory (48 N + 16 columns of the SM's 512), 16 QPs per CTA, one CTA per SM
     h->TL = make_h8t_layout(cfg->kind, cfg->N);
     const size_t h8t_bytes = (size_t)h->TL.total * sizeof(double) * 16 + 4 * 512 + 512;
@@ -614,17 +627,29 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
     const size_t per_qp = (size_t)h->HL.total * sizeof(double);
     const size_t sm_bytes = prop.sharedMemPerMultiprocessor;
     int best_q = 0, best_qpw = 1, best_wpc = 1, best_ctas = 1;
-    const int qs[3] = {4, 2, 1};
-    for (int qi = 0; qi < 3; ++qi) for (int w = 2; w >= 1; --w) {
-      const size_t cta = per_qp * qs[qi] * w + 512 * (size_t)w + 512;
+    // resident factor: prefer many QPs per warp; streamed factor: prefer many warps (ties go to the first candidate)
+    const int qs_res[3] = {4, 2, 1}, qs_str[3] = {1, 2, 4};
+    const int *qs = h->HL.ring ? qs_str : qs_res;
+    for (int qi = 0; qi < 3; ++qi) for (int w = (h->HL.ring ? 1 : 2); w >= 1; --w) {
+      const size_t cta = per_qp * qs[qi] * w + 512 * (size_t)w + 512 + 64 * (size_t)(qs[qi] * w);
       if (cta > (size_t)h->smem_optin) continue;
       int ctas = (int)(sm_bytes / (cta + 1024));
       if (ctas > 32) ctas = 32;
       const int q = ctas * qs[qi] * w;
       if (q > best_q) { best_q = q; best_qpw = qs[qi]; best_wpc = w; best_ctas = ctas; }
     }
+    // tuning knobs for experiments (not part of the ABI): force QPs per warp / cap resident CTAs per SM
+    if (const char *e = std::getenv("LPVMPC_H8_QPW")) {
+      const int q = std::atoi(e);
+      const size_t cta = per_qp * q + 512 + 512 + 64 * (size_t)q;
+      if ((q == 1 || q == 2 || q == 4) && cta <= (size_t)h->smem_optin) {
+        best_qpw = q; best_wpc = 1; best_ctas = (int)(sm_bytes / (cta + 1024));
+        if (best_ctas > 32) best_ctas = 32;
+      }
+    }
+    if (const char *e = std::getenv("LPVMPC_H8_CTAS")) { const int v = std::atoi(e); if (v >= 1 && v < best_ctas) best_ctas = v; }
     h->qpw = best_qpw; h->wpc = best_wpc;
-    h->ws_bytes = per_qp * h->qpw * h->wpc + 512 * (size_t)h->wpc + 512;
+    h->ws_bytes = per_qp * h->qpw * h->wpc + 512 * (size_t)h->wpc + 512 + 64 * (size_t)(h->qpw * h->wpc);
     h->smem_mode = true;
     h->grid_cap = h->sm_count * best_ctas;
     const bool ctrl = cfg->kind == LPVMPC_CONTROLLER;
@@ -709,7 +734,7 @@ void lpvmpc_destroy(lpvmpc_handle *h) {
 int lpvmpc_get_info(const lpvmpc_handle *h, lpvmpc_info *info) {
   if (!h || !info) return LPVMPC_E_ARG;
   info->n = h->n; info->d = h->d; info->N = h->L.N; info->nz = h->L.nz; info->m = h->L.m;
-  info->variant = h->variant;
+  info->variant = (h->variant == 5 && h->HL.ring) ? (h->HL.ring == 4 ? 7 : 8) : h->variant;   // 7 / 8: H8 with the factor streamed (ring of 4 / 8)
   info->workspace_in_smem = h->smem_mode ? 1 : 0;
   info->smem_bytes_per_qp = h->smem_mode ? (int)(h->variant == 6 ? (size_t)h->TL.total * sizeof(double) : h->variant == 5 ? (size_t)h->HL.total * sizeof(double) : ((h->variant == 2 || h->variant == 3) ? h->ws_bytes / h->qpw : h->ws_bytes)) : 0;
   info->workspace_bytes = (long long)(h->stage_bytes + (h->smem_mode ? 0 : h->ws_bytes * (size_t)h->grid_cap));

@@ -69,7 +69,7 @@ def test_schedule_matches_oracle(track):
             np.testing.assert_allclose(r.states_out[b], st, rtol=1e-12, atol=1e-14)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8])
 @pytest.mark.parametrize("iters", [1, 7, 50, 200])
 def test_controller_fixed_iteration_iterates(track, iters, variant):
     N, B = 8, 48
@@ -89,7 +89,7 @@ def test_controller_fixed_iteration_iterates(track, iters, variant):
     assert worst < 1e-9, worst
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8])
 def test_controller_converged_matches_oracle(track, variant):
     N, B = 8, 254  # not a multiple of 4: exercises the idle-group path of the T8 kernel
     w = W.controller_batch(B, N, seed=0)
@@ -109,7 +109,7 @@ def test_controller_converged_matches_oracle(track, variant):
         assert abs(r.obj[b] - o["obj_val"]) <= 1e-6 * abs(o["obj_val"]), (b, r.obj[b], o["obj_val"])
 
 
-@pytest.mark.parametrize("variant", [1, 3, 5])
+@pytest.mark.parametrize("variant", [1, 3, 5, 7, 8])
 def test_planner_fixed_and_converged(track, variant):
     N, B = 40, 24
     w = W.planner_batch(B, N, seed=1)
@@ -143,3 +143,36 @@ def test_planner_fixed_and_converged(track, variant):
             assert abs(r.obj[b] - o["obj_val"]) <= 1e-6 * abs(o["obj_val"])
         else:
             assert np.isnan(r.x_pred[b]).all()
+
+
+@pytest.mark.parametrize("variant", [0, 5, 8])
+def test_long_horizon_controller_matches_oracle(track, variant):
+    """BASELINE configs[4] family: N = 100 (the block factor, 103 KB, is streamed from the L2 slab by TMA bulk copies
+    in variants 7 / 8; variant 0 must pick the streamed kernel, variant 5 keeps it resident: 1 QP per SM)."""
+    N, B = 100, 37
+    w = W.controller_batch(B, N, seed=3, steer_scale=0.2)
+    keys = ("u_prev", "vel_ref", "curv_ref", "lap", "u_old")
+    cfg = oracle.make_cfg("controller", N, W.CTRL_DT, W.CTRL_TT["Q"], W.CTRL_TT["R"], W.CTRL_TT["dR"], track)
+    fixed = dict(max_iter=60, check_termination=0, adaptive_rho=0, polish=0)
+    s = lp.BatchSolver("controller", N, W.CTRL_DT, track=track, max_batch=B, variant=variant, **W.CTRL_TT, **fixed)
+    assert s.info()["variant"] == (7 if variant == 0 else variant)
+    r = s.solve(w["x0"], extra_outputs=("xs", "zs", "ys"), **{k: w[k] for k in keys})
+    st = oracle.default_settings(**fixed)
+    worst = 0.0
+    for b in range(B):
+        o = _oracle_ctrl(cfg, st, w, b)
+        for k in ("xs", "zs", "ys"):
+            worst = max(worst, _relinf(r[k][b], o[k]))
+    assert worst < 1e-9, worst
+    s.update_settings(**{k: getattr(oracle.default_settings(polish=1), k) for k in ("max_iter", "check_termination", "adaptive_rho", "polish")})
+    r = s.solve(w["x0"], extra_outputs=("active_lo", "active_up"), **{k: w[k] for k in keys})
+    st = oracle.default_settings(polish=1)
+    for b in range(B):
+        o = _oracle_ctrl(cfg, st, w, b)
+        assert int(r.status[b]) == o["status"] and int(r.iters[b]) == o["iter"], (b, r.status[b], o["status"], r.iters[b], o["iter"])
+        assert int(r.rho_updates[b]) == o["rho_updates"] and int(r.polish_status[b]) == o["status_polish"], b
+        if o["status"] in (1, 2, -2):
+            _same_active_set(r, o, b)
+            np.testing.assert_allclose(r.u_pred[b], o["uPred"], rtol=0, atol=1e-4)
+            np.testing.assert_allclose(r.x_pred[b], o["xPred"], rtol=0, atol=1e-4)
+            assert abs(r.obj[b] - o["obj_val"]) <= 1e-6 * abs(o["obj_val"])
