@@ -90,6 +90,25 @@ __device__ __forceinline__ int gany(int v) {
   const unsigned m = __ballot_sync(kFull, v);
   return ((m >> ((threadIdx.x & 31) & ~7)) & 0xffu) != 0;
 }
+// reductions of the cold loops: over my group, or over the whole warp when its four groups share ONE QP and split the
+// stages between them (`wide`, warp-uniform: 1 QP per warp)
+__device__ __forceinline__ double wmax(double v, const bool wide) {
+  v = gmax(v);
+  if (wide) {
+    double w = __shfl_xor_sync(kFull, v, 8); v = (w > v) ? w : v;
+    w = __shfl_xor_sync(kFull, v, 16); v = (w > v) ? w : v;
+  }
+  return v;
+}
+__device__ __forceinline__ double wsum(double v, const bool wide) {
+  v = gsum(v);
+  if (wide) { v += __shfl_xor_sync(kFull, v, 8); v += __shfl_xor_sync(kFull, v, 16); }
+  return v;
+}
+__device__ __forceinline__ int wany(int v, const bool wide) {
+  const unsigned m = __ballot_sync(kFull, v);
+  return wide ? (m != 0u) : (((m >> ((threadIdx.x & 31) & ~7)) & 0xffu) != 0);
+}
 // Reciprocal and reciprocal square root from the hardware seed (2^-23) and three Newton steps: ~1 ulp, a dozen
 // instructions and half the latency of the IEEE division / sqrt sequences (70+ instructions each).
 __device__ __forceinline__ double frcp(double x) {
@@ -124,6 +143,8 @@ struct Ctx {
   const Lay *L;
   int N, r;
   int kmask;     // stage -> factor block slot: -1 (resident: slot k) or ring - 1
+  int k0, ks;    // stages of the cold per-stage loops handled by my group: k0, k0 + ks, ... (0, 1; or group index, 4 when the
+                 // warp holds one QP: its four groups then split the stages instead of mirroring each other)
   int ro[4];     // my row of a swizzled block: offset of logical chunk j
   int co[4];     // my column of a swizzled block: offset inside row rr is co[rr >> 1]
   bool xl, ul;   // state lane / input lane (neither: idle lane)
@@ -684,7 +705,7 @@ __device__ __noinline__ void sync_yd(const Ctx<KIND> c, const bool live, const d
   const double cb = alpha * n + (first ? (1.0 - alpha) : 0.0);
   if (n > 0) {
 #pragma unroll 1
-    for (int k = 0; k <= N; ++k) {
+    for (int k = c.k0; k <= N; k += c.ks) {
       if (c.xl) {
         const int o = k * 8 + r;
         const double ax = rowA_dyn<KIND>(c, ED, XS, VS, k);
@@ -710,7 +731,7 @@ __device__ __noinline__ void reproject(const Ctx<KIND> c, const bool doit, const
   const double *X = c.V(V_X);
   const double *YD = c.cd(C_YD), *BE = c.cd(C_BE), *ED = c.cd(C_ED), *QV = c.cd(C_Q);
 #pragma unroll 1
-  for (int k = 0; k <= N; ++k) {
+  for (int k = c.k0; k <= N; k += c.ks) {
     const int o = k * 8 + r, ov = k * VS + r;
     if (c.var_live(k)) {
       const double *gk = c.Gb(k);
@@ -760,7 +781,7 @@ __device__ __noinline__ void update_info(const Ctx<KIND> c, Info *ip, const doub
   double a_rp = 0, a_z = 0, a_Ax = 0, b_rp = 0, b_z = 0, b_Ax = 0;
   double a_rd = 0, a_q = 0, a_Aty = 0, a_Px = 0, b_rd = 0, b_q = 0, b_Aty = 0, b_Px = 0;
 #pragma unroll 1
-  for (int k = 0; k <= N; ++k) {
+  for (int k = c.k0; k <= N; k += c.ks) {
     const int o = k * 8 + r;
     if (c.xl) {
       const double Ax = rowA_dyn<KIND>(c, ED, X, VS, k), z = zsel * BE[o], rr = Ax - z, ei = EINV[o];
@@ -782,10 +803,12 @@ __device__ __noinline__ void update_info(const Ctx<KIND> c, Info *ip, const doub
       b_rd = absmax(b_rd, di * rr); b_q = absmax(b_q, di * QV[o]); b_Aty = absmax(b_Aty, di * Aty); b_Px = absmax(b_Px, di * Px);
     }
   }
-  I.n_rp = gmax(a_rp); I.n_z = gmax(a_z); I.n_Ax = gmax(a_Ax); I.n_rd = gmax(a_rd); I.n_q = gmax(a_q); I.n_Aty = gmax(a_Aty); I.n_Px = gmax(a_Px);
+  const bool wd = c.ks > 1;
+  I.n_rp = wmax(a_rp, wd); I.n_z = wmax(a_z, wd); I.n_Ax = wmax(a_Ax, wd); I.n_rd = wmax(a_rd, wd); I.n_q = wmax(a_q, wd);
+  I.n_Aty = wmax(a_Aty, wd); I.n_Px = wmax(a_Px, wd);
   if (I.unscale) {
-    I.pri_res = gmax(b_rp); I.u_z = gmax(b_z); I.u_Ax = gmax(b_Ax);
-    I.dua_res = I.cinv * gmax(b_rd); I.u_q = gmax(b_q); I.u_Aty = gmax(b_Aty); I.u_Px = gmax(b_Px);
+    I.pri_res = wmax(b_rp, wd); I.u_z = wmax(b_z, wd); I.u_Ax = wmax(b_Ax, wd);
+    I.dua_res = I.cinv * wmax(b_rd, wd); I.u_q = wmax(b_q, wd); I.u_Aty = wmax(b_Aty, wd); I.u_Px = wmax(b_Px, wd);
   } else {
     I.pri_res = I.n_rp; I.u_z = I.n_z; I.u_Ax = I.n_Ax; I.dua_res = I.n_rd; I.u_q = I.n_q; I.u_Aty = I.n_Aty; I.u_Px = I.n_Px;
   }
@@ -806,12 +829,13 @@ __device__ __noinline__ bool primal_infeasible(const Ctx<KIND> c, const Info *ip
   const double *PVYI = c.cd(C_PVYI), *E = c.cd(C_E), *EI = c.cd(C_EI), *DINV = c.cd(C_DINV);
   double *DYD = c.cd(C_DYD), *DYI = c.cd(C_PYI), *XT = c.cd(C_ZT);
   const double ia = 1.0 / alpha, oma = 1.0 - alpha, cb = last_was_first ? 1.0 : alpha;
+  const bool wd = c.ks > 1;
 #pragma unroll 1
-  for (int k = 0; k <= N; ++k) { const int o = k * 8 + r; XT[o] = c.var_live(k) ? (X[k * VS + r] - oma * PVX[o]) * ia : 0.0; }
+  for (int k = c.k0; k <= N; k += c.ks) { const int o = k * 8 + r; XT[o] = c.var_live(k) ? (X[k * VS + r] - oma * PVX[o]) * ia : 0.0; }
   __syncwarp();
   double nrm = 0.0, lhs = 0.0;
 #pragma unroll 1
-  for (int k = 0; k <= N; ++k) {
+  for (int k = c.k0; k <= N; k += c.ks) {
     const int o = k * 8 + r;
     double d = 0.0;
     if (c.xl) d = rho_eq * (alpha * rowA_dyn<KIND>(c, ED, XT, 8, k) - cb * BE[o]);  // equality rows: no projection
@@ -836,20 +860,20 @@ __device__ __noinline__ bool primal_infeasible(const Ctx<KIND> c, const Info *ip
       }
     }
   }
-  nrm = gmax(nrm);
-  lhs = gsum(lhs);
+  nrm = wmax(nrm, wd);
+  lhs = wsum(lhs, wd);
   __syncwarp();
   // the product with A' is only needed when the first two conditions of the certificate hold for some group
   if (!__any_sync(kFull, (nrm > eps) && (lhs < -eps * nrm))) return false;
   double mx = 0.0;
 #pragma unroll 1
-  for (int k = 0; k <= N; ++k) {
+  for (int k = c.k0; k <= N; k += c.ks) {
     if (c.var_live(k)) {
       const double at = colA<KIND>(c, ED, DYD, DYI, false, k);
       mx = absmax(mx, unscale ? DINV[k * 8 + r] * at : at);
     }
   }
-  mx = gmax(mx);
+  mx = wmax(mx, wd);
   return (nrm > eps) && (lhs < -eps * nrm) && (mx < eps * nrm);
 }
 
@@ -864,15 +888,16 @@ __device__ __noinline__ bool dual_infeasible(const Ctx<KIND> c, const Info *ip, 
   const double *PD = c.cd(C_PD), *PO = c.cd(C_PO);
   double *DX = c.cd(C_PX);
   double nrm = 0.0, qdx = 0.0;
+  const bool wd = c.ks > 1;
 #pragma unroll 1
-  for (int k = 0; k <= N; ++k) {
+  for (int k = c.k0; k <= N; k += c.ks) {
     const int o = k * 8 + r;
     const double dx = c.var_live(k) ? X[k * VS + r] - PVX[o] : 0.0;
     DX[o] = dx;
     nrm = absmax(nrm, unscale ? D[o] * dx : dx);
     qdx += QV[o] * dx;
   }
-  nrm = gmax(nrm); qdx = gsum(qdx);
+  nrm = wmax(nrm, wd); qdx = wsum(qdx, wd);
   __syncwarp();
   const double cs = unscale ? ip->csc : 1.0;
   // the products with P and A are only needed when the first two conditions of the certificate hold for some group
@@ -880,7 +905,7 @@ __device__ __noinline__ bool dual_infeasible(const Ctx<KIND> c, const Info *ip, 
   double mx = 0.0;
   int viol = 0;
 #pragma unroll 1
-  for (int k = 0; k <= N; ++k) {
+  for (int k = c.k0; k <= N; k += c.ks) {
     const int o = k * 8 + r;
     if (c.var_live(k)) {
       const double Pdx = rowP<KIND>(c, PD, PO, DX, 8, k);
@@ -900,8 +925,8 @@ __device__ __noinline__ bool dual_infeasible(const Ctx<KIND> c, const Info *ip, 
       }
     }
   }
-  mx = gmax(mx);
-  viol = gany(viol);
+  mx = wmax(mx, wd);
+  viol = wany(viol, wd);
   return (nrm > eps) && (qdx < -cs * eps * nrm) && (mx < cs * eps * nrm) && !viol;
 }
 
@@ -1476,6 +1501,7 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
   c.S = smem; c.cold = p.cold;
   c.L = &L; c.N = N; c.r = r;
   c.kmask = L.ring ? (L.ring - 1) : -1;
+  c.k0 = (QPW == 1) ? g : 0; c.ks = (QPW == 1) ? 4 : 1;
   c.xl = r < NX; c.ul = (r >= NX) && (r < NB);
   if (KIND == LPVMPC_CONTROLLER) c.islot = (r == 0) ? 0 : ((r >= NX) ? (r - NX + 1) * 2 : 0);
   else c.islot = r;
@@ -1596,7 +1622,7 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
           double *PVX = c.cd(C_PVX), *PVYI = c.cd(C_PVYI);
           const double *X = c.V(V_X);
 #pragma unroll 1
-          for (int k = 0; k <= N; ++k) {
+          for (int k = c.k0; k <= N; k += c.ks) {
             PVX[k * 8 + r] = X[k * VS + r];
             if (c.has_in(k)) {
 #pragma unroll
