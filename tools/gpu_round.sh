@@ -18,3 +18,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:lpv_
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-saturated > $OUT/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 kill $SMI
 ls -la $OUT | tail -15
+# closed-loop fleet (configs[3]) bench + its reference arm
+timeout 600 python bench.py --workload mc8192 --steps 24 --warmup 3 > $OUT/${TAG}_bench_mc8192.json 2> $OUT/${TAG}_bench_mc8192.err; echo "mc8192 rc=$?"; cut -c1-200 $OUT/${TAG}_bench_mc8192.json
+timeout 300 python bench.py --impl reference --workload mc8192 --steps 5 --warmup 2 > $OUT/${TAG}_benchref_mc8192.json 2>> $OUT/${TAG}_bench_mc8192.err
+ls -la $OUT | grep ${TAG} | wc -l
