@@ -370,22 +370,24 @@ constexpr int TKB = TKS * 8, VB = VS * 8;  // bytes per stage
 
 // ---- streamed factor: ring of stage blocks filled by TMA bulk copies (cp.async.bulk + mbarrier complete_tx)
 // The sweeps touch the factor in a fixed cycle of 2N+1 stage steps (fwd: blocks 0..N, bwd: blocks N-1..0), so the ring
-// is a plain FIFO: the load of step t goes to slot t mod ring and is issued D steps ahead; every load is consumed
-// exactly once (blocks around the turning points are simply fetched again from L2).
-struct Strm {        // per group, identical in every lane
-  uint32_t t;        // stage steps consumed so far (slot = t & mask, mbarrier phase parity = (t >> lg) & 1)
-  uint32_t ahead;    // loads in flight beyond step t: 0 (cold) or D
+// is a plain FIFO: the load of step t goes to slot t mod kRing and is issued kAhead steps ahead; every load is consumed
+// exactly once (blocks around the turning points are simply fetched again from L2).  Streaming kernels are compiled
+// separately (template flag ST), hold ONE QP per warp and one warp per CTA, so every address below is warp-uniform.
+constexpr int kRing = 4, kAhead = 2;
+struct Strm {
+  uint32_t t;        // stage steps consumed so far (slot = t % kRing, mbarrier phase parity = (t / kRing) & 1)
+  uint32_t ahead;    // loads in flight beyond step t: 0 (cold) or kAhead
+  uint32_t rdy;      // the load of step t was seen complete by the probe at the end of step t-1
 };
 struct StrmC {
-  uint32_t ring;     // shared address of ring slot 0 of my QP
-  uint32_t mbar;     // shared address of my QP's mbarriers (8 bytes per slot)
+  uint32_t ring;     // shared address of ring slot 0
+  uint32_t mbar;     // shared address of the mbarriers (8 bytes per slot)
   const double *gsrc;// slab copy of the factor: block k at + k * TKS
-  uint32_t mask, lg; // ring - 1, log2(ring)
-  int D, N;          // prefetch distance in stage steps (<= ring - 1); horizon
-  bool on, issuer;   // streaming enabled; this lane issues the copies of its group
+  int N;             // horizon
+  bool issuer;       // this lane issues the copies
 };
 __device__ __forceinline__ void strm_wait(const StrmC &sc, const uint32_t t) {
-  const uint32_t bar = sc.mbar + 8u * (t & sc.mask), ph = (t >> sc.lg) & 1u;
+  const uint32_t bar = sc.mbar + 8u * (t & (kRing - 1)), ph = (t / kRing) & 1u;
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
@@ -396,12 +398,22 @@ __device__ __forceinline__ void strm_wait(const StrmC &sc, const uint32_t t) {
       "DONE:\n"
       "}" ::"r"(bar), "r"(ph) : "memory");
 }
-// request the factor block of cycle position `pos` (may run past 2N: wraps) for step t
-__device__ __forceinline__ void strm_issue(const StrmC &sc, const uint32_t t, int pos) {
+// non-blocking probe of the load of step t (its latency, ~40 cycles, hides behind the end of the current stage)
+__device__ __forceinline__ uint32_t strm_probe(const StrmC &sc, const uint32_t t) {
+  const uint32_t bar = sc.mbar + 8u * (t & (kRing - 1)), ph = (t / kRing) & 1u;
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}" : "=r"(ok) : "r"(bar), "r"(ph) : "memory");
+  return ok;
+}
+// request factor block `blk` for step t
+__device__ __forceinline__ void strm_issue(const StrmC &sc, const uint32_t t, const int blk) {
   if (sc.issuer) {
-    if (pos > 2 * sc.N) pos -= 2 * sc.N + 1;
-    const int blk = pos <= sc.N ? pos : 2 * sc.N - pos;
-    const uint32_t slot = t & sc.mask, bar = sc.mbar + 8u * slot, dst = sc.ring + slot * (uint32_t)(TKS * 8);
+    const uint32_t slot = t & (kRing - 1), bar = sc.mbar + 8u * slot, dst = sc.ring + slot * (uint32_t)(TKS * 8);
     const double *src = sc.gsrc + (size_t)blk * TKS;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(TKS * 8) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
@@ -409,34 +421,44 @@ __device__ __forceinline__ void strm_issue(const StrmC &sc, const uint32_t t, in
                  : "memory");
   }
 }
-// entering the stage step at cycle position `pos`: returns the byte offset of its block inside the ring
-__device__ __forceinline__ uint32_t strm_step(const StrmC &sc, Strm &sm, const int pos) {
+// Entering forward stage k / backward stage k: waits for its block (unless the probe already saw it), requests the
+// block kAhead steps further along the cycle, returns the byte offset of the block inside the ring.
+__device__ __forceinline__ uint32_t strm_fwd(const StrmC &sc, Strm &sm, const int k) {
   const uint32_t t = sm.t;
-  strm_wait(sc, t);
-  strm_issue(sc, t + (uint32_t)sc.D, pos + sc.D);
+  if (!sm.rdy) strm_wait(sc, t);
+  strm_issue(sc, t + kAhead, (k + kAhead <= sc.N) ? k + kAhead : 2 * sc.N - k - kAhead);
   sm.t = t + 1u;
-  return (t & sc.mask) * (uint32_t)(TKS * 8);
+  return (t & (kRing - 1)) * (uint32_t)(TKS * 8);
 }
-// before the first stage step after a (re)factorisation: fill the pipeline for positions 0 .. D-1
+__device__ __forceinline__ uint32_t strm_bwd(const StrmC &sc, Strm &sm, const int k) {
+  const uint32_t t = sm.t;
+  if (!sm.rdy) strm_wait(sc, t);
+  strm_issue(sc, t + kAhead, (k >= kAhead) ? k - kAhead : kAhead - 1 - k);
+  sm.t = t + 1u;
+  return (t & (kRing - 1)) * (uint32_t)(TKS * 8);
+}
+__device__ __forceinline__ void strm_post(const StrmC &sc, Strm &sm) { sm.rdy = strm_probe(sc, sm.t); }
+// before the first stage step after a (re)factorisation: fill the pipeline with blocks 0 .. kAhead-1
 __device__ __forceinline__ void strm_warm(const StrmC &sc, Strm &sm) {
-  if (sc.on && sm.ahead == 0u) {
-    for (int d = 0; d < sc.D; ++d) strm_issue(sc, sm.t + (uint32_t)d, d);
-    sm.ahead = (uint32_t)sc.D;
+  if (sm.ahead == 0u) {
+#pragma unroll
+    for (int d = 0; d < kAhead; ++d) strm_issue(sc, sm.t + (uint32_t)d, d);
+    sm.ahead = kAhead;
+    sm.rdy = 0u;
   }
 }
 // nothing in flight after this (the loads issued ahead are waited for and dropped)
 __device__ __forceinline__ void strm_drain(const StrmC &sc, Strm &sm) {
-  if (sc.on) {
-    for (uint32_t d = 0; d < sm.ahead; ++d) strm_wait(sc, sm.t + d);
-    sm.t += sm.ahead;
-    sm.ahead = 0u;
-  }
+  for (uint32_t d = 0; d < sm.ahead; ++d) strm_wait(sc, sm.t + d);
+  sm.t += sm.ahead;
+  sm.ahead = 0u;
+  sm.rdy = 0u;
 }
 
 // Per-lane shared-space addresses of stage 0 (computed once per QP).
 template <int KIND>
 struct Hot {
-  StrmC sc;         // streamed factor (sc.on) or resident
+  StrmC sc;         // streamed factor (ST kernels)
   uint32_t tk[4];   // logical 16-byte chunk j of my row of T_0 (the same chunk of K_1 at +512)
   uint32_t kc[4];   // my column of K_1 in row 2q (row 2q+1 at +64)
   uint32_t v;       // my element of the stage vectors: B +0, X +64, R +128, XS +192, DG +256, CR +320
@@ -455,14 +477,14 @@ __device__ __forceinline__ double dot8(const double2 &a0, const double2 &a1, con
 }
 
 // forward sweep: B holds the right-hand side on entry, W_k = T_k v_k on exit.  `gsel` toggles the gather buffer.
-template <int KIND>
+template <int KIND, bool ST>
 __device__ __forceinline__ void sweep_fwd(const Hot<KIND> &h, Strm &sm, const int N, uint32_t &gsel) {
   uint32_t vb = h.v;
   double v = lds(vb);
-  strm_warm(h.sc, sm);
+  if (ST) strm_warm(h.sc, sm);
 #pragma unroll 1
   for (int k = 0; k < N; ++k) {
-    const uint32_t so = h.sc.on ? strm_step(h.sc, sm, k) : (uint32_t)k * (uint32_t)TKB;
+    const uint32_t so = ST ? strm_fwd(h.sc, sm, k) : (uint32_t)k * (uint32_t)TKB;
     const uint32_t t0 = h.tk[0] + so, t1 = h.tk[1] + so, t2 = h.tk[2] + so, t3 = h.tk[3] + so;
     sts(h.gpub ^ gsel, v);
     const double2 a0 = lds2(t0), a1 = lds2(t1), a2 = lds2(t2), a3 = lds2(t3);
@@ -471,6 +493,7 @@ __device__ __forceinline__ void sweep_fwd(const Hot<KIND> &h, Strm &sm, const in
     __syncwarp();
     const uint32_t gg = h.ggat ^ gsel;
     const double2 g0 = lds2(gg), g1 = lds2<64>(gg), g2 = lds2<128>(gg), g3 = lds2<192>(gg);
+    if (ST) strm_post(h.sc, sm);   // probe the next step's block while the dot products run
     double c0 = fma(-b0.x, g0.x, bn), c1 = -(b1.x * g1.x), c2 = -(b2.x * g2.x), c3 = -(b3.x * g3.x);
     c0 = fma(-b0.y, g0.y, c0); c1 = fma(-b1.y, g1.y, c1); c2 = fma(-b2.y, g2.y, c2); c3 = fma(-b3.y, g3.y, c3);
     v = (c0 + c1) + (c2 + c3);
@@ -478,13 +501,14 @@ __device__ __forceinline__ void sweep_fwd(const Hot<KIND> &h, Strm &sm, const in
     vb += VB; gsel ^= 256u;
   }
   {  // stage N: no K
-    const uint32_t so = h.sc.on ? strm_step(h.sc, sm, N) : (uint32_t)N * (uint32_t)TKB;
+    const uint32_t so = ST ? strm_fwd(h.sc, sm, N) : (uint32_t)N * (uint32_t)TKB;
     const uint32_t t0 = h.tk[0] + so, t1 = h.tk[1] + so, t2 = h.tk[2] + so, t3 = h.tk[3] + so;
     sts(h.gpub ^ gsel, v);
     const double2 a0 = lds2(t0), a1 = lds2(t1), a2 = lds2(t2), a3 = lds2(t3);
     __syncwarp();
     const uint32_t gg = h.ggat ^ gsel;
     const double2 g0 = lds2(gg), g1 = lds2<64>(gg), g2 = lds2<128>(gg), g3 = lds2<192>(gg);
+    if (ST) strm_post(h.sc, sm);
     sts(vb, dot8(a0, a1, a2, a3, g0, g1, g2, g3));
     gsel ^= 256u;
   }
@@ -512,7 +536,7 @@ __device__ __forceinline__ void gather_in(const uint32_t ggat, uint32_t &gsel, d
 }
 
 // backward sweep only (polish): x_k = W_k - K_{k+1}' x_{k+1}, written back into B
-template <int KIND>
+template <int KIND, bool ST>
 __device__ __forceinline__ void sweep_bwd_plain(const Hot<KIND> &h, Strm &sm, const int N, uint32_t &gsel) {
   double gn[8];
   uint32_t vb = h.v + N * VB;
@@ -523,9 +547,10 @@ __device__ __forceinline__ void sweep_bwd_plain(const Hot<KIND> &h, Strm &sm, co
   }
 #pragma unroll 1
   for (int k = N - 1; k >= 0; --k) {
-    const uint32_t so = h.sc.on ? strm_step(h.sc, sm, 2 * N - k) : (uint32_t)k * (uint32_t)TKB;
+    const uint32_t so = ST ? strm_bwd(h.sc, sm, k) : (uint32_t)k * (uint32_t)TKB;
     vb -= VB;
     const double xt = bwd_step(h.kc[0] + so, h.kc[1] + so, h.kc[2] + so, h.kc[3] + so, vb, h.gpub, h.ggat, gsel, gn);
+    if (ST) strm_post(h.sc, sm);
     sts(vb, xt);
     gather_in(h.ggat, gsel, gn);
   }
@@ -609,7 +634,7 @@ __device__ __forceinline__ void update_part2(const Upd<KIND> &u, const uint32_t 
 }
 
 // backward sweep fused with the element-wise update of stage k+1 (hot)
-template <int KIND>
+template <int KIND, bool ST>
 __device__ __forceinline__ void sweep_bwd_admm(const Hot<KIND> &h, Strm &sm, const Upd<KIND> &u, uint32_t &gsel) {
   const int N = u.N;
   double gn[8];
@@ -621,8 +646,9 @@ __device__ __forceinline__ void sweep_bwd_admm(const Hot<KIND> &h, Strm &sm, con
   for (int k = N - 1; k >= 0; --k) {
     UpdIn in;
     update_loads<KIND>(vb, ib, il, pb, pb2, in);   // stage k+1, independent of the chain below
-    const uint32_t so = h.sc.on ? strm_step(h.sc, sm, 2 * N - k) : (uint32_t)k * (uint32_t)TKB;
+    const uint32_t so = ST ? strm_bwd(h.sc, sm, k) : (uint32_t)k * (uint32_t)TKB;
     const double xt = bwd_step(h.kc[0] + so, h.kc[1] + so, h.kc[2] + so, h.kc[3] + so, vb - VB, h.gpub, h.ggat, gsel, gn);
+    if (ST) strm_post(h.sc, sm);
     UpdMid q;
     update_part1<KIND>(u, k + 1, ib, in, x1, xt, x2, q);   // fills the publish -> gather latency
     gather_in(h.ggat, gsel, gn);
@@ -1297,7 +1323,7 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
 // polished (x, z, y) replace the iterate.  Each refinement step is two passes over the stages around one solve:
 //   rhs = -q - P x - A_red'(y - r2 / delta)                                  (one product with the columns of G)
 //   dx  = S^-1 rhs;  A dx gives dy = (A dx - r2) / delta and r2 <- r2 - A dx   (one product with the rows of G)
-template <int KIND>
+template <int KIND, bool ST>
 __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, Strm *smp, const lpvmpc_settings &St, Info *ip, const bool do_pol, uint32_t gsel) {
   Strm &sm = *smp;
   constexpr int NT = Ctx<KIND>::NT, NX = Ctx<KIND>::NX;
@@ -1332,7 +1358,7 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, Strm *s
   }
   __syncwarp();
   FW fw; fw.polish = 1; fw.rho = 0.0; fw.rho_eq = 0.0; fw.idel = idel;
-  strm_drain(h.sc, sm);
+  if (ST) strm_drain(h.sc, sm);
   factor<KIND>(c, fw, delta);
   auto bred_i = [&](int k, int t) { const double a = ACTI[c.ci(k, t)]; return (a == 1.0 || a == 3.0) ? c.lo_of(k, t) : c.ui(k, t); };
   // first solve: rhs = -q + A_red'(b_red / delta); the targets go through R2D / R2I
@@ -1364,8 +1390,8 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, Strm *s
 #pragma unroll 1
   for (int k = 0; k <= N; ++k) BV[k * VS + r] = c.var_live(k) ? (-QV[k * 8 + r] + colAt(R2D, R2I, k)) : 0.0;
   __syncwarp();
-  sweep_fwd<KIND>(h, sm, N, gsel);
-  sweep_bwd_plain<KIND>(h, sm, N, gsel);
+  sweep_fwd<KIND, ST>(h, sm, N, gsel);
+  sweep_bwd_plain<KIND, ST>(h, sm, N, gsel);
   // x, y = (A x - b) / delta, r2 = b - A x on the active rows
 #pragma unroll 1
   for (int k = 0; k <= N; ++k) {
@@ -1411,8 +1437,8 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, Strm *s
       BV[ov] = b;
     }
     __syncwarp();
-    sweep_fwd<KIND>(h, sm, N, gsel);
-    sweep_bwd_plain<KIND>(h, sm, N, gsel);
+    sweep_fwd<KIND, ST>(h, sm, N, gsel);
+    sweep_bwd_plain<KIND, ST>(h, sm, N, gsel);
     // dy = (A dx - r2) / delta, r2 <- r2 - A dx, x <- x + dx
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
@@ -1488,19 +1514,21 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, Strm *s
 // ---------------------------------------------------------------- persistent warps, QPW QPs at a time each
 constexpr int kSyncEvery = 25;  // y_dyn is brought up to date and r re-projected at least every kSyncEvery steps
 
-template <int KIND, int QPW>
+// ST: factor streamed from the slab (one QP per warp, one warp per CTA: every staging address is warp-uniform)
+template <int KIND, int QPW, bool ST>
 __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant__ H8Params p) {
+  static_assert(!ST || QPW == 1, "the streamed kernel holds one QP per warp");
   extern __shared__ __align__(16) double smem[];
   constexpr int NX = Ctx<KIND>::NX, NB = Ctx<KIND>::NB, NT = Ctx<KIND>::NT, NSL = Ctx<KIND>::NSL;
   constexpr int OLI = Ctx<KIND>::OLI, OPM = Ctx<KIND>::OPM;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = ST ? 0 : (int)(threadIdx.x >> 5), wpc = ST ? 1 : (int)(blockDim.x >> 5);
   const int g = lane >> 3, r = lane & 7;
   const Lay &L = p.L;
   const int N = L.N;
   Ctx<KIND> c;
   c.S = smem; c.cold = p.cold;
   c.L = &L; c.N = N; c.r = r;
-  c.kmask = L.ring ? (L.ring - 1) : -1;
+  c.kmask = ST ? (kRing - 1) : -1;
   c.k0 = (QPW == 1) ? g : 0; c.ks = (QPW == 1) ? 4 : 1;
   c.xl = r < NX; c.ul = (r >= NX) && (r < NB);
   if (KIND == LPVMPC_CONTROLLER) c.islot = (r == 0) ? 0 : ((r >= NX) ? (r - NX + 1) * 2 : 0);
@@ -1522,9 +1550,9 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
   const uint32_t mbar0 = gbuf0 + (uint32_t)wpc * 512u + (uint32_t)(warp * QPW) * 64u;
   uint32_t gsel = 0;
   Strm sm;
-  sm.t = 0u; sm.ahead = 0u;
-  if (L.ring) {  // this warp's mbarriers (one arrival: the issuing lane's expect_tx)
-    if (lane < QPW * 8) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar0 + 8u * (uint32_t)lane) : "memory");
+  sm.t = 0u; sm.ahead = 0u; sm.rdy = 0u;
+  if (ST) {  // this warp's mbarriers (one arrival: the issuing lane's expect_tx)
+    if (lane < kRing) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar0 + 8u * (uint32_t)lane) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async;" ::: "memory");
     __syncwarp();
@@ -1538,23 +1566,17 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
     // Groups without a problem of their own (batch tail, or g >= QPW) mirror group 0 exactly: same problem, same
     // shared / scratch region, same values written by the same instruction; only user-visible outputs are guarded.
     const bool valid = (g < QPW) && ((int)(base + g) < p.B);
-    const int gq = valid ? g : 0;
+    const int gq = (QPW == 1) ? 0 : (valid ? g : 0);
     const int b = (int)base + gq;
     c.S = wsm + gq * L.total;
     c.cold = p.cold + (wslot + gq) * L.cold_total;
 
-    {  // groups that mirror group 0 wait on its mbarriers: take over its phase parities (only happens for g >= QPW,
-       // always, and for the groups of the batch tail, which never own a QP again)
-      const uint32_t t0 = __shfl_sync(kFull, sm.t, 0);
-      if (!valid) sm.t = t0;
-    }
     Hot<KIND> h;
     {
       const uint32_t sq = smem_a + (uint32_t)((warp * QPW + gq) * L.total) * 8u;
-      h.sc.on = L.ring != 0; h.sc.issuer = valid && r == 0 && L.ring != 0;
-      h.sc.ring = sq + (uint32_t)L.TK * 8u; h.sc.mbar = mbar0 + (uint32_t)gq * 64u;
-      h.sc.gsrc = c.cold + L.cTK; h.sc.mask = L.ring ? (uint32_t)(L.ring - 1) : 0u; h.sc.lg = (L.ring == 8) ? 3u : 2u;
-      h.sc.D = L.pfd; h.sc.N = N;
+      h.sc.issuer = ST && lane == 0;
+      h.sc.ring = sq + (uint32_t)L.TK * 8u; h.sc.mbar = mbar0;
+      h.sc.gsrc = c.cold + L.cTK; h.sc.N = N;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         h.tk[q] = sq + (uint32_t)(L.TK + c.ro[q]) * 8u;
@@ -1631,8 +1653,8 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
           }
         }
         u.cc = (iter == 0) ? 2.0 : alpha;
-        sweep_fwd<KIND>(h, sm, N, gsel);
-        sweep_bwd_admm<KIND>(h, sm, u, gsel);
+        sweep_fwd<KIND, ST>(h, sm, N, gsel);
+        sweep_bwd_admm<KIND, ST>(h, sm, u, gsel);
         if (iter == 0) first_in = 1;
         ++nsync;
         zsel = 1.0;
@@ -1665,7 +1687,7 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
             if (upd) { rho = rho_new; rho_eq = kRhoEqOverIneq * rho; ++rho_updates; }
             FW fw; fw.polish = 0; fw.rho = rho; fw.rho_eq = rho_eq; fw.idel = 0.0;
             __syncwarp();
-            strm_drain(h.sc, sm);
+            if (ST) strm_drain(h.sc, sm);
             factor<KIND>(c, fw, sigma);
             new_cr = true;
           }
@@ -1725,7 +1747,7 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
     const bool do_pol = S.polish && status == LPVMPC_SOLVED;
     bool polished_sets = false;
     if (__any_sync(kFull, do_pol)) {
-      polish_status = polish<KIND>(c, h, &sm, S, &I, do_pol, gsel);
+      polish_status = polish<KIND, ST>(c, h, &sm, S, &I, do_pol, gsel);
       polished_sets = do_pol;
     }
     // ---- outputs
@@ -1767,7 +1789,7 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
         if (a.dua_res) a.dua_res[b] = failed ? nan("") : I.dua_res;
       }
     }
-    strm_drain(h.sc, sm);   // nothing may be in flight into the ring when the next QP's setup / factor starts
+    if (ST) strm_drain(h.sc, sm);   // nothing may be in flight into the ring when the next QP's setup / factor starts
     __syncwarp();
   }
   (void)NSL; (void)NB;

@@ -267,8 +267,8 @@ lpv::g8::Lay make_g8_layout(int kind, int N) {
   return L;
 }
 
-// ring = 0: block factor resident in shared memory; ring = 4 / 8: factor in the slab, staged through a ring of `ring`
-// stage blocks by TMA bulk copies (prefetch distance ring - 2)
+// ring = 0: block factor resident in shared memory; ring = 4 (lpv::h8::kRing): factor in the slab, staged through a ring
+// of stage blocks by TMA bulk copies issued lpv::h8::kAhead stage steps ahead
 lpv::h8::Lay make_h8_layout(int kind, int N, int ring) {
   const int NX = kind == LPVMPC_CONTROLLER ? 6 : 5;
   lpv::h8::Lay L;
@@ -432,11 +432,20 @@ int launch_g8(lpvmpc_handle *h, const Params &p, cudaStream_t s) {
 
 template <int KIND, int QPW>
 void h8_launch(int grid, int threads, size_t smem, cudaStream_t s, const lpv::h8::H8Params &hp) {
-  lpv::h8::lpv_solve_h8_kernel<KIND, QPW><<<grid, threads, smem, s>>>(hp);
+  lpv::h8::lpv_solve_h8_kernel<KIND, QPW, false><<<grid, threads, smem, s>>>(hp);
 }
 template <int KIND, int QPW>
 cudaError_t h8_attr(size_t smem) {
-  return cudaFuncSetAttribute(lpv::h8::lpv_solve_h8_kernel<KIND, QPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  return cudaFuncSetAttribute(lpv::h8::lpv_solve_h8_kernel<KIND, QPW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+// streamed factor: one QP per warp, one warp per CTA
+template <int KIND>
+void h8s_launch(int grid, size_t smem, cudaStream_t s, const lpv::h8::H8Params &hp) {
+  lpv::h8::lpv_solve_h8_kernel<KIND, 1, true><<<grid, 32, smem, s>>>(hp);
+}
+template <int KIND>
+cudaError_t h8s_attr(size_t smem) {
+  return cudaFuncSetAttribute(lpv::h8::lpv_solve_h8_kernel<KIND, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
 template <int KIND>
@@ -448,7 +457,8 @@ int launch_h8(lpvmpc_handle *h, const Params &p, cudaStream_t s) {
   const int ctas = (p.B + per_cta - 1) / per_cta;
   const int grid = ctas < h->grid_cap ? ctas : h->grid_cap;
   CUDA_TRY(h, cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned), s));
-  if (h->qpw == 4) h8_launch<KIND, 4>(grid, 32 * h->wpc, h->ws_bytes, s, hp);
+  if (h->HL.ring) h8s_launch<KIND>(grid, h->ws_bytes, s, hp);
+  else if (h->qpw == 4) h8_launch<KIND, 4>(grid, 32 * h->wpc, h->ws_bytes, s, hp);
   else if (h->qpw == 2) h8_launch<KIND, 2>(grid, 32 * h->wpc, h->ws_bytes, s, hp);
   else h8_launch<KIND, 1>(grid, 32 * h->wpc, h->ws_bytes, s, hp);
   ++h->launches;
@@ -596,13 +606,13 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
                        (cfg->kind == LPVMPC_CONTROLLER || cfg->N <= 63);
     if (cfg->variant == 5 && !h8_ok) { h->err = "variant 5 (H8) needs diagonal Q and R, steering_delay=0, planner N<=63 and a per-QP state that fits shared memory"; return bail(LPVMPC_E_UNSUPPORTED); }
     if (cfg->variant == 5 || (cfg->variant == 0 && h8_ok)) h->variant = 5;
-    // H8S = H8 with the factor streamed from the slab (variants 7: ring of 4 blocks, 8: ring of 8): N <= 254, stage vectors
-    // and single-variable rows must still fit shared memory
+    // H8S = H8 with the factor streamed from the slab through a ring of 4 stage blocks (variant 7): N <= 254, stage
+    // vectors and single-variable rows must still fit shared memory
     const lpv::h8::Lay SL4 = make_h8_layout(cfg->kind, cfg->N, 4);
     const bool h8s_ok = pdiag && cfg->steering_delay == 0 && cfg->N <= 254 && (size_t)SL4.total * sizeof(double) + 2048 <= (size_t)h->smem_optin &&
                         (cfg->kind == LPVMPC_CONTROLLER || cfg->N <= 63);
-    if ((cfg->variant == 7 || cfg->variant == 8) && !h8s_ok) { h->err = "variants 7/8 (H8S) need diagonal Q and R, steering_delay=0, planner N<=63, N<=254"; return bail(LPVMPC_E_UNSUPPORTED); }
-    if (cfg->variant == 7 || cfg->variant == 8) { h->variant = 5; h->HL = make_h8_layout(cfg->kind, cfg->N, cfg->variant == 7 ? 4 : 8); }
+    if (cfg->variant == 7 && !h8s_ok) { h->err = "variant 7 (H8S) needs diagonal Q and R, steering_delay=0, planner N<=63, N<=254"; return bail(LPVMPC_E_UNSUPPORTED); }
+    if (cfg->variant == 7) { h->variant = 5; h->HL = SL4; }
     else if (cfg->variant == 0 && h8s_ok && (!h8_ok || 2 * (size_t)SL4.total <= (size_t)h->HL.total)) { h->variant = 5; h->HL = SL4; }   // streaming at least doubles the resident QPs
     // H8T kernel: controller, block factor in tensor memory (48 N + 16 columns of the SM's 512), 16 QPs per CTA, one CTA per SM
     h->TL = make_h8t_layout(cfg->kind, cfg->N);
@@ -628,7 +638,7 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
     const size_t sm_bytes = prop.sharedMemPerMultiprocessor;
     int best_q = 0, best_qpw = 1, best_wpc = 1, best_ctas = 1;
     // resident factor: prefer many QPs per warp; streamed factor: prefer many warps (ties go to the first candidate)
-    const int qs_res[3] = {4, 2, 1}, qs_str[3] = {1, 2, 4};
+    const int qs_res[3] = {4, 2, 1}, qs_str[3] = {1, 1, 1};   // the streamed kernel: one QP per warp, one warp per CTA
     const int *qs = h->HL.ring ? qs_str : qs_res;
     for (int qi = 0; qi < 3; ++qi) for (int w = (h->HL.ring ? 1 : 2); w >= 1; --w) {
       const size_t cta = per_qp * qs[qi] * w + 512 * (size_t)w + 512 + 64 * (size_t)(qs[qi] * w);
@@ -642,7 +652,7 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
     if (const char *e = std::getenv("LPVMPC_H8_QPW")) {
       const int q = std::atoi(e);
       const size_t cta = per_qp * q + 512 + 512 + 64 * (size_t)q;
-      if ((q == 1 || q == 2 || q == 4) && cta <= (size_t)h->smem_optin) {
+      if (!h->HL.ring && (q == 1 || q == 2 || q == 4) && cta <= (size_t)h->smem_optin) {
         best_qpw = q; best_wpc = 1; best_ctas = (int)(sm_bytes / (cta + 1024));
         if (best_ctas > 32) best_ctas = 32;
       }
@@ -653,7 +663,8 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
     h->smem_mode = true;
     h->grid_cap = h->sm_count * best_ctas;
     const bool ctrl = cfg->kind == LPVMPC_CONTROLLER;
-    if (h->qpw == 4) CTRY(ctrl ? (h8_attr<LPVMPC_CONTROLLER, 4>(h->ws_bytes)) : (h8_attr<LPVMPC_PLANNER, 4>(h->ws_bytes)));
+    if (h->HL.ring) CTRY(ctrl ? h8s_attr<LPVMPC_CONTROLLER>(h->ws_bytes) : h8s_attr<LPVMPC_PLANNER>(h->ws_bytes));
+    else if (h->qpw == 4) CTRY(ctrl ? (h8_attr<LPVMPC_CONTROLLER, 4>(h->ws_bytes)) : (h8_attr<LPVMPC_PLANNER, 4>(h->ws_bytes)));
     else if (h->qpw == 2) CTRY(ctrl ? (h8_attr<LPVMPC_CONTROLLER, 2>(h->ws_bytes)) : (h8_attr<LPVMPC_PLANNER, 2>(h->ws_bytes)));
     else CTRY(ctrl ? (h8_attr<LPVMPC_CONTROLLER, 1>(h->ws_bytes)) : (h8_attr<LPVMPC_PLANNER, 1>(h->ws_bytes)));
     CTRY(cudaMalloc(&h->d_queue, sizeof(unsigned)));
@@ -734,7 +745,7 @@ void lpvmpc_destroy(lpvmpc_handle *h) {
 int lpvmpc_get_info(const lpvmpc_handle *h, lpvmpc_info *info) {
   if (!h || !info) return LPVMPC_E_ARG;
   info->n = h->n; info->d = h->d; info->N = h->L.N; info->nz = h->L.nz; info->m = h->L.m;
-  info->variant = (h->variant == 5 && h->HL.ring) ? (h->HL.ring == 4 ? 7 : 8) : h->variant;   // 7 / 8: H8 with the factor streamed (ring of 4 / 8)
+  info->variant = (h->variant == 5 && h->HL.ring) ? 7 : h->variant;   // 7: H8 with the factor streamed
   info->workspace_in_smem = h->smem_mode ? 1 : 0;
   info->smem_bytes_per_qp = h->smem_mode ? (int)(h->variant == 6 ? (size_t)h->TL.total * sizeof(double) : h->variant == 5 ? (size_t)h->HL.total * sizeof(double) : ((h->variant == 2 || h->variant == 3) ? h->ws_bytes / h->qpw : h->ws_bytes)) : 0;
   info->workspace_bytes = (long long)(h->stage_bytes + (h->smem_mode ? 0 : h->ws_bytes * (size_t)h->grid_cap));

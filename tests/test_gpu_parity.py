@@ -69,7 +69,7 @@ def test_schedule_matches_oracle(track):
             np.testing.assert_allclose(r.states_out[b], st, rtol=1e-12, atol=1e-14)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7])
 @pytest.mark.parametrize("iters", [1, 7, 50, 200])
 def test_controller_fixed_iteration_iterates(track, iters, variant):
     N, B = 8, 48
@@ -89,7 +89,7 @@ def test_controller_fixed_iteration_iterates(track, iters, variant):
     assert worst < 1e-9, worst
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7])
 def test_controller_converged_matches_oracle(track, variant):
     N, B = 8, 254  # not a multiple of 4: exercises the idle-group path of the T8 kernel
     w = W.controller_batch(B, N, seed=0)
@@ -109,7 +109,7 @@ def test_controller_converged_matches_oracle(track, variant):
         assert abs(r.obj[b] - o["obj_val"]) <= 1e-6 * abs(o["obj_val"]), (b, r.obj[b], o["obj_val"])
 
 
-@pytest.mark.parametrize("variant", [1, 3, 5, 7, 8])
+@pytest.mark.parametrize("variant", [1, 3, 5, 7])
 def test_planner_fixed_and_converged(track, variant):
     N, B = 40, 24
     w = W.planner_batch(B, N, seed=1)
@@ -145,10 +145,10 @@ def test_planner_fixed_and_converged(track, variant):
             assert np.isnan(r.x_pred[b]).all()
 
 
-@pytest.mark.parametrize("variant", [0, 5, 8])
+@pytest.mark.parametrize("variant", [0, 5, 7])
 def test_long_horizon_controller_matches_oracle(track, variant):
     """BASELINE configs[4] family: N = 100 (the block factor, 103 KB, is streamed from the L2 slab by TMA bulk copies
-    in variants 7 / 8; variant 0 must pick the streamed kernel, variant 5 keeps it resident: 1 QP per SM)."""
+    in variant 7; variant 0 must pick the streamed kernel, variant 5 keeps it resident: 1 QP per SM)."""
     N, B = 100, 37
     w = W.controller_batch(B, N, seed=3, steer_scale=0.2)
     keys = ("u_prev", "vel_ref", "curv_ref", "lap", "u_old")
