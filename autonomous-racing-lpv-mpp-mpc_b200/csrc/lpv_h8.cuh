@@ -988,9 +988,9 @@ __device__ __noinline__ double objective(const Ctx<KIND> c, const double *xv, co
   const double *PD = c.cd(C_PD), *PO = c.cd(C_PO), *QV = c.cd(C_Q);
   double acc = 0.0;
 #pragma unroll 1
-  for (int k = 0; k <= c.N; ++k)
+  for (int k = c.k0; k <= c.N; k += c.ks)
     if (c.var_live(k)) acc += (0.5 * rowP<KIND>(c, PD, PO, xv, vs, k) + QV[k * 8 + c.r]) * xv[k * vs + c.r];
-  return gsum(acc) * scale;
+  return wsum(acc, c.ks > 1) * scale;
 }
 
 // ---------------------------------------------------------------- setup: schedule + build + Ruiz (cold, once per QP)
@@ -1115,7 +1115,7 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
     const double uold = (c.ul && a.u_old) ? a.u_old[(size_t)b * 2 + ucomp] : 0.0;
     const double mey = (KIND == LPVMPC_PLANNER) ? a.max_ey[b] : 0.0;
 #pragma unroll 1
-    for (int k = 0; k <= N; ++k) {
+    for (int k = c.k0; k <= N; k += c.ks) {
       const int o = k * 8 + r, ov = k * VS + r;
       double pd = 0.0, po = 0.0, q = 0.0, be = 0.0, ed = 0.0;
       if (c.xl) {
@@ -1140,7 +1140,7 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
     {
       constexpr int NSLc = Ctx<KIND>::NSL, OLIc = Ctx<KIND>::OLI, OPMc = Ctx<KIND>::OPM;
 #pragma unroll 1
-      for (int k = 0; k <= N + 1; ++k) {
+      for (int k = c.k0; k <= N + 1; k += c.ks) {
         double *ibk = c.Ib(k);
         if (r < NSLc) {
           ibk[r * 2] = 0.0; ibk[r * 2 + 1] = 0.0; ibk[NSLc * 2 + r * 2] = 0.0; ibk[NSLc * 2 + r * 2 + 1] = kInfty * kInfty;
@@ -1151,7 +1151,7 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
     }
     __syncwarp();
 #pragma unroll 1
-    for (int k = 0; k <= N; ++k) {
+    for (int k = c.k0; k <= N; k += c.ks) {
       if (c.has_in(k)) {
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
@@ -1180,14 +1180,14 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
     }
     __syncwarp();
   }
-  data_err = gany(data_err);
+  data_err = wany(data_err, c.ks > 1);
 
   // ---- Ruiz equilibration (OSQP scale_data)
   double csc = 1.0;
 #pragma unroll 1
   for (int it = 0; it < St.scaling; ++it) {
 #pragma unroll 1
-    for (int k = 0; k <= N; ++k) {
+    for (int k = c.k0; k <= N; k += c.ks) {
       const int o = k * 8 + r, ov = k * VS + r;
       double pa = fabs(sPD[o]);
       if (c.ul) {
@@ -1218,7 +1218,7 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
     }
     __syncwarp();
 #pragma unroll 1
-    for (int k = 0; k <= N; ++k) {
+    for (int k = c.k0; k <= N; k += c.ks) {
       const int o = k * 8 + r, ov = k * VS + r;
       const double dt = sDt[o];
       if (k < N) {
@@ -1245,7 +1245,7 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
     // cost scaling: mean of the column norms of P (summed per lane, then across the group)
     double qn = 0.0, ct = 0.0;
 #pragma unroll 1
-    for (int k = 0; k <= N; ++k) {
+    for (int k = c.k0; k <= N; k += c.ks) {
       const int o = k * 8 + r;
       double pa = fabs(sPD[o]);
       if (c.ul) {
@@ -1254,14 +1254,14 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
       }
       if (c.var_live(k)) { ct += pa; qn = absmax(qn, QV[k * VS + r]); }
     }
-    qn = gmax(qn);
-    ct = gsum(ct) / nz;
+    qn = wmax(qn, c.ks > 1);
+    ct = wsum(ct, c.ks > 1) / nz;
     qn = limit_scaling(qn);
     ct = ct > qn ? ct : qn;
     ct = limit_scaling(ct);
     ct = frcp(ct);
 #pragma unroll 1
-    for (int k = 0; k <= N; ++k) { const int o = k * 8 + r; sPD[o] *= ct; QV[k * VS + r] *= ct; sPO[o] *= ct; }
+    for (int k = c.k0; k <= N; k += c.ks) { const int o = k * 8 + r; sPD[o] *= ct; QV[k * VS + r] *= ct; sPO[o] *= ct; }
     csc *= ct;
     __syncwarp();
   }
@@ -1272,7 +1272,7 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
     double *cEi = c.cd(C_EI), *cEiI = c.cd(C_EIINV), *cQ = c.cd(C_Q), *cBE = c.cd(C_BE), *cED = c.cd(C_ED), *cYD = c.cd(C_YD);
     uint64_t eqm = 0, loosem = 0;
 #pragma unroll 1
-    for (int k = 0; k <= N; ++k) {
+    for (int k = c.k0; k <= N; k += c.ks) {
       const int o = k * 8 + r, ov = k * VS + r;
       cD[o] = sD[o]; cDI[o] = 1.0 / sD[o]; cE[o] = sE[o]; cEI[o] = 1.0 / sE[o]; cPD[o] = sPD[o]; cPO[o] = sPO[o];
       cEi[o] = sEI[o]; cEiI[o] = 1.0 / sEI[o];
@@ -1281,7 +1281,7 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
     }
     double *Gd = c.cold + L.cG;
 #pragma unroll 1
-    for (int k = 0; k < N; ++k) {
+    for (int k = c.k0; k < N; k += c.ks) {
       if (c.xl) {
         const double *gs = Gs + k * GS + r * 8;
         double *gd = Gd + k * GS + r * 8;
@@ -1291,7 +1291,7 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
     }
     __syncwarp();
 #pragma unroll 1
-    for (int k = 0; k <= N; ++k) {
+    for (int k = c.k0; k <= N; k += c.ks) {
       if (c.has_in(k)) {
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
@@ -1307,11 +1307,15 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
         }
       }
     }
+    if (c.ks > 1) {  // the groups split the stages: merge their bit masks (same lane r in every group)
+      eqm |= __shfl_xor_sync(kFull, eqm, 8); eqm |= __shfl_xor_sync(kFull, eqm, 16);
+      loosem |= __shfl_xor_sync(kFull, loosem, 8); loosem |= __shfl_xor_sync(kFull, loosem, 16);
+    }
     *eqm_out = eqm; *loosem_out = loosem;
     __syncwarp();
     // the scratch homes become hot vectors: XS = 0 (R, CR, B are set by refresh, DG by factor)
 #pragma unroll 1
-    for (int k = 0; k <= N; ++k) c.V(V_XS)[k * VS + r] = 0.0;
+    for (int k = c.k0; k <= N; k += c.ks) c.V(V_XS)[k * VS + r] = 0.0;
     __syncwarp();
   }
   return (sched_err ? 1 : 0) | (data_err ? 2 : 0);
@@ -1339,7 +1343,7 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, Strm *s
   const double delta = St.delta, idel = 1.0 / St.delta;
   // active-set guess (form_Ared): 1 = lower, 2 = upper, 3 = both
 #pragma unroll 1
-  for (int k = 0; k <= N; ++k) {
+  for (int k = c.k0; k <= N; k += c.ks) {
     const int o = k * 8 + r;
     double ad = 0.0;
     // equality row (z == l == u): lower / upper by the sign of the dual.  Upstream drops the row when the dual is exactly
@@ -1363,7 +1367,7 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, Strm *s
   auto bred_i = [&](int k, int t) { const double a = ACTI[c.ci(k, t)]; return (a == 1.0 || a == 3.0) ? c.lo_of(k, t) : c.ui(k, t); };
   // first solve: rhs = -q + A_red'(b_red / delta); the targets go through R2D / R2I
 #pragma unroll 1
-  for (int k = 0; k <= N; ++k) {
+  for (int k = c.k0; k <= N; k += c.ks) {
     const int o = k * 8 + r;
     R2D[k * VS + r] = (c.xl && ACTD[o] != 0.0) ? idel * BE[o] : 0.0;
     if (c.has_in(k)) {
@@ -1388,13 +1392,13 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, Strm *s
     return acc;
   };
 #pragma unroll 1
-  for (int k = 0; k <= N; ++k) BV[k * VS + r] = c.var_live(k) ? (-QV[k * 8 + r] + colAt(R2D, R2I, k)) : 0.0;
+  for (int k = c.k0; k <= N; k += c.ks) BV[k * VS + r] = c.var_live(k) ? (-QV[k * 8 + r] + colAt(R2D, R2I, k)) : 0.0;
   __syncwarp();
   sweep_fwd<KIND, ST>(h, sm, N, gsel);
   sweep_bwd_plain<KIND, ST>(h, sm, N, gsel);
   // x, y = (A x - b) / delta, r2 = b - A x on the active rows
 #pragma unroll 1
-  for (int k = 0; k <= N; ++k) {
+  for (int k = c.k0; k <= N; k += c.ks) {
     const int o = k * 8 + r, ov = k * VS + r;
     const double xk = BV[ov];
     PX[ov] = xk;
@@ -1416,7 +1420,7 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, Strm *s
   for (int it = 0; it < St.polish_refine_iter + kPolishExtraRefine; ++it) {
     // rhs = -q - P x - A'(y - r2 / delta)
 #pragma unroll 1
-    for (int k = 0; k <= N; ++k) {
+    for (int k = c.k0; k <= N; k += c.ks) {
       const int o = k * 8 + r, ov = k * VS + r;
       double b = 0.0;
       if (c.var_live(k)) {
@@ -1441,7 +1445,7 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, Strm *s
     sweep_bwd_plain<KIND, ST>(h, sm, N, gsel);
     // dy = (A dx - r2) / delta, r2 <- r2 - A dx, x <- x + dx
 #pragma unroll 1
-    for (int k = 0; k <= N; ++k) {
+    for (int k = c.k0; k <= N; k += c.ks) {
       const int o = k * 8 + r, ov = k * VS + r;
       const double dx = BV[ov];
       if (c.xl && ACTD[o] != 0.0) {
@@ -1463,7 +1467,7 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, Strm *s
   // pol z = A x, normal-cone projection, residuals, acceptance.  Polished z of the single-variable rows -> R2I.
   double a_rp = 0, a_rd = 0;
 #pragma unroll 1
-  for (int k = 0; k <= N; ++k) {
+  for (int k = c.k0; k <= N; k += c.ks) {
     const int o = k * 8 + r, ov = k * VS + r;
     if (c.xl) {
       const double Ax = rowA_dyn<KIND>(c, ED, PX, VS, k), t = Ax + PYD[ov];
@@ -1485,14 +1489,14 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, Strm *s
   }
   __syncwarp();
 #pragma unroll 1
-  for (int k = 0; k <= N; ++k) {
+  for (int k = c.k0; k <= N; k += c.ks) {
     const int o = k * 8 + r;
     if (c.var_live(k)) {
       const double rr = (QV[o] + rowP<KIND>(c, PD, PO, PX, VS, k)) + colAt(PYD, PYI, k);
       a_rd = absmax(a_rd, unscale ? DINV[o] * rr : rr);
     }
   }
-  const double pol_pri = gmax(a_rp), pol_dua = (unscale ? I.cinv : 1.0) * gmax(a_rd);
+  const double pol_pri = wmax(a_rp, c.ks > 1), pol_dua = (unscale ? I.cinv : 1.0) * wmax(a_rd, c.ks > 1);
   const double pol_obj = objective<KIND>(c, PX, VS, St.scaling ? I.cinv : 1.0);
   const bool ok = (pol_pri < I.pri_res && pol_dua < I.dua_res) || (pol_pri < I.pri_res && I.dua_res < 1e-10) ||
                   (pol_dua < I.dua_res && I.pri_res < 1e-10);
@@ -1500,7 +1504,7 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, Strm *s
   if (!ok) return -1;
   I.obj = pol_obj; I.pri_res = pol_pri; I.dua_res = pol_dua;
 #pragma unroll 1
-  for (int k = 0; k <= N; ++k) {
+  for (int k = c.k0; k <= N; k += c.ks) {
     const int o = k * 8 + r, ov = k * VS + r;
     X[ov] = PX[ov]; YD[o] = PYD[ov];
     if (c.has_in(k)) {

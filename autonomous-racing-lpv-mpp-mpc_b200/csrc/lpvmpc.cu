@@ -613,7 +613,10 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
                         (cfg->kind == LPVMPC_CONTROLLER || cfg->N <= 63);
     if (cfg->variant == 7 && !h8s_ok) { h->err = "variant 7 (H8S) needs diagonal Q and R, steering_delay=0, planner N<=63, N<=254"; return bail(LPVMPC_E_UNSUPPORTED); }
     if (cfg->variant == 7) { h->variant = 5; h->HL = SL4; }
-    else if (cfg->variant == 0 && h8s_ok && (!h8_ok || 2 * (size_t)SL4.total <= (size_t)h->HL.total)) { h->variant = 5; h->HL = SL4; }   // streaming at least doubles the resident QPs
+    // auto: the resident factor wins whenever it fits (planner N=40: 352 vs 394 ms, controller N=100: 73 vs 85 ms per batch,
+    // profiles/r1v_*: the batches are bound by the longest chains, and staging adds latency to every stage step); the
+    // streamed factor takes over when the factor no longer fits shared memory (controller N > ~135)
+    else if (cfg->variant == 0 && h8s_ok && !h8_ok) { h->variant = 5; h->HL = SL4; }
     // H8T kernel: controller, block factor in tensor memory (48 N + 16 columns of the SM's 512), 16 QPs per CTA, one CTA per SM
     h->TL = make_h8t_layout(cfg->kind, cfg->N);
     const size_t h8t_bytes = (size_t)h->TL.total * sizeof(double) * 16 + 4 * 512 + 512;

@@ -8,6 +8,7 @@ synthetic problems.  Workloads:
     ctrl4096   4,096 controller QPs, N=8, trajectory-tracking tune, lap=1       (BASELINE configs[1], default)
     plan16384  16,384 planner QPs, N=40, lateral-box "obstacles"                 (configs[2])
     ctrl1024N100  1,024 controller QPs, N=100                                     (configs[4])
+    ctrl512N160   512 controller QPs, N=160: the factor exceeds shared memory and is streamed by TMA (not a BASELINE config)
     mc8192     Monte-Carlo closed loop, 8,192 vehicles per GPU (configs[3] is 65,536 over 8 GPUs): a step is
                `--ticks-per-step` controller ticks of the whole fleet, each tick = simulate + localise + schedule +
                build + solve on the device (lpvmpc_loop_*); 24 steps x 23 ticks = the 552-tick lap
@@ -54,6 +55,9 @@ WORKLOADS = {
     # (what a Monte-Carlo tick of configs[3] looks like to the solver: 8,192 vehicles per GPU and more)
     "ctrl65536": dict(kind="controller", N=8, B=65536, seed=0),
     "mc8192": dict(kind="fleet", N=8, B=8192, seed=2),
+    # not a BASELINE config: a horizon whose block factor (165 KB) no longer fits shared memory next to the stage vectors,
+    # so the factor is streamed from the L2 slab by TMA bulk copies (kernel variant 7)
+    "ctrl512N160": dict(kind="controller", N=160, B=512, seed=3),
 }
 
 
