@@ -16,7 +16,7 @@ _SOURCES = [os.path.join(_SRC_DIR, f) for f in ("lpvmpc.cu", "lpv_qp.cuh", "lpv_
            [os.path.join(_ROOT, "include", "lpvmpc.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-shared"]
 
 ABI_VERSION = 1
 CONTROLLER, PLANNER = 0, 1
