@@ -241,3 +241,74 @@ long loop_ref_run(const lpv_ref_cfg *c, const osqp_ref_settings *st, const loop_
   }
   return solved_total;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * planner loop: plannerMain.py:128-224 */
+#define NPL 5
+
+void plan_loop_ref_guess(const double *x0, int N, double accel_rate, double dt, double s0, double *xx) {
+  /* plannerMain.py:465-505: Vx integrates Accel = 0.1 + accel_rate i, the other states are held, S integrates with curv = 0 */
+  double Vx = x0[0], S = s0;
+  const double curv = 0;
+  for (int i = 0; i <= N; i++) {
+    double *row = xx + i * 6;
+    row[0] = Vx; row[1] = x0[1]; row[2] = x0[2]; row[3] = x0[3]; row[4] = x0[4]; row[5] = S;
+    if (i < N) {
+      double Accel = 0.1 + accel_rate * i;
+      double Vn = Vx + Accel * dt;
+      S = S + ((Vx * cos(x0[4]) - x0[1] * sin(x0[4])) / (1 - x0[3] * curv)) * dt;
+      Vx = Vn;
+    }
+  }
+}
+
+enum { PC_TICKS = 0, PC_STATUS, PC_ITERS, PC_FAIL, PC_FAIL_TICK };
+
+long plan_loop_ref_run(const lpv_ref_cfg *c, const osqp_ref_settings *st, int B, int n_ticks, double max_ey,
+                       double accel_rate, const double *xstart, double *x_pred, double *u_pred, double *SS, int *ctr,
+                       double *stat, int threads) {
+  const int N = c->N;
+  if (threads < 1) threads = 1;
+  long solved_total = 0;
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 1) reduction(+ : solved_total)
+  for (int b = 0; b < B; b++) {
+    double *xP = x_pred + (size_t)b * (N + 1) * NPL, *uP = u_pred + (size_t)b * N * ND, *ss = SS + (size_t)b * (N + 1);
+    int *ct = ctr + (size_t)b * 8;
+    double *sv = stat + (size_t)b * 4;
+    double *xx = (double *)malloc(sizeof(double) * (size_t)(N + 1) * 6);
+    double *uu = (double *)calloc((size_t)N, sizeof(double));
+    double *nx = (double *)malloc(sizeof(double) * (size_t)(N + 1) * NPL), *nu = (double *)malloc(sizeof(double) * (size_t)N * ND);
+    const double u_old[2] = {0.0, 0.0};
+    for (int t = 0; t < n_ticks; t++) {
+      if (ct[PC_FAIL]) break;
+      lpv_ref_info info; memset(&info, 0, sizeof(info));
+      if (ct[PC_TICKS] == 0) { /* first_it == 1 */
+        plan_loop_ref_guess(xstart + (size_t)b * NPL, N, accel_rate, c->dt, ss[0], xx);
+        lpv_ref_plan_solve(c, st, 2, xstart + (size_t)b * NPL, 0, 0, 0, 0, 0, uu, xx, u_old, max_ey, 0, 0, nx, nu, &info, 0, 0, 0, 0, 0);
+      } else {
+        double x1[NPL];
+        for (int q = 0; q < NPL; q++) x1[q] = xP[NPL + q];
+        lpv_ref_plan_solve(c, st, 1, x1, 0, 0, 0, x1, ss, uP, 0, u_old, max_ey, 0, 0, nx, nu, &info, 0, 0, 0, 0, 0);
+      }
+      int status = info.sched_err ? LOOP_REF_SCHEDULE_ERROR : info.status;
+      ct[PC_STATUS] = status; ct[PC_ITERS] = info.iter;
+      if (!feasible(status)) { ct[PC_FAIL] = status; ct[PC_FAIL_TICK] = ct[PC_TICKS]; break; }
+      if (status == 1) { sv[0] += 1; solved_total += 1; }
+      sv[1] += info.iter;
+      memcpy(xP, nx, sizeof(double) * (size_t)(N + 1) * NPL);
+      memcpy(uP, nu, sizeof(double) * (size_t)N * ND);
+      /* plannerMain.py:201-211 */
+      int err = 0;
+      for (int j = 0; j < N; j++) {
+        double curv = lpv_ref_curvature(ss[j], c->track, c->nseg, &err);
+        const double *x = xP + j * NPL;
+        ss[j + 1] = (ss[j] + ((x[0] * cos(x[4]) - x[1] * sin(x[4])) / (1 - x[3] * curv)) * c->dt);
+      }
+      ss[0] = ss[1];
+      ct[PC_TICKS] += 1;
+      if (err) { ct[PC_FAIL] = LOOP_REF_SCHEDULE_ERROR; ct[PC_FAIL_TICK] = ct[PC_TICKS]; ct[PC_STATUS] = LOOP_REF_SCHEDULE_ERROR; break; }
+    }
+    free(xx); free(uu); free(nx); free(nu);
+  }
+  return solved_total;
+}

@@ -50,6 +50,21 @@ long loop_ref_run(const lpv_ref_cfg *c, const osqp_ref_settings *st, const loop_
                   double *sim, double *cmd, double *u_pred, double *local, int *ctr, double *stat, double *x_pred,
                   int threads);
 
+/* ---- planner loop (plannerMain.py:128-224, Testing-style: re-plan from the previous plan's second state) ---- */
+/* plannerMain.py:465-505 : xx [N+1,6] = [Vx Vy W Ey Epsi S], uu = zeros; s0 = 0 in the reference */
+void plan_loop_ref_guess(const double *x0, int N, double accel_rate, double dt, double s0, double *xx);
+
+/* n_ticks planner ticks for B vehicles.  Tick: first tick _EstimateABC around the guess (plannerMain.py:152-164), later
+ * LPVPrediction(xPred[1], SS, uPred) + solve(xPred[1], ...) (:175-176); uOld = 0 (OldSteering is never popped, :186-187);
+ * then the arc-length integration SS[j+1] = SS[j] + ((vx cos(epsi) - vy sin(epsi)) / (1 - ey kappa(SS[j]))) dt over the
+ * new plan and SS[0] = SS[1] (:201-211).
+ * Arrays (row-major, in place): xstart [B,5], x_pred [B,N+1,5], u_pred [B,N,2], SS [B,N+1] (SS[:,0] = start arc length),
+ * ctr [B,8] = [ticks_done, last_status, last_iters, fail_status, fail_tick, 0, 0, 0], stat [B,4] = [solved ticks,
+ * total ADMM iterations, 0, 0].  Returns the number of SOLVED ticks. */
+long plan_loop_ref_run(const lpv_ref_cfg *c, const osqp_ref_settings *st, int B, int n_ticks, double max_ey,
+                       double accel_rate, const double *xstart, double *x_pred, double *u_pred, double *SS, int *ctr,
+                       double *stat, int threads);
+
 #ifdef __cplusplus
 }
 #endif

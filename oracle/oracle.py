@@ -394,3 +394,29 @@ def loop_run(cfg, settings, lc, state, n_ticks, threads=1):
     return lib().loop_ref_run(C.byref(cfg), C.byref(settings), C.byref(lc), C.c_int(B), C.c_int(n_ticks),
                               _dp(state["sim"]), _dp(state["cmd"]), _dp(state["u_pred"]), _dp(state["local"]),
                               _ip(state["ctr"]), _dp(state["stat"]), _dp(state["x_pred"]), C.c_int(threads))
+
+
+# ------------------------------------------------------------------------------------------------
+# planner loop (oracle/loop_ref.c: plan_loop_ref_*)
+def plan_guess(x0, N, accel_rate=0.2, dt=0.05, s0=0.0):
+    xx = np.zeros((N + 1, 6))
+    lib().plan_loop_ref_guess(_dp(_f64(x0)), C.c_int(N), C.c_double(accel_rate), C.c_double(dt), C.c_double(s0), _dp(xx))
+    return xx
+
+
+def plan_loop_state(xstart, N, s0=None):
+    xs = _f64(xstart).copy()
+    B = xs.shape[0]
+    SS = np.zeros((B, N + 1))
+    if s0 is not None:
+        SS[:, 0] = s0
+    return dict(xstart=xs, x_pred=np.zeros((B, N + 1, 5)), u_pred=np.zeros((B, N, 2)), SS=SS,
+                ctr=np.zeros((B, 8), dtype=np.int32), stat=np.zeros((B, 4)))
+
+
+def plan_loop_run(cfg, settings, state, n_ticks, max_ey=0.3, accel_rate=0.2, threads=1):
+    lib().plan_loop_ref_run.restype = C.c_long
+    B = state["xstart"].shape[0]
+    return lib().plan_loop_ref_run(C.byref(cfg), C.byref(settings), C.c_int(B), C.c_int(n_ticks), C.c_double(max_ey),
+                                   C.c_double(accel_rate), _dp(state["xstart"]), _dp(state["x_pred"]), _dp(state["u_pred"]),
+                                   _dp(state["SS"]), _ip(state["ctr"]), _dp(state["stat"]), C.c_int(threads))

@@ -87,3 +87,33 @@ def test_full_lap_stays_on_track():
         assert ctr[5] == 0 and ctr[7] == 640, (swap, ctr)
         assert ctr[1] == 1 and 500 < stat[3] < 620, (swap, ctr, stat)   # one lap completed
         assert stat[2] < 0.15, (swap, stat)
+
+
+# ------------------------------------------------------------------------------------------------ planner loop
+GP = np.load(os.path.join(os.path.dirname(__file__), "golden", "planner_loop.npz"))
+PLAN_Q = -np.diag([-0.000000000000088, -9.703658572659423, -0.5, 0.000000000213635, -0.153591566469547])
+PLAN_L = -np.array([1.00702414775175, 0.187661946033823, -0.0, 0.0, -0.0329493219494661])
+
+
+def test_planner_guess_matches_reference():
+    xx = oracle.plan_guess(GP["guess_x0"], 40, 0.2, 0.05)
+    np.testing.assert_allclose(xx, GP["guess_xx"], rtol=1e-15, atol=1e-16)
+
+
+@pytest.mark.parametrize("case", [0, 1])
+def test_planner_loop_matches_reference_loop(case):
+    """25 ticks of the reference's LPV_MPC_Planner driven by the planner main loop (QP solved by the oracle's OSQP at the
+    stub seam) against the oracle's own C loop: plans, inputs, arc lengths, statuses, iteration counts."""
+    p = "loop%d_" % case
+    xp, up, SS, status = GP[p + "xpred"], GP[p + "upred"], GP[p + "SS"], GP[p + "status"]
+    N = up.shape[1]
+    cfg = oracle.make_cfg("planner", N, 1.0 / 20.0, PLAN_Q, np.diag([0.8, 0.0]), np.array([6.0, 6.0]), TRACK, L_cf=PLAN_L)
+    st = oracle.default_settings(polish=1)
+    state = oracle.plan_loop_state(GP[p + "x0"][None, :], N)
+    for t in range(xp.shape[0]):
+        oracle.plan_loop_run(cfg, st, state, 1, max_ey=0.2)
+        assert state["ctr"][0, 1] == status[t, 0] and state["ctr"][0, 2] == status[t, 1], (t, state["ctr"][0], status[t])
+        np.testing.assert_allclose(state["x_pred"][0], xp[t], rtol=0, atol=1e-8)
+        np.testing.assert_allclose(state["u_pred"][0], up[t], rtol=0, atol=1e-8)
+        np.testing.assert_allclose(state["SS"][0], SS[t], rtol=0, atol=1e-8)
+    assert state["ctr"][0, 0] == xp.shape[0] and state["ctr"][0, 3] == 0
