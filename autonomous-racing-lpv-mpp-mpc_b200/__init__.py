@@ -4,12 +4,12 @@ from . import _native
 from ._native import (SCHED_ESTIMATE, SCHED_GIVEN, SCHED_PREDICT, STATUS_NAMES, NativeError, build,
                       default_settings)
 from .controller import PathFollowingLPV_MPC
-from .fleet import ClosedLoopFleet, fleet_start
+from .fleet import ClosedLoopFleet, PlannerFleet, fleet_start
 from .planner import LPV_MPC_Planner
 from .solver import BatchResult, BatchSolver
 from .track import Map, curvature
 
-__all__ = ["BatchSolver", "BatchResult", "ClosedLoopFleet", "fleet_start", "PathFollowingLPV_MPC", "LPV_MPC_Planner", "Map", "curvature", "build",
+__all__ = ["BatchSolver", "BatchResult", "ClosedLoopFleet", "PlannerFleet", "fleet_start", "PathFollowingLPV_MPC", "LPV_MPC_Planner", "Map", "curvature", "build",
            "default_settings", "NativeError", "STATUS_NAMES", "SCHED_GIVEN", "SCHED_PREDICT", "SCHED_ESTIMATE",
            "_native"]
 import importlib

@@ -85,11 +85,16 @@ class LoopState(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("sim", "cmd", "u_pred", "x_pred", "local", "stat", "ctr")]
 
 
+class PlanLoopState(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("x_pred", "u_pred", "SS", "stat", "ctr")]
+
+
 EXPORTS = ["lpvmpc_abi_version", "lpvmpc_default_settings", "lpvmpc_device_count", "lpvmpc_create", "lpvmpc_destroy",
            "lpvmpc_last_error", "lpvmpc_get_info", "lpvmpc_update_settings", "lpvmpc_schedule_dev",
            "lpvmpc_schedule_host", "lpvmpc_solve_dev", "lpvmpc_solve_host", "lpvmpc_loop_default_cfg", "lpvmpc_loop_init_dev",
            "lpvmpc_loop_init_host", "lpvmpc_loop_run_dev", "lpvmpc_loop_run_host", "lpvmpc_loop_view_dev",
-           "lpvmpc_loop_read_host"]
+           "lpvmpc_loop_read_host", "lpvmpc_plan_loop_init_host", "lpvmpc_plan_loop_init_dev", "lpvmpc_plan_loop_run_host",
+           "lpvmpc_plan_loop_run_dev", "lpvmpc_plan_loop_view_dev", "lpvmpc_plan_loop_read_host"]
 
 _lib = None
 
@@ -152,6 +157,12 @@ def lib():
     L.lpvmpc_loop_run_host.argtypes = [C.c_void_p, C.c_int32]
     L.lpvmpc_loop_view_dev.argtypes = [C.c_void_p, C.POINTER(LoopState), C.POINTER(C.c_int32)]
     L.lpvmpc_loop_read_host.argtypes = [C.c_void_p, C.POINTER(LoopState)]
+    L.lpvmpc_plan_loop_init_host.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_double]
+    L.lpvmpc_plan_loop_init_dev.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p]
+    L.lpvmpc_plan_loop_run_host.argtypes = [C.c_void_p, C.c_int32]
+    L.lpvmpc_plan_loop_run_dev.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    L.lpvmpc_plan_loop_view_dev.argtypes = [C.c_void_p, C.POINTER(PlanLoopState), C.POINTER(C.c_int32)]
+    L.lpvmpc_plan_loop_read_host.argtypes = [C.c_void_p, C.POINTER(PlanLoopState)]
     if L.lpvmpc_abi_version() != ABI_VERSION:
         raise RuntimeError("liblpvmpc.so ABI version mismatch; rebuild with _native.build(force=True)")
     _lib = L

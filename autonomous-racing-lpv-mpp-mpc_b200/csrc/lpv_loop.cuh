@@ -224,5 +224,96 @@ __global__ void __launch_bounds__(128) lpv_loop_kernel(const __grid_constant__ L
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Planner loop (plannerMain.py:128-224): re-plan from the previous plan's second state, integrate the arc lengths.
+enum { PC_TICKS = 0, PC_STATUS, PC_ITERS, PC_FAIL, PC_FAIL_TICK, PC_COUNT = 8 };
+
+struct PlanLoopParams {
+  double dt, accel_rate;
+  const double *track;
+  int nseg;
+  int N, B;
+  const double *xstart;   // [B,5]   state of the first tick
+  double *x_pred;         // [B,N+1,5] written by the solve
+  double *u_pred;         // [B,N,2]
+  double *SS;             // [B,N+1]
+  int *ctr;               // [B,8]
+  double *stat;           // [B,4]
+  const int *status, *iters;
+  // inputs of the next solve
+  double *x0;             // [B,5]
+  double *u_prev;         // [B,N,2]
+  double *traj;           // [B,N,6]  warm-up tick: predicted_vectors_generation (plannerMain.py:465-505)
+};
+
+// do_apply: fold the last solve in (status, arc-length integration over the new plan, SS[0] = SS[1]).
+// do_prepare: inputs of the next solve (first: the guess around xstart for _EstimateABC; later: x0 = xPred[1], uPred).
+__global__ void __launch_bounds__(128) lpv_plan_loop_kernel(const __grid_constant__ PlanLoopParams p, int do_apply, int do_prepare,
+                                                            int first) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= p.B) return;
+  const int N = p.N;
+  int *ct = p.ctr + (size_t)b * PC_COUNT;
+  double *sv = p.stat + (size_t)b * 4;
+  double *ss = p.SS + (size_t)b * (N + 1);
+  const double *xP = p.x_pred + (size_t)b * (N + 1) * 5;
+  int fail = ct[PC_FAIL];
+  if (do_apply && !fail) {
+    const int status = p.status[b], it = p.iters[b];
+    ct[PC_STATUS] = status; ct[PC_ITERS] = it;
+    if (!feasible(status)) { fail = status; ct[PC_FAIL] = status; ct[PC_FAIL_TICK] = ct[PC_TICKS]; }
+    else {
+      if (status == LPVMPC_SOLVED) sv[0] += 1;
+      sv[1] += it;
+      int err = 0;
+      double s = ss[0];
+      for (int j = 0; j < N; ++j) {   // plannerMain.py:201-208
+        const double curv = curvature(p.track, p.nseg, s, err);
+        const double *x = xP + j * 5;
+        double se, ce;
+        sincos(x[4], &se, &ce);
+        s = (s + ((x[0] * ce - x[1] * se) / (1 - x[3] * curv)) * p.dt);
+        ss[j + 1] = s;
+      }
+      ss[0] = ss[1];                  // :211
+      ct[PC_TICKS] += 1;
+      if (err) { fail = LPVMPC_SCHEDULE_ERROR; ct[PC_FAIL] = fail; ct[PC_FAIL_TICK] = ct[PC_TICKS]; ct[PC_STATUS] = fail; }
+    }
+  }
+  if (!do_prepare) return;
+  double *x0 = p.x0 + (size_t)b * 5;
+  if (!fail) {
+    if (first) {
+      const double *xs = p.xstart + (size_t)b * 5;
+      double *tr = p.traj + (size_t)b * N * 6, *up = p.u_prev + (size_t)b * N * 2;
+      double Vx = xs[0], S = ss[0];
+      double se, ce;
+      sincos(xs[4], &se, &ce);
+      for (int i = 0; i < N; ++i) {
+        tr[i * 6 + 0] = Vx; tr[i * 6 + 1] = xs[1]; tr[i * 6 + 2] = xs[2]; tr[i * 6 + 3] = xs[3]; tr[i * 6 + 4] = xs[4]; tr[i * 6 + 5] = S;
+        up[i * 2 + 0] = 0.0; up[i * 2 + 1] = 0.0;
+        const double Accel = 0.1 + p.accel_rate * i;
+        const double Vn = Vx + Accel * p.dt;
+        S = S + ((Vx * ce - xs[1] * se) / (1 - xs[3] * 0.0)) * p.dt;
+        Vx = Vn;
+      }
+#pragma unroll
+      for (int e = 0; e < 5; ++e) x0[e] = xs[e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < 5; ++e) x0[e] = xP[5 + e];
+      const double *us = p.u_pred + (size_t)b * N * 2;
+      double *up = p.u_prev + (size_t)b * N * 2;
+      for (int i = 0; i < 2 * N; ++i) up[i] = us[i];
+    }
+  } else {  // retired plan: a NaN arc length makes the solve leave at once with LPVMPC_SCHEDULE_ERROR
+    const double qnan = nan("");
+    p.SS[(size_t)b * (N + 1)] = qnan;
+    if (first) for (int i = 0; i < N; ++i) p.traj[((size_t)b * N + i) * 6 + 5] = qnan;
+#pragma unroll
+    for (int e = 0; e < 5; ++e) x0[e] = qnan;
+  }
+}
+
 }  // namespace loop
 }  // namespace lpv

@@ -351,6 +351,10 @@ struct lpvmpc_handle {
   int loop_B = 0;
   long long loop_tick = 0;       // ticks since the last init (selects the warm-up path)
   cudaEvent_t loop_ev = nullptr; // last lpvmpc_loop_run_dev on the caller's stream (lpvmpc_loop_read_host waits for it)
+  // planner loop (lpvmpc_plan_loop_*); shares d_loop_status / d_loop_iters / loop_B / loop_tick / loop_ev with the above
+  char *d_ploop = nullptr;
+  lpv::loop::PlanLoopParams PP;
+  double *d_ploop_maxey = nullptr;
 };
 
 namespace {
@@ -767,7 +771,7 @@ void lpvmpc_destroy(lpvmpc_handle *h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamDestroy(h->stream);
   cudaFree(h->d_track); cudaFree(h->d_gws); cudaFree(h->d_stage); cudaFree(h->d_queue); cudaFree(h->d_cold);
-  cudaFree(h->d_loop);
+  cudaFree(h->d_loop); cudaFree(h->d_ploop);
   if (h->loop_ev) cudaEventDestroy(h->loop_ev);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   delete h;
@@ -977,6 +981,140 @@ int lpvmpc_loop_run_host(lpvmpc_handle *h, int32_t n_ticks) {
   const int rc = lpvmpc_loop_run_dev(h, n_ticks, h->stream);
   if (rc) return rc;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return LPVMPC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// planner loop
+int lpvmpc_plan_loop_init_dev(lpvmpc_handle *h, int32_t B, const double *xstart, const double *s0, double max_ey, double accel_rate,
+                              void *stream) {
+  if (!h || !xstart) return fail(h, LPVMPC_E_ARG, "null handle/xstart");
+  if (h->cfg.kind != LPVMPC_PLANNER) return fail(h, LPVMPC_E_UNSUPPORTED, "the planner loop needs a planner handle");
+  if (B < 1 || B > h->cfg.max_batch) return fail(h, LPVMPC_E_ARG, "fleet size must be in [1, max_batch]");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int N = h->L.N;
+  const size_t D = sizeof(double), mb = (size_t)h->cfg.max_batch;
+  lpv::loop::PlanLoopParams &P = h->PP;
+  if (!h->d_ploop) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t r = off; off += align256(bytes * mb); return r; };
+    const size_t o_xs = take(5 * D), o_xp = take(5 * (N + 1) * D), o_up = take(2 * N * D), o_ss = take((N + 1) * D),
+                 o_ctr = take(8 * sizeof(int32_t)), o_stat = take(4 * D), o_x0 = take(5 * D), o_uprev = take(2 * N * D),
+                 o_traj = take(6 * N * D), o_mey = take(D), o_status = take(sizeof(int32_t)), o_iters = take(sizeof(int32_t));
+    CUDA_TRY(h, cudaMalloc(&h->d_ploop, off));
+    char *base = h->d_ploop;
+    P.xstart = (double *)(base + o_xs); P.x_pred = (double *)(base + o_xp); P.u_pred = (double *)(base + o_up);
+    P.SS = (double *)(base + o_ss); P.ctr = (int *)(base + o_ctr); P.stat = (double *)(base + o_stat);
+    P.x0 = (double *)(base + o_x0); P.u_prev = (double *)(base + o_uprev); P.traj = (double *)(base + o_traj);
+    h->d_ploop_maxey = (double *)(base + o_mey);
+    P.status = (int *)(base + o_status); P.iters = (int *)(base + o_iters);
+  }
+  P.dt = h->M.dt; P.accel_rate = accel_rate; P.track = h->d_track; P.nseg = h->M.nseg; P.N = N; P.B = B;
+  h->loop_B = B; h->loop_tick = 0;
+  CUDA_TRY(h, cudaMemcpyAsync(const_cast<double *>(P.xstart), xstart, 5 * D * (size_t)B, cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(h, cudaMemsetAsync(P.x_pred, 0, 5 * (N + 1) * D * (size_t)B, s));
+  CUDA_TRY(h, cudaMemsetAsync(P.u_pred, 0, 2 * N * D * (size_t)B, s));
+  CUDA_TRY(h, cudaMemsetAsync(P.SS, 0, (N + 1) * D * (size_t)B, s));
+  CUDA_TRY(h, cudaMemsetAsync(P.ctr, 0, 8 * sizeof(int32_t) * (size_t)B, s));
+  CUDA_TRY(h, cudaMemsetAsync(P.stat, 0, 4 * D * (size_t)B, s));
+  CUDA_TRY(h, cudaMemsetAsync(const_cast<int *>(P.status), 0, sizeof(int32_t) * (size_t)B, s));
+  CUDA_TRY(h, cudaMemsetAsync(const_cast<int *>(P.iters), 0, sizeof(int32_t) * (size_t)B, s));
+  if (s0) CUDA_TRY(h, cudaMemcpy2DAsync(P.SS, (N + 1) * D, s0, D, D, (size_t)B, cudaMemcpyDeviceToDevice, s));
+  {
+    std::vector<double> mey((size_t)B, max_ey);
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_ploop_maxey, mey.data(), mey.size() * D, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+  }
+  lpvmpc_args &a = h->loop_args;
+  std::memset(&a, 0, sizeof(a));
+  a.x0 = P.x0; a.x_sched = P.x0; a.u_prev = P.u_prev; a.SS = P.SS; a.traj = P.traj; a.max_ey = h->d_ploop_maxey;
+  a.x_pred = P.x_pred; a.u_pred = P.u_pred; a.status = const_cast<int32_t *>(P.status); a.iters = const_cast<int32_t *>(P.iters);
+  return LPVMPC_OK;
+}
+
+int lpvmpc_plan_loop_run_dev(lpvmpc_handle *h, int32_t n_ticks, void *stream) {
+  if (!h) return LPVMPC_E_ARG;
+  if (!h->d_ploop || h->loop_B < 1 || h->cfg.kind != LPVMPC_PLANNER) return fail(h, LPVMPC_E_ARG, "lpvmpc_plan_loop_init_* first");
+  if (n_ticks < 0) return fail(h, LPVMPC_E_ARG, "n_ticks < 0");
+  if (n_ticks == 0) return LPVMPC_OK;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int B = h->loop_B, grid = (B + 127) / 128;
+  for (int t = 0; t < n_ticks; ++t) {
+    const int first = h->loop_tick == 0 ? 1 : 0;
+    lpv::loop::lpv_plan_loop_kernel<<<grid, 128, 0, s>>>(h->PP, t > 0 ? 1 : 0, 1, first);
+    ++h->launches;
+    CUDA_TRY(h, cudaGetLastError());
+    lpvmpc_args &a = h->loop_args;
+    a.sched_mode = first ? LPVMPC_SCHED_ESTIMATE : LPVMPC_SCHED_PREDICT;
+    const int rc = lpvmpc_solve_dev(h, B, &a, stream);
+    if (rc) return rc;
+    ++h->loop_tick;
+  }
+  lpv::loop::lpv_plan_loop_kernel<<<grid, 128, 0, s>>>(h->PP, 1, 0, 0);
+  ++h->launches;
+  CUDA_TRY(h, cudaGetLastError());
+  if (!h->loop_ev) CUDA_TRY(h, cudaEventCreateWithFlags(&h->loop_ev, cudaEventDisableTiming));
+  CUDA_TRY(h, cudaEventRecord(h->loop_ev, s));
+  return LPVMPC_OK;
+}
+
+int lpvmpc_plan_loop_init_host(lpvmpc_handle *h, int32_t B, const double *xstart, const double *s0, double max_ey, double accel_rate) {
+  if (!h || !xstart) return fail(h, LPVMPC_E_ARG, "null handle/xstart");
+  if (B < 1 || B > h->cfg.max_batch) return fail(h, LPVMPC_E_ARG, "fleet size must be in [1, max_batch]");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const size_t bx = 5 * sizeof(double) * (size_t)B, bs = sizeof(double) * (size_t)B, o2 = align256(bx);
+  if (o2 + bs > h->stage_bytes) return fail(h, LPVMPC_E_ARG, "staging overflow");
+  std::memcpy(h->h_stage, xstart, bx);
+  if (s0) std::memcpy(h->h_stage + o2, s0, bs);
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_stage, h->h_stage, o2 + bs, cudaMemcpyHostToDevice, h->stream));
+  const int rc = lpvmpc_plan_loop_init_dev(h, B, reinterpret_cast<const double *>(h->d_stage),
+                                           s0 ? reinterpret_cast<const double *>(h->d_stage + o2) : nullptr, max_ey, accel_rate, h->stream);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return LPVMPC_OK;
+}
+
+int lpvmpc_plan_loop_run_host(lpvmpc_handle *h, int32_t n_ticks) {
+  if (!h) return LPVMPC_E_ARG;
+  const int rc = lpvmpc_plan_loop_run_dev(h, n_ticks, h->stream);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return LPVMPC_OK;
+}
+
+int lpvmpc_plan_loop_view_dev(lpvmpc_handle *h, lpvmpc_plan_loop_state *view, int32_t *B) {
+  if (!h || !view) return LPVMPC_E_ARG;
+  if (!h->d_ploop || h->loop_B < 1) return fail(h, LPVMPC_E_ARG, "lpvmpc_plan_loop_init_* first");
+  view->x_pred = h->PP.x_pred; view->u_pred = h->PP.u_pred; view->SS = h->PP.SS; view->stat = h->PP.stat; view->ctr = h->PP.ctr;
+  if (B) *B = h->loop_B;
+  return LPVMPC_OK;
+}
+
+int lpvmpc_plan_loop_read_host(lpvmpc_handle *h, const lpvmpc_plan_loop_state *dst) {
+  if (!h || !dst) return LPVMPC_E_ARG;
+  if (!h->d_ploop || h->loop_B < 1) return fail(h, LPVMPC_E_ARG, "lpvmpc_plan_loop_init_* first");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const size_t B = (size_t)h->loop_B, D = sizeof(double), N = (size_t)h->L.N;
+  struct Item { void *dst; const void *src; size_t bytes; };
+  const Item items[] = {{dst->x_pred, h->PP.x_pred, 5 * (N + 1) * D * B}, {dst->u_pred, h->PP.u_pred, 2 * N * D * B},
+                        {dst->SS, h->PP.SS, (N + 1) * D * B}, {dst->stat, h->PP.stat, 4 * D * B}, {dst->ctr, h->PP.ctr, 8 * sizeof(int32_t) * B}};
+  if (h->loop_ev) CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->loop_ev, 0));
+  size_t off = 0;
+  for (const Item &it : items) {
+    if (!it.dst) continue;
+    if (off + it.bytes > h->stage_bytes) return fail(h, LPVMPC_E_ARG, "staging overflow");
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_stage + off, it.src, it.bytes, cudaMemcpyDeviceToHost, h->stream));
+    off += align256(it.bytes);
+  }
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  off = 0;
+  for (const Item &it : items) {
+    if (!it.dst) continue;
+    std::memcpy(it.dst, h->h_stage + off, it.bytes);
+    off += align256(it.bytes);
+  }
   return LPVMPC_OK;
 }
 

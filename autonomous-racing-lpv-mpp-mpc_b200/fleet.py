@@ -12,7 +12,7 @@ import numpy as np
 from . import _native as nat
 from .solver import BatchSolver
 from .track import Map
-from .workloads import CTRL_DT, CTRL_PT
+from .workloads import CTRL_DT, CTRL_PT, PLAN, PLAN_DT
 
 CTR_FIELDS = ("first_it", "lap", "half_track", "status", "iters", "fail_status", "fail_tick", "ticks")
 STAT_FIELDS = ("solved_ticks", "admm_iterations", "max_abs_ey", "lap_tick")
@@ -130,3 +130,60 @@ class ClosedLoopFleet(object):
         B = C.c_int32(0)
         nat.check(nat.lib().lpvmpc_loop_view_dev(self._h, C.byref(st), C.byref(B)), self._h)
         return {k: getattr(st, k) for k, _ in nat.LoopState._fields_}, B.value
+
+
+class PlannerFleet(object):
+    """B independent plans advanced by the reference's planner main loop (plannerMain.py:128-224) on one B200: every
+    tick re-plans from the previous plan's second state (``LPVPrediction(xPred[1], SS, uPred)`` + ``solve``) and
+    integrates the arc lengths ``SS`` over the new plan; the first tick linearises around
+    ``predicted_vectors_generation`` (plannerMain.py:465-505).  ``lpvmpc_plan_loop_*`` of the C-ABI."""
+
+    def __init__(self, track_map=None, N=40, dt=PLAN_DT, tune=None, max_fleet=4096, device=0, max_ey=0.2, accel_rate=0.2,
+                 variant=0, **osqp_settings):
+        self.map = track_map if track_map is not None else Map("L_shape")
+        tune = dict(PLAN if tune is None else tune)
+        self.solver = BatchSolver("planner", N, dt, track=self.map.PointAndTangent, max_batch=max_fleet, device=device,
+                                  variant=variant, **tune, **osqp_settings)
+        self.N, self.device = int(N), int(device)
+        self.max_ey, self.accel_rate = float(max_ey), float(accel_rate)
+        self.B = 0
+
+    @property
+    def _h(self):
+        return self.solver._h
+
+    def close(self):
+        self.solver.close()
+
+    def start(self, xstart, s0=None):
+        """xstart [B,5] = [vx vy wz ey epsi]; s0 [B] start arc lengths (None: 0, the reference's Testing mode)."""
+        x = np.ascontiguousarray(xstart, dtype=np.float64)
+        if x.ndim != 2 or x.shape[1] != 5:
+            raise ValueError("xstart must be [B,5]")
+        self.B = int(x.shape[0])
+        s = None if s0 is None else np.ascontiguousarray(s0, dtype=np.float64).reshape(self.B)
+        nat.check(nat.lib().lpvmpc_plan_loop_init_host(self._h, self.B, C.c_void_p(x.ctypes.data),
+                                                       C.c_void_p(s.ctypes.data) if s is not None else None,
+                                                       self.max_ey, self.accel_rate), self._h)
+        return self
+
+    def run(self, n_ticks, stream=None):
+        L = nat.lib()
+        if stream is None:
+            nat.check(L.lpvmpc_plan_loop_run_host(self._h, int(n_ticks)), self._h)
+        else:
+            nat.check(L.lpvmpc_plan_loop_run_dev(self._h, int(n_ticks), C.c_void_p(int(stream))), self._h)
+        return self
+
+    def read(self, fields=("x_pred", "u_pred", "SS", "stat", "ctr")):
+        B, N = self.B, self.N
+        shapes = dict(x_pred=((B, N + 1, 5), "f8"), u_pred=((B, N, 2), "f8"), SS=((B, N + 1), "f8"), stat=((B, 4), "f8"),
+                      ctr=((B, 8), "i4"))
+        out = {}
+        st = nat.PlanLoopState()
+        for k in fields:
+            shp, dt = shapes[k]
+            out[k] = np.empty(shp, dtype=dt)
+            setattr(st, k, out[k].ctypes.data)
+        nat.check(nat.lib().lpvmpc_plan_loop_read_host(self._h, C.byref(st)), self._h)
+        return out

@@ -241,6 +241,35 @@ int lpvmpc_loop_view_dev(lpvmpc_handle *h, lpvmpc_loop_state *view, int32_t *B);
 /* Copy the non-NULL members of `dst` (HOST pointers) out of the device state. */
 int lpvmpc_loop_read_host(lpvmpc_handle *h, const lpvmpc_loop_state *dst);
 
+/* ------------------------------------------------------------------------------------------------
+ * Planner loop for a fleet (plannerMain.py:128-224): every plan is re-planned from its own second
+ * predicted state.  One tick =
+ *     first tick : _EstimateABC around predicted_vectors_generation(N, x0, accel_rate, dt)   plannerMain.py:152-164, 465-505
+ *     later ticks: LPVPrediction(xPred[1], SS, uPred); solve(xPred[1], ...)                    plannerMain.py:175-176
+ *     uOld = 0 (OldSteering / OldAccelera are appended but never popped)                     plannerMain.py:186-187
+ *     SS[j+1] = SS[j] + ((vx cos(epsi) - vy sin(epsi)) / (1 - ey kappa(SS[j]))) dt over the new plan, SS[0] = SS[1]
+ *                                                                                            plannerMain.py:201-211
+ * A plan whose QP is not feasible, or whose arc length leaves Curvature()'s domain, is retired (ctr[3] = the status).
+ * The handle must be a planner.  The reference starts at s = 0 with [1, 0, 0, 0, 0] (Testing mode, :145-146); here every
+ * plan has its own start state and start arc length.
+ * State, row-major: x_pred [B,N+1,5], u_pred [B,N,2], SS [B,N+1], ctr [B,8] = [ticks_done, last_status, last_iters,
+ * fail_status (0 = running), fail_tick, 0, 0, 0], stat [B,4] = [SOLVED ticks, total ADMM iterations, 0, 0].
+ */
+typedef struct {
+  double *x_pred, *u_pred, *SS, *stat;
+  int32_t *ctr;
+} lpvmpc_plan_loop_state;
+
+/* xstart [B,5] = [vx vy wz ey epsi], s0 [B] start arc lengths (NULL = 0), max_ey = lateral box (plannerMain.py:52 HW),
+ * accel_rate = 0.2 in the reference (plannerMain.py:158). */
+int lpvmpc_plan_loop_init_host(lpvmpc_handle *h, int32_t B, const double *xstart, const double *s0, double max_ey, double accel_rate);
+int lpvmpc_plan_loop_init_dev(lpvmpc_handle *h, int32_t B, const double *xstart, const double *s0, double max_ey, double accel_rate,
+                              void *stream);
+int lpvmpc_plan_loop_run_host(lpvmpc_handle *h, int32_t n_ticks);
+int lpvmpc_plan_loop_run_dev(lpvmpc_handle *h, int32_t n_ticks, void *stream);
+int lpvmpc_plan_loop_view_dev(lpvmpc_handle *h, lpvmpc_plan_loop_state *view, int32_t *B);
+int lpvmpc_plan_loop_read_host(lpvmpc_handle *h, const lpvmpc_plan_loop_state *dst);
+
 #ifdef __cplusplus
 }
 #endif

@@ -85,3 +85,35 @@ def test_full_fleet_one_lap_properties():
     assert np.isfinite(r["sim"]).all()
     assert 0.9 < np.median(r["local"][:, 0]) < 1.1            # settled at the 1 m/s reference
     fleet.close()
+
+
+def test_planner_fleet_matches_oracle_loop():
+    """SURVEY 8f rows 2-3 (planner main loop, plannerMain.py:128-224) through lpvmpc_plan_loop_*: the Testing-mode start
+    [1, 0, 0, 0, 0] at s = 0 plus perturbed starts spread over the track, 12 ticks, against the oracle's planner loop
+    (pinned to the reference's LPV_MPC_Planner by tests/test_oracle_loop.py)."""
+    m = lp.Map("L_shape")
+    rng = np.random.default_rng(21)
+    B, T, N = 40, 12, 40
+    x0 = np.stack([rng.uniform(1.0, 2.0, B), rng.normal(0, 0.01, B), rng.normal(0, 0.05, B), rng.normal(0, 0.02, B), rng.normal(0, 0.02, B)], axis=1)
+    s0 = rng.uniform(0.0, 18.0, B)
+    x0[0] = [1.0, 0.0, 0.0, 0.0, 0.0]; s0[0] = 0.0
+    x0[1, 0] = 0.5                          # below min_vel with x0 pinned: primal infeasible, retired at tick 0
+    fleet = lp.PlannerFleet(m, N=N, max_fleet=64, max_ey=0.2)
+    cfg = oracle.make_cfg("planner", N, W.PLAN_DT, W.PLAN["Q"], W.PLAN["R"], W.PLAN["dR"], m.PointAndTangent, L_cf=W.PLAN["L_cf"])
+    ref = oracle.plan_loop_state(x0, N, s0)
+    fleet.start(x0, s0)
+    # Statuses, iteration counts and tick counters must be identical throughout.  Plans agree to 1e-6 over the first
+    # ticks; they are only solved to OSQP's eps = 1e-3 (polish rarely succeeds on planner QPs) and every tick re-plans
+    # from the previous plan, so round-off level differences grow: within 1e-3 (the solver's own accuracy) after 12.
+    for ticks, tol in ((4, 2e-6), (T - 4, 1e-3)):
+        got = fleet.run(ticks).read()
+        oracle.plan_loop_run(cfg, oracle.default_settings(polish=1), ref, ticks, max_ey=0.2, threads=8)
+        np.testing.assert_array_equal(got["ctr"], ref["ctr"])
+        np.testing.assert_array_equal(got["stat"], ref["stat"])
+        alive = got["ctr"][:, 3] == 0
+        np.testing.assert_allclose(got["SS"][alive], ref["SS"][alive], rtol=0, atol=tol)
+        np.testing.assert_allclose(got["x_pred"][alive], ref["x_pred"][alive], rtol=0, atol=tol)
+        np.testing.assert_allclose(got["u_pred"][alive], ref["u_pred"][alive], rtol=0, atol=tol)
+    assert got["ctr"][1, 3] in (-3, 3) and got["ctr"][1, 0] == 0
+    assert alive.sum() >= B - 4 and (got["ctr"][alive, 0] == T).all()
+    fleet.close()
