@@ -666,6 +666,59 @@ __device__ __forceinline__ void sweep_bwd_admm(const Hot<KIND> &h, Strm &sm, con
   __syncwarp();
 }
 
+// Backward sweep + element-wise updates when the warp holds ONE QP: the chain (x~_k = W_k - K_{k+1}' x~_{k+1}) is serial
+// and runs mirrored in all four lane groups, but the updates are independent per stage, so they are issued once per FOUR
+// chain steps with group g taking stage jtop - g (the fused loop above issues them once per step with all groups doing
+// the same stage).  x~_k is parked in the B slot of its stage between its chain step and its update; the x~ of the
+// stage above a batch comes from the previous batch through a shuffle.
+template <int KIND, bool ST>
+__device__ __forceinline__ void sweep_bwd_admm_w1(const Hot<KIND> &h, Strm &sm, const Upd<KIND> &u, uint32_t &gsel, const int g) {
+  const int N = u.N;
+  const int lane = threadIdx.x & 31;
+  double gn[8];
+  {
+    const double xN = lds(h.v + N * VB);   // stage N: x~_N = W_N, already in its B slot
+    sts(h.gpub ^ gsel, xN);
+    gather_in(h.ggat, gsel, gn);
+  }
+  double xcarry = 0.0;   // x~ of the stage above the batch's top stage
+  int k = N - 1;         // next chain stage
+  int jtop = N;          // top stage of the next batch of updates
+#pragma unroll 1
+  while (jtop >= 0) {
+#pragma unroll 1
+    for (int i = 0; i < 4 && k >= 0; ++i, --k) {
+      const uint32_t so = ST ? strm_bwd(h.sc, sm, k) : (uint32_t)k * (uint32_t)TKB;
+      const uint32_t vb = h.v + (uint32_t)k * VB;
+      const double xt = bwd_step(h.kc[0] + so, h.kc[1] + so, h.kc[2] + so, h.kc[3] + so, vb, h.gpub, h.ggat, gsel, gn);
+      if (ST) strm_post(h.sc, sm);
+      sts(vb, xt);   // W_k has been consumed: park x~_k here until the update of stage k overwrites it
+      gather_in(h.ggat, gsel, gn);
+    }
+    __syncwarp();
+    // stages whose lower neighbour's x~ exists: j >= k + 2, and stage 0 once the chain is done
+    const int jmin = (k < 0) ? 0 : k + 2;
+    const int jlow = (jtop - 3 > jmin) ? jtop - 3 : jmin;
+    const int j = jtop - g;
+    double x1 = 0.0;
+    if (j >= jlow) {
+      const uint32_t vj = h.v + (uint32_t)j * VB, ij = h.ib + (uint32_t)j * h.istr, lj = h.il + (uint32_t)j * h.istr;
+      const uint32_t pj = h.pm + (uint32_t)j * h.pstr, pj2 = h.pm2 + (uint32_t)j * h.pstr;
+      UpdIn in;
+      update_loads<KIND>(vj, ij, lj, pj, pj2, in);
+      x1 = lds(vj);
+      const double xm = (j > 0) ? lds(vj - VB) : 0.0;
+      const double xp = (g > 0) ? lds(vj + VB) : xcarry;
+      UpdMid q;
+      update_part1<KIND>(u, j, ij, in, x1, xm, xp, q);
+      update_part2<KIND>(u, vj, x1, q);
+    }
+    xcarry = __shfl_sync(kFull, x1, (lane & 7) + 8 * (jtop - jlow));   // x~ of the lowest stage of this batch
+    __syncwarp();
+    jtop = jlow - 1;
+  }
+}
+
 // ---------------------------------------------------------------- per-QP scalars shared by the cold routines
 struct Info {
   double pri_res, dua_res, obj;
@@ -1658,7 +1711,8 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
         }
         u.cc = (iter == 0) ? 2.0 : alpha;
         sweep_fwd<KIND, ST>(h, sm, N, gsel);
-        sweep_bwd_admm<KIND, ST>(h, sm, u, gsel);
+        if (QPW == 1) sweep_bwd_admm_w1<KIND, ST>(h, sm, u, gsel, g);
+        else sweep_bwd_admm<KIND, ST>(h, sm, u, gsel);
         if (iter == 0) first_in = 1;
         ++nsync;
         zsel = 1.0;

@@ -58,6 +58,9 @@ WORKLOADS = {
     # not a BASELINE config: a horizon whose block factor (165 KB) no longer fits shared memory next to the stage vectors,
     # so the factor is streamed from the L2 slab by TMA bulk copies (kernel variant 7)
     "ctrl512N160": dict(kind="controller", N=160, B=512, seed=3),
+    # not a BASELINE config: the planner main loop (plannerMain.py:128-224) for a fleet of plans, i.e. planner QPs with the
+    # reference's own closed-loop distribution (SURVEY 8d cfg 3 generator); a step = `--ticks-per-step` re-planning ticks
+    "planloop4096": dict(kind="planfleet", N=40, B=4096, seed=5),
 }
 
 
@@ -363,9 +366,83 @@ def run_fleet(args):
     return 0
 
 
+def planfleet_start(B, seed):
+    rng = np.random.default_rng(seed)
+    x0 = np.stack([rng.uniform(1.0, 2.0, B), rng.normal(0, 0.01, B), rng.normal(0, 0.05, B), rng.normal(0, 0.02, B), rng.normal(0, 0.02, B)], axis=1)
+    return x0, rng.uniform(0.0, 18.0, B)
+
+
+def run_planfleet(args):
+    """Planner main loop for a fleet (lpvmpc_plan_loop_*): single GPU, device-resident; a step = ticks_per_step ticks."""
+    import torch
+    import lpvmpc_b200 as lp
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise SystemExit("planloop4096 is a single-GPU workload")
+    spec = WORKLOADS[args.workload]
+    B, N = spec["B"], spec["N"]
+    tps = min(args.ticks_per_step, 4)
+    m = lp.Map("L_shape")
+    x0, s0 = planfleet_start(B, spec["seed"])
+    fleet = lp.PlannerFleet(m, N=N, max_fleet=B, max_ey=0.2, variant=args.variant)
+    info0 = fleet.solver.info()
+    stream = torch.cuda.current_stream(0).cuda_stream
+    fleet.start(x0, s0)
+    for _ in range(args.warmup):
+        fleet.run(tps, stream=stream)
+    torch.cuda.synchronize()
+    before = fleet.read(("stat", "ctr"))
+    sampler = ClockSampler(0)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = fleet.solver.info()["kernel_launches"]
+    e0.record()
+    for _ in range(args.steps):
+        fleet.run(tps, stream=stream)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    total_ms = e0.elapsed_time(e1)
+    after = fleet.read(("stat", "ctr"))
+    ticks_done = float((after["ctr"][:, 0] - before["ctr"][:, 0]).sum())
+    solved = float((after["stat"][:, 0] - before["stat"][:, 0]).sum())
+    iters_sum = float((after["stat"][:, 1] - before["stat"][:, 1]).sum())
+    F_scale, F_form, F_fac, F_solve, F_iter, F_check = FLOP_TABLE[("planner", N)]
+    flops = ticks_done * (F_scale + F_form + 1.5 * F_fac) + iters_sum * (F_iter + F_check / 25.0)
+    peak, peak_src = fp64_peak_tflops()
+    te = time.perf_counter()
+    fleet.start(x0, s0)
+    fleet.run(tps * min(args.steps, 3))
+    out = fleet.read()
+    e2e_total = time.perf_counter() - te
+    line = {
+        "metric": "LPV-MPC QP solves/sec", "value": ticks_done / (total_ms * 1e-3), "unit": "QP/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "kind": "planner fleet (plannerMain loop: re-plan from xPred[1], arc-length integration)", "N": N,
+                   "plans_per_gpu": B, "ticks_per_step": tps, "kernel_variant": info0["variant"], "l2": "fleet state resident by design; no flush"},
+        "e2e": {"value": float(out["ctr"][:, 0].sum()) / e2e_total, "unit": "QP/s", "h2d_bytes_per_step": int(x0.nbytes + s0.nbytes) // min(args.steps, 3),
+                "d2h_bytes_per_step": int(sum(v.nbytes for v in out.values())) // min(args.steps, 3),
+                "note": "start(host states) + run + read(): from tick 0 (includes the slow first ticks)"},
+        "gpu_launches": int(fleet.solver.info()["kernel_launches"] - launches0), "clocks": clocks,
+        "roofline": {"bound": "fp64_fma", "achieved": flops / (total_ms * 1e-3) * 1e-12, "peak": peak, "unit": "TFLOP/s",
+                     "frac": flops / (total_ms * 1e-3) * 1e-12 / peak, "traffic": None, "peak_source": peak_src,
+                     "kernel": KERNEL_NAMES.get(info0["variant"], "?") + " (one launch per tick) + lpv_plan_loop_kernel"},
+        "solved_fraction": solved / max(ticks_done, 1.0), "iters": {"mean": iters_sum / max(ticks_done, 1.0)},
+        "retired_plans": int((after["ctr"][:, 3] != 0).sum()),
+    }
+    print(json.dumps(line))
+    fleet.close()
+    return 0
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return 0
+    if WORKLOADS[args.workload]["kind"] == "planfleet":
+        print(json.dumps({"impl": "reference", "unavailable": "planloop4096 is not a BASELINE config; use plan16384"}))
         return 0
     if WORKLOADS[args.workload]["kind"] == "fleet":
         return run_fleet_reference(args)
@@ -576,6 +653,8 @@ def main():
         return run_reference(args)
     if WORKLOADS[args.workload]["kind"] == "fleet":
         return run_fleet(args)
+    if WORKLOADS[args.workload]["kind"] == "planfleet":
+        return run_planfleet(args)
     return run_ours(args)
 
 
