@@ -290,7 +290,7 @@ __device__ __noinline__ void factor(const Ctx<KIND> c, const FW fw, const double
       }
       __syncwarp();
 #pragma unroll
-      for (int j = 0; j < 4; ++j) st2(Kk + c.ro[j], kr[2 * j], kr[2 * j + 1]);
+      for (int j = 0; j < 4; ++j) st2(Kk + c.ro[j], -kr[2 * j], -kr[2 * j + 1]);   // the sweeps add (-K): stored negated
     }
     if (!rowlive) {
 #pragma unroll
@@ -494,8 +494,8 @@ __device__ __forceinline__ void sweep_fwd(const Hot<KIND> &h, Strm &sm, const in
     const uint32_t gg = h.ggat ^ gsel;
     const double2 g0 = lds2(gg), g1 = lds2<64>(gg), g2 = lds2<128>(gg), g3 = lds2<192>(gg);
     if (ST) strm_post(h.sc, sm);   // probe the next step's block while the dot products run
-    double c0 = fma(-b0.x, g0.x, bn), c1 = -(b1.x * g1.x), c2 = -(b2.x * g2.x), c3 = -(b3.x * g3.x);
-    c0 = fma(-b0.y, g0.y, c0); c1 = fma(-b1.y, g1.y, c1); c2 = fma(-b2.y, g2.y, c2); c3 = fma(-b3.y, g3.y, c3);
+    double c0 = fma(b0.x, g0.x, bn), c1 = b1.x * g1.x, c2 = b2.x * g2.x, c3 = b3.x * g3.x;   // b = row of -K_{k+1}
+    c0 = fma(b0.y, g0.y, c0); c1 = fma(b1.y, g1.y, c1); c2 = fma(b2.y, g2.y, c2); c3 = fma(b3.y, g3.y, c3);
     v = (c0 + c1) + (c2 + c3);
     sts(vb, dot8(a0, a1, a2, a3, g0, g1, g2, g3));
     vb += VB; gsel ^= 256u;
@@ -514,15 +514,46 @@ __device__ __forceinline__ void sweep_fwd(const Hot<KIND> &h, Strm &sm, const in
   }
 }
 
+// Forward sweep when the warp holds ONE QP: lane group 1 computes W_k = T_k v_k while the other groups run the chain
+// v_{k+1} = b_{k+1} + (-K_{k+1}) v_k (mirrored), with one instruction stream: every lane loads ONE matrix row of the stage
+// block (T_k or -K_{k+1}), forms base + row . v_k with the same FMA order as sweep_fwd, and stores its result at the top
+// of the next stage (chain lanes: into the gather buffer; group 1: W_k into B_k).
+template <int KIND, bool ST>
+__device__ __forceinline__ void sweep_fwd_w1(const Hot<KIND> &h, Strm &sm, const int N, uint32_t &gsel, const int g) {
+  const bool trole = (g == 1);
+  const uint32_t roff = trole ? 0u : 512u;
+  const uint32_t ggat = trole ? h.ggat - 16u : h.ggat;   // group 1 reads the chain's column of the gather buffer
+  uint32_t vb = h.v, wst = h.v;
+  double res = lds(vb);   // chain: v_0 = b_0; group 1: b_0 as well, written back to B_0 unchanged by its first store
+  if (ST) strm_warm(h.sc, sm);
+#pragma unroll 1
+  for (int k = 0; k <= N; ++k) {
+    const uint32_t so = (ST ? strm_fwd(h.sc, sm, k) : (uint32_t)k * (uint32_t)TKB) + roff;
+    sts(trole ? wst : (h.gpub ^ gsel), res);
+    const double2 r0 = lds2(h.tk[0] + so), r1 = lds2(h.tk[1] + so), r2 = lds2(h.tk[2] + so), r3 = lds2(h.tk[3] + so);
+    const double bn = (k < N) ? lds<VB>(vb) : 0.0;
+    __syncwarp();
+    const uint32_t gg = ggat ^ gsel;
+    const double2 g0 = lds2(gg), g1 = lds2<64>(gg), g2 = lds2<128>(gg), g3 = lds2<192>(gg);
+    if (ST) strm_post(h.sc, sm);
+    double c0 = fma(r0.x, g0.x, trole ? 0.0 : bn), c1 = r1.x * g1.x, c2 = r2.x * g2.x, c3 = r3.x * g3.x;
+    c0 = fma(r0.y, g0.y, c0); c1 = fma(r1.y, g1.y, c1); c2 = fma(r2.y, g2.y, c2); c3 = fma(r3.y, g3.y, c3);
+    res = (c0 + c1) + (c2 + c3);
+    wst = vb; vb += VB; gsel ^= 256u;
+  }
+  if (trole) sts(wst, res);   // W_N (the chain lanes' last result is meaningless: stage N has no K)
+  __syncwarp();
+}
+
 // x~_k = W_k - K_{k+1}' x~_{k+1} for one stage: returns my component, refreshes gn with the gathered x~_k
 __device__ __forceinline__ double bwd_step(const uint32_t k0, const uint32_t k1, const uint32_t k2, const uint32_t k3, const uint32_t vb,
                                           const uint32_t gpub, const uint32_t ggat, uint32_t &gsel, double (&gn)[8]) {
   const double e0 = lds(k0), e1 = lds<64>(k0), e2 = lds(k1), e3 = lds<64>(k1), e4 = lds(k2), e5 = lds<64>(k2), e6 = lds(k3), e7 = lds<64>(k3);
   const double w = lds(vb);
-  double a0 = fma(-e0, gn[0], w), a1 = -(e1 * gn[1]);
-  a0 = fma(-e2, gn[2], a0); a1 = fma(-e3, gn[3], a1);
-  a0 = fma(-e4, gn[4], a0); a1 = fma(-e5, gn[5], a1);
-  a0 = fma(-e6, gn[6], a0); a1 = fma(-e7, gn[7], a1);
+  double a0 = fma(e0, gn[0], w), a1 = e1 * gn[1];   // e = column of -K_{k+1}
+  a0 = fma(e2, gn[2], a0); a1 = fma(e3, gn[3], a1);
+  a0 = fma(e4, gn[4], a0); a1 = fma(e5, gn[5], a1);
+  a0 = fma(e6, gn[6], a0); a1 = fma(e7, gn[7], a1);
   const double xt = a0 + a1;
   sts(gpub ^ gsel, xt);
   return xt;
@@ -1710,7 +1741,8 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
           }
         }
         u.cc = (iter == 0) ? 2.0 : alpha;
-        sweep_fwd<KIND, ST>(h, sm, N, gsel);
+        if (QPW == 1) sweep_fwd_w1<KIND, ST>(h, sm, N, gsel, g);
+        else sweep_fwd<KIND, ST>(h, sm, N, gsel);
         if (QPW == 1) sweep_bwd_admm_w1<KIND, ST>(h, sm, u, gsel, g);
         else sweep_bwd_admm<KIND, ST>(h, sm, u, gsel);
         if (iter == 0) first_in = 1;
