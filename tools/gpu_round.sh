@@ -22,3 +22,6 @@ ls -la $OUT | tail -15
 timeout 600 python bench.py --workload mc8192 --steps 24 --warmup 3 > $OUT/${TAG}_bench_mc8192.json 2> $OUT/${TAG}_bench_mc8192.err; echo "mc8192 rc=$?"; cut -c1-200 $OUT/${TAG}_bench_mc8192.json
 timeout 300 python bench.py --impl reference --workload mc8192 --steps 5 --warmup 2 > $OUT/${TAG}_benchref_mc8192.json 2>> $OUT/${TAG}_bench_mc8192.err
 ls -la $OUT | grep ${TAG} | wc -l
+for WL in ctrl512N160 planloop4096; do
+  timeout 600 python bench.py --workload $WL --steps 3 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench_$WL.json 2> $OUT/${TAG}_bench_$WL.err; echo "$WL rc=$?"; cut -c1-160 $OUT/${TAG}_bench_$WL.json
+done
