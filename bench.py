@@ -262,6 +262,7 @@ def run_fleet(args):
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
+        os.environ["NCCL_DEBUG"] = os.environ.get("LPVMPC_NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: one JSON line
         dist.init_process_group("nccl", device_id=dev)
     spec = WORKLOADS[args.workload]
     B, tps = spec["B"], args.ticks_per_step
@@ -486,6 +487,7 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
+        os.environ["NCCL_DEBUG"] = os.environ.get("LPVMPC_NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     spec, track, w, tune, dt, keys = make_workload(args.workload, rank)
