@@ -315,5 +315,97 @@ __global__ void __launch_bounds__(128) lpv_plan_loop_kernel(const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Planner -> controller references (plannerMain.py:196-224, 257-280): global positions along the plan, vehicle pose and
+// curvature per stage, then the cubic resampling to the controller's period and the zero-phase filter of the curvature.
+// For the uniform grids involved both are linear maps, built once on the host (postproc.py): W for x, y, yaw, vx and
+// Wc = F W for the curvature, [n_out, N] row-major.
+
+__device__ __forceinline__ double wrap_angle(double a) {   // trackInitialization.py:413-421
+  if (a < -kPi) return 2 * kPi + a;
+  if (a > kPi) return a - 2 * kPi;
+  return a;
+}
+
+// Map.getGlobalPosition(s, 0) (trackInitialization.py:205-260); err when no unique segment holds s
+__device__ __forceinline__ void global_position0(const double *__restrict__ track, int nseg, double s, double *out, int &err) {
+  const double TrackLength = track[(nseg - 1) * 6 + 3] + track[(nseg - 1) * 6 + 4];
+  if (!(s == s) || s > 1e300) { err = 1; out[0] = out[1] = out[2] = nan(""); return; }
+  while (s > TrackLength) s = s - TrackLength;
+  int i = -1, cnt = 0;
+  for (int k = 0; k < nseg; ++k)
+    if (s >= track[k * 6 + 3] && s < track[k * 6 + 3] + track[k * 6 + 4]) { if (i < 0) i = k; ++cnt; }
+  if (cnt != 1) { err = 1; out[0] = out[1] = out[2] = nan(""); return; }
+  const double *Pi = track + i * 6;
+  const double *Pm = track + ((i == 0) ? (nseg - 1) : (i - 1)) * 6;
+  const double ey = 0.0;
+  if (Pi[5] == 0.0) {
+    const double xf = Pi[0], yf = Pi[1], xs = Pm[0], ys = Pm[1], psi = Pi[2];
+    const double deltaL = Pi[4], reltaL = s - Pi[3];
+    out[0] = (1 - reltaL / deltaL) * xs + reltaL / deltaL * xf + ey * cos(psi + kPi / 2);
+    out[1] = (1 - reltaL / deltaL) * ys + reltaL / deltaL * yf + ey * sin(psi + kPi / 2);
+    out[2] = psi;
+  } else {
+    const double r = 1 / Pi[5], ang = Pm[2];
+    const double direction = (r >= 0) ? 1 : -1;
+    const double CenterX = Pm[0] + fabs(r) * cos(ang + direction * kPi / 2);
+    const double CenterY = Pm[1] + fabs(r) * sin(ang + direction * kPi / 2);
+    const double spanAng = (s - Pi[3]) / (kPi * fabs(r)) * kPi;
+    const double angleNormal = wrap_angle(direction * kPi / 2 + ang);
+    const double angle = -(kPi - fabs(angleNormal)) * ((angleNormal >= 0) ? 1 : -1);
+    out[0] = CenterX + (fabs(r) - direction * ey) * cos(angle + direction * spanAng);
+    out[1] = CenterY + (fabs(r) - direction * ey) * sin(angle + direction * spanAng);
+    out[2] = ang + direction * spanAng;
+  }
+}
+
+struct PlanRefsParams {
+  const double *track;
+  int nseg, N, n_out, B;
+  const double *W, *Wc;       // [n_out, N]
+  const double *x_pred;       // [B,N+1,5]
+  const double *SS;           // [B,N+1]   arc lengths of the plan (entry 0 is not used: the pose of stage 0 is xyth0)
+  const double *xyth0;        // [B,3]     Xlast, Ylast, Thetalast (plannerMain.py:196-198)
+  double *refs;               // [B,5,n_out]  x_d, y_d, psi_d, vx_d, curv_d of My_Planning (plannerMain.py:299-303)
+  int *err;                   // [B] optional: 1 when getGlobalPosition failed
+};
+
+// one CTA per plan: stage poses into shared memory, then one output sample per thread and signal
+__global__ void __launch_bounds__(128) lpv_plan_refs_kernel(const __grid_constant__ PlanRefsParams p) {
+  extern __shared__ double raw[];   // [5][N]: xp, yp, yaw, vel, curv
+  const int b = blockIdx.x, N = p.N;
+  __shared__ int s_err;
+  if (threadIdx.x == 0) s_err = 0;
+  __syncthreads();
+  const double *xP = p.x_pred + (size_t)b * (N + 1) * 5;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    double g[3];
+    int err = 0;
+    if (i == 0) { g[0] = p.xyth0[(size_t)b * 3]; g[1] = p.xyth0[(size_t)b * 3 + 1]; g[2] = p.xyth0[(size_t)b * 3 + 2]; }
+    else global_position0(p.track, p.nseg, p.SS[(size_t)b * (N + 1) + i], g, err);
+    if (err) s_err = 1;
+    const double *x = xP + i * 5;
+    const double yaw = g[2] + x[4];                         // :219
+    raw[2 * N + i] = yaw;
+    raw[0 * N + i] = g[0] - x[3] * sin(yaw);                // :220
+    raw[1 * N + i] = g[1] + x[3] * cos(yaw);                // :221
+    raw[3 * N + i] = x[0];                                  // :223
+    raw[4 * N + i] = x[2] / x[0];                           // :224
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < p.n_out; r += blockDim.x) {
+    const double *w = p.W + (size_t)r * N, *wc = p.Wc + (size_t)r * N;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+    for (int i = 0; i < N; ++i) {
+      const double wi = w[i];
+      a0 = fma(wi, raw[i], a0); a1 = fma(wi, raw[N + i], a1); a2 = fma(wi, raw[2 * N + i], a2); a3 = fma(wi, raw[3 * N + i], a3);
+      a4 = fma(wc[i], raw[4 * N + i], a4);
+    }
+    double *o = p.refs + (size_t)b * 5 * p.n_out + r;
+    o[0] = a0; o[p.n_out] = a1; o[2 * p.n_out] = a2; o[3 * p.n_out] = a3; o[4 * p.n_out] = a4;
+  }
+  if (p.err && threadIdx.x == 0) p.err[b] = s_err;
+}
+
 }  // namespace loop
 }  // namespace lpv

@@ -355,6 +355,9 @@ struct lpvmpc_handle {
   char *d_ploop = nullptr;
   lpv::loop::PlanLoopParams PP;
   double *d_ploop_maxey = nullptr;
+  // planner -> controller references (lpvmpc_plan_refs_*)
+  double *d_refs_W = nullptr;    // W then Wc, each [n_out, N]
+  int refs_n_out = 0;
 };
 
 namespace {
@@ -771,7 +774,7 @@ void lpvmpc_destroy(lpvmpc_handle *h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamDestroy(h->stream);
   cudaFree(h->d_track); cudaFree(h->d_gws); cudaFree(h->d_stage); cudaFree(h->d_queue); cudaFree(h->d_cold);
-  cudaFree(h->d_loop); cudaFree(h->d_ploop);
+  cudaFree(h->d_loop); cudaFree(h->d_ploop); cudaFree(h->d_refs_W);
   if (h->loop_ev) cudaEventDestroy(h->loop_ev);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   delete h;
@@ -1115,6 +1118,63 @@ int lpvmpc_plan_loop_read_host(lpvmpc_handle *h, const lpvmpc_plan_loop_state *d
     std::memcpy(it.dst, h->h_stage + off, it.bytes);
     off += align256(it.bytes);
   }
+  return LPVMPC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// planner -> controller references
+int lpvmpc_plan_refs_setup(lpvmpc_handle *h, int32_t n_out, const double *W, const double *Wc) {
+  if (!h || !W || !Wc) return fail(h, LPVMPC_E_ARG, "null handle/W/Wc");
+  if (h->cfg.kind != LPVMPC_PLANNER) return fail(h, LPVMPC_E_UNSUPPORTED, "references need a planner handle");
+  if (n_out < 1 || n_out > 4096) return fail(h, LPVMPC_E_ARG, "n_out must be in [1, 4096]");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const size_t bytes = sizeof(double) * (size_t)n_out * (size_t)h->L.N;
+  cudaFree(h->d_refs_W); h->d_refs_W = nullptr;
+  CUDA_TRY(h, cudaMalloc(&h->d_refs_W, 2 * bytes));
+  CUDA_TRY(h, cudaMemcpy(h->d_refs_W, W, bytes, cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMemcpy(reinterpret_cast<char *>(h->d_refs_W) + bytes, Wc, bytes, cudaMemcpyHostToDevice));
+  h->refs_n_out = n_out;
+  return LPVMPC_OK;
+}
+
+int lpvmpc_plan_refs_dev(lpvmpc_handle *h, int32_t B, const double *x_pred, const double *SS, const double *xyth0, double *refs,
+                         int32_t *err, void *stream) {
+  if (!h || !x_pred || !SS || !xyth0 || !refs) return fail(h, LPVMPC_E_ARG, "null handle/x_pred/SS/xyth0/refs");
+  if (!h->d_refs_W) return fail(h, LPVMPC_E_ARG, "lpvmpc_plan_refs_setup first");
+  if (B < 0 || B > h->cfg.max_batch) return fail(h, LPVMPC_E_ARG, "batch exceeds max_batch");
+  if (B == 0) return LPVMPC_OK;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  lpv::loop::PlanRefsParams p;
+  p.track = h->d_track; p.nseg = h->M.nseg; p.N = h->L.N; p.n_out = h->refs_n_out; p.B = B;
+  p.W = h->d_refs_W; p.Wc = h->d_refs_W + (size_t)h->refs_n_out * (size_t)h->L.N;
+  p.x_pred = x_pred; p.SS = SS; p.xyth0 = xyth0; p.refs = refs; p.err = err;
+  lpv::loop::lpv_plan_refs_kernel<<<B, 128, sizeof(double) * 5 * (size_t)h->L.N, (cudaStream_t)stream>>>(p);
+  ++h->launches;
+  CUDA_TRY(h, cudaGetLastError());
+  return LPVMPC_OK;
+}
+
+int lpvmpc_plan_refs_host(lpvmpc_handle *h, int32_t B, const double *x_pred, const double *SS, const double *xyth0, double *refs,
+                          int32_t *err) {
+  if (!h || !x_pred || !SS || !xyth0 || !refs) return fail(h, LPVMPC_E_ARG, "null handle/x_pred/SS/xyth0/refs");
+  if (!h->d_refs_W) return fail(h, LPVMPC_E_ARG, "lpvmpc_plan_refs_setup first");
+  if (B < 0 || B > h->cfg.max_batch) return fail(h, LPVMPC_E_ARG, "batch exceeds max_batch");
+  if (B == 0) return LPVMPC_OK;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const size_t D = sizeof(double), N = (size_t)h->L.N, nb = (size_t)B;
+  const size_t b_x = 5 * (N + 1) * D * nb, b_s = (N + 1) * D * nb, b_0 = 3 * D * nb, b_r = 5 * (size_t)h->refs_n_out * D * nb, b_e = sizeof(int32_t) * nb;
+  const size_t o_x = 0, o_s = o_x + align256(b_x), o_0 = o_s + align256(b_s), o_r = o_0 + align256(b_0), o_e = o_r + align256(b_r);
+  if (o_e + align256(b_e) > h->stage_bytes) return fail(h, LPVMPC_E_ARG, "staging overflow");
+  run_copies({{h->h_stage + o_x, x_pred, b_x}, {h->h_stage + o_s, SS, b_s}, {h->h_stage + o_0, xyth0, b_0}});
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_stage, h->h_stage, o_r, cudaMemcpyHostToDevice, h->stream));
+  const int rc = lpvmpc_plan_refs_dev(h, B, reinterpret_cast<const double *>(h->d_stage + o_x), reinterpret_cast<const double *>(h->d_stage + o_s),
+                                      reinterpret_cast<const double *>(h->d_stage + o_0), reinterpret_cast<double *>(h->d_stage + o_r),
+                                      reinterpret_cast<int32_t *>(h->d_stage + o_e), h->stream);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_stage + o_r, h->d_stage + o_r, (o_e - o_r) + align256(b_e), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  run_copies({{refs, h->h_stage + o_r, b_r}});
+  if (err) std::memcpy(err, h->h_stage + o_e, b_e);
   return LPVMPC_OK;
 }
 

@@ -12,6 +12,7 @@ import numpy as np
 from . import _native as nat
 from .solver import BatchSolver
 from .track import Map
+from .postproc import n_out_for, reference_matrices
 from .workloads import CTRL_DT, CTRL_PT, PLAN, PLAN_DT
 
 CTR_FIELDS = ("first_it", "lap", "half_track", "status", "iters", "fail_status", "fail_tick", "ticks")
@@ -187,3 +188,23 @@ class PlannerFleet(object):
             setattr(st, k, out[k].ctypes.data)
         nat.check(nat.lib().lpvmpc_plan_loop_read_host(self._h, C.byref(st)), self._h)
         return out
+
+    def references(self, x_pred, SS, xyth0):
+        """Planner -> controller references of ``My_Planning`` (plannerMain.py:196-224, 257-303) for a batch of plans:
+        x_pred [B,N+1,5], SS [B,N+1] (arc lengths of the plan), xyth0 [B,3] (pose of stage 0: Xlast, Ylast, Thetalast).
+        Returns (refs [B,5,n_out] = x_d, y_d, psi_d, vx_d, curv_d; err [B])."""
+        L = nat.lib()
+        if not getattr(self, "_refs_ready", False):
+            W, Wc = reference_matrices(self.N, self.solver._cfg.dt)
+            self.n_out = W.shape[0]
+            nat.check(L.lpvmpc_plan_refs_setup(self._h, self.n_out, C.c_void_p(W.ctypes.data), C.c_void_p(Wc.ctypes.data)), self._h)
+            self._refs_ready = True
+        x = np.ascontiguousarray(x_pred, dtype=np.float64)
+        s_ = np.ascontiguousarray(SS, dtype=np.float64)
+        p0 = np.ascontiguousarray(xyth0, dtype=np.float64)
+        B = int(x.shape[0])
+        refs = np.empty((B, 5, self.n_out))
+        err = np.zeros(B, dtype=np.int32)
+        nat.check(L.lpvmpc_plan_refs_host(self._h, B, C.c_void_p(x.ctypes.data), C.c_void_p(s_.ctypes.data), C.c_void_p(p0.ctypes.data),
+                                          C.c_void_p(refs.ctypes.data), C.c_void_p(err.ctypes.data)), self._h)
+        return refs, err

@@ -270,6 +270,21 @@ int lpvmpc_plan_loop_run_dev(lpvmpc_handle *h, int32_t n_ticks, void *stream);
 int lpvmpc_plan_loop_view_dev(lpvmpc_handle *h, lpvmpc_plan_loop_state *view, int32_t *B);
 int lpvmpc_plan_loop_read_host(lpvmpc_handle *h, const lpvmpc_plan_loop_state *dst);
 
+/* ------------------------------------------------------------------------------------------------
+ * Planner -> controller references (plannerMain.py:196-224, 257-280, My_Planning of :299-303): for every
+ * plan the stage poses Xref/Yref/Thetaref = Map.getGlobalPosition(SS[j], 0) (stage 0: xyth0 = Xlast, Ylast, Thetalast),
+ * yaw = Thetaref + epsi, xp = Xref - ey sin(yaw), yp = Yref + ey cos(yaw), vel = vx, curv = wz / vx over the first N
+ * stages; then interp1d(kind='cubic') from the planner grid to n_out samples and, for the curvature, filtfilt with the
+ * 4th-order elliptic filter.  Both are linear for the uniform grids involved; the caller supplies them as matrices W
+ * (x, y, yaw, vx) and Wc (curvature), [n_out, N] row-major (postproc.py builds them).  Planner handles only.
+ * refs [B,5,n_out] = x_d, y_d, psi_d, vx_d, curv_d; err [B] optional (1: getGlobalPosition found no segment).
+ */
+int lpvmpc_plan_refs_setup(lpvmpc_handle *h, int32_t n_out, const double *W, const double *Wc); /* HOST matrices; copied */
+int lpvmpc_plan_refs_dev(lpvmpc_handle *h, int32_t B, const double *x_pred, const double *SS, const double *xyth0, double *refs,
+                         int32_t *err, void *stream);
+int lpvmpc_plan_refs_host(lpvmpc_handle *h, int32_t B, const double *x_pred, const double *SS, const double *xyth0, double *refs,
+                          int32_t *err);
+
 #ifdef __cplusplus
 }
 #endif
