@@ -110,6 +110,23 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0, "_fallback": True}
 
 
+def init_nccl_quietly(dist, dev):
+    """init_process_group with file descriptor 1 pointed at stderr: NCCL writes its version banner to stdout when the
+    communicator is created, and stdout must carry exactly one JSON line."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    try:
+        os.dup2(2, 1)
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+        import torch
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 class ClockSampler(object):
     """Samples SM clock / throttle reasons of one GPU during the timed region (NVML)."""
 
@@ -262,8 +279,7 @@ def run_fleet(args):
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
-        os.environ["NCCL_DEBUG"] = os.environ.get("LPVMPC_NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl_quietly(dist, dev)
     spec = WORKLOADS[args.workload]
     B, tps = spec["B"], args.ticks_per_step
     m = lp.Map("L_shape")
@@ -487,8 +503,7 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
-        os.environ["NCCL_DEBUG"] = os.environ.get("LPVMPC_NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl_quietly(dist, dev)
 
     spec, track, w, tune, dt, keys = make_workload(args.workload, rank)
     B = spec["B"]
