@@ -35,8 +35,9 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_sizes_match_header():
     """sizeof() of the ctypes mirrors vs. the C compiler's view of include/lpvmpc.h."""
-    code = ('#include <stdio.h>\n#include "lpvmpc.h"\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(lpvmpc_settings), '
-            'sizeof(lpvmpc_cfg), sizeof(lpvmpc_info), sizeof(lpvmpc_args));return 0;}\n')
+    code = ('#include <stdio.h>\n#include "lpvmpc.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(lpvmpc_settings), '
+            'sizeof(lpvmpc_cfg), sizeof(lpvmpc_info), sizeof(lpvmpc_args), sizeof(lpvmpc_loop_cfg), sizeof(lpvmpc_loop_state), '
+            'sizeof(lpvmpc_plan_loop_state));return 0;}\n')
     exe = os.path.join(ROOT, "tests", "_sizes.out")
     try:
         subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=code.encode(), check=True)
@@ -44,7 +45,8 @@ def test_struct_sizes_match_header():
     finally:
         if os.path.exists(exe):
             os.remove(exe)
-    got = [C.sizeof(nat.Settings), C.sizeof(nat.Cfg), C.sizeof(nat.Info), C.sizeof(nat.Args)]
+    got = [C.sizeof(nat.Settings), C.sizeof(nat.Cfg), C.sizeof(nat.Info), C.sizeof(nat.Args), C.sizeof(nat.LoopCfg),
+           C.sizeof(nat.LoopState), C.sizeof(nat.PlanLoopState)]
     assert [int(v) for v in out] == got
 
 
