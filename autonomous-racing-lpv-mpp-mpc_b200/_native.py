@@ -63,7 +63,7 @@ _OUT_D = ["x_pred", "u_pred"]
 
 class Args(C.Structure):
     _fields_ = ([("sched_mode", C.c_int32), ("x0_from_prediction", C.c_int32), ("lap_all", C.c_int32),
-                 ("reserved", C.c_int32), ("Cf_new", C.c_double)] +
+                 ("natural_order", C.c_int32), ("Cf_new", C.c_double)] +
                 [(k, C.c_void_p) for k in _IN_D] +
                 [("lap", C.c_void_p), ("traj", C.c_void_p), ("u_old", C.c_void_p), ("old_steering", C.c_void_p),
                  ("max_ey", C.c_void_p), ("ey_lo", C.c_void_p), ("ey_hi", C.c_void_p)] +
@@ -72,7 +72,7 @@ class Args(C.Structure):
                  ("polish_status", C.c_void_p), ("obj", C.c_void_p), ("pri_res", C.c_void_p), ("dua_res", C.c_void_p),
                  ("active_lo", C.c_void_p), ("active_up", C.c_void_p), ("y", C.c_void_p), ("A_out", C.c_void_p),
                  ("B_out", C.c_void_p), ("states_out", C.c_void_p), ("xs", C.c_void_p), ("zs", C.c_void_p),
-                 ("ys", C.c_void_p)])
+                 ("ys", C.c_void_p), ("order_hint", C.c_void_p)])
 
 
 class LoopCfg(C.Structure):

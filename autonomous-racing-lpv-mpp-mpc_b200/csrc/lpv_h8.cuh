@@ -68,6 +68,7 @@ struct H8Params {
   lpvmpc_args a;
   int B;
   unsigned *queue;
+  const int *perm;   // visiting order of the batch (NULL: batch order)
   double *cold;
 };
 
@@ -1655,7 +1656,7 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
     // shared / scratch region, same values written by the same instruction; only user-visible outputs are guarded.
     const bool valid = (g < QPW) && ((int)(base + g) < p.B);
     const int gq = (QPW == 1) ? 0 : (valid ? g : 0);
-    const int b = (int)base + gq;
+    const int b = p.perm ? p.perm[(int)base + gq] : (int)base + gq;
     c.S = wsm + gq * L.total;
     c.cold = p.cold + (wslot + gq) * L.cold_total;
 

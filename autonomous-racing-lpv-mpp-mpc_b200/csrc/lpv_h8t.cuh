@@ -49,6 +49,7 @@ struct H8Params {
   lpvmpc_args a;
   int B;
   unsigned *queue;
+  const int *perm;   // visiting order of the batch (NULL: batch order)
   double *cold;
 };
 
@@ -1441,7 +1442,7 @@ __global__ void __launch_bounds__(128, 1) lpv_solve_h8t_kernel(const __grid_cons
     // shared / scratch region, same values written by the same instruction; only user-visible outputs are guarded.
     const bool valid = (g < QPW) && ((int)(base + g) < p.B);
     const int gq = valid ? g : 0;
-    const int b = (int)base + gq;
+    const int b = p.perm ? p.perm[(int)base + gq] : (int)base + gq;
     c.S = wsm + gq * L.total;
     c.cold = p.cold + (wslot + gq) * L.cold_total;
 

@@ -105,7 +105,7 @@ class BatchSolver(object):
         n, d, N, nz, m = self.n, self.d, self.N, self.nz, self.m
         return dict(x0=(B, n), x_sched=(B, n), A=(B, N, n, n), Bm=(B, N, n, d), C=(B, N, n), u_prev=(B, N, d),
                     vel_ref=(B, N + 1), curv_ref=(B, N), SS=(B, N + 1), lap=(B,), traj=(B, N, 6), u_old=(B, d),
-                    old_steering=(B, max(self.steering_delay, 1)), max_ey=(B,), ey_lo=(B, N + 1), ey_hi=(B, N + 1),
+                    old_steering=(B, max(self.steering_delay, 1)), max_ey=(B,), ey_lo=(B, N + 1), ey_hi=(B, N + 1), order_hint=(B,),
                     x_pred=(B, N + 1, n), u_pred=(B, N, d), status=(B,), iters=(B,), rho_updates=(B,),
                     polish_status=(B,), obj=(B,), pri_res=(B,), dua_res=(B,), active_lo=(B, m), active_up=(B, m),
                     y=(B, m), A_out=(B, N, n, n), B_out=(B, N, n, d), states_out=(B, N, n), xs=(B, nz), zs=(B, m),
@@ -144,7 +144,7 @@ class BatchSolver(object):
                 continue
             if k not in shapes:
                 raise KeyError("unknown input %r" % k)
-            want = "i4" if k == "lap" else "f8"
+            want = "i4" if k in ("lap", "order_hint") else "f8"
             if use_torch:
                 tdt = torch.int32 if want == "i4" else torch.float64
                 t = v if self._is_torch(v) else torch.as_tensor(_np.asarray(v))

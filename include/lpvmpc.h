@@ -128,7 +128,9 @@ typedef struct {
   int32_t sched_mode;            /* LPVMPC_SCHED_* */
   int32_t x0_from_prediction;    /* controller lap-0 quirk: QP x0 := first predicted state (controllerMain.py:329-331) */
   int32_t lap_all;               /* used when `lap` is NULL (controller PREDICT: 0 => Curvature(s), else curv_ref) */
-  int32_t reserved;
+  int32_t natural_order;         /* 0 (default): the kernel may visit the problems of a batch in its own order (controller:
+                                    grouped by vel_ref[0] - vx0, which predicts the ADMM iteration count, so that the QPs
+                                    sharing a warp finish together; results do not depend on it); 1: batch order */
   double Cf_new;                 /* controller PREDICT tyre stiffness (controllerMain.py:77: 60) */
   /* inputs */
   const double *x0;              /* [B,n]      QP initial state (and scheduling state unless x_sched given) */
@@ -160,6 +162,8 @@ typedef struct {
   double *A_out, *B_out;         /* [B,N,n,n], [B,N,n,d] optional: scheduled matrices (PREDICT/ESTIMATE) */
   double *states_out;            /* [B,N,n] optional: roll-out states (PREDICT) */
   double *xs, *zs, *ys;          /* [B,nz],[B,m],[B,m] optional scaled ADMM iterates before polish (parity tests) */
+  const int32_t *order_hint;     /* [B] optional input: expected ADMM iterations per problem (e.g. `iters` of the same problems
+                                    at the previous tick); used instead of vel_ref[0] - vx0 to group the batch */
 } lpvmpc_args;
 
 typedef struct lpvmpc_handle lpvmpc_handle;

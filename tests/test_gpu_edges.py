@@ -44,7 +44,7 @@ def test_ragged_batch_sizes(track, B):
     s = lp.BatchSolver("controller", N, W.CTRL_DT, track=track, max_batch=80, **W.CTRL_TT)
     r = s.solve(w["x0"][:B], **{k: w[k][:B] for k in KEYS})
     assert r.status.shape == (B,) and r.u_pred.shape == (B, N, 2) and r.x_pred.shape == (B, N + 1, 6)
-    assert s.info()["kernel_launches"] == (1 if B else 0)
+    assert s.info()["kernel_launches"] == (0 if B == 0 else (1 if B < 8 else 2))   # batches of 8+ controller QPs: order kernel + solve
     _check_ctrl(track, N, w, r, range(B))
     s.close()
 
