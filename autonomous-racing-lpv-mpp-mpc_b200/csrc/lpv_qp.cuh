@@ -32,8 +32,10 @@ constexpr unsigned kFull = 0xffffffffu;
 // The polish system is solved in condensed form with 1/delta row weights, which loses about six digits per
 // solve compared with upstream's LDL' of the full reduced KKT.  Iterative refinement converges to the same
 // KKT point regardless, so we run a few more passes than polish_refine_iter (measured on the cfg-2 batch:
-// +2 passes reproduce the oracle's polish decisions and solutions to 1e-10; see DESIGN.md "Polish").
-constexpr int kPolishExtraRefine = 3;
+// +2 passes reproduce the oracle's polish decisions and solutions to 1e-10; see DESIGN.md "Polish";
+// tools/debug_polish_passes.py on the full 4,096-QP batch: 5 and 6 passes give identical decisions and solutions, 4
+// passes lose 13 accepted polishes).
+constexpr int kPolishExtraRefine = 2;
 
 // Offsets (in doubles) of the per-QP workspace.
 struct Layout {
