@@ -127,6 +127,9 @@ struct Ctx {
   __device__ __forceinline__ uint32_t tT(int k) const { return tm + (uint32_t)(k * 16); }
   __device__ __forceinline__ uint32_t tKr(int k) const { return tm + (uint32_t)(16 * (N + 1) + (k - 1) * 16); }
   __device__ __forceinline__ uint32_t tKc(int k) const { return tm + (uint32_t)(16 * (2 * N + 1) + (k - 1) * 16); }
+  // polish: dual and residual target of my (up to two) single-variable rows at stage k: 8 columns behind the factor
+  // (48 N + 16 + 8 (N + 1) <= 512 for N <= 8)
+  __device__ __forceinline__ uint32_t tP(int k) const { return tm + (uint32_t)(48 * N + 16 + 8 * k); }
   __device__ __forceinline__ double *V(int arr) const { return S + L->V + arr; }          // element (k, q) at [k*VS + q]
   // single-variable rows in shared memory: z, y, coefficient, upper (and lower: planner) bound of my row t at stage k
   __device__ __forceinline__ double *Ib(int k) const { return S + L->I + k * IS; }
@@ -182,6 +185,20 @@ __device__ __forceinline__ void tm_ld8(uint32_t ta, TmRow &t) {
                  "=r"(t.w[8]), "=r"(t.w[9]), "=r"(t.w[10]), "=r"(t.w[11]), "=r"(t.w[12]), "=r"(t.w[13]), "=r"(t.w[14]), "=r"(t.w[15])
                : "r"(ta) : "memory");
 }
+// x8 = 8 consecutive 32-bit columns = 4 doubles
+__device__ __forceinline__ void tm_st4(uint32_t ta, double v0, double v1, double v2, double v3) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(ta), "r"(__double2loint(v0)),
+               "r"(__double2hiint(v0)), "r"(__double2loint(v1)), "r"(__double2hiint(v1)), "r"(__double2loint(v2)), "r"(__double2hiint(v2)),
+               "r"(__double2loint(v3)), "r"(__double2hiint(v3))
+               : "memory");
+}
+struct TmQuad { uint32_t w[8]; };
+__device__ __forceinline__ void tm_ld4(uint32_t ta, TmQuad &t) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(t.w[0]), "=r"(t.w[1]), "=r"(t.w[2]), "=r"(t.w[3]), "=r"(t.w[4]), "=r"(t.w[5]), "=r"(t.w[6]), "=r"(t.w[7])
+               : "r"(ta) : "memory");
+}
+__device__ __forceinline__ double tm_getq(const TmQuad &t, int i) { return __hiloint2double((int)t.w[2 * i + 1], (int)t.w[2 * i]); }
 __device__ __forceinline__ double tm_get(const TmRow &t, int i) { return __hiloint2double((int)t.w[2 * i + 1], (int)t.w[2 * i]); }
 __device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -1214,10 +1231,17 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
   double *PX = c.V(V_R), *PYD = c.V(V_XS), *R2D = c.V(V_DG);       // [k*VS + q]
   double *YD = c.cd(C_YD);
   const double *BE = c.cd(C_BE), *ED = c.cd(C_ED), *QV = c.cd(C_Q);
-  double *PYI = c.cd(C_PYI), *R2I = c.cd(C_R2I), *ACTD = c.cd(C_ACTD), *ACTI = c.cd(C_ACTI);
+  double *ACTD = c.cd(C_ACTD), *ACTI = c.cd(C_ACTI);   // slab copies for factor() and the outputs; the loops below use the register copies
   const double *PD = c.cd(C_PD), *PO = c.cd(C_PO), *EINV = c.cd(C_EINV), *EIINV = c.cd(C_EIINV), *DINV = c.cd(C_DINV);
   const double delta = St.delta, idel = 1.0 / St.delta;
-  // active-set guess (form_Ared): 1 = lower, 2 = upper, 3 = both
+  // The duals / residual targets of the single-variable rows (PYI, R2I) live in the tensor-memory columns behind the
+  // factor (c.tP(k): 4 doubles per lane and stage) instead of the L2 slab, the active-set flags in registers: every
+  // slab access of these loops was an exposed L2 round trip (12 % of the kernel, profiles/r2i_ncu_h8t_*).  The
+  // tcgen05 loads / stores are warp-collective: they sit at the top / bottom of the stage loops, outside any branch.
+  uint64_t acti = 0;   // 2 bits per row (k, t) of mine: 1 = lower, 2 = upper, 3 = both
+  uint32_t actd = 0;   // bit k: my dynamics row (k, r) is in the polish system
+  auto ai_of = [&](int k, int t) { return (int)((acti >> (2 * (k * NT + t))) & 3ull); };
+  // active-set guess (form_Ared)
 #pragma unroll 1
   for (int k = 0; k <= N; ++k) {
     const int o = k * 8 + r;
@@ -1227,32 +1251,37 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
     // of the unweighted state `s`, and the polish system needs every dynamics row: keep it (as "lower").
     if (c.xl && do_pol) ad = (0.0 < YD[o]) ? 2.0 : 1.0;
     ACTD[o] = ad;
+    if (ad != 0.0) actd |= 1u << k;
     if (c.has_in(k)) {
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
-        double ai = 0.0;
-        if (do_pol) { if (c.zi(k, t) - c.lo_of(k, t) < -c.yi(k, t)) ai += 1.0; if (c.ui(k, t) - c.zi(k, t) < c.yi(k, t)) ai += 2.0; }
-        ACTI[c.ci(k, t)] = ai;
+        int ai = 0;
+        if (do_pol) { if (c.zi(k, t) - c.lo_of(k, t) < -c.yi(k, t)) ai += 1; if (c.ui(k, t) - c.zi(k, t) < c.yi(k, t)) ai += 2; }
+        ACTI[c.ci(k, t)] = (double)ai;
+        acti |= (uint64_t)ai << (2 * (k * NT + t));
       }
     }
   }
   __syncwarp();
   FW fw; fw.polish = 1; fw.rho = 0.0; fw.rho_eq = 0.0; fw.idel = idel;
   factor<KIND>(c, fw, delta);
-  auto bred_i = [&](int k, int t) { const double a = ACTI[c.ci(k, t)]; return (a == 1.0 || a == 3.0) ? c.lo_of(k, t) : c.ui(k, t); };
-  // first solve: rhs = -q + A_red'(b_red / delta); the targets go through R2D / R2I
+  auto bred_i = [&](int k, int t) { const int a = ai_of(k, t); return (a == 1 || a == 3) ? c.lo_of(k, t) : c.ui(k, t); };
+  // first solve: rhs = -q + A_red'(b_red / delta); the targets go through R2D / the R2I columns
 #pragma unroll 1
   for (int k = 0; k <= N; ++k) {
     const int o = k * 8 + r;
-    R2D[k * VS + r] = (c.xl && ACTD[o] != 0.0) ? idel * BE[o] : 0.0;
+    R2D[k * VS + r] = (c.xl && ((actd >> k) & 1u)) ? idel * BE[o] : 0.0;
+    double r2[2] = {0.0, 0.0};
     if (c.has_in(k)) {
 #pragma unroll
-      for (int t = 0; t < NT; ++t) R2I[c.ci(k, t)] = (ACTI[c.ci(k, t)] != 0.0) ? idel * bred_i(k, t) : 0.0;
+      for (int t = 0; t < NT; ++t) r2[t] = (ai_of(k, t) != 0) ? idel * bred_i(k, t) : 0.0;
     }
+    tm_st4(c.tP(k), 0.0, 0.0, r2[0], r2[1]);
   }
+  tm_wait_st();
   __syncwarp();
-  // (A' t)_(k, r) with t_dyn = R2D-like array stored [k*VS + q] and t_in from the slab array ti
-  auto colAt = [&](const double *td, const double *ti, int k) {
+  // (A' t)_(k, r) with t_dyn = R2D-like array stored [k*VS + q] and t_in = (ti0, ti1) of my single-variable rows
+  auto colAt = [&](const double *td, const double ti0, const double ti1, int k) {
     double acc = c.xl ? ED[k * 8 + r] * td[k * VS + r] : 0.0;
     if (k < N) {
       double g[8];
@@ -1261,13 +1290,18 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
       acc += coldot<NX>(c.Gb(k), c.co, g);
     }
     if (c.has_in(k)) {
-#pragma unroll
-      for (int t = 0; t < NT; ++t) acc = fma(c.si(k, t), ti[c.ci(k, t)], acc);
+      acc = fma(c.si(k, 0), ti0, acc);
+      if (NT > 1) acc = fma(c.si(k, NT - 1), ti1, acc);
     }
     return acc;
   };
 #pragma unroll 1
-  for (int k = 0; k <= N; ++k) BV[k * VS + r] = c.var_live(k) ? (-QV[k * 8 + r] + colAt(R2D, R2I, k)) : 0.0;
+  for (int k = 0; k <= N; ++k) {
+    TmQuad pq;
+    tm_ld4(c.tP(k), pq);
+    tm_wait_ld();
+    BV[k * VS + r] = c.var_live(k) ? (-QV[k * 8 + r] + colAt(R2D, tm_getq(pq, 2), tm_getq(pq, 3), k)) : 0.0;
+  }
   __syncwarp();
   sweep_fwd<KIND>(h, N, gsel);
   sweep_bwd_plain<KIND>(h, N, gsel);
@@ -1277,19 +1311,18 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
     const int o = k * 8 + r, ov = k * VS + r;
     const double xk = BV[ov];
     PX[ov] = xk;
-    const bool ad = c.xl && ACTD[o] != 0.0;
+    const bool ad = c.xl && ((actd >> k) & 1u);
     const double res = ad ? (BE[o] - rowA_dyn<KIND>(c, ED, BV, VS, k)) : 0.0;
     R2D[ov] = res;
     PYD[ov] = -res * idel;
+    double ri[2] = {0.0, 0.0};
     if (c.has_in(k)) {
 #pragma unroll
-      for (int t = 0; t < NT; ++t) {
-        const int oc = c.ci(k, t);
-        const double ri = (ACTI[oc] != 0.0) ? (bred_i(k, t) - c.si(k, t) * xk) : 0.0;
-        R2I[oc] = ri; PYI[oc] = -ri * idel;
-      }
+      for (int t = 0; t < NT; ++t) ri[t] = (ai_of(k, t) != 0) ? (bred_i(k, t) - c.si(k, t) * xk) : 0.0;
     }
+    tm_st4(c.tP(k), -ri[0] * idel, -ri[1] * idel, ri[0], ri[1]);
   }
+  tm_wait_st();
   __syncwarp();
 #pragma unroll 1
   for (int it = 0; it < St.polish_refine_iter + kPolishExtraRefine; ++it) {
@@ -1297,6 +1330,9 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
       const int o = k * 8 + r, ov = k * VS + r;
+      TmQuad pq;
+      tm_ld4(c.tP(k), pq);
+      tm_wait_ld();
       double b = 0.0;
       if (c.var_live(k)) {
         const double Px = rowP<KIND>(c, PD, PO, PX, VS, k);
@@ -1309,7 +1345,7 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
         }
         if (c.has_in(k)) {
 #pragma unroll
-          for (int t = 0; t < NT; ++t) { const int oc = c.ci(k, t); acc = fma(c.si(k, t), fma(-idel, R2I[oc], PYI[oc]), acc); }
+          for (int t = 0; t < NT; ++t) acc = fma(c.si(k, t), fma(-idel, tm_getq(pq, 2 + t), tm_getq(pq, t)), acc);
         }
         b = (-QV[o] - Px) - acc;
       }
@@ -1322,52 +1358,67 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
       const int o = k * 8 + r, ov = k * VS + r;
+      TmQuad pq;
+      tm_ld4(c.tP(k), pq);
+      tm_wait_ld();
       const double dx = BV[ov];
-      if (c.xl && ACTD[o] != 0.0) {
+      if (c.xl && ((actd >> k) & 1u)) {
         const double z = rowA_dyn<KIND>(c, ED, BV, VS, k), r2 = R2D[ov];
         PYD[ov] += (z - r2) * idel;
         R2D[ov] = r2 - z;
       }
+      double py[2] = {tm_getq(pq, 0), tm_getq(pq, 1)}, r2i[2] = {tm_getq(pq, 2), tm_getq(pq, 3)};
       if (c.has_in(k)) {
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
-          const int oc = c.ci(k, t);
-          if (ACTI[oc] != 0.0) { const double z = c.si(k, t) * dx, r2 = R2I[oc]; PYI[oc] += (z - r2) * idel; R2I[oc] = r2 - z; }
+          if (ai_of(k, t) != 0) { const double z = c.si(k, t) * dx, r2 = r2i[t]; py[t] += (z - r2) * idel; r2i[t] = r2 - z; }
         }
       }
+      tm_st4(c.tP(k), py[0], py[1], r2i[0], r2i[1]);
       PX[ov] += dx;
+      (void)o;
     }
+    tm_wait_st();
     __syncwarp();
   }
-  // pol z = A x, normal-cone projection, residuals, acceptance.  Polished z of the single-variable rows -> R2I.
+  // pol z = A x, normal-cone projection, residuals, acceptance.  Polished z of the single-variable rows -> the R2I columns.
   double a_rp = 0, a_rd = 0;
 #pragma unroll 1
   for (int k = 0; k <= N; ++k) {
     const int o = k * 8 + r, ov = k * VS + r;
+    TmQuad pq;
+    tm_ld4(c.tP(k), pq);
+    tm_wait_ld();
     if (c.xl) {
       const double Ax = rowA_dyn<KIND>(c, ED, PX, VS, k), t = Ax + PYD[ov];
       PYD[ov] = t - BE[o];
       const double rr = Ax - BE[o];
       a_rp = absmax(a_rp, unscale ? EINV[o] * rr : rr);
     } else PYD[ov] = 0.0;
+    double py[2] = {tm_getq(pq, 0), tm_getq(pq, 1)}, zz[2] = {tm_getq(pq, 2), tm_getq(pq, 3)};
     if (c.has_in(k)) {
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
         const int oc = c.ci(k, t);
-        const double ax = c.si(k, t) * PX[ov], tt = ax + PYI[oc];
+        const double ax = c.si(k, t) * PX[ov], tt = ax + py[t];
         const double zc = clampd(tt, c.lo_of(k, t), c.ui(k, t));
-        R2I[oc] = zc; PYI[oc] = tt - zc;
+        zz[t] = zc; py[t] = tt - zc;
         const double rr = ax - zc;
         a_rp = absmax(a_rp, unscale ? EIINV[oc] * rr : rr);
       }
     }
+    tm_st4(c.tP(k), py[0], py[1], zz[0], zz[1]);
   }
+  tm_wait_st();
   __syncwarp();
 #pragma unroll 1
   for (int k = 0; k <= N; ++k) {
     const int o = k * 8 + r;
+    TmQuad pq;
+    tm_ld4(c.tP(k), pq);
+    tm_wait_ld();
     if (c.var_live(k)) {
-      const double rr = (QV[o] + rowP<KIND>(c, PD, PO, PX, VS, k)) + colAt(PYD, PYI, k);
+      const double rr = (QV[o] + rowP<KIND>(c, PD, PO, PX, VS, k)) + colAt(PYD, tm_getq(pq, 0), tm_getq(pq, 1), k);
       a_rd = absmax(a_rd, unscale ? DINV[o] * rr : rr);
     }
   }
@@ -1375,19 +1426,24 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
   const double pol_obj = objective<KIND>(c, PX, VS, St.scaling ? I.cinv : 1.0);
   const bool ok = (pol_pri < I.pri_res && pol_dua < I.dua_res) || (pol_pri < I.pri_res && I.dua_res < 1e-10) ||
                   (pol_dua < I.dua_res && I.pri_res < 1e-10);
-  if (!do_pol) return 0;
-  if (!ok) return -1;
-  I.obj = pol_obj; I.pri_res = pol_pri; I.dua_res = pol_dua;
+  const bool take = do_pol && ok;
+  if (take) { I.obj = pol_obj; I.pri_res = pol_pri; I.dua_res = pol_dua; }
 #pragma unroll 1
-  for (int k = 0; k <= N; ++k) {
+  for (int k = 0; k <= N; ++k) {   // the tensor-memory loads are collective: every group walks the loop, only `take` groups store
     const int o = k * 8 + r, ov = k * VS + r;
-    X[ov] = PX[ov]; YD[o] = PYD[ov];
-    if (c.has_in(k)) {
+    TmQuad pq;
+    tm_ld4(c.tP(k), pq);
+    tm_wait_ld();
+    if (take) {
+      X[ov] = PX[ov]; YD[o] = PYD[ov];
+      if (c.has_in(k)) {
 #pragma unroll
-      for (int t = 0; t < NT; ++t) { c.zi(k, t) = R2I[c.ci(k, t)]; c.yi(k, t) = PYI[c.ci(k, t)]; }
+        for (int t = 0; t < NT; ++t) { c.zi(k, t) = tm_getq(pq, 2 + t); c.yi(k, t) = tm_getq(pq, t); }
+      }
     }
   }
-  return 1;
+  if (!do_pol) return 0;
+  return ok ? 1 : -1;
 }
 
 // ---------------------------------------------------------------- persistent warps, QPW QPs at a time each
