@@ -130,6 +130,9 @@ struct Ctx {
   // polish: dual and residual target of my (up to two) single-variable rows at stage k: 8 columns behind the factor
   // (48 N + 16 + 8 (N + 1) <= 512 for N <= 8)
   __device__ __forceinline__ uint32_t tP(int k) const { return tm + (uint32_t)(48 * N + 16 + 8 * k); }
+  // certificates: my component of the iterate saved before the last step of a chunk (2 columns) and of the scaling D
+  // (2 columns) at stage k, behind the polish columns (60 N + 28 <= 512 for N <= 8)
+  __device__ __forceinline__ uint32_t tQ(int k) const { return tm + (uint32_t)(56 * N + 24 + 4 * k); }
   __device__ __forceinline__ double *V(int arr) const { return S + L->V + arr; }          // element (k, q) at [k*VS + q]
   // single-variable rows in shared memory: z, y, coefficient, upper (and lower: planner) bound of my row t at stage k
   __device__ __forceinline__ double *Ib(int k) const { return S + L->I + k * IS; }
@@ -191,6 +194,16 @@ __device__ __forceinline__ void tm_st4(uint32_t ta, double v0, double v1, double
                "r"(__double2hiint(v0)), "r"(__double2loint(v1)), "r"(__double2hiint(v1)), "r"(__double2loint(v2)), "r"(__double2hiint(v2)),
                "r"(__double2loint(v3)), "r"(__double2hiint(v3))
                : "memory");
+}
+// x2 = one double, x4 = two doubles
+__device__ __forceinline__ void tm_st1(uint32_t ta, double v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(ta), "r"(__double2loint(v)), "r"(__double2hiint(v)) : "memory");
+}
+__device__ __forceinline__ void tm_ld2(uint32_t ta, double &v0, double &v1) {
+  uint32_t w0, w1, w2, w3;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(ta) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  v0 = __hiloint2double((int)w1, (int)w0); v1 = __hiloint2double((int)w3, (int)w2);
 }
 struct TmQuad { uint32_t w[8]; };
 __device__ __forceinline__ void tm_ld4(uint32_t ta, TmQuad &t) {
@@ -761,12 +774,18 @@ __device__ __noinline__ bool primal_infeasible(const Ctx<KIND> c, const Info *ip
   const bool unscale = ip->unscale;
   const int N = c.N, r = c.r;
   const double *X = c.V(V_X);
-  const double *BE = c.cd(C_BE), *ED = c.cd(C_ED), *PVX = c.cd(C_PVX);
+  const double *BE = c.cd(C_BE), *ED = c.cd(C_ED);
   const double *PVYI = c.cd(C_PVYI), *E = c.cd(C_E), *EI = c.cd(C_EI), *DINV = c.cd(C_DINV);
   double *DYD = c.cd(C_DYD), *DYI = c.cd(C_PYI), *XT = c.cd(C_ZT);
   const double ia = 1.0 / alpha, oma = 1.0 - alpha, cb = last_was_first ? 1.0 : alpha;
 #pragma unroll 1
-  for (int k = 0; k <= N; ++k) { const int o = k * 8 + r; XT[o] = c.var_live(k) ? (X[k * VS + r] - oma * PVX[o]) * ia : 0.0; }
+  for (int k = 0; k <= N; ++k) {
+    const int o = k * 8 + r;
+    double pvx, dsc;
+    tm_ld2(c.tQ(k), pvx, dsc);   // the saved iterate lives in tensor memory (collective load: outside any branch)
+    XT[o] = c.var_live(k) ? (X[k * VS + r] - oma * pvx) * ia : 0.0;
+    (void)dsc;
+  }
   __syncwarp();
   double nrm = 0.0, lhs = 0.0;
 #pragma unroll 1
@@ -819,16 +838,18 @@ __device__ __noinline__ bool dual_infeasible(const Ctx<KIND> c, const Info *ip, 
   const int N = c.N, r = c.r;
   const double *X = c.V(V_X);
   const double *QV = c.cd(C_Q), *ED = c.cd(C_ED);
-  const double *PVX = c.cd(C_PVX), *D = c.cd(C_D), *DINV = c.cd(C_DINV), *EINV = c.cd(C_EINV), *EIINV = c.cd(C_EIINV);
+  const double *DINV = c.cd(C_DINV), *EINV = c.cd(C_EINV), *EIINV = c.cd(C_EIINV);
   const double *PD = c.cd(C_PD), *PO = c.cd(C_PO);
   double *DX = c.cd(C_PX);
   double nrm = 0.0, qdx = 0.0;
 #pragma unroll 1
   for (int k = 0; k <= N; ++k) {
     const int o = k * 8 + r;
-    const double dx = c.var_live(k) ? X[k * VS + r] - PVX[o] : 0.0;
+    double pvx, dsc;
+    tm_ld2(c.tQ(k), pvx, dsc);   // saved iterate and scaling D from tensor memory: no L2 round trip in this loop
+    const double dx = c.var_live(k) ? X[k * VS + r] - pvx : 0.0;
     DX[o] = dx;
-    nrm = absmax(nrm, unscale ? D[o] * dx : dx);
+    nrm = absmax(nrm, unscale ? dsc * dx : dx);
     qdx += QV[o] * dx;
   }
   nrm = gmax(nrm); qdx = gsum(qdx);
@@ -1206,6 +1227,7 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
       // element o of every work vector is mine alone: read them all, then overwrite their slots
       const double d = sD[o], e = sE[o], ei = sEI[o], q = QV[ov], be = BE[ov], ed = ED[ov];
       cD[o] = d; cE[o] = e; cEi[o] = ei; cEiI[o] = 1.0 / ei;
+      tm_st1(c.tQ(k) + 2u, d);   // copy of D for the dual-infeasibility certificate
       cQ[o] = c.var_live(k) ? q : 0.0; cBE[o] = e * be; cED[o] = ed; cYD[o] = 0.0; cDI[o] = 1.0 / d; cEI[o] = 1.0 / e;
       if (c.ul) c.pm(k, ucomp) = (k > 0 && k < N) ? sPO[o - 8] : 0.0;   // couples u_{k-1}, u_k
       c.V(V_XS)[ov] = 0.0;   // the scratch homes become hot vectors (R, CR, B are set by reproject, DG by factor)
@@ -1564,17 +1586,18 @@ __global__ void __launch_bounds__(128, 1) lpv_solve_h8t_kernel(const __grid_cons
       u.rho = rho; u.rho_eq = rho_eq; u.rinv = 1.0 / rho; u.rinv_eq = 1.0 / rho_eq; u.live = live;
 #pragma unroll 1
       for (; iter < stop; ++iter) {
-        if (iter == stop - 1 && live) {  // keep the iterate before the last step of the chunk: delta_x, delta_y
-          double *PVX = c.cd(C_PVX), *PVYI = c.cd(C_PVYI);
+        if (iter == stop - 1) {  // keep the iterate before the last step of the chunk: delta_x, delta_y
+          double *PVYI = c.cd(C_PVYI);
           const double *X = c.V(V_X);
 #pragma unroll 1
           for (int k = 0; k <= N; ++k) {
-            PVX[k * 8 + r] = X[k * VS + r];
-            if (c.has_in(k)) {
+            tm_st1(c.tQ(k), X[k * VS + r]);   // collective: every group stores (a frozen group's copy is never read again)
+            if (live && c.has_in(k)) {
 #pragma unroll
               for (int t = 0; t < NT; ++t) PVYI[c.ci(k, t)] = c.yi(k, t);
             }
           }
+          tm_wait_st();
         }
         u.cc = (iter == 0) ? 2.0 : alpha;
         sweep_fwd<KIND>(h, N, gsel);

@@ -698,7 +698,7 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
     // H8T kernel: controller, block factor in tensor memory (48 N + 16 columns of the SM's 512), 16 QPs per CTA, one CTA per SM
     h->TL = make_h8t_layout(cfg->kind, cfg->N);
     const size_t h8t_bytes = (size_t)h->TL.total * sizeof(double) * 16 + 4 * 512 + 512;
-    const bool h8t_ok = pdiag && cfg->steering_delay == 0 && cfg->kind == LPVMPC_CONTROLLER && 48 * cfg->N + 16 + 8 * (cfg->N + 1) <= 512 &&
+    const bool h8t_ok = pdiag && cfg->steering_delay == 0 && cfg->kind == LPVMPC_CONTROLLER && 60 * cfg->N + 28 <= 512 &&
                         h8t_bytes + 64 <= (size_t)h->smem_optin;
     if (cfg->variant == 6 && !h8t_ok) { h->err = "variant 6 (H8T) needs controller, diagonal Q and R, steering_delay=0, N<=10"; return bail(LPVMPC_E_UNSUPPORTED); }
     if (cfg->variant == 6 || (cfg->variant == 0 && h8t_ok)) h->variant = 6;
