@@ -95,7 +95,7 @@ EXPORTS = ["lpvmpc_abi_version", "lpvmpc_default_settings", "lpvmpc_device_count
            "lpvmpc_loop_init_host", "lpvmpc_loop_run_dev", "lpvmpc_loop_run_host", "lpvmpc_loop_view_dev",
            "lpvmpc_loop_read_host", "lpvmpc_plan_loop_init_host", "lpvmpc_plan_loop_init_dev", "lpvmpc_plan_loop_run_host",
            "lpvmpc_plan_loop_run_dev", "lpvmpc_plan_loop_view_dev", "lpvmpc_plan_loop_read_host", "lpvmpc_plan_refs_setup",
-           "lpvmpc_plan_refs_dev", "lpvmpc_plan_refs_host"]
+           "lpvmpc_plan_refs_dev", "lpvmpc_plan_refs_host", "lpvmpc_track_inputs_dev", "lpvmpc_track_inputs_host"]
 
 _lib = None
 
@@ -167,6 +167,10 @@ def lib():
     L.lpvmpc_plan_refs_setup.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     L.lpvmpc_plan_refs_dev.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.lpvmpc_plan_refs_host.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.lpvmpc_track_inputs_dev.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                          C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.lpvmpc_track_inputs_host.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     if L.lpvmpc_abi_version() != ABI_VERSION:
         raise RuntimeError("liblpvmpc.so ABI version mismatch; rebuild with _native.build(force=True)")
     _lib = L

@@ -407,5 +407,44 @@ __global__ void __launch_bounds__(128) lpv_plan_refs_kernel(const __grid_constan
   if (p.err && threadIdx.x == 0) p.err[b] = s_err;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Controller <- planner hand-off: the trajectory-tracking branch of the controller node,
+// controllerMain.py:196-243 with Body_Frame_Errors (:495-506).
+struct TrackInputsParams {
+  int N, n_ref, B;
+  double dt;
+  const double *gstate;   // [B,6]  vx vy wz X Y psi (GlobalState; LocalState[0:3] = GlobalState[0:3], :190-192)
+  const int *lap;         // [B] optional LapNumber (psi -= 2 pi LapNumber, :200)
+  const double *s_prev;   // [B]   SS of the previous tick (:243)
+  const double *refs;     // [B,5,n_ref]  x_d, y_d, psi_d, vx_d, curv_d (My_Planning; lpvmpc_plan_refs_*)
+  const int *index;       // [B] optional window offset (:229-233), NULL = 0
+  double *x0;             // [B,6]   LocalState [vx vy wz epsi s ey]
+  double *vel_ref;        // [B,N+1] window of vx_d; entry N repeats entry N-1 (the reference's vel_ref[-1])
+  double *curv_ref;       // [B,N]
+  double *ex;             // [B] optional longitudinal error (Xerror)
+};
+
+__global__ void __launch_bounds__(128) lpv_track_inputs_kernel(const __grid_constant__ TrackInputsParams p) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= p.B) return;
+  const int N = p.N, o = p.index ? p.index[b] : 0;
+  const double *g = p.gstate + (size_t)b * 6;
+  const double *r = p.refs + (size_t)b * 5 * p.n_ref + o;
+  const double xd = r[0], yd = r[p.n_ref], psid = r[2 * (size_t)p.n_ref], curv = r[4 * (size_t)p.n_ref];
+  const double vx = g[0], vy = g[1], x = g[3], y = g[4];
+  const double psi = wrap_angle(g[5] - 2 * kPi * (p.lap ? p.lap[b] : 0));        // :200-202
+  const double c = cos(psid), s = sin(psid);
+  const double exv = (x - xd) * c + (y - yd) * s;                                // :497
+  const double ey = -(x - xd) * s + (y - yd) * c;                                // :499
+  const double epsi = wrap_angle(psi - psid);                                    // :501
+  const double sn = p.s_prev[b] + ((vx * cos(epsi) - vy * sin(epsi)) / (1 - ey * curv)) * p.dt;   // :504
+  double *x0 = p.x0 + (size_t)b * 6;
+  x0[0] = vx; x0[1] = vy; x0[2] = g[2]; x0[3] = epsi; x0[4] = sn; x0[5] = ey;    // :238-240
+  if (p.ex) p.ex[b] = exv;
+  const double *v = r + 3 * (size_t)p.n_ref, *k = r + 4 * (size_t)p.n_ref;
+  for (int i = 0; i < N; ++i) { p.vel_ref[(size_t)b * (N + 1) + i] = v[i]; p.curv_ref[(size_t)b * N + i] = k[i]; }   // :232-233
+  p.vel_ref[(size_t)b * (N + 1) + N] = v[N - 1];
+}
+
 }  // namespace loop
 }  // namespace lpv

@@ -1224,6 +1224,63 @@ int lpvmpc_plan_refs_host(lpvmpc_handle *h, int32_t B, const double *x_pred, con
   return LPVMPC_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// controller <- planner hand-off (trajectory-tracking branch of the controller node)
+int lpvmpc_track_inputs_dev(lpvmpc_handle *h, int32_t B, const double *gstate, const int32_t *lap, const double *s_prev, const double *refs,
+                            int32_t n_ref, const int32_t *index, int32_t index_max, double *x0, double *vel_ref, double *curv_ref, double *ex,
+                            void *stream) {
+  if (!h || !gstate || !s_prev || !refs || !x0 || !vel_ref || !curv_ref) return fail(h, LPVMPC_E_ARG, "null handle/gstate/s_prev/refs/x0/vel_ref/curv_ref");
+  if (h->cfg.kind != LPVMPC_CONTROLLER) return fail(h, LPVMPC_E_UNSUPPORTED, "the hand-off needs a controller handle");
+  if (index_max < 0 || n_ref < h->L.N + index_max) return fail(h, LPVMPC_E_ARG, "n_ref must hold N + index_max samples");
+  if (B < 0 || B > h->cfg.max_batch) return fail(h, LPVMPC_E_ARG, "batch exceeds max_batch");
+  if (B == 0) return LPVMPC_OK;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  lpv::loop::TrackInputsParams p;
+  p.N = h->L.N; p.n_ref = n_ref; p.B = B; p.dt = h->cfg.dt;
+  p.gstate = gstate; p.lap = lap; p.s_prev = s_prev; p.refs = refs; p.index = index;
+  p.x0 = x0; p.vel_ref = vel_ref; p.curv_ref = curv_ref; p.ex = ex;
+  lpv::loop::lpv_track_inputs_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p);
+  ++h->launches;
+  CUDA_TRY(h, cudaGetLastError());
+  return LPVMPC_OK;
+}
+
+int lpvmpc_track_inputs_host(lpvmpc_handle *h, int32_t B, const double *gstate, const int32_t *lap, const double *s_prev, const double *refs,
+                             int32_t n_ref, const int32_t *index, double *x0, double *vel_ref, double *curv_ref, double *ex) {
+  if (!h || !gstate || !s_prev || !refs || !x0 || !vel_ref || !curv_ref) return fail(h, LPVMPC_E_ARG, "null handle/gstate/s_prev/refs/x0/vel_ref/curv_ref");
+  if (B < 0 || B > h->cfg.max_batch) return fail(h, LPVMPC_E_ARG, "batch exceeds max_batch");
+  if (B == 0) return LPVMPC_OK;
+  int32_t index_max = 0;
+  if (index)
+    for (int32_t b = 0; b < B; ++b) {
+      if (index[b] < 0) return fail(h, LPVMPC_E_ARG, "negative window index");
+      if (index[b] > index_max) index_max = index[b];
+    }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const size_t D = sizeof(double), I = sizeof(int32_t), N = (size_t)h->L.N, nb = (size_t)B;
+  const size_t b_g = 6 * D * nb, b_l = I * nb, b_s = D * nb, b_r = 5 * (size_t)(n_ref > 0 ? n_ref : 0) * D * nb, b_i = I * nb;
+  const size_t b_x = 6 * D * nb, b_v = (N + 1) * D * nb, b_c = N * D * nb, b_e = D * nb;
+  const size_t o_g = 0, o_l = o_g + align256(b_g), o_s = o_l + align256(b_l), o_r = o_s + align256(b_s), o_i = o_r + align256(b_r);
+  const size_t o_x = o_i + align256(b_i), o_v = o_x + align256(b_x), o_c = o_v + align256(b_v), o_e = o_c + align256(b_c);
+  if (o_e + align256(b_e) > h->stage_bytes) return fail(h, LPVMPC_E_ARG, "staging overflow");
+  run_copies({{h->h_stage + o_g, gstate, b_g}, {h->h_stage + o_s, s_prev, b_s}, {h->h_stage + o_r, refs, b_r}});
+  if (lap) std::memcpy(h->h_stage + o_l, lap, b_l);
+  if (index) std::memcpy(h->h_stage + o_i, index, b_i);
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_stage, h->h_stage, o_x, cudaMemcpyHostToDevice, h->stream));
+  const int rc = lpvmpc_track_inputs_dev(h, B, reinterpret_cast<const double *>(h->d_stage + o_g),
+                                         lap ? reinterpret_cast<const int32_t *>(h->d_stage + o_l) : nullptr,
+                                         reinterpret_cast<const double *>(h->d_stage + o_s), reinterpret_cast<const double *>(h->d_stage + o_r), n_ref,
+                                         index ? reinterpret_cast<const int32_t *>(h->d_stage + o_i) : nullptr, index_max,
+                                         reinterpret_cast<double *>(h->d_stage + o_x), reinterpret_cast<double *>(h->d_stage + o_v),
+                                         reinterpret_cast<double *>(h->d_stage + o_c), reinterpret_cast<double *>(h->d_stage + o_e), h->stream);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_stage + o_x, h->d_stage + o_x, (o_e - o_x) + align256(b_e), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  run_copies({{x0, h->h_stage + o_x, b_x}, {vel_ref, h->h_stage + o_v, b_v}, {curv_ref, h->h_stage + o_c, b_c}});
+  if (ex) std::memcpy(ex, h->h_stage + o_e, b_e);
+  return LPVMPC_OK;
+}
+
 int lpvmpc_loop_view_dev(lpvmpc_handle *h, lpvmpc_loop_state *view, int32_t *B) {
   if (!h || !view) return LPVMPC_E_ARG;
   if (!h->d_loop || h->loop_B < 1) return fail(h, LPVMPC_E_ARG, "lpvmpc_loop_init_* first");

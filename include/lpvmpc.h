@@ -289,6 +289,25 @@ int lpvmpc_plan_refs_dev(lpvmpc_handle *h, int32_t B, const double *x_pred, cons
 int lpvmpc_plan_refs_host(lpvmpc_handle *h, int32_t B, const double *x_pred, const double *SS, const double *xyth0, double *refs,
                           int32_t *err);
 
+/* ------------------------------------------------------------------------------------------------
+ * Controller <- planner hand-off: the trajectory-tracking branch of the controller node's main
+ * loop, controllerMain.py:196-243, with Body_Frame_Errors (controllerMain.py:495-506).  For every vehicle: psi =
+ * wrap(psi - 2 pi lap); the window [index, index + N) of the planner's references (controllerMain.py:229-233; the
+ * reference's own index state machine is ReferenceWindow in handoff.py); ex, ey, epsi against the first reference pose
+ * of the window and s = s_prev + (vx cos(epsi) - vy sin(epsi)) / (1 - ey curv) dt.  Outputs are the inputs of
+ * lpvmpc_solve_* with LPVMPC_SCHED_PREDICT and lap != 0 (controllerMain.py:361-363): x0 = LocalState [vx vy wz epsi s ey],
+ * vel_ref (entry N repeats entry N-1: the reference hands N samples and its cost uses vel_ref[-1] for the terminal
+ * stage), curv_ref.  Controller handles only.
+ *   gstate [B,6] vx vy wz X Y psi (GlobalState); lap [B] optional; s_prev [B]; refs [B,5,n_ref] = x_d, y_d, psi_d, vx_d,
+ *   curv_d (the layout lpvmpc_plan_refs_* writes); index [B] optional (NULL = 0), `_dev`: index_max = upper bound of its
+ *   entries (n_ref >= N + index_max is checked; `_host` checks the entries themselves); ex [B] optional.
+ */
+int lpvmpc_track_inputs_dev(lpvmpc_handle *h, int32_t B, const double *gstate, const int32_t *lap, const double *s_prev, const double *refs,
+                            int32_t n_ref, const int32_t *index, int32_t index_max, double *x0, double *vel_ref, double *curv_ref, double *ex,
+                            void *stream);
+int lpvmpc_track_inputs_host(lpvmpc_handle *h, int32_t B, const double *gstate, const int32_t *lap, const double *s_prev, const double *refs,
+                             int32_t n_ref, const int32_t *index, double *x0, double *vel_ref, double *curv_ref, double *ex);
+
 #ifdef __cplusplus
 }
 #endif

@@ -312,3 +312,23 @@ long plan_loop_ref_run(const lpv_ref_cfg *c, const osqp_ref_settings *st, int B,
   }
   return solved_total;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * controller <- planner hand-off: controllerMain.py:196-243 (lap >= 1 branch) with Body_Frame_Errors (:495-506) */
+double track_inputs_ref(const double *g, int lap, double s_prev, const double *refs, int n_ref, int index, int N, double dt,
+                        double *x0, double *vel_ref, double *curv_ref) {
+  const double *x_d = refs + index, *y_d = refs + n_ref + index, *psi_d = refs + 2 * n_ref + index;
+  const double *vx_d = refs + 3 * n_ref + index, *curv_d = refs + 4 * n_ref + index;
+  double psi = g[5] - 2 * kPi * lap;                                  /* :200 */
+  psi = wrap_angle(psi);                                              /* :202 */
+  const double x = g[3], y = g[4], vx = g[0], vy = g[1];
+  const double xd = x_d[0], yd = y_d[0], psid = psi_d[0], curv = curv_d[0];   /* :238-240: x_ref[0], ..., curv_ref[0] */
+  const double ex = (x - xd) * cos(psid) + (y - yd) * sin(psid);      /* :497 */
+  const double ey = -(x - xd) * sin(psid) + (y - yd) * cos(psid);     /* :499 */
+  const double epsi = wrap_angle(psi - psid);                         /* :501 */
+  const double s = s_prev + ((vx * cos(epsi) - vy * sin(epsi)) / (1 - ey * curv)) * dt;   /* :504 */
+  x0[0] = vx; x0[1] = vy; x0[2] = g[2]; x0[3] = epsi; x0[4] = s; x0[5] = ey;
+  for (int i = 0; i < N; ++i) { vel_ref[i] = vx_d[i]; curv_ref[i] = curv_d[i]; }   /* :232-233 */
+  vel_ref[N] = vx_d[N - 1];
+  return ex;
+}

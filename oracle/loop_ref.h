@@ -65,6 +65,13 @@ long plan_loop_ref_run(const lpv_ref_cfg *c, const osqp_ref_settings *st, int B,
                        double accel_rate, const double *xstart, double *x_pred, double *u_pred, double *SS, int *ctr,
                        double *stat, int threads);
 
+/* ---- controller <- planner hand-off (controllerMain.py:196-243, Body_Frame_Errors :495-506) ---- */
+/* One vehicle: g [6] = vx vy wz X Y psi (GlobalState), refs [5, n_ref] = x_d y_d psi_d vx_d curv_d, window offset
+ * `index`; out: x0 [6] = LocalState [vx vy wz epsi s ey], vel_ref [N+1] (entry N = entry N-1: the reference's
+ * vel_ref[-1]), curv_ref [N]; returns ex. */
+double track_inputs_ref(const double *g, int lap, double s_prev, const double *refs, int n_ref, int index, int N, double dt,
+                        double *x0, double *vel_ref, double *curv_ref);
+
 #ifdef __cplusplus
 }
 #endif

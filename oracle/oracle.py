@@ -420,3 +420,17 @@ def plan_loop_run(cfg, settings, state, n_ticks, max_ey=0.3, accel_rate=0.2, thr
     return lib().plan_loop_ref_run(C.byref(cfg), C.byref(settings), C.c_int(B), C.c_int(n_ticks), C.c_double(max_ey),
                                    C.c_double(accel_rate), _dp(state["xstart"]), _dp(state["x_pred"]), _dp(state["u_pred"]),
                                    _dp(state["SS"]), _ip(state["ctr"]), _dp(state["stat"]), C.c_int(threads))
+
+
+def track_inputs(gstate, s_prev, refs, N, dt, lap=None, index=None):
+    """controllerMain.py:196-243 + Body_Frame_Errors for a batch (see loop_ref.h: track_inputs_ref)."""
+    g, sp, r = _f64(gstate), _f64(s_prev), _f64(refs)
+    B, n_ref = g.shape[0], r.shape[2]
+    out = dict(x0=np.zeros((B, 6)), vel_ref=np.zeros((B, N + 1)), curv_ref=np.zeros((B, N)), ex=np.zeros(B))
+    f = lib().track_inputs_ref
+    f.restype = C.c_double
+    for b in range(B):
+        out["ex"][b] = f(_dp(g[b]), C.c_int(0 if lap is None else int(lap[b])), C.c_double(sp[b]), _dp(r[b]), C.c_int(n_ref),
+                         C.c_int(0 if index is None else int(index[b])), C.c_int(N), C.c_double(dt), _dp(out["x0"][b]),
+                         _dp(out["vel_ref"][b]), _dp(out["curv_ref"][b]))
+    return out
