@@ -371,6 +371,8 @@ struct lpvmpc_handle {
   // staging for the host API
   char *d_stage = nullptr, *h_stage = nullptr;
   size_t stage_bytes = 0;
+  bool zc_in = false;          // host API: the kernel reads its inputs from the pinned arena (LPVMPC_ZERO_COPY_IN=1; measured equal to the H2D copy at ctrl4096, off by default)
+  bool zc_out = true;          // host API: the kernel writes its results straight into the pinned arena (LPVMPC_ZERO_COPY_OUT=0: D2H copy)
   cudaStream_t stream = nullptr;
   long long launches = 0;
   std::string err;
@@ -576,6 +578,22 @@ inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 // Host-side staging copies (user arrays <-> the pinned arena) are most of the gap between the kernel and the end-to-end
 // time of the _host entry points (3.8 MB per 4,096-QP controller call): spread them over a few OpenMP threads.
 struct CopyJob { void *dst; const void *src; size_t bytes; };
+#ifdef _OPENMP
+// Threads of one process: at most 8, and the host's cores shared out over the processes of the node (one per GPU under
+// torchrun: LOCAL_WORLD_SIZE) — 8 ranks x 8 spinning OpenMP threads on a 16-core host cost 22 % of the end-to-end rate
+// (profiles/r2l_bench_ctrl4096_g8.json).  LPVMPC_COPY_THREADS overrides.
+int copy_threads() {
+  static const int n = [] {
+    if (const char *e = std::getenv("LPVMPC_COPY_THREADS")) { const int v = std::atoi(e); if (v >= 1) return v > 64 ? 64 : v; }
+    int procs = 1;
+    if (const char *e = std::getenv("LOCAL_WORLD_SIZE")) { const int v = std::atoi(e); if (v >= 1) procs = v; }
+    int t = omp_get_num_procs() / procs;
+    if (t > omp_get_max_threads()) t = omp_get_max_threads();
+    return t < 1 ? 1 : (t > 8 ? 8 : t);
+  }();
+  return n;
+}
+#endif
 void run_copies(const std::vector<CopyJob> &jobs) {
   constexpr size_t kChunk = 128 * 1024;
   std::vector<CopyJob> parts;
@@ -591,9 +609,12 @@ void run_copies(const std::vector<CopyJob> &jobs) {
   }
   const int n = (int)parts.size();
 #ifdef _OPENMP
-  int threads = omp_get_max_threads();
-  if (threads > 8) threads = 8;
+  const int threads = copy_threads();
+  if (threads > 1) {
 #pragma omp parallel for schedule(static) num_threads(threads)
+    for (int i = 0; i < n; ++i) std::memcpy(parts[i].dst, parts[i].src, parts[i].bytes);
+    return;
+  }
 #endif
   for (int i = 0; i < n; ++i) std::memcpy(parts[i].dst, parts[i].src, parts[i].bytes);
 }
@@ -808,6 +829,8 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
   h->stage_bytes = per;
   CTRY(cudaMalloc(&h->d_stage, per));
   CTRY(cudaMallocHost(&h->h_stage, per));
+  if (const char *e = std::getenv("LPVMPC_ZERO_COPY_OUT")) h->zc_out = std::atoi(e) != 0;
+  if (const char *e = std::getenv("LPVMPC_ZERO_COPY_IN")) h->zc_in = std::atoi(e) != 0;
 #undef CTRY
   *out = h;
   return LPVMPC_OK;
@@ -888,7 +911,9 @@ static int run_host(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, int32_t *
     if (cptr_at(a, f.off_args)) {
       const size_t bytes = f.elem * (size_t)B;
       if (!f.output) jobs.push_back({h->h_stage + off, cptr_at(a, f.off_args), bytes});
-      ptr_at(&dev, f.off_args) = h->d_stage + off;
+      // results: written by the kernel through the pinned arena's device mapping (posted PCIe writes behind the compute:
+      // no D2H copy after the kernel); the kernels only ever write their outputs
+      ptr_at(&dev, f.off_args) = ((f.output ? h->zc_out : h->zc_in) ? h->h_stage : h->d_stage) + off;
       off += align256(bytes);
       if (!f.output) in_end = off;
     }
@@ -898,11 +923,12 @@ static int run_host(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, int32_t *
   int32_t *d_se = nullptr;
   if (sched_err) { d_se = reinterpret_cast<int32_t *>(h->d_stage + off); off += align256(sizeof(int32_t) * (size_t)B); }
   if (off > h->stage_bytes) return fail(h, LPVMPC_E_ARG, "staging overflow");
-  if (in_end) CUDA_TRY(h, cudaMemcpyAsync(h->d_stage, h->h_stage, in_end, cudaMemcpyHostToDevice, h->stream));
+  if (in_end && !h->zc_in) CUDA_TRY(h, cudaMemcpyAsync(h->d_stage, h->h_stage, in_end, cudaMemcpyHostToDevice, h->stream));
   rc = solve ? lpvmpc_solve_dev(h, B, &dev, h->stream) : lpvmpc_schedule_dev(h, B, &dev, d_se, h->stream);
   if (rc) return rc;
-  if (off > out_begin)
-    CUDA_TRY(h, cudaMemcpyAsync(h->h_stage + out_begin, h->d_stage + out_begin, off - out_begin, cudaMemcpyDeviceToHost, h->stream));
+  const size_t d2h_begin = (h->zc_out && !first_out) ? se_off : out_begin;   // zero-copy results: only sched_err comes back by copy
+  if (off > d2h_begin)
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_stage + d2h_begin, h->d_stage + d2h_begin, off - d2h_begin, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   jobs.clear();
   for (size_t i = 0; i < fields.size(); ++i) {

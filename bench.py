@@ -596,6 +596,8 @@ def run_ours(args):
                    "smem_bytes_per_qp": info0["smem_bytes_per_qp"]},
         "e2e": {"value": e2e_value, "unit": "QP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * e2e_total / args.steps,
+                "d2h": ("kernel writes the results into the pinned host arena (zero-copy, posted PCIe writes behind the compute)"
+                        if os.environ.get("LPVMPC_ZERO_COPY_OUT", "1") != "0" else "one cudaMemcpyAsync after the kernel"),
                 "latency_ms": {"p50": 1e3 * float(np.percentile(e2e_t, 50)), "p99": 1e3 * float(np.percentile(e2e_t, 99)),
                                "max": 1e3 * float(np.max(e2e_t))}},
         "gpu_launches": int(launches),
