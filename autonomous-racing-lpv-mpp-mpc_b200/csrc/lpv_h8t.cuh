@@ -1114,16 +1114,20 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
   data_err = gany(data_err);
 
   // ---- Ruiz equilibration (OSQP scale_data)
-  double csc = 1.0;
+  // The cost scale of a pass (OSQP: c = 1 / max(mean column norm of P, |q|_inf)) is not applied by a loop of its own: it
+  // stays pending in `cp` and is folded into the next pass's reads (x * 1.0 is exact, and (x * cp) is the value the
+  // separate loop used to store, so every product is formed in the same order); the cost norms are taken from the
+  // registers of the scaling loop.  Both loops were chains of exposed shared-memory round trips (3 % of the kernel).
+  double csc = 1.0, cp = 1.0;
 #pragma unroll 1
   for (int it = 0; it < St.scaling; ++it) {
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
       const int o = k * 8 + r, ov = k * VS + r;
-      double pa = fabs(sPD[o]);
+      double pa = fabs(sPD[o] * cp);
       if (c.ul) {
-        if (k < N - 1) pa = absmax(pa, sPO[o]);
-        if (k > 0 && k < N) pa = absmax(pa, sPO[o - 8]);
+        if (k < N - 1) pa = absmax(pa, sPO[o] * cp);
+        if (k > 0 && k < N) pa = absmax(pa, sPO[o - 8] * cp);
       }
       double qa = c.xl ? fabs(ED[ov]) : 0.0;
       if (k < N) {
@@ -1148,15 +1152,17 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
       sEt[o] = frsqrt(limit_scaling(ea));
     }
     __syncwarp();
+    double qn = 0.0, ct = 0.0, npo_prev = 0.0;
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
       const int o = k * 8 + r, ov = k * VS + r;
       const double dt = sDt[o];
+      double npo = 0.0;
       if (k < N) {
         double *gk = Gs + k * GS;
 #pragma unroll
         for (int rr = 0; rr < NX; ++rr) { double *e = gk + rr * 8 + c.co[rr >> 1]; *e = (*e * sEt[(k + 1) * 8 + rr]) * dt; }
-        if (k < N - 1 && c.ul) sPO[o] = (sPO[o] * dt) * sDt[o + 8];
+        if (k < N - 1 && c.ul) { npo = ((sPO[o] * cp) * dt) * sDt[o + 8]; sPO[o] = npo; }
       }
       if (c.has_in(k)) {
 #pragma unroll
@@ -1167,33 +1173,34 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
         }
       }
       if (c.xl) ED[ov] = (ED[ov] * sEt[o]) * dt;
-      sPD[o] = (sPD[o] * dt) * dt;
-      QV[ov] = dt * QV[ov];
+      const double npd = ((sPD[o] * cp) * dt) * dt;
+      sPD[o] = npd;
+      const double nq = dt * (QV[ov] * cp);
+      QV[ov] = nq;
       sD[o] = sD[o] * dt;
       sE[o] = sE[o] * sEt[o];
+      // cost scaling: mean of the column norms of P (summed per lane, then across the group)
+      double pc = fabs(npd);
+      if (c.ul) {
+        if (k < N - 1) pc = absmax(pc, npo);
+        if (k > 0 && k < N) pc = absmax(pc, npo_prev);
+      }
+      if (c.var_live(k)) { ct += pc; qn = absmax(qn, nq); }
+      npo_prev = npo;
     }
     __syncwarp();
-    // cost scaling: mean of the column norms of P (summed per lane, then across the group)
-    double qn = 0.0, ct = 0.0;
-#pragma unroll 1
-    for (int k = 0; k <= N; ++k) {
-      const int o = k * 8 + r;
-      double pa = fabs(sPD[o]);
-      if (c.ul) {
-        if (k < N - 1) pa = absmax(pa, sPO[o]);
-        if (k > 0 && k < N) pa = absmax(pa, sPO[o - 8]);
-      }
-      if (c.var_live(k)) { ct += pa; qn = absmax(qn, QV[k * VS + r]); }
-    }
     qn = gmax(qn);
     ct = gsum(ct) / nz;
     qn = limit_scaling(qn);
     ct = ct > qn ? ct : qn;
     ct = limit_scaling(ct);
     ct = frcp(ct);
-#pragma unroll 1
-    for (int k = 0; k <= N; ++k) { const int o = k * 8 + r; sPD[o] *= ct; QV[k * VS + r] *= ct; sPO[o] *= ct; }
+    cp = ct;
     csc *= ct;
+  }
+  if (St.scaling > 0) {
+#pragma unroll 1
+    for (int k = 0; k <= N; ++k) { const int o = k * 8 + r; sPD[o] *= cp; QV[k * VS + r] *= cp; sPO[o] *= cp; }
     __syncwarp();
   }
   *csc_out = csc;

@@ -126,3 +126,26 @@ def test_fleet_with_the_long_controller_horizon():
     np.testing.assert_allclose(got["sim"], ref["sim"], rtol=0, atol=1e-6)
     np.testing.assert_allclose(got["cmd"], ref["cmd"], rtol=0, atol=1e-6)
     fleet.close()
+
+
+def test_host_copy_modes_agree(track, monkeypatch):
+    """The _host entry points return the same bits whether the kernel writes its results into the pinned arena
+    (default), the results come back by a D2H copy (LPVMPC_ZERO_COPY_OUT=0), or the inputs are read from the arena too
+    (LPVMPC_ZERO_COPY_IN=1); the modes are read when the handle is created."""
+    N, B = 8, 300
+    w = W.controller_batch(B, N, seed=17)
+    outs = ("active_lo", "active_up", "y", "A_out", "states_out")
+    res = []
+    for zo, zi in (("1", "0"), ("0", "0"), ("1", "1")):
+        monkeypatch.setenv("LPVMPC_ZERO_COPY_OUT", zo)
+        monkeypatch.setenv("LPVMPC_ZERO_COPY_IN", zi)
+        s = lp.BatchSolver("controller", N, W.CTRL_DT, track=track, max_batch=B, **W.CTRL_TT)
+        res.append(s.solve(w["x0"], extra_outputs=outs, **{k: w[k] for k in KEYS}))
+        sch = s.schedule(x0=w["x0"], **{k: w[k] for k in ("u_prev", "vel_ref", "curv_ref", "lap")})
+        res[-1]["sched_A"] = sch["A_out"]
+        res[-1]["sched_err"] = sch["sched_err"]
+        s.close()
+    for r in res[1:]:
+        for k in ("x_pred", "u_pred", "status", "iters", "obj", "pri_res", "dua_res", "sched_A", "sched_err") + outs:
+            np.testing.assert_array_equal(r[k], res[0][k], err_msg=k)
+    assert (res[0].status == 1).mean() > 0.9
