@@ -172,9 +172,115 @@ __global__ void __launch_bounds__(32) lpv_solve_kernel(const __grid_constant__ P
   }
 }
 
-// Stand-alone LPVPrediction / _EstimateABC: one thread per QP (the roll-out is serial in k).
+// Stand-alone LPVPrediction / _EstimateABC: one thread per QP (the roll-out is serial in k), HBM-bound (3.8 KB per
+// controller QP at N = 8, 91 % of it the matrices written).  A thread's own records are 288 / 96 / 48 bytes per stage, 2.3 KB
+// apart from its neighbour's, so the stage results of a warp's 32 QPs go through a shared-memory tile and leave as runs
+// of consecutive 16-byte pieces, 512 bytes per store instruction.  Tile row = one QP's record [A | B | state]; its stride
+// in 16-byte units is odd (27 controller, 21 planner), which makes the 128-bit row writes of a quarter-warp conflict-free.
+constexpr int kSchedThreads = 64;
+template <int KIND> struct SchedTile {
+  static constexpr int NX = Spec<KIND>::NX, NA = NX * NX, NBm = NX * NU, REC = NA + NBm + NX;
+  static constexpr int STRIDE = (((REC + 1) / 2) | 1) * 2;   // doubles: 54 (controller), 42 (planner)
+  static constexpr bool PAIRS = (NA % 2 == 0) && (NX % 2 == 0);   // every record a whole number of 16-byte pieces
+};
+// copy records of `len` doubles (QP q of the warp at tile[q * STRIDE + off]) to dst[(b0 + q) * qstride + e]
+template <int STRIDE, int LEN, bool PAIRS>
+__device__ __forceinline__ void sched_copy_out(const double *tile, int off, double *dst, size_t qstride, int nq, int lane) {
+  if (PAIRS) {
+    constexpr int L2 = LEN / 2, STEP_Q = 32 / L2, STEP_E = 32 % L2;
+    int q = lane / L2, e = lane - q * L2;
+    for (; q < nq; ) {
+      const double2 v = *reinterpret_cast<const double2 *>(tile + q * STRIDE + off + 2 * e);
+      *reinterpret_cast<double2 *>(dst + (size_t)q * qstride + 2 * e) = v;
+      q += STEP_Q; e += STEP_E;
+      if (e >= L2) { e -= L2; ++q; }
+    }
+  } else {
+    constexpr int STEP_Q = 32 / LEN, STEP_E = 32 % LEN;
+    int q = lane / LEN, e = lane - q * LEN;
+    for (; q < nq; ) {
+      dst[(size_t)q * qstride + e] = tile[q * STRIDE + off + e];
+      q += STEP_Q; e += STEP_E;
+      if (e >= LEN) { e -= LEN; ++q; }
+    }
+  }
+}
 template <int KIND>
-__global__ void __launch_bounds__(128) lpv_schedule_kernel(const __grid_constant__ Params p, int *sched_err) {
+__global__ void __launch_bounds__(kSchedThreads) lpv_schedule_kernel(const __grid_constant__ Params p, int *sched_err) {
+  using T = SchedTile<KIND>;
+  constexpr int NX = T::NX, NA = T::NA, NBm = T::NBm, STRIDE = T::STRIDE;
+  __shared__ __align__(16) double tile_s[kSchedThreads / 32][32 * STRIDE];   // 27 KB: 8 CTAs = 16 warps per SM
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b0 = blockIdx.x * blockDim.x + warp * 32;      // first QP of my warp
+  if (b0 >= p.B) return;
+  const int nq = (p.B - b0 < 32) ? p.B - b0 : 32;          // QPs of my warp
+  const bool live = lane < nq;
+  const int b = live ? b0 + lane : b0;                      // idle lanes mirror the warp's first QP (no output of their own)
+  double *tile = tile_s[warp], *mine = tile + lane * STRIDE;
+  const Model &M = p.M;
+  const lpvmpc_args &a = p.a;
+  const int N = p.L.N;
+  int err = 0;
+  double st[NX], Ai[NA], Bi[NBm];
+  const bool estimate = a.sched_mode == LPVMPC_SCHED_ESTIMATE;
+  const double *up = a.u_prev + (size_t)b * N * NU;
+  int lap = 0;
+  if (!estimate) {
+    const double *xs = a.x_sched ? a.x_sched + (size_t)b * NX : a.x0 + (size_t)b * NX;
+#pragma unroll
+    for (int r = 0; r < NX; ++r) st[r] = xs[r];
+    lap = a.lap ? a.lap[b] : a.lap_all;
+  }
+  // per-stage inputs one stage ahead of their use (the first touch of every record is a DRAM round trip)
+  auto in0 = [&](int i) { return estimate ? 0.0 : (KIND == LPVMPC_CONTROLLER ? a.vel_ref[(size_t)b * (N + 1) + i] : a.SS[(size_t)b * (N + 1) + i]); };
+  auto in1 = [&](int i) { return (!estimate && KIND == LPVMPC_CONTROLLER && lap != 0) ? a.curv_ref[(size_t)b * N + i] : 0.0; };
+  double n_u0 = up[0], n_u1 = up[1], n_a = in0(0), n_c = in1(0);
+  for (int i = 0; i < N; ++i) {
+    const double u01[2] = {n_u0, n_u1}, va = n_a, vc = n_c;
+    if (i + 1 < N) { n_u0 = up[(i + 1) * NU]; n_u1 = up[(i + 1) * NU + 1]; n_a = in0(i + 1); n_c = in1(i + 1); }
+    if (estimate) {
+      const double *t = a.traj + ((size_t)b * N + i) * 6;
+      if (KIND == LPVMPC_CONTROLLER) ctrl_stage(M, M.Cf, M.Cr, t[0], t[1], t[3], t[5], curvature(M.track, M.nseg, t[4], err), u01[0], Ai, Bi);
+      else plan_stage(M, t[0], t[1], t[3], t[4], curvature(M.track, M.nseg, t[5], err), u01[0], Ai, Bi);
+    } else if (KIND == LPVMPC_CONTROLLER) {
+      const double cur = (lap == 0) ? curvature(M.track, M.nseg, st[4], err) : vc;
+      ctrl_stage(M, a.Cf_new, a.Cf_new, va, st[1], st[3], st[5], cur, u01[0], Ai, Bi);
+    } else {
+      plan_stage(M, st[0], st[1], st[3], st[4], curvature(M.track, M.nseg, va, err), u01[0], Ai, Bi);
+    }
+    if (!estimate) propagate<NX>(Ai, Bi, u01, st);
+    if (T::PAIRS) {
+#pragma unroll
+      for (int e = 0; e < NA; e += 2) *reinterpret_cast<double2 *>(mine + e) = make_double2(Ai[e], Ai[e + 1]);
+#pragma unroll
+      for (int e = 0; e < NBm; e += 2) *reinterpret_cast<double2 *>(mine + NA + e) = make_double2(Bi[e], Bi[e + 1]);
+      if (!estimate) {
+#pragma unroll
+        for (int r = 0; r < NX; r += 2) *reinterpret_cast<double2 *>(mine + NA + NBm + r) = make_double2(st[r], st[r + 1 < NX ? r + 1 : r]);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < NA; ++e) mine[e] = Ai[e];
+#pragma unroll
+      for (int e = 0; e < NBm; ++e) mine[NA + e] = Bi[e];
+      if (!estimate) {
+#pragma unroll
+        for (int r = 0; r < NX; ++r) mine[NA + NBm + r] = st[r];
+      }
+    }
+    __syncwarp();
+    if (a.A_out) sched_copy_out<STRIDE, NA, T::PAIRS>(tile, 0, a.A_out + ((size_t)b0 * N + i) * NA, (size_t)N * NA, nq, lane);
+    if (a.B_out) sched_copy_out<STRIDE, NBm, T::PAIRS>(tile, NA, a.B_out + ((size_t)b0 * N + i) * NBm, (size_t)N * NBm, nq, lane);
+    if (a.states_out && !estimate) sched_copy_out<STRIDE, NX, T::PAIRS>(tile, NA + NBm, a.states_out + ((size_t)b0 * N + i) * NX, (size_t)N * NX, nq, lane);
+    __syncwarp();
+  }
+  if (sched_err && live) sched_err[b] = err;
+}
+
+// The first version of the stand-alone kernel (every thread stores its own records): kept for the A/B line of
+// bench.py --workload sched65536 (LPVMPC_SCHED_NAIVE=1), not used otherwise.
+template <int KIND>
+__global__ void __launch_bounds__(128) lpv_schedule_naive_kernel(const __grid_constant__ Params p, int *sched_err) {
   constexpr int NX = Spec<KIND>::NX;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= p.B) return;
@@ -884,9 +990,20 @@ int lpvmpc_schedule_dev(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, int32
   if (B == 0) return LPVMPC_OK;
   CUDA_TRY(h, cudaSetDevice(h->device));
   const Params p = make_params(h, B, a);
-  const int grid = (B + 127) / 128;
-  if (h->cfg.kind == LPVMPC_CONTROLLER) lpv::lpv_schedule_kernel<LPVMPC_CONTROLLER><<<grid, 128, 0, (cudaStream_t)stream>>>(p, sched_err);
-  else lpv::lpv_schedule_kernel<LPVMPC_PLANNER><<<grid, 128, 0, (cudaStream_t)stream>>>(p, sched_err);
+  static const bool naive = [] { const char *e = std::getenv("LPVMPC_SCHED_NAIVE"); return e && std::atoi(e) != 0; }();
+  // the tiled kernel stores 16-byte pieces: output arrays that are only 8-byte aligned take the plain kernel
+  const bool misaligned = (((uintptr_t)a->A_out | (uintptr_t)a->B_out | (uintptr_t)a->states_out) & 15u) != 0;
+  if (naive || misaligned) {
+    const int g = (B + 127) / 128;
+    if (h->cfg.kind == LPVMPC_CONTROLLER) lpv::lpv_schedule_naive_kernel<LPVMPC_CONTROLLER><<<g, 128, 0, (cudaStream_t)stream>>>(p, sched_err);
+    else lpv::lpv_schedule_naive_kernel<LPVMPC_PLANNER><<<g, 128, 0, (cudaStream_t)stream>>>(p, sched_err);
+    ++h->launches;
+    CUDA_TRY(h, cudaGetLastError());
+    return LPVMPC_OK;
+  }
+  const int grid = (B + lpv::kSchedThreads - 1) / lpv::kSchedThreads;
+  if (h->cfg.kind == LPVMPC_CONTROLLER) lpv::lpv_schedule_kernel<LPVMPC_CONTROLLER><<<grid, lpv::kSchedThreads, 0, (cudaStream_t)stream>>>(p, sched_err);
+  else lpv::lpv_schedule_kernel<LPVMPC_PLANNER><<<grid, lpv::kSchedThreads, 0, (cudaStream_t)stream>>>(p, sched_err);
   ++h->launches;
   CUDA_TRY(h, cudaGetLastError());
   return LPVMPC_OK;

@@ -203,7 +203,7 @@ class BatchSolver(object):
         L = nat.lib()
         if use_torch:
             import torch
-            err = torch.zeros(B, dtype=torch.int32, device=torch.device("cuda", self.device))
+            err = torch.empty(B, dtype=torch.int32, device=torch.device("cuda", self.device))   # every entry is written
             stream = torch.cuda.current_stream(self.device).cuda_stream
             nat.check(L.lpvmpc_schedule_dev(self._h, B, C.byref(a), C.c_void_p(err.data_ptr()), C.c_void_p(stream)), self._h)
             res["_keepalive"] = keep

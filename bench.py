@@ -61,6 +61,9 @@ WORKLOADS = {
     # not a BASELINE config: the planner main loop (plannerMain.py:128-224) for a fleet of plans, i.e. planner QPs with the
     # reference's own closed-loop distribution (SURVEY 8d cfg 3 generator); a step = `--ticks-per-step` re-planning ticks
     "planloop4096": dict(kind="planfleet", N=40, B=4096, seed=5),
+    # not a BASELINE config: the stand-alone LPVPrediction kernel (lpvmpc_schedule_*: A_k, B_k and the roll-out written to
+    # HBM) on the cfg-2 distribution — the HBM-bound kernel of SURVEY 8d; 65,536 QPs = 250 MB per launch (> L2)
+    "sched65536": dict(kind="schedule", N=8, B=65536, seed=0),
 }
 
 
@@ -461,6 +464,9 @@ def run_reference(args):
     if WORKLOADS[args.workload]["kind"] == "planfleet":
         print(json.dumps({"impl": "reference", "unavailable": "planloop4096 is not a BASELINE config; use plan16384"}))
         return 0
+    if WORKLOADS[args.workload]["kind"] == "schedule":
+        print(json.dumps({"impl": "reference", "unavailable": "sched65536 is not a BASELINE config (scheduling only); its cpu_baseline is on the ours line"}))
+        return 0
     if WORKLOADS[args.workload]["kind"] == "fleet":
         return run_fleet_reference(args)
     threads = os.cpu_count() or 1
@@ -652,6 +658,92 @@ def run_ours(args):
     return 0
 
 
+def run_schedule(args):
+    """Stand-alone scheduling kernel (LPVPrediction for a batch, matrices materialised): HBM roofline."""
+    import torch
+    import lpvmpc_b200 as lp
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise SystemExit("sched65536 is a single-GPU workload")
+    W = lp.workloads
+    spec = WORKLOADS[args.workload]
+    B, N = spec["B"], spec["N"]
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    track = lp.Map("L_shape")
+    w = W.controller_batch(B, N, seed=spec["seed"], track=track)
+    solver = lp.BatchSolver("controller", N, W.CTRL_DT, track=track.PointAndTangent, max_batch=B, device=0, **W.CTRL_TT)
+    keys = ("u_prev", "vel_ref", "curv_ref", "lap")
+    tin = {k: torch.as_tensor(w[k]).to(dev) for k in keys}
+    tin["x0"] = torch.as_tensor(w["x0"]).to(dev)
+    # 1 GiB flush (~170 us of memset): besides emptying L2 it keeps the GPU busy while the host prepares the next call, so the
+    # event pair brackets the kernel and not the ~40 us of Python / ctypes argument packing in front of a 75 us launch
+    flush = torch.empty(1024 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    for _ in range(args.warmup):
+        r = solver.schedule(**tin)
+    torch.cuda.synchronize()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    sampler = ClockSampler(0)
+    launches0 = solver.info()["kernel_launches"]
+    sampler.start()
+    torch.cuda.synchronize()
+    for i in range(args.steps):
+        flush.zero_()
+        starts[i].record()
+        r = solver.schedule(**tin)
+        ends[i].record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    launches = solver.info()["kernel_launches"] - launches0
+    step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, ends)])
+    ms = float(step_ms.mean())
+    # algorithmic bytes per QP (SURVEY 8d): inputs x0 (6) + u_prev (2N) + vel_ref (N+1) + curv_ref (N) doubles + lap (int32);
+    # outputs A_k (36N) + B_k (12N) + roll-out states (6N) doubles + sched_err (int32)
+    in_b = 8 * (6 + 2 * N + (N + 1) + N) + 4
+    out_b = 8 * (36 * N + 12 * N + 6 * N) + 4
+    mp = measured_peaks()
+    peak = float(mp.get("hbm_gbs", 6650.0))
+    achieved = (in_b + out_b) * B / (ms * 1e-3) * 1e-9
+    # end to end: numpy in -> numpy out through lpvmpc_schedule_host
+    hin = {k: w[k] for k in keys}
+    hin["x0"] = w["x0"]
+    for _ in range(2):
+        solver.schedule(**hin)
+    t0 = time.perf_counter()
+    ne = max(3, min(args.steps, 10))
+    for _ in range(ne):
+        rh = solver.schedule(**hin)
+    e2e_s = (time.perf_counter() - t0) / ne
+    assert np.array_equal(rh["A_out"], r["A_out"].cpu().numpy()), "host and device paths disagree"
+    line = {
+        "metric": "LPV-MPC QP solves/sec", "value": B / (ms * 1e-3), "unit": "QP/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "kind": "stand-alone LPVPrediction (scheduling only: A_k, B_k, roll-out states to HBM; value = QPs SCHEDULED per second, no solve)",
+                   "N": N, "batch_per_gpu": B, "l2": "flushed between steps (1 GiB memset outside the per-step event pairs); 250 MB per launch > L2",
+                   "kernel": "lpv_schedule_naive_kernel" if os.environ.get("LPVMPC_SCHED_NAIVE", "0") != "0" else "lpv_schedule_kernel"},
+        "e2e": {"value": B / e2e_s, "unit": "QP/s", "h2d_bytes_per_step": int(sum(np.asarray(v).nbytes for v in hin.values())),
+                "d2h_bytes_per_step": int(sum(v.nbytes for v in rh.values() if hasattr(v, "nbytes"))), "ms_per_step": 1e3 * e2e_s},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if not mp.get("_fallback") else "fallback (B200_PROFILING.md)",
+                     "kernel": "lpv_schedule_kernel<CONTROLLER>", "algorithmic_bytes_per_qp": in_b + out_b,
+                     "algorithmic_bytes_per_launch": (in_b + out_b) * B},
+        "kernel_latency_ms": {"p50": float(np.percentile(step_ms, 50)), "max": float(step_ms.max())},
+    }
+    if not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle
+        cfg = oracle.make_cfg("controller", N, W.CTRL_DT, W.CTRL_TT["Q"], W.CTRL_TT["R"], W.CTRL_TT["dR"], track.PointAndTangent)
+        ns = 4096
+        t0 = time.perf_counter()
+        for b in range(ns):
+            oracle.ctrl_predict(cfg, w["x0"][b], w["u_prev"][b], w["vel_ref"][b], w["curv_ref"][b], 60.0, int(w["lap"][b]))
+        line["cpu_baseline"] = {"value": ns / (time.perf_counter() - t0), "unit": "QP/s", "cores": 1, "kind": "port",
+                                "sample": "%d QPs of the same batch, one C call of the oracle's LPVPrediction per QP from Python (ctypes overhead included)" % ns}
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -674,6 +766,8 @@ def main():
         return run_fleet(args)
     if WORKLOADS[args.workload]["kind"] == "planfleet":
         return run_planfleet(args)
+    if WORKLOADS[args.workload]["kind"] == "schedule":
+        return run_schedule(args)
     return run_ours(args)
 
 

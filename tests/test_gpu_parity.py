@@ -177,3 +177,69 @@ def test_long_horizon_controller_matches_oracle(track, variant, N):
             np.testing.assert_allclose(r.u_pred[b], o["uPred"], rtol=0, atol=1e-4)
             np.testing.assert_allclose(r.x_pred[b], o["xPred"], rtol=0, atol=1e-4)
             assert abs(r.obj[b] - o["obj_val"]) <= 1e-6 * abs(o["obj_val"])
+
+
+def test_schedule_kernel_paths(track, monkeypatch):
+    """The stand-alone scheduling kernel (records staged through a shared-memory tile, 16-byte stores): ragged batches
+    (a partial warp, a partial CTA), the planner's odd-sized records, _EstimateABC, and the plain kernel that takes
+    over for output arrays that are only 8-byte aligned — all against the oracle, and the two kernels bit for bit."""
+    import ctypes as C
+    import torch
+    nat = lp._native
+    N = 8
+    cfg = oracle.make_cfg("controller", N, W.CTRL_DT, W.CTRL_TT["Q"], W.CTRL_TT["R"], W.CTRL_TT["dR"], track)
+    for B in (1, 31, 77, 200):
+        w = W.controller_batch(B, N, seed=40 + B)
+        s = lp.BatchSolver("controller", N, W.CTRL_DT, track=track, max_batch=B, **W.CTRL_TT)
+        r = s.schedule(x0=w["x0"], u_prev=w["u_prev"], vel_ref=w["vel_ref"], curv_ref=w["curv_ref"], lap=w["lap"])
+        for b in range(B):
+            st, A, Bm, _, err = oracle.ctrl_predict(cfg, w["x0"][b], w["u_prev"][b], w["vel_ref"][b], w["curv_ref"][b], 60.0, int(w["lap"][b]))
+            assert err == int(r.sched_err[b])
+            np.testing.assert_allclose(r.A_out[b], A, rtol=1e-14, atol=1e-16)
+            np.testing.assert_allclose(r.B_out[b], Bm, rtol=1e-14, atol=1e-16)
+            np.testing.assert_allclose(r.states_out[b], st, rtol=1e-12, atol=1e-14)
+        # _EstimateABC around the roll-out just computed (traj rows [vx vy wz epsi s ey]); no states_out in this mode
+        traj = r.states_out.copy()
+        e = s.schedule(sched_mode=lp.SCHED_ESTIMATE, traj=traj, u_prev=w["u_prev"])
+        for b in range(0, B, 7):
+            A, Bm, _, err = oracle.ctrl_estimate(cfg, traj[b], w["u_prev"][b])
+            assert err == int(e.sched_err[b])
+            np.testing.assert_allclose(e.A_out[b], A, rtol=1e-14, atol=1e-16)
+            np.testing.assert_allclose(e.B_out[b], Bm, rtol=1e-14, atol=1e-16)
+        if B == 77:
+            # device path with outputs that are only 8-byte aligned -> plain kernel; must equal the tiled kernel's bits
+            dev = torch.device("cuda", 0)
+            tin = {k: torch.as_tensor(w[k]).to(dev) for k in ("x0", "u_prev", "vel_ref", "curv_ref", "lap")}
+            bufA = torch.zeros(B * N * 36 + 1, dtype=torch.float64, device=dev)
+            bufB = torch.zeros(B * N * 12 + 1, dtype=torch.float64, device=dev)
+            bufS = torch.zeros(B * N * 6 + 1, dtype=torch.float64, device=dev)
+            a = nat.Args()
+            a.sched_mode = lp.SCHED_PREDICT
+            a.lap_all = 1
+            a.Cf_new = 60.0
+            for k, t in tin.items():
+                setattr(a, k, t.data_ptr())
+            for k, t in (("A_out", bufA), ("B_out", bufB), ("states_out", bufS)):
+                assert (t.data_ptr() + 8) % 16 == 8
+                setattr(a, k, t.data_ptr() + 8)
+            err = torch.empty(B, dtype=torch.int32, device=dev)
+            nat.check(nat.lib().lpvmpc_schedule_dev(s._h, B, C.byref(a), C.c_void_p(err.data_ptr()),
+                                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)), s._h)
+            torch.cuda.synchronize()
+            np.testing.assert_array_equal(bufA[1:].cpu().numpy().reshape(B, N, 6, 6), r.A_out)
+            np.testing.assert_array_equal(bufB[1:].cpu().numpy().reshape(B, N, 6, 2), r.B_out)
+            np.testing.assert_array_equal(bufS[1:].cpu().numpy().reshape(B, N, 6), r.states_out)
+        s.close()
+    # planner: 25 + 10 + 5 doubles per record (scalar tile path)
+    Np, Bp = 40, 45
+    wp = W.planner_batch(Bp, Np, seed=3)
+    sp = lp.BatchSolver("planner", Np, W.PLAN_DT, track=track, max_batch=Bp, **W.PLAN)
+    cfgp = oracle.make_cfg("planner", Np, W.PLAN_DT, W.PLAN["Q"], W.PLAN["R"], W.PLAN["dR"], track, L_cf=W.PLAN["L_cf"])
+    rp = sp.schedule(x0=wp["x0"], SS=wp["SS"], u_prev=wp["u_prev"])
+    for b in range(Bp):
+        st, A, Bm, _, err = oracle.plan_predict(cfgp, wp["x0"][b], wp["SS"][b], wp["u_prev"][b])
+        assert err == int(rp.sched_err[b])
+        np.testing.assert_allclose(rp.A_out[b], A, rtol=1e-14, atol=1e-16)
+        np.testing.assert_allclose(rp.B_out[b], Bm, rtol=1e-14, atol=1e-16)
+        np.testing.assert_allclose(rp.states_out[b], st, rtol=1e-12, atol=1e-14)
+    sp.close()
