@@ -182,7 +182,8 @@ def test_long_horizon_controller_matches_oracle(track, variant, N):
 def test_schedule_kernel_paths(track, monkeypatch):
     """The stand-alone scheduling kernel (records staged through a shared-memory tile, 16-byte stores): ragged batches
     (a partial warp, a partial CTA), the planner's odd-sized records, _EstimateABC, and the plain kernel that takes
-    over for output arrays that are only 8-byte aligned — all against the oracle, and the two kernels bit for bit."""
+    over for output arrays that are only 8-byte aligned — all against the oracle, and the two kernels bit for bit.  Tolerance 1e-13: entries formed by
+    a cancellation (A23 = -(...)/(m vx) - vx) amplify the 1-ulp difference of CUDA's and libm's sin / cos."""
     import ctypes as C
     import torch
     nat = lp._native
@@ -195,8 +196,8 @@ def test_schedule_kernel_paths(track, monkeypatch):
         for b in range(B):
             st, A, Bm, _, err = oracle.ctrl_predict(cfg, w["x0"][b], w["u_prev"][b], w["vel_ref"][b], w["curv_ref"][b], 60.0, int(w["lap"][b]))
             assert err == int(r.sched_err[b])
-            np.testing.assert_allclose(r.A_out[b], A, rtol=1e-14, atol=1e-16)
-            np.testing.assert_allclose(r.B_out[b], Bm, rtol=1e-14, atol=1e-16)
+            np.testing.assert_allclose(r.A_out[b], A, rtol=1e-13, atol=1e-15)
+            np.testing.assert_allclose(r.B_out[b], Bm, rtol=1e-13, atol=1e-15)
             np.testing.assert_allclose(r.states_out[b], st, rtol=1e-12, atol=1e-14)
         # _EstimateABC around the roll-out just computed (traj rows [vx vy wz epsi s ey]); no states_out in this mode
         traj = r.states_out.copy()
@@ -204,8 +205,8 @@ def test_schedule_kernel_paths(track, monkeypatch):
         for b in range(0, B, 7):
             A, Bm, _, err = oracle.ctrl_estimate(cfg, traj[b], w["u_prev"][b])
             assert err == int(e.sched_err[b])
-            np.testing.assert_allclose(e.A_out[b], A, rtol=1e-14, atol=1e-16)
-            np.testing.assert_allclose(e.B_out[b], Bm, rtol=1e-14, atol=1e-16)
+            np.testing.assert_allclose(e.A_out[b], A, rtol=1e-13, atol=1e-15)
+            np.testing.assert_allclose(e.B_out[b], Bm, rtol=1e-13, atol=1e-15)
         if B == 77:
             # device path with outputs that are only 8-byte aligned -> plain kernel; must equal the tiled kernel's bits
             dev = torch.device("cuda", 0)
@@ -239,7 +240,7 @@ def test_schedule_kernel_paths(track, monkeypatch):
     for b in range(Bp):
         st, A, Bm, _, err = oracle.plan_predict(cfgp, wp["x0"][b], wp["SS"][b], wp["u_prev"][b])
         assert err == int(rp.sched_err[b])
-        np.testing.assert_allclose(rp.A_out[b], A, rtol=1e-14, atol=1e-16)
-        np.testing.assert_allclose(rp.B_out[b], Bm, rtol=1e-14, atol=1e-16)
+        np.testing.assert_allclose(rp.A_out[b], A, rtol=1e-13, atol=1e-15)
+        np.testing.assert_allclose(rp.B_out[b], Bm, rtol=1e-13, atol=1e-15)
         np.testing.assert_allclose(rp.states_out[b], st, rtol=1e-12, atol=1e-14)
     sp.close()
