@@ -186,7 +186,25 @@ template <int KIND> struct SchedTile {
 // copy records of `len` doubles (QP q of the warp at tile[q * STRIDE + off]) to dst[(b0 + q) * qstride + e]
 template <int STRIDE, int LEN, bool PAIRS>
 __device__ __forceinline__ void sched_copy_out(const double *tile, int off, double *dst, size_t qstride, int nq, int lane) {
-  if (PAIRS) {
+  if (PAIRS && nq == 32) {
+    // full warp: 32 records = LEN / 2 pieces per lane exactly; up to 9 tile reads in flight before their stores
+    constexpr int L2 = LEN / 2, STEP_Q = 32 / L2, STEP_E = 32 % L2, CH = (L2 % 9 == 0) ? 9 : ((L2 % 6 == 0) ? 6 : ((L2 % 3 == 0) ? 3 : 1));
+    int q = lane / L2, e = lane - q * L2;
+#pragma unroll 1
+    for (int c0 = 0; c0 < L2; c0 += CH) {
+      double2 v[CH];
+      int go[CH];
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        v[j] = *reinterpret_cast<const double2 *>(tile + q * STRIDE + off + 2 * e);
+        go[j] = q * (int)qstride + 2 * e;
+        q += STEP_Q; e += STEP_E;
+        if (e >= L2) { e -= L2; ++q; }
+      }
+#pragma unroll
+      for (int j = 0; j < CH; ++j) *reinterpret_cast<double2 *>(dst + go[j]) = v[j];
+    }
+  } else if (PAIRS) {
     constexpr int L2 = LEN / 2, STEP_Q = 32 / L2, STEP_E = 32 % L2;
     int q = lane / L2, e = lane - q * L2;
     for (; q < nq; ) {
@@ -206,7 +224,7 @@ __device__ __forceinline__ void sched_copy_out(const double *tile, int off, doub
   }
 }
 template <int KIND>
-__global__ void __launch_bounds__(kSchedThreads) lpv_schedule_kernel(const __grid_constant__ Params p, int *sched_err) {
+__global__ void __launch_bounds__(kSchedThreads, 8) lpv_schedule_kernel(const __grid_constant__ Params p, int *sched_err) {
   using T = SchedTile<KIND>;
   constexpr int NX = T::NX, NA = T::NA, NBm = T::NBm, STRIDE = T::STRIDE;
   __shared__ __align__(16) double tile_s[kSchedThreads / 32][32 * STRIDE];   // 27 KB: 8 CTAs = 16 warps per SM
@@ -693,8 +711,9 @@ int copy_threads() {
     if (const char *e = std::getenv("LPVMPC_COPY_THREADS")) { const int v = std::atoi(e); if (v >= 1) return v > 64 ? 64 : v; }
     int procs = 1;
     if (const char *e = std::getenv("LOCAL_WORLD_SIZE")) { const int v = std::atoi(e); if (v >= 1) procs = v; }
-    int t = omp_get_num_procs() / procs;
-    if (t > omp_get_max_threads()) t = omp_get_max_threads();
+    // not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to every rank, which made these copies serial
+    // (2.4 M instead of 3.0 M QP/s per rank end to end, profiles/r2q_*); the num_threads clause overrides it
+    const int t = omp_get_num_procs() / procs;
     return t < 1 ? 1 : (t > 8 ? 8 : t);
   }();
   return n;
