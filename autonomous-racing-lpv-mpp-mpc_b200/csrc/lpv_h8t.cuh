@@ -1119,28 +1119,39 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
   // separate loop used to store, so every product is formed in the same order); the cost norms are taken from the
   // registers of the scaling loop.  Both loops were chains of exposed shared-memory round trips (3 % of the kernel).
   double csc = 1.0, cp = 1.0;
+  // Likewise the column norms of a pass are taken while the previous pass scales the columns (every entry of column
+  // (k, r) is written by lane r in the scaling loop): max |P column| (before the pending cost scale) and max |A column|
+  // wait in two free stage vectors (DG: set by factor; B: set by reproject, re-zeroed below), and the norms of the
+  // single-variable rows go straight to sEti.  Only the first pass reads the columns.
+  double *sPC = c.V(V_DG), *sQA = c.V(V_B);
 #pragma unroll 1
   for (int it = 0; it < St.scaling; ++it) {
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
       const int o = k * 8 + r, ov = k * VS + r;
-      double pa = fabs(sPD[o] * cp);
-      if (c.ul) {
-        if (k < N - 1) pa = absmax(pa, sPO[o] * cp);
-        if (k > 0 && k < N) pa = absmax(pa, sPO[o - 8] * cp);
-      }
-      double qa = c.xl ? fabs(ED[ov]) : 0.0;
-      if (k < N) {
-        const double *gk = Gs + k * GS;
-#pragma unroll
-        for (int rr = 0; rr < NX; ++rr) qa = absmax(qa, gk[rr * 8 + c.co[rr >> 1]]);
-      }
-      if (c.has_in(k)) {
-#pragma unroll
-        for (int t = 0; t < NT; ++t) {
-          qa = absmax(qa, c.si(k, t));
-          sEti[c.ci(k, t)] = frsqrt(limit_scaling(fabs(c.si(k, t))));
+      double pa, qa;
+      if (it == 0) {
+        pa = fabs(sPD[o]);
+        if (c.ul) {
+          if (k < N - 1) pa = absmax(pa, sPO[o]);
+          if (k > 0 && k < N) pa = absmax(pa, sPO[o - 8]);
         }
+        qa = c.xl ? fabs(ED[ov]) : 0.0;
+        if (k < N) {
+          const double *gk = Gs + k * GS;
+#pragma unroll
+          for (int rr = 0; rr < NX; ++rr) qa = absmax(qa, gk[rr * 8 + c.co[rr >> 1]]);
+        }
+        if (c.has_in(k)) {
+#pragma unroll
+          for (int t = 0; t < NT; ++t) {
+            qa = absmax(qa, c.si(k, t));
+            sEti[c.ci(k, t)] = frsqrt(limit_scaling(fabs(c.si(k, t))));
+          }
+        }
+      } else {
+        pa = sPC[ov] * cp;   // max |x| * cp == max |x * cp| (cp > 0, rounding is monotone)
+        qa = sQA[ov];
       }
       sDt[o] = frsqrt(limit_scaling(pa > qa ? pa : qa));
       double ea = c.xl ? fabs(ED[ov]) : 0.0;
@@ -1157,22 +1168,31 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
     for (int k = 0; k <= N; ++k) {
       const int o = k * 8 + r, ov = k * VS + r;
       const double dt = sDt[o];
-      double npo = 0.0;
+      double npo = 0.0, qan = 0.0;   // qan: max |entry| of my column of A after this pass
       if (k < N) {
         double *gk = Gs + k * GS;
 #pragma unroll
-        for (int rr = 0; rr < NX; ++rr) { double *e = gk + rr * 8 + c.co[rr >> 1]; *e = (*e * sEt[(k + 1) * 8 + rr]) * dt; }
+        for (int rr = 0; rr < NX; ++rr) {
+          double *e = gk + rr * 8 + c.co[rr >> 1];
+          const double g = (*e * sEt[(k + 1) * 8 + rr]) * dt;
+          *e = g;
+          qan = absmax(qan, g);
+        }
         if (k < N - 1 && c.ul) { npo = ((sPO[o] * cp) * dt) * sDt[o + 8]; sPO[o] = npo; }
       }
       if (c.has_in(k)) {
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
           const int oc = c.ci(k, t);
-          c.si(k, t) = (c.si(k, t) * sEti[oc]) * dt;
-          sEI[oc] = sEI[oc] * sEti[oc];
+          const double et = sEti[oc], sn = (c.si(k, t) * et) * dt;
+          c.si(k, t) = sn;
+          sEI[oc] = sEI[oc] * et;
+          qan = absmax(qan, sn);
+          sEti[oc] = frsqrt(limit_scaling(fabs(sn)));   // next pass's norm of this one-entry row
         }
       }
-      if (c.xl) ED[ov] = (ED[ov] * sEt[o]) * dt;
+      if (c.xl) { const double en = (ED[ov] * sEt[o]) * dt; ED[ov] = en; qan = absmax(qan, en); }
+      sQA[ov] = qan;
       const double npd = ((sPD[o] * cp) * dt) * dt;
       sPD[o] = npd;
       const double nq = dt * (QV[ov] * cp);
@@ -1186,6 +1206,7 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
         if (k > 0 && k < N) pc = absmax(pc, npo_prev);
       }
       if (c.var_live(k)) { ct += pc; qn = absmax(qn, nq); }
+      sPC[ov] = pc;
       npo_prev = npo;
     }
     __syncwarp();
@@ -1238,6 +1259,7 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
       cQ[o] = c.var_live(k) ? q : 0.0; cBE[o] = e * be; cED[o] = ed; cYD[o] = 0.0; cDI[o] = 1.0 / d; cEI[o] = 1.0 / e;
       if (c.ul) c.pm(k, ucomp) = (k > 0 && k < N) ? sPO[o - 8] : 0.0;   // couples u_{k-1}, u_k
       c.V(V_XS)[ov] = 0.0;   // the scratch homes become hot vectors (R, CR, B are set by reproject, DG by factor)
+      c.V(V_B)[ov] = 0.0;
     }
     __syncwarp();
   }
