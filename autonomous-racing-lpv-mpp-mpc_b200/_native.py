@@ -11,8 +11,9 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "liblpvmpc.so")
+HASH_PATH = os.path.join(_PKG, "liblpvmpc.srchash")
 _SRC_DIR = os.path.join(_PKG, "csrc")
-_SOURCES = [os.path.join(_SRC_DIR, f) for f in ("lpvmpc.cu", "lpv_qp.cuh", "lpv_t8.cuh", "lpv_g8.cuh", "lpv_h8.cuh", "lpv_h8t.cuh", "lpv_model.cuh", "lpv_loop.cuh")] + \
+_SOURCES = [os.path.join(_SRC_DIR, f) for f in ("lpvmpc.cu", "lpv_qp.cuh", "lpv_h8.cuh", "lpv_h8t.cuh", "lpv_model.cuh", "lpv_loop.cuh")] + \
            [os.path.join(_ROOT, "include", "lpvmpc.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
@@ -107,24 +108,47 @@ def _nvcc():
     return None
 
 
+def _source_hash():
+    """sha256 over the sources and the build flags: what the built library is checked against (mtimes do not survive
+    the copy to a GPU box, content does)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for s in _SOURCES:
+        with open(s, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def is_stale():
+    if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
+        return True
+    with open(HASH_PATH) as fh:
+        return fh.read().strip() != _source_hash()
+
+
 def build(force=False, verbose=False):
-    """Compile csrc/lpvmpc.cu for sm_100a into liblpvmpc.so (in-tree) when missing or stale."""
-    stale = force or not os.path.exists(LIB_PATH)
-    if not stale:
-        t = os.path.getmtime(LIB_PATH)
-        stale = any(os.path.getmtime(s) > t for s in _SOURCES)
-    if not stale:
+    """Compile csrc/lpvmpc.cu for sm_100a into liblpvmpc.so (in-tree) when it is missing or was built from other
+    sources (content hash kept beside it in liblpvmpc.srchash)."""
+    if not force and not is_stale():
         return LIB_PATH
     nvcc = _nvcc()
     if nvcc is None:
         raise RuntimeError("liblpvmpc.so is missing/stale and nvcc was not found; there is no CPU fallback")
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(_ROOT, "include"), "-o", LIB_PATH, os.path.join(_SRC_DIR, "lpvmpc.cu")]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    env = dict(os.environ)
-    env.pop("CC", None)
-    env.pop("CXX", None)
-    subprocess.check_call(cmd, env=env)
+    import fcntl
+    with open(LIB_PATH + ".lock", "w") as lock:     # ranks of one node may arrive here together
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if force or is_stale():
+            tmp = LIB_PATH + ".tmp.%d" % os.getpid()
+            cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(_ROOT, "include"), "-o", tmp, os.path.join(_SRC_DIR, "lpvmpc.cu")]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            env = dict(os.environ)
+            env.pop("CC", None)
+            env.pop("CXX", None)
+            subprocess.check_call(cmd, env=env)
+            os.replace(tmp, LIB_PATH)
+            with open(HASH_PATH, "w") as fh:
+                fh.write(_source_hash() + "\n")
     return LIB_PATH
 
 
@@ -133,8 +157,7 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        build()
+    build()   # no-op unless the library is missing or its sources changed since it was built
     L = C.CDLL(LIB_PATH)
     L.lpvmpc_abi_version.restype = C.c_int
     L.lpvmpc_device_count.restype = C.c_int

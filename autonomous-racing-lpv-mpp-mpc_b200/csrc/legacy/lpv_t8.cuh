@@ -14,7 +14,7 @@
 #include <math.h>
 #include <stdint.h>
 
-#include "lpv_qp.cuh"
+#include "../lpv_qp.cuh"
 
 namespace lpv {
 namespace t8 {

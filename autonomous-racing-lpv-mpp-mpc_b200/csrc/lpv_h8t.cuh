@@ -891,7 +891,7 @@ __device__ __noinline__ int check_termination(const Ctx<KIND> c, const lpvmpc_se
                                              const double rho_eq, const int last_was_first, const bool have_prev) {
   Info &I = *ip;
   double eps_abs = S.eps_abs, eps_rel = S.eps_rel, eps_pi = S.eps_prim_inf, eps_di = S.eps_dual_inf;
-  const bool ncvx = (I.pri_res > kInfty) || (I.dua_res > kInfty);
+  const bool ncvx = !(I.pri_res <= kInfty) || !(I.dua_res <= kInfty);   // also NaN
   if (approximate) { eps_abs *= 10; eps_rel *= 10; eps_pi *= 10; eps_di *= 10; }
   const double eps_prim = eps_abs + eps_rel * (I.u_z > I.u_Ax ? I.u_z : I.u_Ax);
   const bool prim_ok = I.pri_res < eps_prim;
@@ -955,6 +955,8 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
         double row[8];
 #pragma unroll
         for (int cc = 0; cc < 8; ++cc) row[cc] = (cc < NX) ? -Ar[cc < NX ? cc : 0] : ((cc < NB) ? -Br[cc - NX < 2 ? cc - NX : 0] : 0.0);
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) if (notfinite(row[cc])) data_err = 1;
         double *gk = Gs + k * GS;
 #pragma unroll
         for (int j = 0; j < 4; ++j) st2(gk + c.ro[j], row[2 * j], row[2 * j + 1]);
@@ -1010,6 +1012,7 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
           }
         }
         row[cc] = v;
+        if (notfinite(v)) data_err = 1;   // e.g. vx = 0 or 1 - ey kappa = 0 in the stage matrices
       }
       if (c.xl) {
         double *gk = Gs + k * GS;
@@ -1063,6 +1066,7 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
         else q = (k == 0) ? -2 * (uold * dRc) : 0.0;
         po = (k < N - 1) ? 2 * (-dRc) : 0.0;
       }
+      if (notfinite(q) || notfinite(be)) data_err = 1;   // NaN / inf in x0, C, vel_ref or u_old
       sPD[o] = pd; sPO[o] = po; QV[ov] = q; BE[ov] = be; ED[ov] = ed;
       sD[o] = 1.0; sE[o] = 1.0; sEI[o] = 1.0; sEti[o] = 1.0;
       X[ov] = 0.0; BV[ov] = 0.0;
@@ -1101,9 +1105,9 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
               if (r == 3 && a.ey_hi) up = a.ey_hi[(size_t)b * (N + 1) + k];
             } else { lo = ucomp ? -0.7 : -0.249; up = ucomp ? 2.0 : 0.249; }
           }
-          lo = (lo > -kInfty) ? lo : -kInfty;  // python wrapper: l = max(l, -OSQP_INFTY), u = min(u, OSQP_INFTY)
-          up = (up < kInfty) ? up : kInfty;
-          if (lo > up) data_err = 1;
+          lo = (lo > -kInfty || lo != lo) ? lo : -kInfty;  // python wrapper: l = max(l, -OSQP_INFTY), u = min(u, OSQP_INFTY); NaN stays NaN
+          up = (up < kInfty || up != up) ? up : kInfty;
+          if (!(lo <= up)) data_err = 1;   // l > u or a NaN bound
           c.si(k, t) = si; c.ui(k, t) = up; c.zi(k, t) = 0.0; c.yi(k, t) = 0.0;
           if (KIND == LPVMPC_PLANNER) c.li(k, t) = lo;
         }

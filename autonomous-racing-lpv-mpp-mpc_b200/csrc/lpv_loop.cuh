@@ -330,7 +330,7 @@ __device__ __forceinline__ double wrap_angle(double a) {   // trackInitializatio
 // Map.getGlobalPosition(s, 0) (trackInitialization.py:205-260); err when no unique segment holds s
 __device__ __forceinline__ void global_position0(const double *__restrict__ track, int nseg, double s, double *out, int &err) {
   const double TrackLength = track[(nseg - 1) * 6 + 3] + track[(nseg - 1) * 6 + 4];
-  if (!(s == s) || s > 1e300) { err = 1; out[0] = out[1] = out[2] = nan(""); return; }
+  if (!(s <= kMaxLaps * TrackLength)) { err = 1; out[0] = out[1] = out[2] = nan(""); return; }   // NaN / runaway arc length (lpv_model.cuh)
   while (s > TrackLength) s = s - TrackLength;
   int i = -1, cnt = 0;
   for (int k = 0; k < nseg; ++k)

@@ -23,10 +23,17 @@ struct Model {
   int delay;
 };
 
-// utilities.py:36-48.  Returns NaN and sets err when no unique segment holds s (the reference raises).
+// Laps the arc-length reduction `while s > TrackLength: s -= TrackLength` (utilities.py:40-41) may take on the device.
+// The reference's loop is unbounded (and never ends once s - TrackLength == s); one such element would stall a whole
+// batch kernel, so beyond this many laps the element is a schedule error instead.  Below it the subtract loop is kept
+// as written: bit parity with the reference / oracle.
+constexpr double kMaxLaps = 1.0e4;
+
+// utilities.py:36-48.  Returns NaN and sets err when no unique segment holds s (the reference raises), when s is not
+// finite, or when it is more than kMaxLaps track lengths (lpvmpc_create guarantees 0 < TrackLength < inf).
 __device__ __forceinline__ double curvature(const double *__restrict__ track, int nseg, double s, int &err) {
   const double track_len = track[(nseg - 1) * 6 + 3] + track[(nseg - 1) * 6 + 4];
-  if (!(s == s) || s > 1e300) { err = 1; return nan(""); }
+  if (!(s <= kMaxLaps * track_len)) { err = 1; return nan(""); }   // also NaN
   while (s > track_len) s = s - track_len;
   int found = -1, cnt = 0;
   for (int i = 0; i < nseg; ++i) {

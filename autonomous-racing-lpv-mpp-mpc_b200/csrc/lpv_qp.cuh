@@ -109,6 +109,9 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 __device__ __forceinline__ int warp_or(int v) { return __any_sync(kFull, v); }
 __device__ __forceinline__ double absmax(double mx, double v) { const double a = fabs(v); return (a > mx) ? a : mx; }
+// NaN or +-inf.  absmax() and the clamps drop NaN (every comparison with it is false), so problem data is screened once,
+// when it is built: a non-finite entry makes the QP a LPVMPC_DATA_ERROR instead of a "solved" all-NaN answer.
+__device__ __forceinline__ bool notfinite(double v) { return !(fabs(v) <= 1.7976931348623157e308); }
 __device__ __forceinline__ double limit_scaling(double v) {
   v = v < kMinScaling ? 1.0 : v;
   v = v > kMaxScaling ? kMaxScaling : v;
@@ -264,17 +267,19 @@ struct QP {
         }
       }
       // python wrapper: l = max(l, -OSQP_INFTY), u = min(u, OSQP_INFTY)
-      lo[L.md + s] = (l_ > -kInfty) ? l_ : -kInfty;
-      up[L.md + s] = (u_ < kInfty) ? u_ : kInfty;
+      lo[L.md + s] = (l_ > -kInfty || l_ != l_) ? l_ : -kInfty;   // a NaN bound stays NaN: bounds_invalid() reports it
+      up[L.md + s] = (u_ < kInfty || u_ != u_) ? u_ : kInfty;
     }
     __syncwarp();
   }
 
   // l > u anywhere => upstream osqp.setup() rejects the problem
   __device__ bool bounds_invalid() const {
-    const double *lo = w + L.l, *up = w + L.u;
+    const double *lo = w + L.l, *up = w + L.u, *q = w + L.q, *G = w + L.G;
     int bad = 0;
-    for (int i = lane; i < L.m; i += 32) bad |= (lo[i] > up[i]);
+    for (int i = lane; i < L.m; i += 32) bad |= !(lo[i] <= up[i]);   // l > u, or a NaN bound / x0 / C
+    for (int j = lane; j < L.nz; j += 32) bad |= notfinite(q[j]);
+    for (int e = lane; e < L.N * NX * NB; e += 32) bad |= notfinite(G[e]);
     return warp_or(bad);
   }
 
@@ -679,7 +684,7 @@ __device__ void admm_run(QP<KIND> &qp, const lpvmpc_settings &S, double c, Outco
   // returns 1 when a termination status was set
   auto check_termination = [&](int approximate) -> int {
     double eps_abs = S.eps_abs, eps_rel = S.eps_rel, eps_pi = S.eps_prim_inf, eps_di = S.eps_dual_inf;
-    if ((pri_res > kInfty) || (dua_res > kInfty)) { status = LPVMPC_NON_CVX; out.obj = nan(""); return 1; }
+    if (!(pri_res <= kInfty) || !(dua_res <= kInfty)) { status = LPVMPC_NON_CVX; out.obj = nan(""); return 1; }
     if (approximate) { eps_abs *= 10; eps_rel *= 10; eps_pi *= 10; eps_di *= 10; }
     bool prim_ok = false, dual_ok = false, prim_inf = false, dual_inf = false;
     if (L.m == 0) prim_ok = true;

@@ -15,8 +15,10 @@
 #include "lpvmpc.h"
 #include "lpv_model.cuh"
 #include "lpv_qp.cuh"
-#include "lpv_t8.cuh"
-#include "lpv_g8.cuh"
+#ifdef LPVMPC_LEGACY   // earlier kernel generations (variants 2, 3, 4): A/B measurements only, not in the product build
+#include "legacy/lpv_t8.cuh"
+#include "legacy/lpv_g8.cuh"
+#endif
 #include "lpv_h8.cuh"
 #include "lpv_h8t.cuh"
 #include "lpv_loop.cuh"
@@ -409,6 +411,7 @@ Layout make_layout(int kind, int N, int delay) {
   return L;
 }
 
+#ifdef LPVMPC_LEGACY
 lpv::g8::Lay make_g8_layout(int kind, int N) {
   const int NX = kind == LPVMPC_CONTROLLER ? 6 : 5;
   lpv::g8::Lay L;
@@ -424,6 +427,7 @@ lpv::g8::Lay make_g8_layout(int kind, int N) {
   L.cold_total = lpv::g8::C_COUNT * v;
   return L;
 }
+#endif
 
 // ring = 0: block factor resident in shared memory; ring = 4 (lpv::h8::kRing): factor in the slab, staged through a ring
 // of stage blocks by TMA bulk copies issued lpv::h8::kAhead stage steps ahead
@@ -484,7 +488,9 @@ struct lpvmpc_handle {
   double *d_track = nullptr;
   double *d_gws = nullptr;
   int variant = 1;           // 1: generic warp-per-QP kernel, 2: T8 register/shared-resident kernel, 3: G8 compact kernel
+#ifdef LPVMPC_LEGACY
   lpv::g8::Lay GL;           // G8 shared-memory layout
+#endif
   lpv::h8::Lay HL;           // H8 layout (shared memory + slab)
   lpv::h8t::Lay TL;          // H8T layout (tensor memory + shared memory + slab)
   int wpc = 1;               // H8: warps per CTA
@@ -498,6 +504,11 @@ struct lpvmpc_handle {
   bool zc_in = false;          // host API: the kernel reads its inputs from the pinned arena (LPVMPC_ZERO_COPY_IN=1; measured equal to the H2D copy at ctrl4096, off by default)
   bool zc_out = true;          // host API: the kernel writes its results straight into the pinned arena (LPVMPC_ZERO_COPY_OUT=0: D2H copy)
   cudaStream_t stream = nullptr;
+  // The _dev entry points launch on the caller's stream but share per-handle device scratch (work queue, visiting order,
+  // slab, loop buffers): a call arriving on another stream than the previous one first waits for that one's work.
+  cudaEvent_t last_ev = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool last_valid = false;
   long long launches = 0;
   std::string err;
   // closed-loop fleet (lpvmpc_loop_*)
@@ -531,6 +542,49 @@ int fail(lpvmpc_handle *h, int code, const std::string &msg) {
       return fail(h, LPVMPC_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));     \
   } while (0)
 
+// Restores the calling thread's current device on every return path (a process that drives several GPUs keeps its own
+// current device; torch's allocator and default stream follow it).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err;
+  explicit DeviceGuard(int dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard &) = delete;
+  DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+#define ON_DEVICE(h)                                                                           \
+  DeviceGuard dev_guard__((h)->device);                                                        \
+  if (dev_guard__.err != cudaSuccess)                                                          \
+    return fail(h, LPVMPC_E_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(dev_guard__.err))
+
+// Stream hand-over of the per-handle scratch (see lpvmpc_handle::last_ev).
+int stream_enter(lpvmpc_handle *h, cudaStream_t s) {
+  if (h->last_valid && h->last_stream != s) CUDA_TRY(h, cudaStreamWaitEvent(s, h->last_ev, 0));
+  return LPVMPC_OK;
+}
+int stream_leave(lpvmpc_handle *h, cudaStream_t s) {
+  CUDA_TRY(h, cudaEventRecord(h->last_ev, s));
+  h->last_stream = s; h->last_valid = true;
+  return LPVMPC_OK;
+}
+
+const char *settings_error(const lpvmpc_settings *s) {
+  if (s->max_iter < 1) return "settings: max_iter must be >= 1";
+  if (!(s->rho > 0) || !(s->sigma > 0) || !(s->delta > 0)) return "settings: rho, sigma and delta must be > 0";
+  if (!(s->alpha > 0) || !(s->alpha < 2)) return "settings: alpha must be in (0, 2)";
+  if (!(s->eps_abs >= 0) || !(s->eps_rel >= 0) || !(s->eps_prim_inf > 0) || !(s->eps_dual_inf > 0)) return "settings: negative / NaN tolerance";
+  if (s->check_termination < 0 || s->scaling < 0 || s->polish_refine_iter < 0 || s->adaptive_rho_interval < 0)
+    return "settings: check_termination, scaling, polish_refine_iter and adaptive_rho_interval must be >= 0";
+  if (s->adaptive_rho && !(s->adaptive_rho_tolerance >= 1)) return "settings: adaptive_rho_tolerance must be >= 1";
+  return nullptr;
+}
+
 Params make_params(const lpvmpc_handle *h, int B, const lpvmpc_args *a) {
   Params p;
   p.L = h->L; p.M = h->M; p.S = h->cfg.settings; p.a = *a; p.B = B; p.gws = h->d_gws;
@@ -559,6 +613,7 @@ int validate_args(lpvmpc_handle *h, int B, const lpvmpc_args *a, bool solve) {
   return LPVMPC_OK;
 }
 
+#ifdef LPVMPC_LEGACY
 constexpr int kT8N = 8;
 
 int launch_t8(lpvmpc_handle *h, const Params &p, cudaStream_t s) {
@@ -597,6 +652,7 @@ int launch_g8(lpvmpc_handle *h, const Params &p, cudaStream_t s) {
   CUDA_TRY(h, cudaGetLastError());
   return LPVMPC_OK;
 }
+#endif  // LPVMPC_LEGACY
 
 // controller batches: the grouped visiting order (NULL when the caller wants the batch order or it does not apply)
 const int *batch_order(lpvmpc_handle *h, const Params &p, cudaStream_t s) {
@@ -661,8 +717,10 @@ int launch_h8t(lpvmpc_handle *h, const Params &p, cudaStream_t s) {
 template <int KIND>
 int launch_solve(lpvmpc_handle *h, const Params &p, cudaStream_t s) {
   if (h->variant == 6) return launch_h8t(h, p, s);
+#ifdef LPVMPC_LEGACY
   if (h->variant == 2) return launch_t8(h, p, s);
   if (h->variant == 3) return launch_g8<KIND>(h, p, s);
+#endif
   if (h->variant == 5) return launch_h8<KIND>(h, p, s);
   const int grid = p.B < h->grid_cap ? p.B : h->grid_cap;
   if (grid == 0) return LPVMPC_OK;
@@ -778,6 +836,16 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
   if (!cfg->track || cfg->n_track_seg < 1) return fail(nullptr, LPVMPC_E_ARG, "track table required");
   if (cfg->steering_delay < 0 || cfg->steering_delay > cfg->N || (cfg->kind == LPVMPC_PLANNER && cfg->steering_delay))
     return fail(nullptr, LPVMPC_E_ARG, "bad steering_delay");
+  if (const char *why = settings_error(&cfg->settings)) return fail(nullptr, LPVMPC_E_ARG, why);
+  {
+    // Curvature() reduces s modulo TrackLength = start + length of the last segment: it must be a positive finite number
+    const double *last = cfg->track + 6 * (size_t)(cfg->n_track_seg - 1);
+    const double track_len = last[3] + last[4];
+    if (!(track_len > 0.0) || !(track_len <= 1e300)) return fail(nullptr, LPVMPC_E_ARG, "track table: TrackLength must be positive and finite");
+    for (int i = 0; i < 6 * cfg->n_track_seg; ++i)
+      if (!(cfg->track[i] == cfg->track[i])) return fail(nullptr, LPVMPC_E_ARG, "track table holds NaN");
+  }
+  if (!(cfg->dt > 0.0)) return fail(nullptr, LPVMPC_E_ARG, "dt must be > 0");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();
@@ -798,32 +866,39 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
     cudaError_t e__ = (expr);                                                                        \
     if (e__ != cudaSuccess) { h->err = std::string(#expr) + ": " + cudaGetErrorString(e__); return bail(LPVMPC_E_CUDA); } \
   } while (0)
-  CTRY(cudaSetDevice(h->device));
+  DeviceGuard dev_guard(h->device);
+  CTRY(dev_guard.err);
   cudaDeviceProp prop;
   CTRY(cudaGetDeviceProperties(&prop, h->device));
   if (prop.major < 10) { h->err = "built for sm_100a (B200); device is older"; return bail(LPVMPC_E_UNSUPPORTED); }
   h->sm_count = prop.multiProcessorCount;
   h->smem_optin = (int)prop.sharedMemPerBlockOptin;
   {
-    // T8 kernel: controller, N = 8, no steering delay, diagonal Q and R
-    bool diag = true;
-    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) if (i != j && cfg->Q[i * 6 + j] != 0.0) diag = false;
-    if (cfg->R[1] != 0.0 || cfg->R[2] != 0.0) diag = false;
-    const bool eligible = cfg->kind == LPVMPC_CONTROLLER && cfg->N == kT8N && cfg->steering_delay == 0 && diag;
-    if ((cfg->variant == 2 || cfg->variant == 4) && !eligible) { h->err = "variants 2/4 (T8) need controller, N=8, steering_delay=0, diagonal Q and R"; return bail(LPVMPC_E_UNSUPPORTED); }
-    h->variant = (cfg->variant == 1 || !eligible) ? 1 : 2;
-    h->qpw = (cfg->variant == 4) ? 2 : 4;
-    // G8 kernel: diagonal Q and R, no steering delay, per-QP state fits shared memory; planner rows use 64-bit stage masks
+    // the specialised kernels need diagonal Q and R and no steering delay; planner rows use 64-bit stage masks (N <= 63)
     bool pdiag = true;
     const int nxk = cfg->kind == LPVMPC_CONTROLLER ? 6 : 5;
     for (int i = 0; i < nxk; ++i) for (int j = 0; j < nxk; ++j) if (i != j && cfg->Q[i * nxk + j] != 0.0) pdiag = false;
     if (cfg->R[1] != 0.0 || cfg->R[2] != 0.0) pdiag = false;
-    h->GL = make_g8_layout(cfg->kind, cfg->N);
-    const size_t per_qp = (size_t)h->GL.total * sizeof(double);
-    const bool g8_ok = pdiag && cfg->steering_delay == 0 && per_qp <= (size_t)h->smem_optin &&
-                       (cfg->kind == LPVMPC_CONTROLLER || cfg->N <= 63);
-    if (cfg->variant == 3 && !g8_ok) { h->err = "variant 3 (G8) needs diagonal Q and R, steering_delay=0, planner N<=63 and a per-QP state that fits shared memory"; return bail(LPVMPC_E_UNSUPPORTED); }
-    if (cfg->variant == 3) h->variant = 3;
+    h->variant = 1;
+#ifdef LPVMPC_LEGACY
+    {
+      // T8 kernel: controller, N = 8, no steering delay, diagonal Q and R
+      const bool eligible = cfg->kind == LPVMPC_CONTROLLER && cfg->N == kT8N && cfg->steering_delay == 0 && pdiag;
+      if ((cfg->variant == 2 || cfg->variant == 4) && !eligible) { h->err = "variants 2/4 (T8) need controller, N=8, steering_delay=0, diagonal Q and R"; return bail(LPVMPC_E_UNSUPPORTED); }
+      if (cfg->variant == 2 || cfg->variant == 4) h->variant = 2;
+      h->qpw = (cfg->variant == 4) ? 2 : 4;
+      // G8 kernel: per-QP state fits shared memory
+      h->GL = make_g8_layout(cfg->kind, cfg->N);
+      const size_t per_qp = (size_t)h->GL.total * sizeof(double);
+      const bool g8_ok = pdiag && cfg->steering_delay == 0 && per_qp <= (size_t)h->smem_optin &&
+                         (cfg->kind == LPVMPC_CONTROLLER || cfg->N <= 63);
+      if (cfg->variant == 3 && !g8_ok) { h->err = "variant 3 (G8) needs diagonal Q and R, steering_delay=0, planner N<=63 and a per-QP state that fits shared memory"; return bail(LPVMPC_E_UNSUPPORTED); }
+      if (cfg->variant == 3) h->variant = 3;
+    }
+#else
+    if (cfg->variant >= 2 && cfg->variant <= 4) { h->err = "variants 2-4 (T8 / G8, earlier kernel generations) are only in builds with -DLPVMPC_LEGACY"; return bail(LPVMPC_E_UNSUPPORTED); }
+#endif
+    if (cfg->variant < 0 || cfg->variant > 8) { h->err = "unknown kernel variant"; return bail(LPVMPC_E_ARG); }
     // H8 kernel: same restrictions as G8, smaller shared-memory footprint (cold data in an L2 slab)
     h->HL = make_h8_layout(cfg->kind, cfg->N, 0);
     const bool h8_ok = pdiag && cfg->steering_delay == 0 && (size_t)h->HL.total * sizeof(double) + 1024 <= (size_t)h->smem_optin &&
@@ -846,7 +921,7 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
     const size_t h8t_bytes = (size_t)h->TL.total * sizeof(double) * 16 + 4 * 512 + 512;
     const bool h8t_ok = pdiag && cfg->steering_delay == 0 && cfg->kind == LPVMPC_CONTROLLER && 60 * cfg->N + 28 <= 512 &&
                         h8t_bytes + 64 <= (size_t)h->smem_optin;
-    if (cfg->variant == 6 && !h8t_ok) { h->err = "variant 6 (H8T) needs controller, diagonal Q and R, steering_delay=0, N<=10"; return bail(LPVMPC_E_UNSUPPORTED); }
+    if (cfg->variant == 6 && !h8t_ok) { h->err = "variant 6 (H8T) needs controller, diagonal Q and R, steering_delay=0, N<=8 (60 N + 28 tensor-memory columns <= 512)"; return bail(LPVMPC_E_UNSUPPORTED); }
     if (cfg->variant == 6 || (cfg->variant == 0 && h8t_ok)) h->variant = 6;
   }
   h->ws_bytes = (size_t)h->L.total * sizeof(double);
@@ -896,6 +971,7 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
     else CTRY(ctrl ? (h8_attr<LPVMPC_CONTROLLER, 1>(h->ws_bytes)) : (h8_attr<LPVMPC_PLANNER, 1>(h->ws_bytes)));
     CTRY(cudaMalloc(&h->d_queue, sizeof(unsigned)));
     CTRY(cudaMalloc(&h->d_cold, sizeof(double) * (size_t)h->grid_cap * h->wpc * h->qpw * h->HL.cold_total));
+#ifdef LPVMPC_LEGACY
   } else if (h->variant == 3) {
     const size_t per_qp = (size_t)h->GL.total * sizeof(double);
     h->qpw = (4 * per_qp <= (size_t)h->smem_optin) ? 4 : ((2 * per_qp <= (size_t)h->smem_optin) ? 2 : 1);
@@ -923,6 +999,7 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
     else CTRY((cudaFuncSetAttribute(lpv::t8::lpv_solve_t8_kernel<kT8N, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ws_bytes)));
     CTRY(cudaMalloc(&h->d_queue, sizeof(unsigned)));
     CTRY(cudaMalloc(&h->d_cold, sizeof(double) * (size_t)h->grid_cap * 32 * lpv::t8::Cold<kT8N>::TOTAL));
+#endif
   } else if (h->smem_mode) {
     int per_sm = (int)(prop.sharedMemPerMultiprocessor / (h->ws_bytes + 1024));
     if (per_sm < 1) per_sm = 1;
@@ -941,6 +1018,7 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
   CTRY(cudaMalloc(&h->d_track, sizeof(double) * 6 * (size_t)cfg->n_track_seg));
   CTRY(cudaMemcpy(h->d_track, cfg->track, sizeof(double) * 6 * (size_t)cfg->n_track_seg, cudaMemcpyHostToDevice));
   CTRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CTRY(cudaEventCreateWithFlags(&h->last_ev, cudaEventDisableTiming));
   lpv::Model &M = h->M;
   M.dt = cfg->dt; M.lf = cfg->lf; M.lr = cfg->lr; M.m = cfg->m; M.Iz = cfg->Iz; M.Cf = cfg->Cf; M.Cr = cfg->Cr; M.mu = cfg->mu;
   M.max_vel = cfg->max_vel; M.min_vel = cfg->min_vel;
@@ -963,8 +1041,9 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
 
 void lpvmpc_destroy(lpvmpc_handle *h) {
   if (!h) return;
-  cudaSetDevice(h->device);
+  DeviceGuard dev_guard(h->device);
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->last_ev) cudaEventDestroy(h->last_ev);
   cudaFree(h->d_perm);
   cudaFree(h->d_track); cudaFree(h->d_gws); cudaFree(h->d_stage); cudaFree(h->d_queue); cudaFree(h->d_cold);
   cudaFree(h->d_loop); cudaFree(h->d_ploop); cudaFree(h->d_refs_W);
@@ -986,9 +1065,7 @@ int lpvmpc_get_info(const lpvmpc_handle *h, lpvmpc_info *info) {
 
 int lpvmpc_update_settings(lpvmpc_handle *h, const lpvmpc_settings *s) {
   if (!h || !s) return LPVMPC_E_ARG;
-  if (s->max_iter < 1 || s->rho <= 0 || s->sigma <= 0 || s->alpha <= 0 || s->alpha >= 2 || s->check_termination < 0 ||
-      s->scaling < 0 || s->delta <= 0 || s->polish_refine_iter < 0)
-    return fail(h, LPVMPC_E_ARG, "invalid settings");
+  if (const char *why = settings_error(s)) return fail(h, LPVMPC_E_ARG, why);
   h->cfg.settings = *s;
   return LPVMPC_OK;
 }
@@ -996,10 +1073,12 @@ int lpvmpc_update_settings(lpvmpc_handle *h, const lpvmpc_settings *s) {
 int lpvmpc_solve_dev(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, void *stream) {
   int rc = validate_args(h, B, a, true);
   if (rc) return rc;
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
+  if ((rc = stream_enter(h, (cudaStream_t)stream))) return rc;
   const Params p = make_params(h, B, a);
-  return h->cfg.kind == LPVMPC_CONTROLLER ? launch_solve<LPVMPC_CONTROLLER>(h, p, (cudaStream_t)stream)
-                                          : launch_solve<LPVMPC_PLANNER>(h, p, (cudaStream_t)stream);
+  rc = h->cfg.kind == LPVMPC_CONTROLLER ? launch_solve<LPVMPC_CONTROLLER>(h, p, (cudaStream_t)stream)
+                                        : launch_solve<LPVMPC_PLANNER>(h, p, (cudaStream_t)stream);
+  return rc ? rc : stream_leave(h, (cudaStream_t)stream);
 }
 
 int lpvmpc_schedule_dev(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, int32_t *sched_err, void *stream) {
@@ -1007,7 +1086,8 @@ int lpvmpc_schedule_dev(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, int32
   if (rc) return rc;
   if (a->sched_mode == LPVMPC_SCHED_GIVEN) return fail(h, LPVMPC_E_ARG, "schedule needs PREDICT or ESTIMATE");
   if (B == 0) return LPVMPC_OK;
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
+  if ((rc = stream_enter(h, (cudaStream_t)stream))) return rc;
   const Params p = make_params(h, B, a);
   static const bool naive = [] { const char *e = std::getenv("LPVMPC_SCHED_NAIVE"); return e && std::atoi(e) != 0; }();
   // the tiled kernel stores 16-byte pieces: output arrays that are only 8-byte aligned take the plain kernel
@@ -1018,14 +1098,14 @@ int lpvmpc_schedule_dev(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, int32
     else lpv::lpv_schedule_naive_kernel<LPVMPC_PLANNER><<<g, 128, 0, (cudaStream_t)stream>>>(p, sched_err);
     ++h->launches;
     CUDA_TRY(h, cudaGetLastError());
-    return LPVMPC_OK;
+    return stream_leave(h, (cudaStream_t)stream);
   }
   const int grid = (B + lpv::kSchedThreads - 1) / lpv::kSchedThreads;
   if (h->cfg.kind == LPVMPC_CONTROLLER) lpv::lpv_schedule_kernel<LPVMPC_CONTROLLER><<<grid, lpv::kSchedThreads, 0, (cudaStream_t)stream>>>(p, sched_err);
   else lpv::lpv_schedule_kernel<LPVMPC_PLANNER><<<grid, lpv::kSchedThreads, 0, (cudaStream_t)stream>>>(p, sched_err);
   ++h->launches;
   CUDA_TRY(h, cudaGetLastError());
-  return LPVMPC_OK;
+  return stream_leave(h, (cudaStream_t)stream);
 }
 
 // Host-pointer variants: pack every non-NULL input into one pinned arena, one H2D, kernel, one D2H.
@@ -1033,7 +1113,7 @@ static int run_host(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, int32_t *
   int rc = validate_args(h, B, a, solve);
   if (rc) return rc;
   if (B == 0) return LPVMPC_OK;
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   lpvmpc_args dev = *a;
   const std::vector<Field> fields = staged_fields(h);
   size_t off = 0, in_end = 0, out_begin = 0;
@@ -1093,8 +1173,9 @@ int lpvmpc_loop_init_dev(lpvmpc_handle *h, int32_t B, const lpvmpc_loop_cfg *c, 
     return fail(h, LPVMPC_E_UNSUPPORTED, "the closed loop needs a controller handle with N <= 20 and steering_delay = 0");
   if (B < 1 || B > h->cfg.max_batch) return fail(h, LPVMPC_E_ARG, "fleet size must be in [1, max_batch]");
   if (c->substeps < 0 || c->warmup_ticks < 0 || !(c->sim_dt > 0)) return fail(h, LPVMPC_E_ARG, "bad loop cfg");
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   cudaStream_t s = (cudaStream_t)stream;
+  if (int rc = stream_enter(h, s)) return rc;
   const int N = h->L.N;
   const size_t D = sizeof(double), mb = (size_t)h->cfg.max_batch;
   if (!h->d_loop) {
@@ -1141,7 +1222,7 @@ int lpvmpc_loop_init_dev(lpvmpc_handle *h, int32_t B, const lpvmpc_loop_cfg *c, 
   a.lap_all = 0; a.Cf_new = c->Cf_new;
   a.x0 = P.x0; a.u_prev = P.u_prev; a.vel_ref = h->d_loop_velref; a.traj = P.traj; a.u_old = P.u_old;
   a.x_pred = h->d_loop_xpred; a.u_pred = P.u_pred; a.status = h->d_loop_status; a.iters = h->d_loop_iters;
-  return LPVMPC_OK;
+  return stream_leave(h, s);
 }
 
 int lpvmpc_loop_run_dev(lpvmpc_handle *h, int32_t n_ticks, void *stream) {
@@ -1149,8 +1230,9 @@ int lpvmpc_loop_run_dev(lpvmpc_handle *h, int32_t n_ticks, void *stream) {
   if (!h->d_loop || h->loop_B < 1) return fail(h, LPVMPC_E_ARG, "lpvmpc_loop_init_* first");
   if (n_ticks < 0) return fail(h, LPVMPC_E_ARG, "n_ticks < 0");
   if (n_ticks == 0) return LPVMPC_OK;
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   cudaStream_t s = (cudaStream_t)stream;
+  if (int rc = stream_enter(h, s)) return rc;
   const int B = h->loop_B, grid = (B + 127) / 128;
   for (int t = 0; t < n_ticks; ++t) {
     const int warm = h->loop_tick < (long long)h->LP.lc.warmup_ticks ? 1 : 0;
@@ -1170,13 +1252,13 @@ int lpvmpc_loop_run_dev(lpvmpc_handle *h, int32_t n_ticks, void *stream) {
   CUDA_TRY(h, cudaGetLastError());
   if (!h->loop_ev) CUDA_TRY(h, cudaEventCreateWithFlags(&h->loop_ev, cudaEventDisableTiming));
   CUDA_TRY(h, cudaEventRecord(h->loop_ev, s));
-  return LPVMPC_OK;
+  return stream_leave(h, s);
 }
 
 int lpvmpc_loop_init_host(lpvmpc_handle *h, int32_t B, const lpvmpc_loop_cfg *c, const double *sim0) {
   if (!h || !sim0) return fail(h, LPVMPC_E_ARG, "null handle/sim0");
   if (B < 1 || B > h->cfg.max_batch) return fail(h, LPVMPC_E_ARG, "fleet size must be in [1, max_batch]");
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   const size_t bytes = 8 * sizeof(double) * (size_t)B;
   if (bytes > h->stage_bytes) return fail(h, LPVMPC_E_ARG, "staging overflow");
   std::memcpy(h->h_stage, sim0, bytes);
@@ -1202,8 +1284,9 @@ int lpvmpc_plan_loop_init_dev(lpvmpc_handle *h, int32_t B, const double *xstart,
   if (!h || !xstart) return fail(h, LPVMPC_E_ARG, "null handle/xstart");
   if (h->cfg.kind != LPVMPC_PLANNER) return fail(h, LPVMPC_E_UNSUPPORTED, "the planner loop needs a planner handle");
   if (B < 1 || B > h->cfg.max_batch) return fail(h, LPVMPC_E_ARG, "fleet size must be in [1, max_batch]");
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   cudaStream_t s = (cudaStream_t)stream;
+  if (int rc = stream_enter(h, s)) return rc;
   const int N = h->L.N;
   const size_t D = sizeof(double), mb = (size_t)h->cfg.max_batch;
   lpv::loop::PlanLoopParams &P = h->PP;
@@ -1241,7 +1324,7 @@ int lpvmpc_plan_loop_init_dev(lpvmpc_handle *h, int32_t B, const double *xstart,
   std::memset(&a, 0, sizeof(a));
   a.x0 = P.x0; a.x_sched = P.x0; a.u_prev = P.u_prev; a.SS = P.SS; a.traj = P.traj; a.max_ey = h->d_ploop_maxey;
   a.x_pred = P.x_pred; a.u_pred = P.u_pred; a.status = const_cast<int32_t *>(P.status); a.iters = const_cast<int32_t *>(P.iters);
-  return LPVMPC_OK;
+  return stream_leave(h, s);
 }
 
 int lpvmpc_plan_loop_run_dev(lpvmpc_handle *h, int32_t n_ticks, void *stream) {
@@ -1249,8 +1332,9 @@ int lpvmpc_plan_loop_run_dev(lpvmpc_handle *h, int32_t n_ticks, void *stream) {
   if (!h->d_ploop || h->loop_B < 1 || h->cfg.kind != LPVMPC_PLANNER) return fail(h, LPVMPC_E_ARG, "lpvmpc_plan_loop_init_* first");
   if (n_ticks < 0) return fail(h, LPVMPC_E_ARG, "n_ticks < 0");
   if (n_ticks == 0) return LPVMPC_OK;
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   cudaStream_t s = (cudaStream_t)stream;
+  if (int rc = stream_enter(h, s)) return rc;
   const int B = h->loop_B, grid = (B + 127) / 128;
   for (int t = 0; t < n_ticks; ++t) {
     const int first = h->loop_tick == 0 ? 1 : 0;
@@ -1268,13 +1352,13 @@ int lpvmpc_plan_loop_run_dev(lpvmpc_handle *h, int32_t n_ticks, void *stream) {
   CUDA_TRY(h, cudaGetLastError());
   if (!h->loop_ev) CUDA_TRY(h, cudaEventCreateWithFlags(&h->loop_ev, cudaEventDisableTiming));
   CUDA_TRY(h, cudaEventRecord(h->loop_ev, s));
-  return LPVMPC_OK;
+  return stream_leave(h, s);
 }
 
 int lpvmpc_plan_loop_init_host(lpvmpc_handle *h, int32_t B, const double *xstart, const double *s0, double max_ey, double accel_rate) {
   if (!h || !xstart) return fail(h, LPVMPC_E_ARG, "null handle/xstart");
   if (B < 1 || B > h->cfg.max_batch) return fail(h, LPVMPC_E_ARG, "fleet size must be in [1, max_batch]");
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   const size_t bx = 5 * sizeof(double) * (size_t)B, bs = sizeof(double) * (size_t)B, o2 = align256(bx);
   if (o2 + bs > h->stage_bytes) return fail(h, LPVMPC_E_ARG, "staging overflow");
   std::memcpy(h->h_stage, xstart, bx);
@@ -1306,7 +1390,7 @@ int lpvmpc_plan_loop_view_dev(lpvmpc_handle *h, lpvmpc_plan_loop_state *view, in
 int lpvmpc_plan_loop_read_host(lpvmpc_handle *h, const lpvmpc_plan_loop_state *dst) {
   if (!h || !dst) return LPVMPC_E_ARG;
   if (!h->d_ploop || h->loop_B < 1) return fail(h, LPVMPC_E_ARG, "lpvmpc_plan_loop_init_* first");
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   const size_t B = (size_t)h->loop_B, D = sizeof(double), N = (size_t)h->L.N;
   struct Item { void *dst; const void *src; size_t bytes; };
   const Item items[] = {{dst->x_pred, h->PP.x_pred, 5 * (N + 1) * D * B}, {dst->u_pred, h->PP.u_pred, 2 * N * D * B},
@@ -1335,7 +1419,7 @@ int lpvmpc_plan_refs_setup(lpvmpc_handle *h, int32_t n_out, const double *W, con
   if (!h || !W || !Wc) return fail(h, LPVMPC_E_ARG, "null handle/W/Wc");
   if (h->cfg.kind != LPVMPC_PLANNER) return fail(h, LPVMPC_E_UNSUPPORTED, "references need a planner handle");
   if (n_out < 1 || n_out > 4096) return fail(h, LPVMPC_E_ARG, "n_out must be in [1, 4096]");
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   const size_t bytes = sizeof(double) * (size_t)n_out * (size_t)h->L.N;
   cudaFree(h->d_refs_W); h->d_refs_W = nullptr;
   CUDA_TRY(h, cudaMalloc(&h->d_refs_W, 2 * bytes));
@@ -1351,7 +1435,7 @@ int lpvmpc_plan_refs_dev(lpvmpc_handle *h, int32_t B, const double *x_pred, cons
   if (!h->d_refs_W) return fail(h, LPVMPC_E_ARG, "lpvmpc_plan_refs_setup first");
   if (B < 0 || B > h->cfg.max_batch) return fail(h, LPVMPC_E_ARG, "batch exceeds max_batch");
   if (B == 0) return LPVMPC_OK;
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   lpv::loop::PlanRefsParams p;
   p.track = h->d_track; p.nseg = h->M.nseg; p.N = h->L.N; p.n_out = h->refs_n_out; p.B = B;
   p.W = h->d_refs_W; p.Wc = h->d_refs_W + (size_t)h->refs_n_out * (size_t)h->L.N;
@@ -1368,7 +1452,7 @@ int lpvmpc_plan_refs_host(lpvmpc_handle *h, int32_t B, const double *x_pred, con
   if (!h->d_refs_W) return fail(h, LPVMPC_E_ARG, "lpvmpc_plan_refs_setup first");
   if (B < 0 || B > h->cfg.max_batch) return fail(h, LPVMPC_E_ARG, "batch exceeds max_batch");
   if (B == 0) return LPVMPC_OK;
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   const size_t D = sizeof(double), N = (size_t)h->L.N, nb = (size_t)B;
   const size_t b_x = 5 * (N + 1) * D * nb, b_s = (N + 1) * D * nb, b_0 = 3 * D * nb, b_r = 5 * (size_t)h->refs_n_out * D * nb, b_e = sizeof(int32_t) * nb;
   const size_t o_x = 0, o_s = o_x + align256(b_x), o_0 = o_s + align256(b_s), o_r = o_0 + align256(b_0), o_e = o_r + align256(b_r);
@@ -1396,7 +1480,7 @@ int lpvmpc_track_inputs_dev(lpvmpc_handle *h, int32_t B, const double *gstate, c
   if (index_max < 0 || n_ref < h->L.N + index_max) return fail(h, LPVMPC_E_ARG, "n_ref must hold N + index_max samples");
   if (B < 0 || B > h->cfg.max_batch) return fail(h, LPVMPC_E_ARG, "batch exceeds max_batch");
   if (B == 0) return LPVMPC_OK;
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   lpv::loop::TrackInputsParams p;
   p.N = h->L.N; p.n_ref = n_ref; p.B = B; p.dt = h->cfg.dt;
   p.gstate = gstate; p.lap = lap; p.s_prev = s_prev; p.refs = refs; p.index = index;
@@ -1418,7 +1502,7 @@ int lpvmpc_track_inputs_host(lpvmpc_handle *h, int32_t B, const double *gstate, 
       if (index[b] < 0) return fail(h, LPVMPC_E_ARG, "negative window index");
       if (index[b] > index_max) index_max = index[b];
     }
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   const size_t D = sizeof(double), I = sizeof(int32_t), N = (size_t)h->L.N, nb = (size_t)B;
   const size_t b_g = 6 * D * nb, b_l = I * nb, b_s = D * nb, b_r = 5 * (size_t)(n_ref > 0 ? n_ref : 0) * D * nb, b_i = I * nb;
   const size_t b_x = 6 * D * nb, b_v = (N + 1) * D * nb, b_c = N * D * nb, b_e = D * nb;
@@ -1455,7 +1539,7 @@ int lpvmpc_loop_view_dev(lpvmpc_handle *h, lpvmpc_loop_state *view, int32_t *B) 
 int lpvmpc_loop_read_host(lpvmpc_handle *h, const lpvmpc_loop_state *dst) {
   if (!h || !dst) return LPVMPC_E_ARG;
   if (!h->d_loop || h->loop_B < 1) return fail(h, LPVMPC_E_ARG, "lpvmpc_loop_init_* first");
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   const size_t B = (size_t)h->loop_B, D = sizeof(double), N = (size_t)h->L.N;
   struct Item { void *dst; const void *src; size_t bytes; };
   const Item items[] = {{dst->sim, h->LP.sim, 8 * D * B}, {dst->cmd, h->LP.cmd, 2 * D * B}, {dst->u_pred, h->LP.u_pred, 2 * N * D * B},

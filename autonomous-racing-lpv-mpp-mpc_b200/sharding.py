@@ -22,17 +22,19 @@ def shard_inputs(inputs, B, rank, world):
     return {k: (None if v is None else v[lo:hi]) for k, v in inputs.items()}
 
 
-def gather_results(local, B, dist=None, dst=0):
+def gather_results(local, B, dist=None, dst=0, group=None):
     """Gather per-rank result arrays (dict of numpy arrays whose leading dimension is the shard size) onto rank
     `dst` in problem order.  Returns the full dict on `dst`, None elsewhere.  With dist=None (single process)
-    the local dict is returned unchanged."""
+    the local dict is returned unchanged.  `group`: the process group of the gather — on a GPU box pass a gloo group
+    (``dist.new_group(backend="gloo")``): the results are host arrays and this is a host-side gather; with the default
+    (NCCL) group the pickled shards would take a detour through device memory."""
     if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
         return local
     world, rank = dist.get_world_size(), dist.get_rank()
     host = {k: np.ascontiguousarray(v.detach().cpu().numpy() if hasattr(v, "detach") else v)
             for k, v in local.items() if not k.startswith("_")}
     parts = [None] * world if rank == dst else None
-    dist.gather_object(host, parts, dst=dst)
+    dist.gather_object(host, parts, dst=dst, group=group)
     if rank != dst:
         return None
     out = {}
@@ -43,7 +45,7 @@ def gather_results(local, B, dist=None, dst=0):
     return out
 
 
-def solve_sharded(solver, B, x0, dist=None, gather=True, **inputs):
+def solve_sharded(solver, B, x0, dist=None, gather=True, group=None, **inputs):
     """Solve this rank's contiguous slice of a B-problem batch on this rank's GPU; optionally gather on rank 0.
 
     `solver` is this rank's ``BatchSolver`` (device = LOCAL_RANK).  Every rank passes the same full-batch host
@@ -55,4 +57,4 @@ def solve_sharded(solver, B, x0, dist=None, gather=True, **inputs):
         x0 = x0[lo:hi]
         inputs = {k: (v[lo:hi] if (v is not None and hasattr(v, "shape") and v.shape[0] == B) else v) for k, v in inputs.items()}
     res = solver.solve(x0, **inputs)
-    return gather_results(res, B, dist) if gather else res
+    return gather_results(res, B, dist, group=group) if gather else res

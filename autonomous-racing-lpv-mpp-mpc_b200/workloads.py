@@ -45,9 +45,49 @@ def controller_batch(B, N=8, seed=0, track=None, steer_scale=1.0):
                 u_old=u_prev[:, 0, :].copy())
 
 
+_HARVEST = None
+
+
+def planner_harvest():
+    """The (x0 = xPred[1], SS, uPred) tuples recorded from the reference's own Testing-mode planner loop
+    (plannerMain.py:145-146, 152-176, 201-211; HW = 0.2; 216 ticks until the loop turns infeasible at vx = 2.6 m/s):
+    data/planner_harvest.npz, written by tests/golden/make_planner_harvest.py."""
+    global _HARVEST
+    if _HARVEST is None:
+        import os
+        with np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "planner_harvest.npz")) as z:
+            _HARVEST = {k: np.array(z[k]) for k in z.files}
+    return _HARVEST
+
+
+def planner_batch_harvest(B, N=40, seed=1, obstacle_share=0.25):
+    """Config 3 inputs exactly as SURVEY.md 8d words them: (i) tuples harvested from the reference's planner loop,
+    (ii) tuple index drawn uniformly, N(0, sigma) with sigma = [.05, .01, .05, .01, .01] added to [vx, vy, wz, ey, epsi],
+    max_ey = HW = 0.2 for 75 % of the problems and for 25 % an 'obstacle': stages [k0, k0 + 8), k0 ~ U{10..30}, get
+    ey in [0.05, HW]; uOld = 0 (what the reference effectively does).  A share of these QPs is genuinely
+    infeasible (the unperturbed tuples already sit on the velocity / yaw-rate boxes in the corners)."""
+    h = planner_harvest()
+    if N != int(h["N"]):
+        raise ValueError("the harvest was recorded at N = %d" % int(h["N"]))
+    hw = float(h["half_width"])
+    rng = np.random.default_rng(seed)
+    idx = rng.integers(0, h["x0"].shape[0], B)
+    x0 = h["x0"][idx] + rng.standard_normal((B, 5)) * np.array([0.05, 0.01, 0.05, 0.01, 0.01])[None, :]
+    max_ey = np.full(B, hw)
+    ey_lo = np.repeat(-max_ey[:, None], N + 1, axis=1)
+    ey_hi = np.repeat(max_ey[:, None], N + 1, axis=1)
+    obs = rng.uniform(0, 1, B) < obstacle_share
+    k0 = rng.integers(10, 31, B)
+    for b in np.nonzero(obs)[0]:
+        ey_lo[b, k0[b]:k0[b] + 8] = 0.05
+    return dict(x0=x0, SS=h["SS"][idx].copy(), u_prev=h["u_pred"][idx].copy(), u_old=np.zeros((B, 2)), max_ey=max_ey, ey_lo=ey_lo, ey_hi=ey_hi,
+                tuple_index=idx.astype(np.int32))
+
+
 def planner_batch(B, N=40, seed=1, track=None, half_width=0.3, obstacle_share=0.25):
-    """Config 3 inputs: planner states near a nominal straight/cornering roll-out, per-problem max_ey and,
-    for a share of problems, an 'obstacle' = tightened lateral interval on 8 consecutive stages."""
+    """Planner inputs near a nominal straight/cornering roll-out (any horizon; used by the parity tests): per-problem
+    max_ey and, for a share of problems, an 'obstacle' = tightened lateral interval on 8 consecutive stages.
+    BASELINE configs[2] itself is `planner_batch_harvest`."""
     pt = (track if track is not None else Map("L_shape")).PointAndTangent
     rng = np.random.default_rng(seed)
     vx = rng.uniform(1.0, 2.4, B)

@@ -49,7 +49,9 @@ KERNEL_NAMES = {1: "lpv_solve_kernel (generic warp-per-QP)", 2: "lpv_solve_t8_ke
 
 WORKLOADS = {
     "ctrl4096": dict(kind="controller", N=8, B=4096, seed=0),
-    "plan16384": dict(kind="planner", N=40, B=16384, seed=1),
+    "plan16384": dict(kind="planner", N=40, B=16384, seed=1, harvest=True),
+    # round 1's planner batch (nominal roll-outs, half width 0.3): kept for comparison with the round-1 numbers
+    "plan16384nominal": dict(kind="planner", N=40, B=16384, seed=1),
     "ctrl1024N100": dict(kind="controller", N=100, B=1024, seed=3),
     # not a BASELINE config: the cfg-2 distribution at a batch that fills every QP slot of the GPU many times over
     # (what a Monte-Carlo tick of configs[3] looks like to the solver: 8,192 vehicles per GPU and more)
@@ -65,6 +67,18 @@ WORKLOADS = {
     # HBM) on the cfg-2 distribution — the HBM-bound kernel of SURVEY 8d; 65,536 QPs = 250 MB per launch (> L2)
     "sched65536": dict(kind="schedule", N=8, B=65536, seed=0),
 }
+
+
+OSQP_NOTE = "defaults (eps 1e-3, rho 0.1 adaptive@100, sigma 1e-6, alpha 1.6, 10 Ruiz passes, max_iter 4000) + polish"
+
+
+def base_config(name, ticks_per_step=None):
+    """The workload description both arms print (identical keys and values: the driver compares them)."""
+    spec = WORKLOADS[name]
+    c = {"workload": name, "kind": spec["kind"], "N": spec["N"], "batch_per_gpu": spec["B"], "seed": spec["seed"], "osqp": OSQP_NOTE}
+    if spec["kind"] in ("fleet", "planfleet"):
+        c["ticks_per_step"] = ticks_per_step
+    return c
 
 
 def flops_per_qp(kind, N, iters, rho_updates, polished):
@@ -191,7 +205,8 @@ def make_workload(name, rank):
         tune, dt = W.CTRL_TT, W.CTRL_DT
         keys = ("u_prev", "vel_ref", "curv_ref", "lap", "u_old")
     else:
-        w = W.planner_batch(spec["B"], spec["N"], seed=seed, track=track)
+        # BASELINE configs[2] as SURVEY 8d words it: tuples harvested from the reference's own planner loop, perturbed
+        w = W.planner_batch_harvest(spec["B"], spec["N"], seed=seed) if spec.get("harvest") else W.planner_batch(spec["B"], spec["N"], seed=seed, track=track)
         tune, dt = W.PLAN, W.PLAN_DT
         keys = ("SS", "u_prev", "u_old", "max_ey", "ey_lo", "ey_hi")
     return spec, track, w, tune, dt, keys
@@ -254,9 +269,9 @@ def run_fleet_reference(args):
         "impl": "reference", "metric": "LPV-MPC QP solves/sec", "value": value, "unit": "QP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "kind": "fleet", "N": 8, "vehicles_per_step": vehicles, "ticks_per_step": ticks,
-                   "note": "CPU oracle port of the closed loop (controller main loop + Simulator.f + getLocalPosition + OSQP "
-                           "restatement), every step restarts the sample fleet from tick 0; the reference's Python overhead is NOT included"},
+        "config": base_config(args.workload, ticks),
+        "note": "CPU oracle port of the closed loop (controller main loop + Simulator.f + getLocalPosition + OSQP restatement) on a bounded "
+                "sample fleet of %d vehicles, every step restarts it from tick 0; the reference's Python overhead is NOT included" % vehicles,
         "cpu_baseline": {"value": value, "unit": "QP/s", "cores": threads, "kind": "port",
                          "sample": "%d vehicles x %d ticks per step x %d steps" % (vehicles, ticks, len(times))},
         "e2e": {"value": value, "unit": "QP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -356,10 +371,10 @@ def run_fleet(args):
         "metric": "LPV-MPC QP solves/sec", "value": ticks_all / (total_ms * 1e-3), "unit": "QP/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "kind": "fleet (closed loop: Simulator.f x7 + getLocalPosition + LPVPrediction + build + OSQP + polish per tick)",
-                   "N": spec["N"], "vehicles_per_gpu": B, "ticks_per_step": tps, "tune": "path tracking (controllerMain.py:139-141)",
-                   "osqp": "defaults + polish", "l2": "fleet state + solver slab stay resident by design (closed loop); no flush",
-                   "kernel_variant": info0["variant"], "swap_ey_epsi": 1},
+        "config": base_config(args.workload, tps),
+        "setup": {"what": "closed loop: Simulator.f x7 + getLocalPosition + LPVPrediction + build + OSQP + polish per tick",
+                  "tune": "path tracking (controllerMain.py:139-141)", "l2": "fleet state + solver slab stay resident by design (closed loop); no flush",
+                  "kernel_variant": info0["variant"], "swap_ey_epsi": 1},
         "e2e": {"value": e2e_ticks_all / e2e_total, "unit": "QP/s", "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
                 "ms_per_step": 1e3 * e2e_total / args.steps, "note": "start(host states) + run(steps x ticks) + read(): one H2D and one D2H per run, nothing per tick"},
         "gpu_launches": int(launches),
@@ -481,10 +496,10 @@ def run_reference(args):
         "impl": "reference", "metric": "LPV-MPC QP solves/sec", "value": value, "unit": "QP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "kind": spec["kind"], "N": spec["N"], "batch_per_step": B,
-                   "note": "CPU oracle port (C restatement of the reference's LPVPrediction + QP build + OSQP 0.6 "
-                           "algorithm); upstream osqp is an absent PyPI dependency; Python overhead of the reference "
-                           "(about 1.7 ms/QP at N=8) is NOT included, which favours this arm"},
+        "config": base_config(args.workload),
+        "note": "CPU oracle port (C restatement of the reference's LPVPrediction + QP build + OSQP 0.6 algorithm) on %d QPs of the batch per step; "
+                "upstream osqp is an absent PyPI dependency; Python overhead of the reference (about 1.7 ms/QP at N=8) is NOT included, "
+                "which favours this arm" % B,
         "cpu_baseline": {"value": value, "unit": "QP/s", "cores": threads, "kind": "port",
                          "sample": "%d QPs per step x %d steps (%s of the workload batch)" % (B, len(times), "all" if B == spec["B"] else "a slice")},
         "e2e": {"value": value, "unit": "QP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -567,6 +582,18 @@ def run_ours(args):
     d2h = int(sum(rh[k].nbytes for k in rh if hasattr(rh[k], "nbytes")))
     assert np.array_equal(rh.status, status), "host and device paths disagree"
 
+    # ---------------------------------------------------------------- the other BASELINE configs (all ranks take part)
+    configs = None
+    if args.workload == "ctrl4096" and not args.no_configs:
+        gloo = None
+        if dist is not None:
+            try:
+                gloo = dist.new_group(backend="gloo")   # host-side gather of the sharded results ("final host gather")
+            except Exception:
+                gloo = None
+        ctx = dict(rank=rank, world=world, local=local, dev=dev, dist=dist, barrier=barrier, flush=flush, gloo=gloo)
+        configs = secondary_configs(args, ctx)
+
     # ---------------------------------------------------------------- reduce over ranks (max time)
     if dist is not None:
         t = torch.tensor([total_ms, e2e_total, float(solved), float(flops)], dtype=torch.float64, device=dev)
@@ -595,11 +622,10 @@ def run_ours(args):
         "metric": "LPV-MPC QP solves/sec", "value": value, "unit": "QP/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "kind": spec["kind"], "N": spec["N"], "batch_per_gpu": B,
-                   "osqp": "defaults (eps 1e-3, rho 0.1 adaptive@100, sigma 1e-6, alpha 1.6, 10 Ruiz passes, max_iter 4000) + polish",
-                   "sched": "fused LPVPrediction (lap=1)", "l2": "flushed between steps (256 MiB memset outside the per-step event pairs)",
-                   "kernel_variant": info0["variant"], "workspace_in_smem": info0["workspace_in_smem"],
-                   "smem_bytes_per_qp": info0["smem_bytes_per_qp"]},
+        "config": base_config(args.workload),
+        "setup": {"sched": "fused LPVPrediction", "l2": "flushed between steps (256 MiB memset outside the per-step event pairs)",
+                  "kernel_variant": info0["variant"], "workspace_in_smem": info0["workspace_in_smem"],
+                  "smem_bytes_per_qp": info0["smem_bytes_per_qp"]},
         "e2e": {"value": e2e_value, "unit": "QP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * e2e_total / args.steps,
                 "d2h": ("kernel writes the results into the pinned host arena (zero-copy, posted PCIe writes behind the compute)"
@@ -618,6 +644,8 @@ def run_ours(args):
         "solved_fraction": solved_all / float(world * B),
         "iters": {"mean": float(iters.mean()), "p50": float(np.percentile(iters, 50)), "p99": float(np.percentile(iters, 99)), "max": float(iters.max())},
     }
+    if configs is not None:
+        line["configs"] = configs
     # the same kernel with every QP slot of the GPU filled many times over (ctrl4096 fills them 1.7 times: its second
     # round is 73 % full); reported beside the headline, not instead of it
     if world == 1 and args.workload == "ctrl4096" and not args.no_saturated:
@@ -652,6 +680,19 @@ def run_ours(args):
         Bs, times, _ = cpu_reference_rate(args.workload, threads, 3 if sample <= 4096 else 1, sample=sample)
         line["cpu_baseline"] = {"value": Bs * len(times) / float(np.sum(times)), "unit": "QP/s", "cores": threads, "kind": "port",
                                 "sample": "%d QPs x %d passes of the same workload, OpenMP over all host cores; C port without the reference's Python overhead" % (Bs, len(times))}
+        # the same port on ONE core (the reference loop is single-threaded), and the reference's real Python loop as
+        # measured in the build container (tools/ref_python_baseline.py; /root/reference does not exist on this box)
+        s1 = min(Bs, 1024 if spec["N"] <= 20 else 32)
+        B1, t1, _ = cpu_reference_rate(args.workload, 1, 1, sample=s1)
+        line["cpu_baseline_1core"] = {"value": B1 / float(np.sum(t1)), "unit": "QP/s", "cores": 1, "kind": "port", "sample": "%d QPs of the same workload, one thread" % B1}
+        try:
+            with open(os.path.join(ROOT, "profiles", "r3_cpu_reference_python.json")) as fh:
+                rp = json.load(fh)
+            line["cpu_reference_python"] = {"value": rp["qp_per_s_1core"], "unit": "QP/s", "cores": 1, "kind": "reference Python build + oracle OSQP",
+                                            "ms_per_qp": rp["ms_per_qp"], "measured": "build container, not this box (profiles/r3_cpu_reference_python.json)",
+                                            "applies_to": "ctrl4096"} if args.workload == "ctrl4096" else None
+        except Exception:
+            pass
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -744,6 +785,233 @@ def run_schedule(args):
     return 0
 
 
+# ------------------------------------------------------------------------------------------------
+# The other BASELINE configs, measured inside the default run so that they land in the driver's records
+# (VERDICT r1 item 4): compact versions of the per-workload runs above.
+def _reduce(dist, dev, vals_max, vals_sum):
+    """max / sum over the ranks of two float lists (identity without a process group)."""
+    import torch
+    if dist is None:
+        return list(vals_max), list(vals_sum)
+    a = torch.tensor(list(vals_max), dtype=torch.float64, device=dev)
+    b = torch.tensor(list(vals_sum), dtype=torch.float64, device=dev)
+    dist.all_reduce(a, op=dist.ReduceOp.MAX)
+    dist.all_reduce(b, op=dist.ReduceOp.SUM)
+    return a.tolist(), b.tolist()
+
+
+def cfg_solve(name, ctx, steps, warmup, sharded, variant=0, e2e=True):
+    """One solve workload, device-timed (L2 flushed between steps).  sharded: the workload's B problems are split over
+    the ranks by contiguous index range (sharding.shard_range), every rank solves its slice, and the end-to-end leg
+    goes host arrays -> sharding.solve_sharded -> gather_results on rank 0 (the "final host gather")."""
+    import torch
+    import lpvmpc_b200 as lp
+    rank, world, local, dev, dist, barrier, flush = ctx["rank"], ctx["world"], ctx["local"], ctx["dev"], ctx["dist"], ctx["barrier"], ctx["flush"]
+    spec, track, w, tune, dt, keys = make_workload(name, 0 if sharded else rank)
+    Btot = spec["B"]
+    lo, hi = lp.sharding.shard_range(Btot, rank, world) if sharded else (0, Btot)
+    B = hi - lo
+    solver = lp.BatchSolver(spec["kind"], spec["N"], dt, track=track.PointAndTangent, max_batch=max(B, 1), device=local, variant=variant, **tune)
+    info0 = solver.info()
+    tin = {k: torch.as_tensor(np.ascontiguousarray(w[k][lo:hi])).to(dev) for k in keys}
+    tx0 = torch.as_tensor(np.ascontiguousarray(w["x0"][lo:hi])).to(dev)
+    for _ in range(warmup):
+        r = solver.solve(tx0, **tin)
+    barrier()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    launches0 = solver.info()["kernel_launches"]
+    for i in range(steps):
+        flush.zero_()
+        starts[i].record()
+        r = solver.solve(tx0, **tin)
+        ends[i].record()
+    barrier()
+    launches = solver.info()["kernel_launches"] - launches0
+    step_ms = np.array([a.elapsed_time(b) for a, b in zip(starts, ends)])
+    status = r.status.cpu().numpy()
+    iters = r.iters.cpu().numpy().astype(np.float64)
+    flops = float(flops_per_qp(spec["kind"], spec["N"], iters, r.rho_updates.cpu().numpy().astype(np.float64),
+                               (r.polish_status.cpu().numpy() != 0).astype(np.float64)).sum()) if B else 0.0
+    e2e_s, gathered_ok = None, None
+    if e2e:
+        hin = {k: w[k] for k in keys}
+        gdist = ctx["gloo"] if world > 1 else None
+        for rep in range(2):   # first pass warms the pinned staging path
+            barrier()
+            t0 = time.perf_counter()
+            if sharded:
+                full = lp.sharding.solve_sharded(solver, Btot, w["x0"], dist=dist, group=gdist, **hin)
+            else:
+                full = solver.solve(w["x0"], **hin)
+            barrier()
+            e2e_s = time.perf_counter() - t0
+        if rank == 0:
+            st_full = np.asarray(full["status"])
+            gathered_ok = bool(st_full.shape[0] == (Btot if sharded else B) and np.array_equal(st_full[lo:hi], status))
+    peak, _ = fp64_peak_tflops()
+    mx, sm = _reduce(dist, dev, [float(step_ms.sum()), e2e_s or 0.0], [float((status == 1).sum()), float(np.isin(status, (1, 2, -2)).sum()), float(iters.sum()), float(B), flops, float(launches)])
+    total_ms = mx[0]
+    ms = total_ms / steps
+    out = {"workload": name, "kind": spec["kind"], "N": spec["N"], "batch_total": int(sm[3]), "scaling": "strong" if sharded else "weak",
+           "sharded": bool(sharded), "value": sm[3] * steps / (total_ms * 1e-3), "unit": "QP/s", "ms_per_step": ms, "steps": steps,
+           "kernel_variant": info0["variant"], "gpu_launches": int(sm[5]),
+           "roofline": {"bound": "fp64_fma", "achieved": sm[4] / world / (ms * 1e-3) * 1e-12, "peak": peak, "unit": "TFLOP/s",
+                        "frac": sm[4] / world / (ms * 1e-3) * 1e-12 / peak, "note": "mean over ranks of flops per launch / max-over-ranks launch time"},
+           "solved_fraction": sm[0] / max(sm[3], 1.0), "feasible_fraction": sm[1] / max(sm[3], 1.0), "iters_mean": sm[2] / max(sm[3], 1.0),
+           "l2": "flushed between steps"}
+    if e2e:
+        out["e2e"] = {"value": sm[3] / mx[1], "unit": "QP/s", "ms_per_step": 1e3 * mx[1],
+                      "path": ("host arrays -> sharding.solve_sharded (shard_range slice per rank, lpvmpc_solve_host) -> gather_results on rank 0 (gloo group)"
+                               if sharded else "host arrays -> lpvmpc_solve_host"), "gathered_matches_device": gathered_ok}
+    solver.close()
+    return out
+
+
+def cfg_fleet(ctx, ticks, variant=0):
+    """configs[3]: 8,192 vehicles per GPU (65,536 on 8), one step of `ticks` controller ticks after the warm-up ticks."""
+    import torch
+    import lpvmpc_b200 as lp
+    rank, world, local, dev, dist, barrier = ctx["rank"], ctx["world"], ctx["local"], ctx["dev"], ctx["dist"], ctx["barrier"]
+    spec = WORKLOADS["mc8192"]
+    B = spec["B"]
+    m = lp.Map("L_shape")
+    sim0 = lp.fleet_start(B, seed=spec["seed"] + 1000 * rank, track_map=m)
+    fleet = lp.ClosedLoopFleet(m, N=spec["N"], max_fleet=B, device=local, variant=variant)
+    stream = torch.cuda.current_stream(local).cuda_stream
+    fleet.start(torch.as_tensor(sim0).to(dev))
+    fleet.run(ticks, stream=stream)       # carries the fleet past the 9 _EstimateABC ticks
+    barrier()
+    before = fleet.read(("stat", "ctr"))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = fleet.solver.info()["kernel_launches"]
+    barrier()
+    e0.record()
+    fleet.run(ticks, stream=stream)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = fleet.solver.info()["kernel_launches"] - launches0
+    after = fleet.read(("stat", "ctr"))
+    ticks_done = float((after["ctr"][:, 7] - before["ctr"][:, 7]).sum())
+    solved = float((after["stat"][:, 0] - before["stat"][:, 0]).sum())
+    iters_sum = float((after["stat"][:, 1] - before["stat"][:, 1]).sum())
+    F_scale, F_form, F_fac, F_solve, F_iter, F_check = FLOP_TABLE[("controller", spec["N"])]
+    flops = ticks_done * (F_scale + F_form + F_fac + (F_fac + 4 * F_solve)) + iters_sum * (F_iter + F_check / 25.0)
+    peak, _ = fp64_peak_tflops()
+    mx, sm = _reduce(dist, dev, [ms], [ticks_done, solved, iters_sum, flops, float(launches), float((after["ctr"][:, 5] != 0).sum())])
+    out = {"workload": "mc8192", "kind": "fleet", "N": spec["N"], "vehicles_total": B * world, "ticks_per_step": ticks, "scaling": "weak",
+           "value": sm[0] / (mx[0] * 1e-3), "unit": "QP/s (vehicle-ticks/s)", "ms_per_step": mx[0], "ms_per_tick": mx[0] / ticks, "steps": 1,
+           "kernel_variant": fleet.solver.info()["variant"], "gpu_launches": int(sm[4]),
+           "roofline": {"bound": "fp64_fma", "achieved": sm[3] / world / (mx[0] * 1e-3) * 1e-12, "peak": peak, "unit": "TFLOP/s",
+                        "frac": sm[3] / world / (mx[0] * 1e-3) * 1e-12 / peak},
+           "solved_fraction": sm[1] / max(sm[0], 1.0), "iters_mean": sm[2] / max(sm[0], 1.0), "retired_vehicles": int(sm[5]),
+           "l2": "fleet state resident by design; no flush"}
+    fleet.close()
+    return out
+
+
+def cfg_schedule(ctx, steps=10, warmup=3):
+    """sched65536 on rank 0's GPU: the stand-alone LPVPrediction kernel against the HBM roofline."""
+    import torch
+    import lpvmpc_b200 as lp
+    local, dev = ctx["local"], ctx["dev"]
+    W = lp.workloads
+    spec = WORKLOADS["sched65536"]
+    B, N = spec["B"], spec["N"]
+    track = lp.Map("L_shape")
+    w = W.controller_batch(B, N, seed=spec["seed"], track=track)
+    solver = lp.BatchSolver("controller", N, W.CTRL_DT, track=track.PointAndTangent, max_batch=B, device=local, **W.CTRL_TT)
+    keys = ("u_prev", "vel_ref", "curv_ref", "lap")
+    tin = {k: torch.as_tensor(w[k]).to(dev) for k in keys}
+    tin["x0"] = torch.as_tensor(w["x0"]).to(dev)
+    flush = torch.empty(1024 * 1024 * 1024, dtype=torch.uint8, device=dev)   # see run_schedule
+    for _ in range(warmup):
+        solver.schedule(**tin)
+    torch.cuda.synchronize()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    for i in range(steps):
+        flush.zero_()
+        starts[i].record()
+        solver.schedule(**tin)
+        ends[i].record()
+    torch.cuda.synchronize()
+    del flush
+    ms = float(np.mean([a.elapsed_time(b) for a, b in zip(starts, ends)]))
+    in_b = 8 * (6 + 2 * N + (N + 1) + N) + 4
+    out_b = 8 * (36 * N + 12 * N + 6 * N) + 4
+    mp = measured_peaks()
+    peak = float(mp.get("hbm_gbs", 6650.0))
+    achieved = (in_b + out_b) * B / (ms * 1e-3) * 1e-9
+    solver.close()
+    return {"workload": "sched65536", "kind": "schedule", "N": N, "batch_total": B, "value": B / (ms * 1e-3), "unit": "QPs scheduled/s", "ms_per_step": ms,
+            "steps": steps, "gpu_launches": steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic("sched65536", 0), "algorithmic_bytes_per_launch": (in_b + out_b) * B,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if not mp.get("_fallback") else "fallback (B200_PROFILING.md)"},
+            "l2": "flushed between steps (1 GiB memset); 250 MB per launch > L2"}
+
+
+def cfg_latency(ctx, variant=0, reps=50):
+    """configs[0]'s use case: ONE controller QP per call (controllerMain.py:329-331).  Kernel latency by CUDA events and
+    end to end through the host API, beside one CPU core of the oracle port on the same QPs."""
+    import torch
+    import lpvmpc_b200 as lp
+    local, dev = ctx["local"], ctx["dev"]
+    W = lp.workloads
+    track = lp.Map("L_shape")
+    w = W.controller_batch(64, 8, seed=0, track=track)
+    keys = ("u_prev", "vel_ref", "curv_ref", "lap", "u_old")
+    out = {}
+    for B in (1, 32):
+        solver = lp.BatchSolver("controller", 8, W.CTRL_DT, track=track.PointAndTangent, max_batch=B, device=local, variant=variant, **W.CTRL_TT)
+        tin = {k: torch.as_tensor(w[k][:B]).to(dev) for k in keys}
+        tx0 = torch.as_tensor(w["x0"][:B]).to(dev)
+        for _ in range(5):
+            r = solver.solve(tx0, **tin)
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for a, b in ev:
+            a.record()
+            r = solver.solve(tx0, **tin)
+            b.record()
+        torch.cuda.synchronize()
+        k_ms = np.array([a.elapsed_time(b) for a, b in ev])
+        hin = {k: w[k][:B] for k in keys}
+        for _ in range(3):
+            solver.solve(w["x0"][:B], **hin)
+        t = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            solver.solve(w["x0"][:B], **hin)
+            t.append(time.perf_counter() - t0)
+        out["b%d" % B] = {"kernel_ms_p50": float(np.percentile(k_ms, 50)), "kernel_ms_p99": float(np.percentile(k_ms, 99)),
+                          "e2e_ms_p50": 1e3 * float(np.percentile(t, 50)), "e2e_ms_p99": 1e3 * float(np.percentile(t, 99)),
+                          "iters": [int(v) for v in r.iters.cpu().numpy()[:4]], "kernel_variant": solver.info()["variant"]}
+        solver.close()
+    return out
+
+
+def secondary_configs(args, ctx):
+    """Every BASELINE config besides the headline one, inside the default run.  Runs on all ranks (collective)."""
+    import torch
+    cfgs = {}
+    t0 = time.perf_counter()
+    # configs[2]: 16,384 planner QPs SHARDED over the ranks (strong scaling) — SURVEY 8d's harvested generator
+    cfgs["plan16384"] = cfg_solve("plan16384", ctx, steps=2, warmup=1, sharded=True, variant=args.variant)
+    # configs[3]: 8,192 vehicles per GPU x one step of 23 ticks (65,536 vehicles on 8 GPUs)
+    cfgs["mc8192"] = cfg_fleet(ctx, args.ticks_per_step, variant=args.variant)
+    # configs[4]: N = 100, 1,024 QPs per GPU
+    cfgs["ctrl1024N100"] = cfg_solve("ctrl1024N100", ctx, steps=3, warmup=1, sharded=False, variant=args.variant, e2e=False)
+    if ctx["rank"] == 0:
+        cfgs["sched65536"] = cfg_schedule(ctx)
+        cfgs["latency_ctrl_n8"] = cfg_latency(ctx, variant=args.variant)
+    ctx["barrier"]()
+    cfgs["_seconds"] = time.perf_counter() - t0
+    return cfgs
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -753,6 +1021,7 @@ def main():
     ap.add_argument("--workload", default="ctrl4096", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-saturated", action="store_true", help="skip the 65,536-QP secondary measurement of the ctrl4096 run")
+    ap.add_argument("--no-configs", action="store_true", help="skip the `configs` block (the other BASELINE configs) of the default ctrl4096 run")
     ap.add_argument("--variant", type=int, default=0, help="kernel variant (0 = auto)")
     ap.add_argument("--batch", type=int, default=0, help="override the workload's batch per GPU (profiling runs; not a BASELINE config)")
     ap.add_argument("--ticks-per-step", type=int, default=23, help="mc8192: controller ticks per step (24 x 23 = one lap)")

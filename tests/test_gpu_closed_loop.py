@@ -72,8 +72,10 @@ class Plant(object):
             self.vx = abs(self.vx)
 
 
-def test_controller_closed_loop_through_the_dropin_class():
-    N, dt, ticks = 8, 1.0 / 30.0, 75
+def _drive(max_ticks, until_s=None):
+    """Runs the loop for `max_ticks` ticks (or until the plant's arc length passes `until_s`); returns the plant, the
+    number of ticks driven and the worst deviations from the oracle."""
+    N, dt = 8, 1.0 / 30.0
     track_map = lp.Map("L_shape")
     track = track_map.PointAndTangent
     Q = np.diag([100.0, 1.0, 1.0, 20.0, 0.0, 900.0])
@@ -87,7 +89,11 @@ def test_controller_closed_loop_through_the_dropin_class():
     first_it = 1
     u_pred_o = None
     worst_u = worst_x = 0.0
-    for tick in range(ticks):
+    ey_max = 0.0
+    tick = 0
+    for tick in range(max_ticks):
+        if until_s is not None and plant.s >= until_s:
+            break
         x = plant.state()
         ctl.OldSteering.append(float(cmd[0])); ctl.OldAccelera.append(float(cmd[1]))
         ctl.OldSteering.pop(0); ctl.OldAccelera.pop(0)
@@ -107,12 +113,32 @@ def test_controller_closed_loop_through_the_dropin_class():
             o = oracle.ctrl_solve(cfg, st, so[0, :], A=Ao, B=Bo, Cc=Co, mode=0, vel_ref=vel_ref, old_steering=old[0], old_accel=old[1])
         assert ctl.status_val == o["status"], (tick, ctl.status_val, o["status"])
         assert int(ctl.info["iters"]) == o["iter"], (tick, ctl.info["iters"], o["iter"])
+        assert ctl.feasible == 1, tick
         worst_u = max(worst_u, np.abs(ctl.uPred - o["uPred"]).max())
         worst_x = max(worst_x, np.abs(ctl.xPred - o["xPred"]).max())
         assert ctl.xPred.shape == (N + 1, 6) and ctl.uPred.shape == (N, 2) and ctl.LinPoints.shape == (N + 1, 6)
         u_pred_o = o["uPred"]
         cmd = ctl.uPred[0, :].copy()           # controllerMain.py:381-383 (delays are 0)
         plant.step(cmd[0], cmd[1], dt)
+        ey_max = max(ey_max, abs(plant.ey))
+    return plant, tick, worst_u, worst_x, ey_max, track_map
+
+
+def test_controller_closed_loop_through_the_dropin_class():
+    plant, ticks, worst_u, worst_x, ey_max, _ = _drive(75)
     assert worst_u < 1e-6 and worst_x < 1e-6, (worst_u, worst_x)
     # the car accelerates towards the 1 m/s reference and stays on the centre line
     assert 0.5 < plant.vx < 1.2 and abs(plant.ey) < 0.1 and plant.s > 0.5
+
+
+def test_controller_one_full_lap_through_the_dropin_class():
+    """BASELINE configs[0] as stated: the single controller stepped closed loop for ONE LAP of the L-shaped track
+    (19.23 m at the 1 m/s path-tracking reference: 552 ticks in the survey's probe of the reference loop),
+    every tick solved by the GPU through the drop-in class and by the oracle beside it: status and iteration count
+    identical on every tick, controls and predicted states within 1e-6."""
+    track_len = float(lp.Map("L_shape").TrackLength)
+    plant, ticks, worst_u, worst_x, ey_max, _ = _drive(700, until_s=track_len)
+    assert plant.s >= track_len, (plant.s, ticks)       # the lap was completed ...
+    assert 540 <= ticks <= 620, ticks                    # ... in about the reference's 552 ticks
+    assert worst_u < 1e-6 and worst_x < 1e-6, (worst_u, worst_x)
+    assert ey_max < 0.1 and 0.9 < plant.vx < 1.1, (ey_max, plant.vx)

@@ -69,14 +69,14 @@ def test_schedule_matches_oracle(track):
             np.testing.assert_allclose(r.states_out[b], st, rtol=1e-12, atol=1e-14)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("variant", [1, 5, 6, 7])
 @pytest.mark.parametrize("iters", [1, 7, 50, 200])
 def test_controller_fixed_iteration_iterates(track, iters, variant):
     N, B = 8, 48
     w = W.controller_batch(B, N, seed=11)
     fixed = dict(max_iter=iters, check_termination=0, adaptive_rho=0, polish=0)
     s = lp.BatchSolver("controller", N, W.CTRL_DT, track=track, max_batch=B, variant=variant, **W.CTRL_TT, **fixed)
-    assert s.info()["variant"] == (2 if variant == 4 else variant)
+    assert s.info()["variant"] == variant
     r = s.solve(w["x0"], extra_outputs=("xs", "zs", "ys"), **{k: w[k] for k in ("u_prev", "vel_ref", "curv_ref", "lap", "u_old")})
     cfg = oracle.make_cfg("controller", N, W.CTRL_DT, W.CTRL_TT["Q"], W.CTRL_TT["R"], W.CTRL_TT["dR"], track)
     st = oracle.default_settings(**fixed)
@@ -89,7 +89,7 @@ def test_controller_fixed_iteration_iterates(track, iters, variant):
     assert worst < 1e-9, worst
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("variant", [1, 5, 6, 7])
 def test_controller_converged_matches_oracle(track, variant):
     N, B = 8, 254  # not a multiple of 4: exercises the idle-group path of the T8 kernel
     w = W.controller_batch(B, N, seed=0)
@@ -109,7 +109,7 @@ def test_controller_converged_matches_oracle(track, variant):
         assert abs(r.obj[b] - o["obj_val"]) <= 1e-6 * abs(o["obj_val"]), (b, r.obj[b], o["obj_val"])
 
 
-@pytest.mark.parametrize("variant", [1, 3, 5, 7])
+@pytest.mark.parametrize("variant", [1, 5, 7])
 def test_planner_fixed_and_converged(track, variant):
     N, B = 40, 24
     w = W.planner_batch(B, N, seed=1)
