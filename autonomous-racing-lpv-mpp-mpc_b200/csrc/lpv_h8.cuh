@@ -1454,19 +1454,8 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, Strm *s
   if (ST) strm_drain(h.sc, sm);
   factor<KIND>(c, fw, delta);
   auto bred_i = [&](int k, int t) { const double a = ACTI[c.ci(k, t)]; return (a == 1.0 || a == 3.0) ? c.lo_of(k, t) : c.ui(k, t); };
-  // first solve: rhs = -q + A_red'(b_red / delta); the targets go through R2D / R2I
-#pragma unroll 1
-  for (int k = c.k0; k <= N; k += c.ks) {
-    const int o = k * 8 + r;
-    R2D[k * VS + r] = (c.xl && ACTD[o] != 0.0) ? idel * BE[o] : 0.0;
-    if (c.has_in(k)) {
-#pragma unroll
-      for (int t = 0; t < NT; ++t) R2I[c.ci(k, t)] = (ACTI[c.ci(k, t)] != 0.0) ? idel * bred_i(k, t) : 0.0;
-    }
-  }
-  __syncwarp();
-  // (A' t)_(k, r) with t_dyn = R2D-like array stored [k*VS + q] and t_in from the slab array ti
-  auto colAt = [&](const double *td, const double *ti, int k) {
+  // (A' t)_(k, r) with t_dyn stored [k*VS + q] and t_in = (ti0, ti1) of my single-variable rows
+  auto colAt2 = [&](const double *td, const double ti0, const double ti1, int k) {
     double acc = c.xl ? ED[k * 8 + r] * td[k * VS + r] : 0.0;
     if (k < N) {
       double g[8];
@@ -1475,83 +1464,118 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, Strm *s
       acc += pcoldot<NX>(c.Gb(k), r, g);
     }
     if (c.has_in(k)) {
-#pragma unroll
-      for (int t = 0; t < NT; ++t) acc = fma(c.si(k, t), ti[c.ci(k, t)], acc);
+      acc = fma(c.si(k, 0), ti0, acc);
+      if (NT > 1) acc = fma(c.si(k, NT - 1), ti1, acc);
     }
     return acc;
   };
+  auto colAt = [&](const double *td, const double *ti, int k) {
+    double t2[2] = {0.0, 0.0};
+    if (c.has_in(k)) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) t2[t] = ti[c.ci(k, t)];
+    }
+    return colAt2(td, t2[0], t2[1], k);
+  };
+  // Upstream's refinement, pass for pass (see polish() in lpv_h8t.cuh for the scheme): t = (PX, PYD, PYI) is the tentative
+  // iterate, DX the x part of the increment of the running K_reg solve, TMP a row temporary.
+  double *DX = R2D, *TMP = c.V(V_CR);
+  auto solve = [&]() {
+    __syncwarp();
+    sweep_fwd<KIND, ST>(h, sm, N, gsel);
+    sweep_bwd_plain<KIND, ST>(h, sm, N, gsel);
+  };
+  auto inner = [&]() {
 #pragma unroll 1
-  for (int k = c.k0; k <= N; k += c.ks) BV[k * VS + r] = c.var_live(k) ? (-QV[k * 8 + r] + colAt(R2D, R2I, k)) : 0.0;
+    for (int ii = 0; ii < kPolishInner; ++ii) {
+#pragma unroll 1
+      for (int k = c.k0; k <= N; k += c.ks) {
+        const int o = k * 8 + r, ov = k * VS + r;
+        double b = 0.0;
+        if (c.var_live(k)) b = ((-QV[o] - rowP<KIND>(c, PD, PO, PX, VS, k)) - colAt(PYD, PYI, k)) - delta * DX[ov];
+        BV[ov] = b;
+      }
+      solve();
+#pragma unroll 1
+      for (int k = c.k0; k <= N; k += c.ks) {
+        const int o = k * 8 + r, ov = k * VS + r;
+        const double ddx = BV[ov];
+        if (c.xl && ACTD[o] != 0.0) PYD[ov] += idel * rowA_dyn<KIND>(c, ED, BV, VS, k);
+        if (c.has_in(k)) {
+#pragma unroll
+          for (int t = 0; t < NT; ++t) { const int oc = c.ci(k, t); if (ACTI[oc] != 0.0) PYI[oc] += idel * (c.si(k, t) * ddx); }
+        }
+        PX[ov] += ddx; DX[ov] += ddx;
+      }
+      __syncwarp();
+    }
+  };
+  // ---- s_0 = K_reg^-1 (-q, b_red): rhs = -q + A_red'(b_red / delta)
+#pragma unroll 1
+  for (int k = c.k0; k <= N; k += c.ks) TMP[k * VS + r] = (c.xl && ACTD[k * 8 + r] != 0.0) ? idel * BE[k * 8 + r] : 0.0;
   __syncwarp();
-  sweep_fwd<KIND, ST>(h, sm, N, gsel);
-  sweep_bwd_plain<KIND, ST>(h, sm, N, gsel);
-  // x, y = (A x - b) / delta, r2 = b - A x on the active rows
+#pragma unroll 1
+  for (int k = c.k0; k <= N; k += c.ks) {
+    double t2[2] = {0.0, 0.0};
+    if (c.has_in(k)) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) t2[t] = (ACTI[c.ci(k, t)] != 0.0) ? idel * bred_i(k, t) : 0.0;
+    }
+    BV[k * VS + r] = c.var_live(k) ? (-QV[k * 8 + r] + colAt2(TMP, t2[0], t2[1], k)) : 0.0;
+  }
+  solve();
 #pragma unroll 1
   for (int k = c.k0; k <= N; k += c.ks) {
     const int o = k * 8 + r, ov = k * VS + r;
     const double xk = BV[ov];
-    PX[ov] = xk;
-    const bool ad = c.xl && ACTD[o] != 0.0;
-    const double res = ad ? (BE[o] - rowA_dyn<KIND>(c, ED, BV, VS, k)) : 0.0;
-    R2D[ov] = res;
-    PYD[ov] = -res * idel;
+    PX[ov] = xk; DX[ov] = xk;
+    PYD[ov] = (c.xl && ACTD[o] != 0.0) ? idel * (rowA_dyn<KIND>(c, ED, BV, VS, k) - BE[o]) : 0.0;
     if (c.has_in(k)) {
 #pragma unroll
-      for (int t = 0; t < NT; ++t) {
-        const int oc = c.ci(k, t);
-        const double ri = (ACTI[oc] != 0.0) ? (bred_i(k, t) - c.si(k, t) * xk) : 0.0;
-        R2I[oc] = ri; PYI[oc] = -ri * idel;
-      }
+      for (int t = 0; t < NT; ++t) { const int oc = c.ci(k, t); PYI[oc] = (ACTI[oc] != 0.0) ? idel * (c.si(k, t) * xk - bred_i(k, t)) : 0.0; }
     }
   }
   __syncwarp();
+  inner();
 #pragma unroll 1
-  for (int it = 0; it < St.polish_refine_iter + kPolishExtraRefine; ++it) {
-    // rhs = -q - P x - A'(y - r2 / delta)
+  for (int it = 0; it < St.polish_refine_iter; ++it) {
+    // s_{j+1} = s_j + K_reg^-1 (rhs - K s_j): condensed right-hand side -q - P tx - A'(ty - r2 / delta), r2 = b_red - A tx
+#pragma unroll 1
+    for (int k = c.k0; k <= N; k += c.ks) {
+      const int o = k * 8 + r, ov = k * VS + r;
+      TMP[ov] = (c.xl && ACTD[o] != 0.0) ? fma(-idel, BE[o] - rowA_dyn<KIND>(c, ED, PX, VS, k), PYD[ov]) : 0.0;
+    }
+    __syncwarp();
 #pragma unroll 1
     for (int k = c.k0; k <= N; k += c.ks) {
       const int o = k * 8 + r, ov = k * VS + r;
       double b = 0.0;
       if (c.var_live(k)) {
-        const double Px = rowP<KIND>(c, PD, PO, PX, VS, k);
-        double acc = c.xl ? ED[o] * fma(-idel, R2D[ov], PYD[ov]) : 0.0;
-        if (k < N) {
-          double g[8];
-#pragma unroll
-          for (int rr = 0; rr < 8; ++rr) g[rr] = (rr < NX) ? fma(-idel, R2D[(k + 1) * VS + rr], PYD[(k + 1) * VS + rr]) : 0.0;
-          acc += pcoldot<NX>(c.Gb(k), r, g);
-        }
+        double t2[2] = {0.0, 0.0};
         if (c.has_in(k)) {
 #pragma unroll
-          for (int t = 0; t < NT; ++t) { const int oc = c.ci(k, t); acc = fma(c.si(k, t), fma(-idel, R2I[oc], PYI[oc]), acc); }
+          for (int t = 0; t < NT; ++t) { const int oc = c.ci(k, t); t2[t] = (ACTI[oc] != 0.0) ? fma(-idel, bred_i(k, t) - c.si(k, t) * PX[ov], PYI[oc]) : 0.0; }
         }
-        b = (-QV[o] - Px) - acc;
+        b = (-QV[o] - rowP<KIND>(c, PD, PO, PX, VS, k)) - colAt2(TMP, t2[0], t2[1], k);
       }
       BV[ov] = b;
     }
+    solve();
+#pragma unroll 1
+    for (int k = c.k0; k <= N; k += c.ks) { const int ov = k * VS + r; const double ddx = BV[ov]; DX[ov] = ddx; PX[ov] += ddx; }
     __syncwarp();
-    sweep_fwd<KIND, ST>(h, sm, N, gsel);
-    sweep_bwd_plain<KIND, ST>(h, sm, N, gsel);
-    // dy = (A dx - r2) / delta, r2 <- r2 - A dx, x <- x + dx
+    // ty += (A ddx - r2) / delta = (A tx_new - b_red) / delta
 #pragma unroll 1
     for (int k = c.k0; k <= N; k += c.ks) {
       const int o = k * 8 + r, ov = k * VS + r;
-      const double dx = BV[ov];
-      if (c.xl && ACTD[o] != 0.0) {
-        const double z = rowA_dyn<KIND>(c, ED, BV, VS, k), r2 = R2D[ov];
-        PYD[ov] += (z - r2) * idel;
-        R2D[ov] = r2 - z;
-      }
+      if (c.xl && ACTD[o] != 0.0) PYD[ov] += idel * (rowA_dyn<KIND>(c, ED, PX, VS, k) - BE[o]);
       if (c.has_in(k)) {
 #pragma unroll
-        for (int t = 0; t < NT; ++t) {
-          const int oc = c.ci(k, t);
-          if (ACTI[oc] != 0.0) { const double z = c.si(k, t) * dx, r2 = R2I[oc]; PYI[oc] += (z - r2) * idel; R2I[oc] = r2 - z; }
-        }
+        for (int t = 0; t < NT; ++t) { const int oc = c.ci(k, t); if (ACTI[oc] != 0.0) PYI[oc] += idel * (c.si(k, t) * PX[ov] - bred_i(k, t)); }
       }
-      PX[ov] += dx;
     }
     __syncwarp();
+    inner();
   }
   // pol z = A x, normal-cone projection, residuals, acceptance.  Polished z of the single-variable rows -> R2I.
   double a_rp = 0, a_rd = 0;

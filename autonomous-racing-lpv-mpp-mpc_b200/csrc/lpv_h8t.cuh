@@ -1271,11 +1271,20 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
 }
 
 // ---------------------------------------------------------------- polish (cold, once per QP)
-// Reduced KKT system of the active rows solved in condensed form (row weights 1/delta) with iterative refinement.
-// The work vectors sit in the stage vectors ADMM no longer needs (x -> R, y_dyn -> XS, r2_dyn -> DG); on success the
-// polished (x, z, y) replace the iterate.  Each refinement step is two passes over the stages around one solve:
-//   rhs = -q - P x - A_red'(y - r2 / delta)                                  (one product with the columns of G)
-//   dx  = S^-1 rhs;  A dx gives dy = (A dx - r2) / delta and r2 <- r2 - A dx   (one product with the rows of G)
+// OSQP's polish (upstream polish.c; oracle/osqp_ref.c:polish): the reduced KKT system of the active rows,
+//   [P A_red'; A_red 0] (x, y) = (-q, b_red),
+// by iterative refinement with the regularised matrix K_reg = [P + delta I, A_red'; A_red, -delta I]:
+//   s_0 = K_reg^-1 rhs;   s_{j+1} = s_j + K_reg^-1 (rhs - K s_j),   j < polish_refine_iter        (exactly as upstream)
+// A solve with K_reg is done in condensed form, (P + delta I + A_red' A_red / delta) dx = r1 + A_red' r2 / delta,
+// dy = (A_red dx - r2) / delta, with the block factor of the ADMM steps (row weights 1 / delta).  That solve loses
+// about 6 digits to the 1 / delta weights, where upstream's quasi-definite LDL' is accurate to round-off, so every
+// K_reg solve is followed by kPolishInner refinement passes ON THE REGULARISED SYSTEM (residual
+// r1 - (P + delta I) dx - A_red' dy, dy slaved to dx): the outer iteration then is upstream's, pass for pass, and so are
+// the polished iterates of the slowly converging (ill-conditioned) problems.  (Round 1 ran polish_refine_iter + 2 outer
+// passes instead: 2 of 16,384 planner QPs ended 6e-3 away from the oracle)
+// State: t = s + w (tentative iterate: x part TX, dynamics duals TY, duals of my single-variable rows in tensor memory),
+// the x part DX of the increment w of the running K_reg solve; residuals are formed from t and DX alone:
+//   r1 - (P + delta I) dx - A' dy = -q - P tx - A' ty - delta dx.
 template <int KIND>
 __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const lpvmpc_settings &St, Info *ip, const bool do_pol, uint32_t gsel) {
   constexpr int NT = Ctx<KIND>::NT, NX = Ctx<KIND>::NX;
@@ -1283,16 +1292,15 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
   const bool unscale = I.unscale;
   const int N = c.N, r = c.r;
   double *X = c.V(V_X), *BV = c.V(V_B);
-  double *PX = c.V(V_R), *PYD = c.V(V_XS), *R2D = c.V(V_DG);       // [k*VS + q]
+  double *PX = c.V(V_R), *PYD = c.V(V_XS), *DX = c.V(V_DG), *TMP = c.V(V_CR);       // [k*VS + q]: tx, ty (dynamics rows), dx, row temporary
   double *YD = c.cd(C_YD);
   const double *BE = c.cd(C_BE), *ED = c.cd(C_ED), *QV = c.cd(C_Q);
   double *ACTD = c.cd(C_ACTD), *ACTI = c.cd(C_ACTI);   // slab copies for factor() and the outputs; the loops below use the register copies
   const double *PD = c.cd(C_PD), *PO = c.cd(C_PO), *EINV = c.cd(C_EINV), *EIINV = c.cd(C_EIINV), *DINV = c.cd(C_DINV);
   const double delta = St.delta, idel = 1.0 / St.delta;
-  // The duals / residual targets of the single-variable rows (PYI, R2I) live in the tensor-memory columns behind the
-  // factor (c.tP(k): 4 doubles per lane and stage) instead of the L2 slab, the active-set flags in registers: every
-  // slab access of these loops was an exposed L2 round trip (12 % of the kernel, profiles/r2i_ncu_h8t_*).  The
-  // tcgen05 loads / stores are warp-collective: they sit at the top / bottom of the stage loops, outside any branch.
+  // The duals of the single-variable rows (and at the end their polished z) live in the tensor-memory columns behind the
+  // factor (c.tP(k): 4 doubles per lane and stage), the active-set flags in registers.  The tcgen05 loads / stores are
+  // warp-collective: they sit at the top / bottom of the stage loops, outside any branch.
   uint64_t acti = 0;   // 2 bits per row (k, t) of mine: 1 = lower, 2 = upper, 3 = both
   uint32_t actd = 0;   // bit k: my dynamics row (k, r) is in the polish system
   auto ai_of = [&](int k, int t) { return (int)((acti >> (2 * (k * NT + t))) & 3ull); };
@@ -1302,8 +1310,10 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
     const int o = k * 8 + r;
     double ad = 0.0;
     // equality row (z == l == u): lower / upper by the sign of the dual.  Upstream drops the row when the dual is exactly
-    // 0.0; round-off makes that impossible there, but y_dyn recovered from the running sum can be exactly 0.0 on the rows
-    // of the unweighted state `s`, and the polish system needs every dynamics row: keep it (as "lower").
+    // 0.0 (its polish system is then singular and the polish is rejected: a floating-point accident that happens to 4 of the
+    // 4,096 QPs of configs[1] in the oracle, on the initial-condition row of the unweighted state `s`).  y_dyn recovered from
+    // the running sum is exactly 0.0 on such rows far more often, and the polish system needs every dynamics row: keep it
+    // (as "lower").
     if (c.xl && do_pol) ad = (0.0 < YD[o]) ? 2.0 : 1.0;
     ACTD[o] = ad;
     if (ad != 0.0) actd |= 1u << k;
@@ -1321,21 +1331,7 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
   FW fw; fw.polish = 1; fw.rho = 0.0; fw.rho_eq = 0.0; fw.idel = idel;
   factor<KIND>(c, fw, delta);
   auto bred_i = [&](int k, int t) { const int a = ai_of(k, t); return (a == 1 || a == 3) ? c.lo_of(k, t) : c.ui(k, t); };
-  // first solve: rhs = -q + A_red'(b_red / delta); the targets go through R2D / the R2I columns
-#pragma unroll 1
-  for (int k = 0; k <= N; ++k) {
-    const int o = k * 8 + r;
-    R2D[k * VS + r] = (c.xl && ((actd >> k) & 1u)) ? idel * BE[o] : 0.0;
-    double r2[2] = {0.0, 0.0};
-    if (c.has_in(k)) {
-#pragma unroll
-      for (int t = 0; t < NT; ++t) r2[t] = (ai_of(k, t) != 0) ? idel * bred_i(k, t) : 0.0;
-    }
-    tm_st4(c.tP(k), 0.0, 0.0, r2[0], r2[1]);
-  }
-  tm_wait_st();
-  __syncwarp();
-  // (A' t)_(k, r) with t_dyn = R2D-like array stored [k*VS + q] and t_in = (ti0, ti1) of my single-variable rows
+  // (A' t)_(k, r) with t_dyn stored [k*VS + q] and t_in = (ti0, ti1) of my single-variable rows
   auto colAt = [&](const double *td, const double ti0, const double ti1, int k) {
     double acc = c.xl ? ED[k * 8 + r] * td[k * VS + r] : 0.0;
     if (k < N) {
@@ -1350,38 +1346,92 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
     }
     return acc;
   };
+  // one K_reg solve in condensed form: BV holds the right-hand side on entry, ddx on exit
+  auto solve = [&]() {
+    __syncwarp();
+    sweep_fwd<KIND>(h, N, gsel);
+    sweep_bwd_plain<KIND>(h, N, gsel);
+  };
+  // refinement passes of the running K_reg solve: rhs = -q - P tx - A' ty - delta dx; tx, dx += ddx; ty += A ddx / delta
+  auto inner = [&]() {
+#pragma unroll 1
+    for (int ii = 0; ii < kPolishInner; ++ii) {
+#pragma unroll 1
+      for (int k = 0; k <= N; ++k) {
+        const int o = k * 8 + r, ov = k * VS + r;
+        TmQuad pq;
+        tm_ld4(c.tP(k), pq);
+        tm_wait_ld();
+        double b = 0.0;
+        if (c.var_live(k)) {
+          const double Px = rowP<KIND>(c, PD, PO, PX, VS, k);
+          const double Aty = colAt(PYD, tm_getq(pq, 0), tm_getq(pq, 1), k);
+          b = ((-QV[o] - Px) - Aty) - delta * DX[ov];
+        }
+        BV[ov] = b;
+      }
+      solve();
+#pragma unroll 1
+      for (int k = 0; k <= N; ++k) {
+        const int ov = k * VS + r;
+        TmQuad pq;
+        tm_ld4(c.tP(k), pq);
+        tm_wait_ld();
+        const double ddx = BV[ov];
+        if (c.xl && ((actd >> k) & 1u)) PYD[ov] += idel * rowA_dyn<KIND>(c, ED, BV, VS, k);
+        double py[2] = {tm_getq(pq, 0), tm_getq(pq, 1)};
+        if (c.has_in(k)) {
+#pragma unroll
+          for (int t = 0; t < NT; ++t) if (ai_of(k, t) != 0) py[t] += idel * (c.si(k, t) * ddx);
+        }
+        tm_st4(c.tP(k), py[0], py[1], 0.0, 0.0);
+        PX[ov] += ddx; DX[ov] += ddx;
+      }
+      tm_wait_st();
+      __syncwarp();
+    }
+  };
+  // ---- s_0 = K_reg^-1 (-q, b_red): rhs = -q + A_red'(b_red / delta)
+#pragma unroll 1
+  for (int k = 0; k <= N; ++k) TMP[k * VS + r] = (c.xl && ((actd >> k) & 1u)) ? idel * BE[k * 8 + r] : 0.0;
+  __syncwarp();
 #pragma unroll 1
   for (int k = 0; k <= N; ++k) {
-    TmQuad pq;
-    tm_ld4(c.tP(k), pq);
-    tm_wait_ld();
-    BV[k * VS + r] = c.var_live(k) ? (-QV[k * 8 + r] + colAt(R2D, tm_getq(pq, 2), tm_getq(pq, 3), k)) : 0.0;
+    double t2[2] = {0.0, 0.0};
+    if (c.has_in(k)) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) t2[t] = (ai_of(k, t) != 0) ? idel * bred_i(k, t) : 0.0;
+    }
+    BV[k * VS + r] = c.var_live(k) ? (-QV[k * 8 + r] + colAt(TMP, t2[0], t2[1], k)) : 0.0;
   }
-  __syncwarp();
-  sweep_fwd<KIND>(h, N, gsel);
-  sweep_bwd_plain<KIND>(h, N, gsel);
-  // x, y = (A x - b) / delta, r2 = b - A x on the active rows
+  solve();
+  // tx = dx = ddx;  ty = (A tx - b_red) / delta on the active rows
 #pragma unroll 1
   for (int k = 0; k <= N; ++k) {
     const int o = k * 8 + r, ov = k * VS + r;
     const double xk = BV[ov];
-    PX[ov] = xk;
-    const bool ad = c.xl && ((actd >> k) & 1u);
-    const double res = ad ? (BE[o] - rowA_dyn<KIND>(c, ED, BV, VS, k)) : 0.0;
-    R2D[ov] = res;
-    PYD[ov] = -res * idel;
-    double ri[2] = {0.0, 0.0};
+    PX[ov] = xk; DX[ov] = xk;
+    PYD[ov] = (c.xl && ((actd >> k) & 1u)) ? idel * (rowA_dyn<KIND>(c, ED, BV, VS, k) - BE[o]) : 0.0;
+    double py[2] = {0.0, 0.0};
     if (c.has_in(k)) {
 #pragma unroll
-      for (int t = 0; t < NT; ++t) ri[t] = (ai_of(k, t) != 0) ? (bred_i(k, t) - c.si(k, t) * xk) : 0.0;
+      for (int t = 0; t < NT; ++t) py[t] = (ai_of(k, t) != 0) ? idel * (c.si(k, t) * xk - bred_i(k, t)) : 0.0;
     }
-    tm_st4(c.tP(k), -ri[0] * idel, -ri[1] * idel, ri[0], ri[1]);
+    tm_st4(c.tP(k), py[0], py[1], 0.0, 0.0);
   }
   tm_wait_st();
   __syncwarp();
+  inner();
 #pragma unroll 1
-  for (int it = 0; it < St.polish_refine_iter + kPolishExtraRefine; ++it) {
-    // rhs = -q - P x - A'(y - r2 / delta)
+  for (int it = 0; it < St.polish_refine_iter; ++it) {
+    // s_{j+1} = s_j + K_reg^-1 (rhs - K s_j): r1 = -q - P tx - A' ty, r2 = b_red - A tx;
+    // condensed right-hand side r1 + A' r2 / delta = -q - P tx - A'(ty - r2 / delta)
+#pragma unroll 1
+    for (int k = 0; k <= N; ++k) {
+      const int o = k * 8 + r, ov = k * VS + r;
+      TMP[ov] = (c.xl && ((actd >> k) & 1u)) ? fma(-idel, BE[o] - rowA_dyn<KIND>(c, ED, PX, VS, k), PYD[ov]) : 0.0;
+    }
+    __syncwarp();
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
       const int o = k * 8 + r, ov = k * VS + r;
@@ -1391,52 +1441,41 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
       double b = 0.0;
       if (c.var_live(k)) {
         const double Px = rowP<KIND>(c, PD, PO, PX, VS, k);
-        double acc = c.xl ? ED[o] * fma(-idel, R2D[ov], PYD[ov]) : 0.0;
-        if (k < N) {
-          double g[8];
-#pragma unroll
-          for (int rr = 0; rr < 8; ++rr) g[rr] = (rr < NX) ? fma(-idel, R2D[(k + 1) * VS + rr], PYD[(k + 1) * VS + rr]) : 0.0;
-          acc += coldot<NX>(c.Gb(k), c.co, g);
-        }
+        double t2[2] = {0.0, 0.0};
         if (c.has_in(k)) {
 #pragma unroll
-          for (int t = 0; t < NT; ++t) acc = fma(c.si(k, t), fma(-idel, tm_getq(pq, 2 + t), tm_getq(pq, t)), acc);
+          for (int t = 0; t < NT; ++t)
+            t2[t] = (ai_of(k, t) != 0) ? fma(-idel, bred_i(k, t) - c.si(k, t) * PX[ov], tm_getq(pq, t)) : 0.0;
         }
-        b = (-QV[o] - Px) - acc;
+        b = (-QV[o] - Px) - colAt(TMP, t2[0], t2[1], k);
       }
       BV[ov] = b;
     }
+    solve();
+    // dx = ddx; tx += ddx (every stage, before the rows of A are applied to the new tx)
+#pragma unroll 1
+    for (int k = 0; k <= N; ++k) { const int ov = k * VS + r; const double ddx = BV[ov]; DX[ov] = ddx; PX[ov] += ddx; }
     __syncwarp();
-    sweep_fwd<KIND>(h, N, gsel);
-    sweep_bwd_plain<KIND>(h, N, gsel);
-    // dy = (A dx - r2) / delta, r2 <- r2 - A dx, x <- x + dx
+    // ty += (A ddx - r2) / delta = (A tx_new - b_red) / delta
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
       const int o = k * 8 + r, ov = k * VS + r;
       TmQuad pq;
       tm_ld4(c.tP(k), pq);
       tm_wait_ld();
-      const double dx = BV[ov];
-      if (c.xl && ((actd >> k) & 1u)) {
-        const double z = rowA_dyn<KIND>(c, ED, BV, VS, k), r2 = R2D[ov];
-        PYD[ov] += (z - r2) * idel;
-        R2D[ov] = r2 - z;
-      }
-      double py[2] = {tm_getq(pq, 0), tm_getq(pq, 1)}, r2i[2] = {tm_getq(pq, 2), tm_getq(pq, 3)};
+      if (c.xl && ((actd >> k) & 1u)) PYD[ov] += idel * (rowA_dyn<KIND>(c, ED, PX, VS, k) - BE[o]);
+      double py[2] = {tm_getq(pq, 0), tm_getq(pq, 1)};
       if (c.has_in(k)) {
 #pragma unroll
-        for (int t = 0; t < NT; ++t) {
-          if (ai_of(k, t) != 0) { const double z = c.si(k, t) * dx, r2 = r2i[t]; py[t] += (z - r2) * idel; r2i[t] = r2 - z; }
-        }
+        for (int t = 0; t < NT; ++t) if (ai_of(k, t) != 0) py[t] += idel * (c.si(k, t) * PX[ov] - bred_i(k, t));
       }
-      tm_st4(c.tP(k), py[0], py[1], r2i[0], r2i[1]);
-      PX[ov] += dx;
-      (void)o;
+      tm_st4(c.tP(k), py[0], py[1], 0.0, 0.0);
     }
     tm_wait_st();
     __syncwarp();
+    inner();
   }
-  // pol z = A x, normal-cone projection, residuals, acceptance.  Polished z of the single-variable rows -> the R2I columns.
+  // pol z = A x, normal-cone projection, residuals, acceptance.  Polished z of the single-variable rows -> columns 2, 3.
   double a_rp = 0, a_rd = 0;
 #pragma unroll 1
   for (int k = 0; k <= N; ++k) {
@@ -1446,11 +1485,11 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
     tm_wait_ld();
     if (c.xl) {
       const double Ax = rowA_dyn<KIND>(c, ED, PX, VS, k), t = Ax + PYD[ov];
-      PYD[ov] = t - BE[o];
+      TMP[ov] = t - BE[o];       // projected dual (PYD keeps feeding rowA-free reads of this loop's neighbours: none, but keep the pass pure)
       const double rr = Ax - BE[o];
       a_rp = absmax(a_rp, unscale ? EINV[o] * rr : rr);
-    } else PYD[ov] = 0.0;
-    double py[2] = {tm_getq(pq, 0), tm_getq(pq, 1)}, zz[2] = {tm_getq(pq, 2), tm_getq(pq, 3)};
+    } else TMP[ov] = 0.0;
+    double py[2] = {tm_getq(pq, 0), tm_getq(pq, 1)}, zz[2] = {0.0, 0.0};
     if (c.has_in(k)) {
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
@@ -1473,7 +1512,7 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
     tm_ld4(c.tP(k), pq);
     tm_wait_ld();
     if (c.var_live(k)) {
-      const double rr = (QV[o] + rowP<KIND>(c, PD, PO, PX, VS, k)) + colAt(PYD, tm_getq(pq, 0), tm_getq(pq, 1), k);
+      const double rr = (QV[o] + rowP<KIND>(c, PD, PO, PX, VS, k)) + colAt(TMP, tm_getq(pq, 0), tm_getq(pq, 1), k);
       a_rd = absmax(a_rd, unscale ? DINV[o] * rr : rr);
     }
   }
@@ -1490,7 +1529,7 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, const l
     tm_ld4(c.tP(k), pq);
     tm_wait_ld();
     if (take) {
-      X[ov] = PX[ov]; YD[o] = PYD[ov];
+      X[ov] = PX[ov]; YD[o] = TMP[ov];
       if (c.has_in(k)) {
 #pragma unroll
         for (int t = 0; t < NT; ++t) { c.zi(k, t) = tm_getq(pq, 2 + t); c.yi(k, t) = tm_getq(pq, t); }

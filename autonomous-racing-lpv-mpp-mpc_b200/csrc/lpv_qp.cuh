@@ -35,12 +35,15 @@ constexpr unsigned kFull = 0xffffffffu;
 // +2 passes reproduce the oracle's polish decisions and solutions to 1e-10; see DESIGN.md "Polish";
 // tools/debug_polish_passes.py on the full 4,096-QP batch: 5 and 6 passes give identical decisions and solutions, 4
 // passes lose 13 accepted polishes).
-constexpr int kPolishExtraRefine = 2;
+constexpr int kPolishExtraRefine = 2;   // legacy kernels only (polish_refine_iter + 2 outer passes of the condensed refinement)
+// Refinement passes on the REGULARISED polish system after every condensed K_reg solve (see polish() in lpv_h8t.cuh):
+// the condensed solve is accurate to ~1e-6 relative, one pass brings a K_reg solve to ~1e-12, upstream's LDL' level.
+constexpr int kPolishInner = 1;
 
 // Offsets (in doubles) of the per-QP workspace.
 struct Layout {
   int N, nx, nz, md, ms, m;
-  int G, gI, sc, Pxx, Puu, Pud, q, D, Dinv, E, Einv, l, u, z, y, x, xp, xt, tn, dy, tm, K, T, So, type, total;
+  int G, gI, sc, Pxx, Puu, Pud, q, D, Dinv, E, Einv, l, u, z, y, x, xp, xt, tn, pdx, dy, tm, K, T, So, type, total;
 };
 
 struct Params {
@@ -802,6 +805,24 @@ __device__ void admm_run(QP<KIND> &qp, const lpvmpc_settings &S, double c, Outco
     double *px = xp, *py = dy, *pz = tm;  // polished x, y (reduced rows, 0 elsewhere), z
     // active-row targets: l for lower-active (priority), u for upper-active
     auto bred = [&](int i) { return (ty[i] & 4) ? lo[i] : up[i]; };
+    // Upstream's refinement, pass for pass: s_0 = K_reg^-1 rhs, s_{j+1} = s_j + K_reg^-1 (rhs - K s_j); every K_reg solve
+    // (condensed form, accurate to ~1e-6) is refined kPolishInner times on the regularised system.  See polish() in lpv_h8t.cuh.
+    double *dxv = w + L.pdx;   // x part of the increment of the running K_reg solve
+    auto inner = [&]() {
+      for (int ii = 0; ii < kPolishInner; ++ii) {
+        for (int j = lane; j < L.nz; j += 32) {
+          const double Px = qp.rowP(j, [&](int jj) { return px[jj]; });
+          const double Aty = qp.colA(j, [&](int i) { return py[i]; });
+          xt[j] = ((-q[j] - Px) - Aty) - delta * dxv[j];
+        }
+        __syncwarp();
+        qp.solve(xt);
+        for (int i = lane; i < L.m; i += 32)
+          if (ty[i] & 12) py[i] += idel * qp.rowA(i, [&](int j) { return xt[j]; });
+        for (int j = lane; j < L.nz; j += 32) { px[j] += xt[j]; dxv[j] += xt[j]; }
+        __syncwarp();
+      }
+    };
     // first solve: rhs = [-q ; b_red]
     for (int j = lane; j < L.nz; j += 32) {
       const double at = qp.colA(j, [&](int i) { return (ty[i] & 12) ? idel * bred(i) : 0.0; });
@@ -809,7 +830,7 @@ __device__ void admm_run(QP<KIND> &qp, const lpvmpc_settings &S, double c, Outco
     }
     __syncwarp();
     qp.solve(xt);
-    for (int j = lane; j < L.nz; j += 32) px[j] = xt[j];
+    for (int j = lane; j < L.nz; j += 32) { px[j] = xt[j]; dxv[j] = xt[j]; }
     __syncwarp();
     for (int i = lane; i < L.m; i += 32) {
       double v = 0.0;
@@ -817,24 +838,25 @@ __device__ void admm_run(QP<KIND> &qp, const lpvmpc_settings &S, double c, Outco
       py[i] = v;
     }
     __syncwarp();
-    for (int it = 0; it < S.polish_refine_iter + kPolishExtraRefine; ++it) {
-      // residual of the un-regularised reduced KKT; r2 goes to pz (scratch)
+    inner();
+    for (int it = 0; it < S.polish_refine_iter; ++it) {
+      // condensed right-hand side of rhs - K s_j: -q - P tx - A'(ty - r2 / delta), r2 = b_red - A tx (row temporary in pz)
       for (int i = lane; i < L.m; i += 32)
-        pz[i] = (ty[i] & 12) ? (bred(i) - qp.rowA(i, [&](int j) { return px[j]; })) : 0.0;
+        pz[i] = (ty[i] & 12) ? fma(-idel, bred(i) - qp.rowA(i, [&](int j) { return px[j]; }), py[i]) : 0.0;
       __syncwarp();
       for (int j = lane; j < L.nz; j += 32) {
         const double Px = qp.rowP(j, [&](int jj) { return px[jj]; });
-        const double Aty = qp.colA(j, [&](int i) { return py[i]; });
-        const double r1 = (-q[j] - Px) - Aty;
-        const double at = qp.colA(j, [&](int i) { return idel * pz[i]; });
-        xt[j] = r1 + at;
+        const double At = qp.colA(j, [&](int i) { return pz[i]; });
+        xt[j] = (-q[j] - Px) - At;
       }
       __syncwarp();
       qp.solve(xt);
-      for (int i = lane; i < L.m; i += 32)
-        if (ty[i] & 12) py[i] += (qp.rowA(i, [&](int j) { return xt[j]; }) - pz[i]) * idel;
-      for (int j = lane; j < L.nz; j += 32) px[j] += xt[j];
+      for (int j = lane; j < L.nz; j += 32) { dxv[j] = xt[j]; px[j] += xt[j]; }
       __syncwarp();
+      for (int i = lane; i < L.m; i += 32)
+        if (ty[i] & 12) py[i] += idel * (qp.rowA(i, [&](int j) { return px[j]; }) - bred(i));
+      __syncwarp();
+      inner();
     }
     // pol->z = A x ; project (z, y) onto the normal cone
     for (int i = lane; i < L.m; i += 32) {

@@ -403,7 +403,7 @@ Layout make_layout(int kind, int N, int delay) {
   L.Pxx = take((N + 1) * NX * NX); L.Puu = take(N * NUc * NUc); L.Pud = take((N > 1 ? N - 1 : 0) * NUc);
   L.q = take(L.nz); L.D = take(L.nz); L.Dinv = take(L.nz);
   L.E = take(L.m); L.Einv = take(L.m); L.l = take(L.m); L.u = take(L.m); L.z = take(L.m); L.y = take(L.m);
-  L.x = take(L.nz); L.xp = take(L.nz); L.xt = take(L.nz); L.tn = take(L.nz);
+  L.x = take(L.nz); L.xp = take(L.nz); L.xt = take(L.nz); L.tn = take(L.nz); L.pdx = take(L.nz);
   L.dy = take(L.m); L.tm = take(L.m);
   L.K = take((N + 1) * NB * NB); L.T = take((N + 1) * NB * NB); L.So = take(NB * NB);
   L.type = take((L.m + 7) / 8);

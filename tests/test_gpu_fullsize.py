@@ -1,16 +1,20 @@
 """Parity at BASELINE.json's FULL sizes: every QP of the bench workloads (configs[1], [2], [4]) against the CPU oracle's
 batch loop on the same seeded inputs — status and ADMM iteration count identical for every problem, solutions of the
-solved problems within 1e-4.
+solved problems within 1e-4 (relative to max(1, |x|_inf): the N = 100 roll-outs reach |x| ~ 2e3).
 
-Documented exceptions, at most 0.2 % of a batch, each with the same status and iteration count and objectives within
-1e-6 relative: (i) ill-conditioned long-horizon problems whose Euler roll-out has diverged (|x| ~ 1e3 at N = 100: 2 of
-1,024), compared relative to |x|_inf; (ii) a handful of QPs (4 of 4,096 at configs[1]) where the polish accept / reject
-decision differs — the device's condensed polish (3 extra refinement passes) reaches residuals of 1e-15 / 1e-11 and is accepted,
-the oracle's full-KKT polish does not improve both residuals and is rejected, so the oracle keeps its ADMM iterate
-(accurate to OSQP's eps = 1e-3).  For those the test requires: same status and iteration count, device residuals not
-larger than the oracle's, objectives within 1e-6 relative, solutions within OSQP's own termination tolerance; and that they stay
-below 0.2 % of the batch; (iii) 2 of the 16,384 planner QPs whose polish is marginal on both sides (accepted with
-post-polish residuals of 1e-4 / 1e-3), differing by up to 6e-3 with objectives within 1.5e-4 relative."""
+There is NO percentage allowance.  The one admitted class of differences is decided by the oracle's own output:
+
+  exact-zero dual accident — OSQP's polish takes an equality row into its reduced KKT system only when the row's dual
+  is non-zero (`z - l < -y` or `u - z < y`, strict).  On the initial-condition row of the unweighted state `s`
+  (Q[4,4] = 0, controllerMain.py:139,146) the dual is zero up to round-off; when ADMM's floating-point value is EXACTLY
+  0.0 the row is dropped, the reduced KKT matrix is singular, the polished point is garbage and the polish is rejected
+  (4 of the 4,096 QPs of configs[1] with the oracle's LDL' back-end, 5 other QPs with its LU back-end — the accident
+  moves with the last bit of the arithmetic).  The device keeps every dynamics row (its dual is recovered from running
+  sums and is exactly 0.0 far more often), so there its polish succeeds.  Such a QP is recognised by: oracle polish
+  rejected AND an equality row missing from the oracle's active set with dual == 0.0.  For it the test requires the
+  same status and iteration count, a device polish with residuals <= 1e-9, objectives within 1e-6 relative and
+  solutions within OSQP's own termination tolerance of the oracle's (unpolished) iterate.
+"""
 import os
 
 import numpy as np
@@ -29,6 +33,16 @@ def _track():
     return lp.Map("L_shape").PointAndTangent
 
 
+def _zero_dual_accident(oo, n_eq_first, n_eq):
+    """True when the oracle's polish was rejected after dropping an equality row whose dual is exactly 0.0."""
+    if oo["status_polish"] != -1:
+        return False
+    rows = slice(n_eq_first, n_eq_first + n_eq)
+    act = (oo["active_lo"] | oo["active_up"])[rows]
+    ys = oo["ys"][rows]
+    return bool(((act == 0) & (ys == 0.0)).any())
+
+
 @pytest.mark.parametrize("N,B,seed,steer", [(8, 4096, 0, 1.0), (100, 1024, 3, 0.2)])
 def test_controller_bench_workloads_every_qp(N, B, seed, steer):
     track = _track()
@@ -44,25 +58,31 @@ def test_controller_bench_workloads_every_qp(N, B, seed, steer):
     assert ok.mean() > 0.99
     d = np.maximum(np.abs(r.u_pred - o["uPred"]).reshape(B, -1).max(1), np.abs(r.x_pred - o["xPred"]).reshape(B, -1).max(1))
     d[~ok] = 0.0
-    scale = np.maximum(1.0, np.abs(np.nan_to_num(o["xPred"])).reshape(B, -1).max(1))   # N = 100 roll-outs reach |x| ~ 2e3
+    scale = np.maximum(1.0, np.abs(np.nan_to_num(o["xPred"])).reshape(B, -1).max(1))
     odd = np.nonzero(d >= 1e-4 * scale)[0]
-    assert len(odd) <= 0.002 * B, len(odd)
     st = oracle.default_settings(polish=1)
-    for b in odd:   # see the module docstring
+    accidents = []
+    for b in odd:
         oo = oracle.ctrl_solve(cfg, st, w["x0"][b], mode=1, x_sched=w["x0"][b], u_prev=w["u_prev"][b], vel_ref=w["vel_ref"][b],
                                curv_ref=w["curv_ref"][b], lap=int(w["lap"][b]), old_steering=[w["u_old"][b, 0]], old_accel=float(w["u_old"][b, 1]))
+        assert _zero_dual_accident(oo, 6 * N, 6 * (N + 1)), (b, d[b], int(r.polish_status[b]), oo["status_polish"])
+        assert int(r.polish_status[b]) == 1 and r.pri_res[b] <= 1e-9 and r.dua_res[b] <= 1e-9, (b, r.pri_res[b], r.dua_res[b])
         assert abs(r.obj[b] - oo["obj_val"]) <= 1e-6 * abs(oo["obj_val"]), b
         assert d[b] < 1e-2 * scale[b], (b, d[b])   # OSQP's own tolerance: eps_abs + eps_rel * |z|_inf
-        if int(r.polish_status[b]) != oo["status_polish"]:
-            assert int(r.polish_status[b]) == 1 and oo["status_polish"] == -1, (b, r.polish_status[b], oo["status_polish"])
-            assert r.pri_res[b] <= oo["pri_res"] and r.dua_res[b] <= oo["dua_res"], b
+        accidents.append(int(b))
+    print("exact-zero-dual accidents of the oracle's polish:", accidents)
+    assert len(accidents) <= 8          # 4 at configs[1]; more would mean the class is being used as a dustbin
     s.close()
 
 
-def test_planner_bench_workload_every_qp():
+@pytest.mark.parametrize("gen", ["harvest", "nominal"])
+def test_planner_bench_workload_every_qp(gen):
+    """configs[2]: `harvest` is the BASELINE workload (SURVEY 8d: tuples from the reference's own planner loop, perturbed);
+    `nominal` is round 1's generator, kept because its 16,384 QPs hold the two slowly-converging polishes that told the
+    condensed refinement of round 1 apart from upstream's."""
     track = _track()
     N, B = 40, 16384
-    w = W.planner_batch(B, N, seed=1)
+    w = W.planner_batch_harvest(B, N, seed=1) if gen == "harvest" else W.planner_batch(B, N, seed=1)
     keys = ("SS", "u_prev", "u_old", "max_ey", "ey_lo", "ey_hi")
     s = lp.BatchSolver("planner", N, W.PLAN_DT, track=track, max_batch=B, **W.PLAN)
     r = s.solve(w["x0"], **{k: w[k] for k in keys})
@@ -72,15 +92,12 @@ def test_planner_bench_workload_every_qp():
     np.testing.assert_array_equal(r.status, o["status"])
     np.testing.assert_array_equal(r.iters, o["iters"])
     ok = o["status"] == 1
-    assert ok.mean() > 0.98
+    assert ok.mean() > (0.9 if gen == "harvest" else 0.98)
     d = np.maximum(np.abs(r.u_pred - o["uPred"]).reshape(B, -1).max(1), np.abs(r.x_pred - o["xPred"]).reshape(B, -1).max(1))
     d[~ok] = 0.0
     odd = np.nonzero(d >= 1e-4)[0]
-    assert len(odd) <= 0.001 * B, len(odd)      # measured: 2 of 16,384 (10 above 1e-6)
-    st = oracle.default_settings(polish=1)
-    for b in odd:   # marginal polish (post-polish residuals ~1e-4 / 1e-3 on both sides): see the module docstring
-        oo = oracle.plan_solve(cfg, st, w["x0"][b], mode=1, x_sched=w["x0"][b], SS=w["SS"][b], u_prev=w["u_prev"][b], u_old=w["u_old"][b],
-                               max_ey=float(w["max_ey"][b]), ey_lo=w["ey_lo"][b], ey_hi=w["ey_hi"][b])
-        assert abs(r.obj[b] - oo["obj_val"]) <= 1e-3 * abs(oo["obj_val"]), (b, r.obj[b], oo["obj_val"])
-        assert d[b] < 2e-2, (b, d[b])
+    assert len(odd) == 0, (odd[:10], d[odd][:10])
+    # the problems OSQP could not solve carry NaN outputs on the device, exactly where the oracle reports no solution
+    bad = ~np.isin(o["status"], (1, 2, -2))
+    assert np.isnan(r.x_pred[bad]).all() and not np.isnan(r.x_pred[~bad]).any()
     s.close()
