@@ -13,7 +13,7 @@ _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "liblpvmpc.so")
 HASH_PATH = os.path.join(_PKG, "liblpvmpc.srchash")
 _SRC_DIR = os.path.join(_PKG, "csrc")
-_SOURCES = [os.path.join(_SRC_DIR, f) for f in ("lpvmpc.cu", "lpv_qp.cuh", "lpv_h8.cuh", "lpv_h8t.cuh", "lpv_model.cuh", "lpv_loop.cuh")] + \
+_SOURCES = [os.path.join(_SRC_DIR, f) for f in ("lpvmpc.cu", "lpv_qp.cuh", "lpv_h8.cuh", "lpv_h8t.cuh", "lpv_h16t.cuh", "lpv_model.cuh", "lpv_loop.cuh")] + \
            [os.path.join(_ROOT, "include", "lpvmpc.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",

@@ -21,6 +21,7 @@
 #endif
 #include "lpv_h8.cuh"
 #include "lpv_h8t.cuh"
+#include "lpv_h16t.cuh"
 #include "lpv_loop.cuh"
 
 namespace lpv {
@@ -472,6 +473,15 @@ lpv::h8t::Lay make_h8t_layout(int kind, int N) {
   return L;
 }
 
+// H16T: the H8T layout without the factorisation scratch (it lives in dead stage-vector slots)
+lpv::h8t::Lay make_h16t_layout(int kind, int N) {
+  lpv::h8t::Lay L = make_h8t_layout(kind, N);
+  int o = L.FS;              // FS was the last block
+  while (o % 16 != 8) o += 2;
+  L.FS = 0; L.total = o;
+  return L;
+}
+
 }  // namespace
 
 struct lpvmpc_handle {
@@ -493,6 +503,7 @@ struct lpvmpc_handle {
 #endif
   lpv::h8::Lay HL;           // H8 layout (shared memory + slab)
   lpv::h8t::Lay TL;          // H8T layout (tensor memory + shared memory + slab)
+  lpv::h8t::Lay TL16;        // H16T layout
   int wpc = 1;               // H8: warps per CTA
   int qpw = 4;               // T8 / G8 / H8: QPs per warp
   unsigned *d_queue = nullptr;  // work-queue counter of the persistent T8 kernel
@@ -714,8 +725,23 @@ int launch_h8t(lpvmpc_handle *h, const Params &p, cudaStream_t s) {
   return LPVMPC_OK;
 }
 
+int launch_h16t(lpvmpc_handle *h, const Params &p, cudaStream_t s) {
+  if (p.B == 0) return LPVMPC_OK;
+  lpv::h8t::H8Params hp;
+  hp.L = h->TL16; hp.M = p.M; hp.S = p.S; hp.a = p.a; hp.B = p.B; hp.queue = h->d_queue; hp.cold = h->d_cold;
+  hp.perm = batch_order(h, p, s);
+  const int ctas = (p.B + 15) / 16;
+  const int grid = ctas < h->grid_cap ? ctas : h->grid_cap;
+  CUDA_TRY(h, cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned), s));
+  lpv::h16t::lpv_solve_h16t_kernel<<<grid, 256, h->ws_bytes, s>>>(hp);
+  ++h->launches;
+  CUDA_TRY(h, cudaGetLastError());
+  return LPVMPC_OK;
+}
+
 template <int KIND>
 int launch_solve(lpvmpc_handle *h, const Params &p, cudaStream_t s) {
+  if (h->variant == 8) return launch_h16t(h, p, s);
   if (h->variant == 6) return launch_h8t(h, p, s);
 #ifdef LPVMPC_LEGACY
   if (h->variant == 2) return launch_t8(h, p, s);
@@ -923,10 +949,27 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
                         h8t_bytes + 64 <= (size_t)h->smem_optin;
     if (cfg->variant == 6 && !h8t_ok) { h->err = "variant 6 (H8T) needs controller, diagonal Q and R, steering_delay=0, N<=8 (60 N + 28 tensor-memory columns <= 512)"; return bail(LPVMPC_E_UNSUPPORTED); }
     if (cfg->variant == 6 || (cfg->variant == 0 && h8t_ok)) h->variant = 6;
+    // H16T kernel: 16 lanes per QP, twisted factorisation (both ends towards the middle stage), 8 warps per CTA; the
+    // reference's controller horizon only (the factorisation scratch borrows stage-vector rows 0..7; N = 2 NL)
+    h->TL16 = make_h16t_layout(cfg->kind, cfg->N);
+    const size_t h16t_bytes = (size_t)h->TL16.total * sizeof(double) * 16 + 8 * 512 + 512;
+    const bool h16t_ok = pdiag && cfg->steering_delay == 0 && cfg->kind == LPVMPC_CONTROLLER && cfg->N == 8 &&
+                         h16t_bytes + 64 <= (size_t)h->smem_optin;
+    if (cfg->variant == 8 && !h16t_ok) { h->err = "variant 8 (H16T) needs controller, N=8, diagonal Q and R, steering_delay=0"; return bail(LPVMPC_E_UNSUPPORTED); }
+    static const bool auto16 = [] { const char *e = std::getenv("LPVMPC_AUTO_H16T"); return !e || std::atoi(e) != 0; }();   // LPVMPC_AUTO_H16T=0: H8T
+    if (cfg->variant == 8 || (cfg->variant == 0 && h16t_ok && auto16)) h->variant = 8;
   }
   h->ws_bytes = (size_t)h->L.total * sizeof(double);
   h->smem_mode = h->ws_bytes <= (size_t)h->smem_optin;
-  if (h->variant == 6) {
+  if (h->variant == 8) {
+    h->qpw = 2; h->wpc = 8;
+    h->ws_bytes = (size_t)h->TL16.total * sizeof(double) * 16 + 8 * 512 + 512;
+    h->smem_mode = true;
+    h->grid_cap = h->sm_count;
+    CTRY((cudaFuncSetAttribute(lpv::h16t::lpv_solve_h16t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ws_bytes)));
+    CTRY(cudaMalloc(&h->d_queue, sizeof(unsigned)));
+    CTRY(cudaMalloc(&h->d_cold, sizeof(double) * (size_t)h->grid_cap * 16 * h->TL16.cold_total));
+  } else if (h->variant == 6) {
     h->qpw = 4; h->wpc = 4;
     h->ws_bytes = (size_t)h->TL.total * sizeof(double) * 16 + 4 * 512 + 512;
     h->smem_mode = true;
@@ -1057,7 +1100,7 @@ int lpvmpc_get_info(const lpvmpc_handle *h, lpvmpc_info *info) {
   info->n = h->n; info->d = h->d; info->N = h->L.N; info->nz = h->L.nz; info->m = h->L.m;
   info->variant = (h->variant == 5 && h->HL.ring) ? 7 : h->variant;   // 7: H8 with the factor streamed
   info->workspace_in_smem = h->smem_mode ? 1 : 0;
-  info->smem_bytes_per_qp = h->smem_mode ? (int)(h->variant == 6 ? (size_t)h->TL.total * sizeof(double) : h->variant == 5 ? (size_t)h->HL.total * sizeof(double) : ((h->variant == 2 || h->variant == 3) ? h->ws_bytes / h->qpw : h->ws_bytes)) : 0;
+  info->smem_bytes_per_qp = h->smem_mode ? (int)(h->variant == 8 ? (size_t)h->TL16.total * sizeof(double) : h->variant == 6 ? (size_t)h->TL.total * sizeof(double) : h->variant == 5 ? (size_t)h->HL.total * sizeof(double) : ((h->variant == 2 || h->variant == 3) ? h->ws_bytes / h->qpw : h->ws_bytes)) : 0;
   info->workspace_bytes = (long long)(h->stage_bytes + (h->smem_mode ? 0 : h->ws_bytes * (size_t)h->grid_cap));
   info->kernel_launches = h->launches;
   return LPVMPC_OK;

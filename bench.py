@@ -45,7 +45,8 @@ FP64_PEAK_FILE = os.path.join(ROOT, "profiles", "r1_fp64_peak.jsonl")
 NCU_TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # {workload: {"variant": v, "dram_bytes_per_launch": b, "source": ...}}
 KERNEL_NAMES = {1: "lpv_solve_kernel (generic warp-per-QP)", 2: "lpv_solve_t8_kernel", 3: "lpv_solve_g8_kernel",
                 5: "lpv_solve_h8_kernel (factor in shared memory)", 6: "lpv_solve_h8t_kernel (factor in tensor memory)",
-                7: "lpv_solve_h8_kernel (factor streamed from the L2 slab by TMA bulk copies, ring of 4 stage blocks)"}
+                7: "lpv_solve_h8_kernel (factor streamed from the L2 slab by TMA bulk copies, ring of 4 stage blocks)",
+                8: "lpv_solve_h16t_kernel (16 lanes per QP, twisted block factor in tensor memory)"}
 
 WORKLOADS = {
     "ctrl4096": dict(kind="controller", N=8, B=4096, seed=0),

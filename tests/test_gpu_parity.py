@@ -69,7 +69,7 @@ def test_schedule_matches_oracle(track):
             np.testing.assert_allclose(r.states_out[b], st, rtol=1e-12, atol=1e-14)
 
 
-@pytest.mark.parametrize("variant", [1, 5, 6, 7])
+@pytest.mark.parametrize("variant", [1, 5, 6, 7, 8])
 @pytest.mark.parametrize("iters", [1, 7, 50, 200])
 def test_controller_fixed_iteration_iterates(track, iters, variant):
     N, B = 8, 48
@@ -89,7 +89,7 @@ def test_controller_fixed_iteration_iterates(track, iters, variant):
     assert worst < 1e-9, worst
 
 
-@pytest.mark.parametrize("variant", [1, 5, 6, 7])
+@pytest.mark.parametrize("variant", [1, 5, 6, 7, 8])
 def test_controller_converged_matches_oracle(track, variant):
     N, B = 8, 254  # not a multiple of 4: exercises the idle-group path of the T8 kernel
     w = W.controller_batch(B, N, seed=0)
