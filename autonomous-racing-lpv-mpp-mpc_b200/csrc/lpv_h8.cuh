@@ -751,6 +751,276 @@ __device__ __forceinline__ void sweep_bwd_admm_w1(const Hot<KIND> &h, Strm &sm, 
   }
 }
 
+// ---------------------------------------------------------------- twisted variants (one QP per warp, even N)
+// The block-tridiagonal system is eliminated FROM BOTH ENDS towards the middle stage m = N / 2 (two-sided / "twisted"
+// factorisation, the same scheme as lpv_h16t.cuh): lane groups 0 and 2 own the left half (stages 0 .. m-1, ascending),
+// groups 1 and 3 the right half (stages N .. m+1, descending); in LOCAL steps j (stage j on the left, N - j on the right)
+// both halves run one instruction stream on mirrored addresses, so a sweep is N/2 + 1 dependent stage steps instead of N + 1.
+//   left : T_k = S~_k^-1,  K_k = S_{k,k-1} T_{k-1},  S~_k = S_k - K_k S_{k,k-1}'        v_k = b_k - K_k v_{k-1}
+//   right: T_k = S^_k^-1,  J_k = S_{k,k+1} T_{k+1},  S^_k = S_k - J_k S_{k,k+1}'        v_k = b_k - J_k v_{k+1}
+//   middle: S~_m = S_m - K_m S_{m,m-1}' - J_m S_{m,m+1}',  v_m = b_m - K_m v_{m-1} - J_m v_{m+1},  x_m = T_m v_m
+//   back : x_k = T_k v_k - K_{k+1}' x_{k+1} (left),  x_k = T_k v_k - J_{k-1}' x_{k-1} (right)
+// Factor slot k holds [T_k | M_k], M_k = -K_{k+1} for k < m and -J_{k-1} for k > m (slot m: T_m only): the multiplier used
+// when LEAVING stage k forwards and when ENTERING it backwards, so both sweeps address slot (stage of local step j) in
+// both halves.  The middle stage is owned by both halves: identical operands, identical values, the same addresses.
+template <int KIND>
+__device__ __noinline__ void factor_tw(const Ctx<KIND> c, const FW fw, const double sigma, const int half) {
+  constexpr int NX = Ctx<KIND>::NX, NB = Ctx<KIND>::NB, NT = Ctx<KIND>::NT;
+  const int N = c.N, r = c.r, NL = N >> 1;
+  const double *PD = c.cd(C_PD), *PO = c.cd(C_PO), *ACTD = c.cd(C_ACTD), *ACTI = c.cd(C_ACTI), *ED = c.cd(C_ED);
+  double *DG = c.V(V_DG);
+  auto wd = [&](int k) -> double {  // weight of my dynamics row (k, r)
+    if (!c.xl) return 0.0;
+    return fw.polish ? ((ACTD[k * 8 + r] != 0.0) ? fw.idel : 0.0) : fw.rho_eq;
+  };
+  __syncwarp();
+#pragma unroll 1
+  for (int j = 0; j <= NL; ++j) {
+    const int k = half ? N - j : j;
+    const bool mid = (j == NL);
+    const int nbk = (k < N) ? NB : NX;
+    const bool rowlive = r < nbk;
+    double s[8], so[8];
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) { s[cc] = 0.0; so[cc] = 0.0; }
+    const double wdk = wd(k);
+    const double edk = c.xl ? ED[k * 8 + r] : 0.0;
+    const bool diag = !(mid && half);   // the middle stage's own block enters once: through the left half
+    {
+      double d = PD[k * 8 + r] + sigma;
+      if (c.has_in(k)) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const double a = c.si(k, t);
+          const double w = fw.polish ? ((ACTI[c.ci(k, t)] != 0.0) ? fw.idel : 0.0) : c.rho_of(k, fw.rho, fw.rho_eq);
+          d = fma(w * a, a, d);
+        }
+      }
+      if (!fw.polish && diag) DG[k * VS + r] = rowlive ? d : 1.0;
+      if (c.xl) d = fma(wdk * edk, edk, d);
+      if (!rowlive) d = 1.0;
+      if (!diag) d = 0.0;
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) if (cc == r) s[cc] = d;
+    }
+    // weights of the next stage's dynamics rows (every shuffle stays outside the half-dependent branches)
+    const double *gk = c.Gb(k < N ? k : N - 1);
+    const double wn = (k < N) ? wd(k + 1) : 0.0;
+    const double fn = (k < N && c.xl) ? wn * ED[(k + 1) * 8 + r] : 0.0;
+#pragma unroll
+    for (int rr = 0; rr < NX; ++rr) {  // next-stage dynamics rows: sum_rr w(k+1, rr) G[rr][r] G[rr][cc]
+      const double wcol = gshfl(wn, rr);
+      if (k < N && diag) {
+        const double col = wcol * gk[rr * 8 + r];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double2 e = ld2(gk + rr * 8 + 2 * q);
+          s[2 * q] = fma(col, e.x, s[2 * q]);
+          s[2 * q + 1] = fma(col, e.y, s[2 * q + 1]);
+        }
+      }
+    }
+    if (j > 0) {
+      // my row of the block that couples stage k to the neighbour eliminated before it
+      if (!half) {  // left: S_{k,k-1}
+        if (c.xl) {
+          const double f = wdk * edk;
+          const double *gp = c.Gb(k - 1);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { const double2 e = ld2(gp + r * 8 + 2 * q); so[2 * q] = f * e.x; so[2 * q + 1] = f * e.y; }
+        } else if (c.ul && k < N) {
+#pragma unroll
+          for (int cc = NX; cc < NB; ++cc) if (cc == r) so[cc] = PO[(k - 1) * 8 + r];
+        }
+      }
+#pragma unroll
+      for (int cc = 0; cc < NX; ++cc) {  // right: S_{k,k+1} = S_{k+1,k}': my row is column r of S_{k+1,k}
+        const double f = gshfl(fn, cc);
+        if (half && c.var_live(k)) so[cc] = f * gk[cc * 8 + r];
+      }
+      if (half && c.ul && k < N - 1) {
+#pragma unroll
+        for (int cc = NX; cc < NB; ++cc) if (cc == r) so[cc] = PO[k * 8 + r];
+      }
+      const int kp = half ? k + 1 : k - 1;
+      double *Mk = c.Tb(kp) + 64;
+      const double *Tp = c.Tb(kp);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) st2(Mk + c.ro[q], so[2 * q], so[2 * q + 1]);  // park the block in the multiplier's slot
+      __syncwarp();
+      double kr[8];
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) kr[cc] = 0.0;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double2 e = ld2(Tp + chunk(jj, q));
+          kr[2 * q] = fma(so[jj], e.x, kr[2 * q]);
+          kr[2 * q + 1] = fma(so[jj], e.y, kr[2 * q + 1]);
+        }
+      }
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) {
+        double acc = s[cc];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double2 e = ld2(Mk + chunk(cc, q));  // block[cc][2q..2q+1]
+          acc = fma(-kr[2 * q], e.x, acc);
+          acc = fma(-kr[2 * q + 1], e.y, acc);
+        }
+        s[cc] = acc;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) st2(Mk + c.ro[q], -kr[2 * q], -kr[2 * q + 1]);   // the sweeps add (-K): stored negated
+    }
+    if (mid) {  // S~_m = (S_m - K_m S_{m,m-1}') + (- J_m S_{m,m+1}'): the halves exchange their terms
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) s[cc] = s[cc] + __shfl_xor_sync(kFull, s[cc], 8);
+    }
+    if (!rowlive) {
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) s[cc] = (cc == r) ? 1.0 : 0.0;
+    }
+    // Gauss-Jordan inverse of the pivot block, rows across lanes (no pivoting: the block is SPD)
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      double pr[8];
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) pr[cc] = gshfl(s[cc], p);
+      if (p < nbk) {
+        const double piv = frcp(pr[p]);
+        if (r == p) {
+#pragma unroll
+          for (int cc = 0; cc < 8; ++cc) s[cc] = (cc == p) ? piv : s[cc] * piv;
+        } else {
+          const double fp = s[p] * piv;
+#pragma unroll
+          for (int cc = 0; cc < 8; ++cc) s[cc] = (cc == p) ? -fp : fma(-fp, pr[cc], s[cc]);
+        }
+      }
+    }
+    double *Tk = c.Tb(k);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) st2(Tk + c.ro[q], s[2 * q], s[2 * q + 1]);
+    __syncwarp();
+  }
+}
+
+// Forward sweep: groups 0 / 1 run the chains of their halves (v_next = b_next + M_k v_k), groups 2 / 3 form W_k = T_k v_k of
+// their halves one step behind; one instruction stream: every lane loads ONE row of the stage slot (T_k or M_k).
+template <int KIND>
+__device__ __forceinline__ void sweep_fwd_tw(const Hot<KIND> &h, const int N, uint32_t &gsel, const int g) {
+  const int NL = N >> 1;
+  const bool half = g & 1, trole = (g >> 1) != 0;
+  const uint32_t tstr = half ? (uint32_t)(-TKB) : (uint32_t)TKB, vstr = half ? (uint32_t)(-VB) : (uint32_t)VB;
+  const uint32_t ggat = trole ? h.ggat - 32u : h.ggat;   // the T lanes read the chain column of their half
+  uint32_t so = (half ? (uint32_t)N * (uint32_t)TKB : 0u) + (trole ? 0u : 512u);
+  uint32_t vb = h.v + (half ? (uint32_t)N * (uint32_t)VB : 0u), wst = vb;
+  double res = lds(vb);   // chain: v of local step 0 = b; T lanes: b as well, written back unchanged by their first store
+#pragma unroll 1
+  for (int j = 0; j < NL; ++j) {
+    sts(trole ? wst : (h.gpub ^ gsel), res);
+    const double2 r0 = lds2(h.tk[0] + so), r1 = lds2(h.tk[1] + so), r2 = lds2(h.tk[2] + so), r3 = lds2(h.tk[3] + so);
+    double bn = lds(vb + vstr);
+    if (trole || (half && j == NL - 1)) bn = 0.0;   // the middle stage's right-hand side enters once: through the left half
+    __syncwarp();
+    const uint32_t gg = ggat ^ gsel;
+    const double2 g0 = lds2(gg), g1 = lds2<64>(gg), g2 = lds2<128>(gg), g3 = lds2<192>(gg);
+    double c0 = fma(r0.x, g0.x, bn), c1 = r1.x * g1.x, c2 = r2.x * g2.x, c3 = r3.x * g3.x;
+    c0 = fma(r0.y, g0.y, c0); c1 = fma(r1.y, g1.y, c1); c2 = fma(r2.y, g2.y, c2); c3 = fma(r3.y, g3.y, c3);
+    res = (c0 + c1) + (c2 + c3);
+    wst = vb; vb += vstr; so += tstr; gsel ^= 256u;
+  }
+  if (trole) sts(wst, res);   // W of local step NL-1
+  const double vm = res + __shfl_xor_sync(kFull, res, 8);   // chain lanes: v_m = (b_m - K_m v_{m-1}) + (- J_m v_{m+1})
+  {  // the middle stage: W_m = T_m v_m (every group, same value to the same slot)
+    sts(h.gpub ^ gsel, vm);   // T lanes publish into their own, unread column
+    const uint32_t sm_ = (uint32_t)NL * (uint32_t)TKB;
+    const double2 a0 = lds2(h.tk[0] + sm_), a1 = lds2(h.tk[1] + sm_), a2 = lds2(h.tk[2] + sm_), a3 = lds2(h.tk[3] + sm_);
+    __syncwarp();
+    const uint32_t gg = ggat ^ gsel;
+    const double2 g0 = lds2(gg), g1 = lds2<64>(gg), g2 = lds2<128>(gg), g3 = lds2<192>(gg);
+    sts(vb, dot8(a0, a1, a2, a3, g0, g1, g2, g3));
+    gsel ^= 256u;
+  }
+  __syncwarp();
+}
+
+// backward sweep only (polish): x written back into B; groups 2 / 3 mirror groups 0 / 1
+template <int KIND>
+__device__ __forceinline__ void sweep_bwd_plain_tw(const Hot<KIND> &h, const int N, uint32_t &gsel, const int g) {
+  const int NL = N >> 1;
+  const bool half = g & 1;
+  double gn[8];
+  {
+    const double x = lds(h.v + (uint32_t)NL * VB);
+    sts(h.gpub ^ gsel, x);
+    gather_in(h.ggat, gsel, gn);
+  }
+#pragma unroll 1
+  for (int j = NL - 1; j >= 0; --j) {
+    const uint32_t k = (uint32_t)(half ? N - j : j), so = k * (uint32_t)TKB, vb = h.v + k * (uint32_t)VB;
+    const double xt = bwd_step(h.kc[0] + so, h.kc[1] + so, h.kc[2] + so, h.kc[3] + so, vb, h.gpub, h.ggat, gsel, gn);
+    sts(vb, xt);
+    gather_in(h.ggat, gsel, gn);
+  }
+  __syncwarp();
+}
+
+// Backward sweep + element-wise updates.  The chains run from the middle outwards (groups 2 / 3 mirror groups 0 / 1), two
+// local steps at a time; behind them one update round: group (half, idx) updates the stage of local step jt - idx of its
+// half (round jt = NL: both halves update the middle stage, identically).  x~_k is parked in the B slot of its stage
+// between its chain step and its update; the x~ of the neighbour TOWARDS THE MIDDLE of an idx-0 stage was overwritten by
+// the previous round and comes from that round's idx-1 group through a shuffle.
+template <int KIND>
+__device__ __forceinline__ void sweep_bwd_admm_tw(const Hot<KIND> &h, const Upd<KIND> &u, uint32_t &gsel, const int g) {
+  const int N = u.N, NL = N >> 1;
+  const int lane = threadIdx.x & 31;
+  const bool half = g & 1;
+  const int idx = g >> 1;
+  double gn[8];
+  {
+    const double xm_ = lds(h.v + (uint32_t)NL * VB);   // x~_m = W_m
+    sts(h.gpub ^ gsel, xm_);
+    gather_in(h.ggat, gsel, gn);
+  }
+  double carry = 0.0;
+  int jc = NL - 1;   // next local step of the chains
+  int jt = NL;       // top local step of the next update round
+#pragma unroll 1
+  while (jt >= 0) {
+#pragma unroll 1
+    for (int i = 0; i < 2 && jc >= 0; ++i, --jc) {
+      const uint32_t k = (uint32_t)(half ? N - jc : jc), so = k * (uint32_t)TKB, vb = h.v + k * (uint32_t)VB;
+      const double xt = bwd_step(h.kc[0] + so, h.kc[1] + so, h.kc[2] + so, h.kc[3] + so, vb, h.gpub, h.ggat, gsel, gn);
+      sts(vb, xt);   // W_k has been consumed: park x~_k here until the update of stage k overwrites it
+      gather_in(h.ggat, gsel, gn);
+    }
+    __syncwarp();
+    const int jl = jt - idx;
+    double x1 = 0.0;
+    if (jl >= 0) {
+      const int k = half ? N - jl : jl;
+      const uint32_t vj = h.v + (uint32_t)k * VB, ij = h.ib + (uint32_t)k * h.istr, lj = h.il + (uint32_t)k * h.istr;
+      const uint32_t pj = h.pm + (uint32_t)k * h.pstr, pj2 = h.pm2 + (uint32_t)k * h.pstr;
+      UpdIn in;
+      update_loads<KIND>(vj, ij, lj, pj, pj2, in);
+      x1 = lds(vj);
+      double xm = (k > 0) ? lds(vj - VB) : 0.0;
+      double xp = (k < N) ? lds(vj + VB) : 0.0;
+      if (idx == 0 && jl < NL) { if (half) xm = carry; else xp = carry; }
+      UpdMid q;
+      update_part1<KIND>(u, k, ij, in, x1, xm, xp, q);
+      update_part2<KIND>(u, vj, x1, q);
+    }
+    carry = __shfl_sync(kFull, x1, (lane & 7) + 8 * ((half ? 1 : 0) + 2));   // x~ of my half's idx-1 stage of this round
+    __syncwarp();
+    jt -= 2;
+  }
+}
+
 // ---------------------------------------------------------------- per-QP scalars shared by the cold routines
 struct Info {
   double pri_res, dua_res, obj;
@@ -1416,9 +1686,10 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
 // polished (x, z, y) replace the iterate.  Each refinement step is two passes over the stages around one solve:
 //   rhs = -q - P x - A_red'(y - r2 / delta)                                  (one product with the columns of G)
 //   dx  = S^-1 rhs;  A dx gives dy = (A dx - r2) / delta and r2 <- r2 - A dx   (one product with the rows of G)
-template <int KIND, bool ST>
+template <int KIND, bool ST, bool TW>
 __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, Strm *smp, const lpvmpc_settings &St, Info *ip, const bool do_pol, uint32_t gsel) {
   Strm &sm = *smp;
+  const int g = (threadIdx.x & 31) >> 3;
   constexpr int NT = Ctx<KIND>::NT, NX = Ctx<KIND>::NX;
   Info &I = *ip;
   const bool unscale = I.unscale;
@@ -1452,7 +1723,8 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, Strm *s
   __syncwarp();
   FW fw; fw.polish = 1; fw.rho = 0.0; fw.rho_eq = 0.0; fw.idel = idel;
   if (ST) strm_drain(h.sc, sm);
-  factor<KIND>(c, fw, delta);
+  if (TW) factor_tw<KIND>(c, fw, delta, g & 1);
+  else factor<KIND>(c, fw, delta);
   auto bred_i = [&](int k, int t) { const double a = ACTI[c.ci(k, t)]; return (a == 1.0 || a == 3.0) ? c.lo_of(k, t) : c.ui(k, t); };
   // (A' t)_(k, r) with t_dyn stored [k*VS + q] and t_in = (ti0, ti1) of my single-variable rows
   auto colAt2 = [&](const double *td, const double ti0, const double ti1, int k) {
@@ -1482,8 +1754,13 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, Strm *s
   double *DX = R2D, *TMP = c.V(V_CR);
   auto solve = [&]() {
     __syncwarp();
-    sweep_fwd<KIND, ST>(h, sm, N, gsel);
-    sweep_bwd_plain<KIND, ST>(h, sm, N, gsel);
+    if (TW) {
+      sweep_fwd_tw<KIND>(h, N, gsel, g);
+      sweep_bwd_plain_tw<KIND>(h, N, gsel, g);
+    } else {
+      sweep_fwd<KIND, ST>(h, sm, N, gsel);
+      sweep_bwd_plain<KIND, ST>(h, sm, N, gsel);
+    }
   };
   auto inner = [&]() {
 #pragma unroll 1
@@ -1632,9 +1909,11 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, Strm *s
 constexpr int kSyncEvery = 25;  // y_dyn is brought up to date and r re-projected at least every kSyncEvery steps
 
 // ST: factor streamed from the slab (one QP per warp, one warp per CTA: every staging address is warp-uniform)
-template <int KIND, int QPW, bool ST>
+// TW: twisted factorisation (one QP per warp, resident factor, even N: checked by the host)
+template <int KIND, int QPW, bool ST, bool TW = false>
 __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant__ H8Params p) {
   static_assert(!ST || QPW == 1, "the streamed kernel holds one QP per warp");
+  static_assert(!TW || (QPW == 1 && !ST), "the twisted kernel holds one QP per warp with the factor resident");
   extern __shared__ __align__(16) double smem[];
   constexpr int NX = Ctx<KIND>::NX, NB = Ctx<KIND>::NB, NT = Ctx<KIND>::NT, NSL = Ctx<KIND>::NSL;
   constexpr int OLI = Ctx<KIND>::OLI, OPM = Ctx<KIND>::OPM;
@@ -1733,7 +2012,8 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
     double rho_eq = kRhoEqOverIneq * rho;
     {
       FW fw; fw.polish = 0; fw.rho = rho; fw.rho_eq = rho_eq; fw.idel = 0.0;
-      factor<KIND>(c, fw, sigma);
+      if (TW) factor_tw<KIND>(c, fw, sigma, g & 1);
+      else factor<KIND>(c, fw, sigma);
     }
     reproject<KIND>(c, true, rho, rho_eq, sigma, 0.0, true);
     bool live = (flags == 0);
@@ -1770,9 +2050,11 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
           }
         }
         u.cc = (iter == 0) ? 2.0 : alpha;
-        if (QPW == 1) sweep_fwd_w1<KIND, ST>(h, sm, N, gsel, g);
+        if (TW) sweep_fwd_tw<KIND>(h, N, gsel, g);
+        else if (QPW == 1) sweep_fwd_w1<KIND, ST>(h, sm, N, gsel, g);
         else sweep_fwd<KIND, ST>(h, sm, N, gsel);
-        if (QPW == 1) sweep_bwd_admm_w1<KIND, ST>(h, sm, u, gsel, g);
+        if (TW) sweep_bwd_admm_tw<KIND>(h, u, gsel, g);
+        else if (QPW == 1) sweep_bwd_admm_w1<KIND, ST>(h, sm, u, gsel, g);
         else sweep_bwd_admm<KIND, ST>(h, sm, u, gsel);
         if (iter == 0) first_in = 1;
         ++nsync;
@@ -1807,7 +2089,8 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
             FW fw; fw.polish = 0; fw.rho = rho; fw.rho_eq = rho_eq; fw.idel = 0.0;
             __syncwarp();
             if (ST) strm_drain(h.sc, sm);
-            factor<KIND>(c, fw, sigma);
+            if (TW) factor_tw<KIND>(c, fw, sigma, g & 1);
+            else factor<KIND>(c, fw, sigma);
             new_cr = true;
           }
         }
@@ -1866,7 +2149,7 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
     const bool do_pol = S.polish && status == LPVMPC_SOLVED;
     bool polished_sets = false;
     if (__any_sync(kFull, do_pol)) {
-      polish_status = polish<KIND, ST>(c, h, &sm, S, &I, do_pol, gsel);
+      polish_status = polish<KIND, ST, TW>(c, h, &sm, S, &I, do_pol, gsel);
       polished_sets = do_pol;
     }
     // ---- outputs

@@ -441,7 +441,7 @@ lpv::h8::Lay make_h8_layout(int kind, int N, int ring) {
   L.ring = ring; L.pfd = ring ? ring - 2 : 0;
   int o = 0;
   auto take = [&](int n) { const int r = o; o += (n + 1) & ~1; return r; };
-  L.TK = take(ring ? ring * lpv::h8::TKS : (N + 1) * lpv::h8::TKS - 64);
+  L.TK = take(ring ? ring * lpv::h8::TKS : (N + 1) * lpv::h8::TKS);   // slot N's multiplier half is used by the twisted kernels
   L.V = take((N + 1) * lpv::h8::VS);
   L.I = take((N + 2) * L.is);
   while (o % 16 != 8) o += 2;  // neighbouring groups of a warp 64 B apart mod 128
@@ -505,6 +505,7 @@ struct lpvmpc_handle {
   lpv::h8t::Lay TL;          // H8T layout (tensor memory + shared memory + slab)
   lpv::h8t::Lay TL16;        // H16T layout
   int wpc = 1;               // H8: warps per CTA
+  bool twisted = false;      // H8, one QP per warp: twisted factorisation kernel
   int qpw = 4;               // T8 / G8 / H8: QPs per warp
   unsigned *d_queue = nullptr;  // work-queue counter of the persistent T8 kernel
   int *d_perm = nullptr;        // visiting order of the batch (lpv_order_kernel)
@@ -682,6 +683,15 @@ template <int KIND, int QPW>
 cudaError_t h8_attr(size_t smem) {
   return cudaFuncSetAttribute(lpv::h8::lpv_solve_h8_kernel<KIND, QPW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
+// twisted factorisation: one QP per warp, resident factor, even N
+template <int KIND>
+void h8w_launch(int grid, int threads, size_t smem, cudaStream_t s, const lpv::h8::H8Params &hp) {
+  lpv::h8::lpv_solve_h8_kernel<KIND, 1, false, true><<<grid, threads, smem, s>>>(hp);
+}
+template <int KIND>
+cudaError_t h8w_attr(size_t smem) {
+  return cudaFuncSetAttribute(lpv::h8::lpv_solve_h8_kernel<KIND, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
 // streamed factor: one QP per warp, one warp per CTA
 template <int KIND>
 void h8s_launch(int grid, size_t smem, cudaStream_t s, const lpv::h8::H8Params &hp) {
@@ -705,6 +715,7 @@ int launch_h8(lpvmpc_handle *h, const Params &p, cudaStream_t s) {
   if (h->HL.ring) h8s_launch<KIND>(grid, h->ws_bytes, s, hp);
   else if (h->qpw == 4) h8_launch<KIND, 4>(grid, 32 * h->wpc, h->ws_bytes, s, hp);
   else if (h->qpw == 2) h8_launch<KIND, 2>(grid, 32 * h->wpc, h->ws_bytes, s, hp);
+  else if (h->twisted) h8w_launch<KIND>(grid, 32 * h->wpc, h->ws_bytes, s, hp);
   else h8_launch<KIND, 1>(grid, 32 * h->wpc, h->ws_bytes, s, hp);
   ++h->launches;
   CUDA_TRY(h, cudaGetLastError());
@@ -1011,7 +1022,13 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
     if (h->HL.ring) CTRY(ctrl ? h8s_attr<LPVMPC_CONTROLLER>(h->ws_bytes) : h8s_attr<LPVMPC_PLANNER>(h->ws_bytes));
     else if (h->qpw == 4) CTRY(ctrl ? (h8_attr<LPVMPC_CONTROLLER, 4>(h->ws_bytes)) : (h8_attr<LPVMPC_PLANNER, 4>(h->ws_bytes)));
     else if (h->qpw == 2) CTRY(ctrl ? (h8_attr<LPVMPC_CONTROLLER, 2>(h->ws_bytes)) : (h8_attr<LPVMPC_PLANNER, 2>(h->ws_bytes)));
-    else CTRY(ctrl ? (h8_attr<LPVMPC_CONTROLLER, 1>(h->ws_bytes)) : (h8_attr<LPVMPC_PLANNER, 1>(h->ws_bytes)));
+    else {
+      // one QP per warp, even horizon: twisted factorisation (both ends towards the middle stage); LPVMPC_H8_TWISTED=0: plain
+      static const bool tw_on = [] { const char *e = std::getenv("LPVMPC_H8_TWISTED"); return !e || std::atoi(e) != 0; }();
+      h->twisted = tw_on && (cfg->N % 2 == 0) && cfg->N >= 4;
+      if (h->twisted) CTRY(ctrl ? h8w_attr<LPVMPC_CONTROLLER>(h->ws_bytes) : h8w_attr<LPVMPC_PLANNER>(h->ws_bytes));
+      else CTRY(ctrl ? (h8_attr<LPVMPC_CONTROLLER, 1>(h->ws_bytes)) : (h8_attr<LPVMPC_PLANNER, 1>(h->ws_bytes)));
+    }
     CTRY(cudaMalloc(&h->d_queue, sizeof(unsigned)));
     CTRY(cudaMalloc(&h->d_cold, sizeof(double) * (size_t)h->grid_cap * h->wpc * h->qpw * h->HL.cold_total));
 #ifdef LPVMPC_LEGACY
