@@ -139,7 +139,10 @@ def build(force=False, verbose=False):
         fcntl.flock(lock, fcntl.LOCK_EX)
         if force or is_stale():
             tmp = LIB_PATH + ".tmp.%d" % os.getpid()
-            cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(_ROOT, "include"), "-o", tmp, os.path.join(_SRC_DIR, "lpvmpc.cu")]
+            # LPVMPC_NVCC_EXTRA: extra flags for development builds (e.g. --split-compile=0); not part of the source hash
+            import shlex
+            cmd = [nvcc] + NVCC_FLAGS + shlex.split(os.environ.get("LPVMPC_NVCC_EXTRA", "")) + \
+                  ["-I", os.path.join(_ROOT, "include"), "-o", tmp, os.path.join(_SRC_DIR, "lpvmpc.cu")]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             env = dict(os.environ)

@@ -1,5 +1,6 @@
 // Kernels and C-ABI (include/lpvmpc.h) of the B200-native batched LPV-MPC QP solver.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+#include <cuda.h>           // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -226,18 +227,26 @@ __device__ __forceinline__ void sched_copy_out(const double *tile, int off, doub
     }
   }
 }
-template <int KIND>
+// 256-bit global store (sm_100: STG.E.256): one full 32-byte sector per lane and instruction
+__device__ __forceinline__ void stg256(double *p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+// DIRECT (controller, 32-byte aligned outputs): every thread stores its own records straight from registers with 256-bit
+// stores (A_k: 9, B_k: 3 per stage; the 48-byte state with three 128-bit stores) -- whole sectors, no shared-memory
+// staging, 15 memory instructions per stage instead of 27 tile writes + 27 tile reads + 27 stores.
+template <int KIND, bool DIRECT = false>
 __global__ void __launch_bounds__(kSchedThreads, 8) lpv_schedule_kernel(const __grid_constant__ Params p, int *sched_err) {
   using T = SchedTile<KIND>;
   constexpr int NX = T::NX, NA = T::NA, NBm = T::NBm, STRIDE = T::STRIDE;
-  __shared__ __align__(16) double tile_s[kSchedThreads / 32][32 * STRIDE];   // 27 KB: 8 CTAs = 16 warps per SM
+  static_assert(!DIRECT || (NA % 4 == 0 && NBm % 4 == 0 && NX % 2 == 0), "direct stores need records of whole 32-byte pieces");
+  __shared__ __align__(16) double tile_s[DIRECT ? 1 : kSchedThreads / 32][DIRECT ? 2 : 32 * STRIDE];   // 27 KB: 8 CTAs = 16 warps per SM
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b0 = blockIdx.x * blockDim.x + warp * 32;      // first QP of my warp
   if (b0 >= p.B) return;
   const int nq = (p.B - b0 < 32) ? p.B - b0 : 32;          // QPs of my warp
   const bool live = lane < nq;
   const int b = live ? b0 + lane : b0;                      // idle lanes mirror the warp's first QP (no output of their own)
-  double *tile = tile_s[warp], *mine = tile + lane * STRIDE;
+  double *tile = tile_s[DIRECT ? 0 : warp], *mine = tile + (DIRECT ? 0 : lane * STRIDE);
   const Model &M = p.M;
   const lpvmpc_args &a = p.a;
   const int N = p.L.N;
@@ -270,6 +279,26 @@ __global__ void __launch_bounds__(kSchedThreads, 8) lpv_schedule_kernel(const __
       plan_stage(M, st[0], st[1], st[3], st[4], curvature(M.track, M.nseg, va, err), u01[0], Ai, Bi);
     }
     if (!estimate) propagate<NX>(Ai, Bi, u01, st);
+    if (DIRECT) {
+      if (live) {
+        if (a.A_out) {
+          double *d = a.A_out + ((size_t)b * N + i) * NA;
+#pragma unroll
+          for (int e = 0; e < NA; e += 4) stg256(d + e, Ai[e], Ai[e + 1], Ai[e + 2], Ai[e + 3]);
+        }
+        if (a.B_out) {
+          double *d = a.B_out + ((size_t)b * N + i) * NBm;
+#pragma unroll
+          for (int e = 0; e < NBm; e += 4) stg256(d + e, Bi[e], Bi[e + 1], Bi[e + 2], Bi[e + 3]);
+        }
+        if (a.states_out && !estimate) {
+          double *d = a.states_out + ((size_t)b * N + i) * NX;
+#pragma unroll
+          for (int r = 0; r < NX; r += 2) *reinterpret_cast<double2 *>(d + r) = make_double2(st[r], st[r + 1 < NX ? r + 1 : r]);
+        }
+      }
+      continue;
+    }
     if (T::PAIRS) {
 #pragma unroll
       for (int e = 0; e < NA; e += 2) *reinterpret_cast<double2 *>(mine + e) = make_double2(Ai[e], Ai[e + 1]);
@@ -295,6 +324,117 @@ __global__ void __launch_bounds__(kSchedThreads, 8) lpv_schedule_kernel(const __
     if (a.states_out && !estimate) sched_copy_out<STRIDE, NX, T::PAIRS>(tile, NA + NBm, a.states_out + ((size_t)b0 * N + i) * NX, (size_t)N * NX, nq, lane);
     __syncwarp();
   }
+  if (sched_err && live) sched_err[b] = err;
+}
+
+// TMA variant (controller; A_out / states_out 16-byte, B_out 32-byte aligned).  What bounds this kernel is the WRITE PATTERN
+// (tools/write_pattern3.cu, profiles/r3_write_pattern.jsonl): with one thread per QP the three arrays are written stage by
+// stage, 288 / 96 / 48 bytes per QP at strides of 2,304 / 768 / 384 bytes, and the 48-byte state records in particular
+// (one and a half sectors) halve what the memory system sustains (3.45 TB/s for the pattern against 5.0 TB/s when B_k and
+// the states of FOUR consecutive stages leave together; A_k is indifferent to it).  So:
+//   A_k     one dense shared-memory box [32][36] per stage -> cp.async.bulk.tensor store, tensor {36, N, B}, box {36, 1, 32}
+//   states  shared-memory box [32][4][6], stored once per four stages, tensor {6, N, B}, box {6, 4, 32} (192 bytes per QP)
+//   B_k     its three varying entries stay in registers for four stages, then 12 256-bit stores per lane (384 bytes per QP;
+//           a third TMA box would not fit next to the other two at 14 resident warps per SM, and writing it over the A box
+//           needs an exposed wait for the A store every second stage: measured 64.5 against 62.5 us)
+// The TMA unit walks the strides between neighbouring QPs and clips partial warps and partial chunks; one lane issues.
+struct SchedMaps { CUtensorMap A, S; };
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1),
+               "r"(c2)
+               : "memory");
+}
+constexpr int kTmaWarps = 2;   // warps per CTA
+constexpr int kTmaChunk = 4;   // stages of B_k / states written together
+__global__ void __launch_bounds__(32 * kTmaWarps, 7) lpv_schedule_tma_kernel(const __grid_constant__ Params p, int *sched_err,
+                                                                           const __grid_constant__ SchedMaps maps) {
+  constexpr int NX = 6, NA = 36, NBm = 12, CH = kTmaChunk;
+  __shared__ __align__(128) double tile_s[kTmaWarps][32 * (NA + CH * NX)];   // per warp: A box 9,216 B | state box 6,144 B
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b0 = blockIdx.x * blockDim.x + warp * 32;      // first QP of my warp
+  if (b0 >= p.B) return;
+  const int nq = (p.B - b0 < 32) ? p.B - b0 : 32;
+  const bool live = lane < nq;
+  const int b = live ? b0 + lane : b0;                      // idle lanes mirror the warp's first QP (their rows are clipped)
+  double *tA = tile_s[warp], *tS = tA + 32 * NA;
+  double *mA = tA + lane * NA, *mS = tS + lane * (CH * NX);
+  const uint32_t sA = (uint32_t)__cvta_generic_to_shared(tA), sS = (uint32_t)__cvta_generic_to_shared(tS);
+  const Model &M = p.M;
+  const lpvmpc_args &a = p.a;
+  const int N = p.L.N;
+  int err = 0;
+  double st[NX], Ai[NA], Bi[NBm];
+  const bool estimate = a.sched_mode == LPVMPC_SCHED_ESTIMATE;
+  const double *up = a.u_prev + (size_t)b * N * NU;
+  int lap = 0;
+  if (!estimate) {
+    const double *xs = a.x_sched ? a.x_sched + (size_t)b * NX : a.x0 + (size_t)b * NX;
+#pragma unroll
+    for (int r = 0; r < NX; ++r) st[r] = xs[r];
+    lap = a.lap ? a.lap[b] : a.lap_all;
+  }
+  // curv_ref is read whenever it is given (it is only USED when lap != 0): the load must not wait for `lap` to arrive
+  const bool have_cr = !estimate && a.curv_ref != nullptr;
+  auto in0 = [&](int i) { return estimate ? 0.0 : a.vel_ref[(size_t)b * (N + 1) + i]; };
+  auto in1 = [&](int i) { return have_cr ? a.curv_ref[(size_t)b * N + i] : 0.0; };
+  // per-stage inputs two stages ahead of their use
+  double n_u0 = up[0], n_u1 = up[1], n_a = in0(0), n_c = in1(0);
+  double m_u0 = 0.0, m_u1 = 0.0, m_a = 0.0, m_c = 0.0;
+  if (N > 1) { m_u0 = up[NU]; m_u1 = up[NU + 1]; m_a = in0(1); m_c = in1(1); }
+  const bool wantS = a.states_out && !estimate;
+#pragma unroll 1
+  for (int i0 = 0; i0 < N; i0 += CH) {
+    double bq[CH][3];
+#pragma unroll
+    for (int s = 0; s < CH; ++s) {
+      const int i = i0 + s;
+      bq[s][0] = bq[s][1] = bq[s][2] = 0.0;
+      if (i < N) {
+        const double u01[2] = {n_u0, n_u1}, va = n_a, vc = n_c;
+        n_u0 = m_u0; n_u1 = m_u1; n_a = m_a; n_c = m_c;
+        if (i + 2 < N) { m_u0 = up[(i + 2) * NU]; m_u1 = up[(i + 2) * NU + 1]; m_a = in0(i + 2); m_c = in1(i + 2); }
+        if (estimate) {
+          const double *t = a.traj + ((size_t)b * N + i) * 6;
+          ctrl_stage(M, M.Cf, M.Cr, t[0], t[1], t[3], t[5], curvature(M.track, M.nseg, t[4], err), u01[0], Ai, Bi);
+        } else {
+          const double cur = (lap == 0) ? curvature(M.track, M.nseg, st[4], err) : vc;
+          ctrl_stage(M, a.Cf_new, a.Cf_new, va, st[1], st[3], st[5], cur, u01[0], Ai, Bi);
+          propagate<NX>(Ai, Bi, u01, st);
+        }
+        bq[s][0] = Bi[0]; bq[s][1] = Bi[2]; bq[s][2] = Bi[4];
+        // the stores issued so far have read their boxes (the last one a whole stage of arithmetic ago)
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < NA; e += 2) *reinterpret_cast<double2 *>(mA + e) = make_double2(Ai[e], Ai[e + 1]);
+        if (!estimate) {
+#pragma unroll
+          for (int r = 0; r < NX; r += 2) *reinterpret_cast<double2 *>(mS + s * NX + r) = make_double2(st[r], st[r + 1]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // my generic-proxy writes, before the async-proxy reads
+        __syncwarp();
+        if (lane == 0) {
+          if (a.A_out) tma_store_3d(&maps.A, sA, 0, i, b0);
+          if (wantS && (s == CH - 1 || i == N - 1)) tma_store_3d(&maps.S, sS, 0, i0, b0);   // rows of stages >= N are clipped
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+    }
+    if (a.B_out && live) {   // B_k = dt [[B11, 1], [B21, 0], [B31, 0], 0 ...]: the chunk's records, 96 bytes each
+      double *d = a.B_out + ((size_t)b * N + i0) * NBm;
+      const double one = Bi[1], zero = Bi[3];   // dt * 1.0, dt * 0.0 as ctrl_stage forms them
+#pragma unroll
+      for (int s = 0; s < CH; ++s) {
+        if (i0 + s < N) {
+          stg256(d + s * NBm, bq[s][0], one, bq[s][1], zero);
+          stg256(d + s * NBm + 4, bq[s][2], zero, zero, zero);
+          stg256(d + s * NBm + 8, zero, zero, zero, zero);
+        }
+      }
+    }
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory must outlive the reads
+  __syncwarp();
   if (sched_err && live) sched_err[b] = err;
 }
 
@@ -1141,6 +1281,20 @@ int lpvmpc_solve_dev(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, void *st
   return rc ? rc : stream_leave(h, (cudaStream_t)stream);
 }
 
+// cuTensorMapEncodeTiled through the runtime (no link against libcuda)
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                      const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn sched_maps_fn() {
+  static TensorMapEncodeFn fn = [] {
+    void *f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+    return (TensorMapEncodeFn)f;
+  }();
+  return fn;
+}
+
 int lpvmpc_schedule_dev(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, int32_t *sched_err, void *stream) {
   int rc = validate_args(h, B, a, false);
   if (rc) return rc;
@@ -1161,7 +1315,37 @@ int lpvmpc_schedule_dev(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, int32
     return stream_leave(h, (cudaStream_t)stream);
   }
   const int grid = (B + lpv::kSchedThreads - 1) / lpv::kSchedThreads;
-  if (h->cfg.kind == LPVMPC_CONTROLLER) lpv::lpv_schedule_kernel<LPVMPC_CONTROLLER><<<grid, lpv::kSchedThreads, 0, (cudaStream_t)stream>>>(p, sched_err);
+  // controller, 16-byte aligned outputs: dense shared-memory boxes + TMA tensor stores (LPVMPC_SCHED_MODE: 2 = TMA (default),
+  // 1 = 256-bit stores straight from registers (needs 32-byte alignment), 0 = tile-staged 16-byte stores)
+  static const int sched_mode = [] { const char *e = std::getenv("LPVMPC_SCHED_MODE"); return e ? std::atoi(e) : 2; }();
+  if (h->cfg.kind == LPVMPC_CONTROLLER && sched_mode == 2 && sched_maps_fn() && ((uintptr_t)a->B_out & 31u) == 0) {
+    lpv::SchedMaps maps;
+    std::memset(&maps, 0, sizeof(maps));
+    const int N = h->L.N;
+    bool ok = true;
+    auto enc = [&](CUtensorMap *m, double *base, int len, int stages) {
+      if (!base) return;
+      const cuuint64_t gdim[3] = {(cuuint64_t)len, (cuuint64_t)N, (cuuint64_t)B};
+      const cuuint64_t gstr[2] = {(cuuint64_t)len * 8, (cuuint64_t)len * 8 * (cuuint64_t)N};
+      const cuuint32_t box[3] = {(cuuint32_t)len, (cuuint32_t)stages, 32}, es[3] = {1, 1, 1};
+      ok = ok && sched_maps_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    enc(&maps.A, a->A_out, 36, 1);
+    if (a->sched_mode != LPVMPC_SCHED_ESTIMATE) enc(&maps.S, a->states_out, 6, lpv::kTmaChunk);
+    if (ok) {
+      const int g2 = (B + 32 * lpv::kTmaWarps - 1) / (32 * lpv::kTmaWarps);
+      lpv::lpv_schedule_tma_kernel<<<g2, 32 * lpv::kTmaWarps, 0, (cudaStream_t)stream>>>(p, sched_err, maps);
+      ++h->launches;
+      CUDA_TRY(h, cudaGetLastError());
+      return stream_leave(h, (cudaStream_t)stream);
+    }
+  }
+  const bool direct_on = sched_mode == 1;
+  const bool al32 = (((uintptr_t)a->A_out | (uintptr_t)a->B_out) & 31u) == 0;
+  if (h->cfg.kind == LPVMPC_CONTROLLER && direct_on && al32)
+    lpv::lpv_schedule_kernel<LPVMPC_CONTROLLER, true><<<grid, lpv::kSchedThreads, 0, (cudaStream_t)stream>>>(p, sched_err);
+  else if (h->cfg.kind == LPVMPC_CONTROLLER) lpv::lpv_schedule_kernel<LPVMPC_CONTROLLER><<<grid, lpv::kSchedThreads, 0, (cudaStream_t)stream>>>(p, sched_err);
   else lpv::lpv_schedule_kernel<LPVMPC_PLANNER><<<grid, lpv::kSchedThreads, 0, (cudaStream_t)stream>>>(p, sched_err);
   ++h->launches;
   CUDA_TRY(h, cudaGetLastError());

@@ -200,3 +200,50 @@ def test_one_handle_two_streams_and_current_device_is_kept(track):
         np.testing.assert_array_equal(r.status, ref.status[:8].cpu().numpy())
         s_other.close()
     s.close()
+
+
+@pytest.mark.gpu
+def test_schedule_tma_kernel_chunks_and_tails(track):
+    """The TMA scheduling kernel writes the states in chunks of four stages (one tensor store, box {6, 4, 32}) and B_k in
+    chunks of four stages from registers: horizons that are not multiples of four (the last chunk is clipped), ragged
+    batches (the last warp's box rows are clipped), lap = 0 (Curvature from the rolled-out s) and lap != 0 -- against the
+    oracle; and a B_out that is only 16-byte aligned (the tile-staged kernel takes over) bit for bit against it."""
+    import ctypes as C
+    import torch
+    nat = lp._native
+    W = lp.workloads
+    for N, B in ((5, 70), (7, 33), (10, 129), (8, 64)):
+        w = W.controller_batch(B, N, seed=100 + N)
+        w["lap"][::3] = 0   # a third of the QPs take their curvature from the track table
+        cfg = oracle.make_cfg("controller", N, W.CTRL_DT, W.CTRL_TT["Q"], W.CTRL_TT["R"], W.CTRL_TT["dR"], track)
+        s = lp.BatchSolver("controller", N, W.CTRL_DT, track=track, max_batch=B, **W.CTRL_TT)
+        dev = torch.device("cuda", 0)
+        tin = {k: torch.as_tensor(w[k]).to(dev) for k in ("x0", "u_prev", "vel_ref", "curv_ref", "lap")}
+        r = s.schedule(**tin)
+        A_out, B_out, S_out = (r[k].cpu().numpy() for k in ("A_out", "B_out", "states_out"))
+        for b in range(B):
+            st, A, Bm, _, err = oracle.ctrl_predict(cfg, w["x0"][b], w["u_prev"][b], w["vel_ref"][b], w["curv_ref"][b], 60.0, int(w["lap"][b]))
+            assert err == int(r.sched_err[b])
+            np.testing.assert_allclose(A_out[b], A, rtol=1e-13, atol=1e-15)
+            np.testing.assert_allclose(B_out[b], Bm, rtol=1e-13, atol=1e-15)
+            np.testing.assert_allclose(S_out[b], st, rtol=1e-12, atol=1e-14)
+        # B_out 16- but not 32-byte aligned: another kernel, the same bits
+        bufB = torch.zeros(B * N * 12 + 2, dtype=torch.float64, device=dev)
+        bufA = torch.zeros(B * N * 36, dtype=torch.float64, device=dev)
+        bufS = torch.zeros(B * N * 6, dtype=torch.float64, device=dev)
+        a = nat.Args()
+        a.sched_mode = lp.SCHED_PREDICT
+        a.lap_all = 1
+        a.Cf_new = 60.0
+        for k, t in tin.items():
+            setattr(a, k, t.data_ptr())
+        assert bufB.data_ptr() % 32 == 0
+        a.A_out, a.B_out, a.states_out = bufA.data_ptr(), bufB.data_ptr() + 16, bufS.data_ptr()
+        err = torch.empty(B, dtype=torch.int32, device=dev)
+        nat.check(nat.lib().lpvmpc_schedule_dev(s._h, B, C.byref(a), C.c_void_p(err.data_ptr()),
+                                                C.c_void_p(torch.cuda.current_stream().cuda_stream)), s._h)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(bufA.cpu().numpy().reshape(B, N, 6, 6), A_out)
+        np.testing.assert_array_equal(bufB[2:].cpu().numpy().reshape(B, N, 6, 2), B_out)
+        np.testing.assert_array_equal(bufS.cpu().numpy().reshape(B, N, 6), S_out)
+        s.close()
