@@ -1294,11 +1294,29 @@ __global__ void __launch_bounds__(256, 1) lpv_solve_h16t_kernel(const __grid_con
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   c.tm = tmem_base_s + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(256 * (warp >> 2));
 
+  __shared__ unsigned round_base_s;
   for (;;) {
     unsigned base = 0;
-    if (lane == 0) base = atomicAdd(p.queue, 2u);
-    base = __shfl_sync(kFull, base, 0);
-    if ((int)base >= p.B) break;
+    if (p.cta_rounds) {
+      // One round: every warp of the CTA takes its two QPs at the same time.  The kernel is 280 KB of SASS against a 32 KB
+      // instruction cache per SM; warps that drift into different phases (setup / ADMM loop / polish) evict each other's
+      // code (profiles/r3o_*: 8.2 stall cycles per issue waiting for instructions on long batches, instruction-cache hit
+      // rate 56 %), warps that start together stay in the same code for most of a round.
+      __syncthreads();
+      if (threadIdx.x == 0) round_base_s = atomicAdd(p.queue, 2u * (unsigned)wpc);
+      __syncthreads();
+      const unsigned rb = round_base_s;
+      if ((int)rb >= p.B) break;
+      base = rb + 2u * (unsigned)warp;
+      if ((int)base >= p.B) {
+        if (p.cta_rounds > 1) __syncthreads();   // the phase barrier in front of the polish (below)
+        continue;
+      }
+    } else {
+      if (lane == 0) base = atomicAdd(p.queue, 2u);
+      base = __shfl_sync(kFull, base, 0);
+      if ((int)base >= p.B) break;
+    }
     // the second QP slot of a warp at the batch tail mirrors the first: same problem, same shared / slab region, same values
     // written by the same instruction; only user-visible outputs are guarded
     const bool valid = (int)(base + gq0) < p.B;
@@ -1477,6 +1495,8 @@ __global__ void __launch_bounds__(256, 1) lpv_solve_h16t_kernel(const __grid_con
       }
     }
     int polish_status = 0;
+    // second phase barrier (cta_rounds = 2): nobody enters the polish code while another warp of the CTA still runs the ADMM loop
+    if (p.cta_rounds > 1) __syncthreads();
     const bool do_pol = S.polish && status == LPVMPC_SOLVED;
     bool polished_sets = false;
     if (__any_sync(kFull, do_pol)) {

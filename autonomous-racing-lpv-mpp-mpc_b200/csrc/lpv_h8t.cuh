@@ -51,6 +51,8 @@ struct H8Params {
   unsigned *queue;
   const int *perm;   // visiting order of the batch (NULL: batch order)
   double *cold;
+  int cta_rounds;    // H16T: the CTA's warps take their QPs from the queue TOGETHER (one round = 2 QPs per warp) and meet again
+                     // before the next round, so that they run the same phase of the kernel at the same time (instruction cache)
 };
 
 template <int KIND> struct Dims;

@@ -867,6 +867,7 @@ int launch_h8t(lpvmpc_handle *h, const Params &p, cudaStream_t s) {
   lpv::h8t::H8Params hp;
   hp.L = h->TL; hp.M = p.M; hp.S = p.S; hp.a = p.a; hp.B = p.B; hp.queue = h->d_queue; hp.cold = h->d_cold;
   hp.perm = batch_order(h, p, s);
+  hp.cta_rounds = 0;
   const int ctas = (p.B + 15) / 16;
   const int grid = ctas < h->grid_cap ? ctas : h->grid_cap;
   CUDA_TRY(h, cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned), s));
@@ -881,6 +882,8 @@ int launch_h16t(lpvmpc_handle *h, const Params &p, cudaStream_t s) {
   lpv::h8t::H8Params hp;
   hp.L = h->TL16; hp.M = p.M; hp.S = p.S; hp.a = p.a; hp.B = p.B; hp.queue = h->d_queue; hp.cold = h->d_cold;
   hp.perm = batch_order(h, p, s);
+  static const int rounds = [] { const char *e = std::getenv("LPVMPC_H16T_ROUNDS"); return e ? std::atoi(e) : 2; }();   // 0: every warp pulls on its own, 1: rounds, 2: rounds + phase barrier before the polish
+  hp.cta_rounds = rounds;
   const int ctas = (p.B + 15) / 16;
   const int grid = ctas < h->grid_cap ? ctas : h->grid_cap;
   CUDA_TRY(h, cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned), s));
