@@ -43,8 +43,8 @@ namespace lpv {
 namespace h8 {
 
 constexpr int TKS = 128;  // doubles per stage of the factor: T_k (64) then K_{k+1} (64)
-constexpr int VS = 48;    // doubles per stage of the stage vectors
-enum { V_B = 0, V_X = 8, V_R = 16, V_XS = 24, V_DG = 32, V_CR = 40 };
+constexpr int VS = 56;    // doubles per stage of the stage vectors
+enum { V_B = 0, V_X = 8, V_R = 16, V_XS = 24, V_DG = 32, V_CR = 40, V_XT = 48 };   // XT: x~ of the backward sweep (helper-warp kernels)
 
 struct Lay {  // per-QP offsets (doubles); computed on the host (lpvmpc.cu: make_h8_layout)
   int N, nsl;                  // horizon; single-variable-row slots per stage (6 controller, 7 planner)
@@ -1021,6 +1021,176 @@ __device__ __forceinline__ void sweep_bwd_admm_tw(const Hot<KIND> &h, const Upd<
   }
 }
 
+// ---------------------------------------------------------------- helper warps (twisted kernels, one QP per CTA)
+// The element-wise ADMM update is independent per stage, yet in the one-warp kernels it sits on the critical path: 11 update
+// rounds of 4 stages behind the 20 chain steps of a planner sweep.  Here the CTA has NH more warps that do nothing but
+// updates: the main warp runs the forward sweep and the backward CHAIN (x~_k goes to its own stage vector XT instead of
+// being parked in B, so an update never reads a slot another update writes), publishes how far the chain has come, and the
+// 4 NH lane groups of the helpers update the stages behind it, in the order in which their neighbours' x~ appear
+// (m, m-1, m+1, m-2, ...).  When the chain ends only the last round of updates is still outstanding.
+//   main -> helpers: `go` (iteration sequence number, st.release after the parameters), `prog` (x~ known for local
+//                    distances 0 .. prog-1 from the middle stage, st.release after the XT stores)
+//   helpers -> main: `done` (atom.add.release after a helper's last update of the iteration)
+struct HwShared {
+  uint32_t go, prog, done, quit;
+  double rho, rho_eq, rinv, rinv_eq, sigma, alpha, oma, cc;
+  uint32_t live, N;
+  uint64_t eqm[8], loosem[8];
+};
+__device__ __forceinline__ uint32_t ld_acq(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_rel(uint32_t a, uint32_t v) { asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// progress of the backward chain: a plain (relaxed) store.  Every x~ it announces was stored by this warp BEFORE it -- the
+// lanes' XT stores, the __syncwarp of the all-gather, then lane 0's store -- and shared-memory accesses of one warp are
+// performed in issue order, so a helper that reads the new value reads the new x~ too; a MEMBAR.ALL.CTA per chain step
+// (st.release) costs more than the step itself.
+__device__ __forceinline__ void st_prog(uint32_t a, uint32_t v) { asm volatile("st.relaxed.cta.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void add_rel(uint32_t a, uint32_t v) {
+  asm volatile("red.release.cta.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
+// Per-lane addresses of a QP region (main warp and helpers alike)
+template <int KIND>
+__device__ __forceinline__ void init_hot(Hot<KIND> &h, const Lay &L, const uint32_t sq, const uint32_t gbuf, const int N, const int g, const int r,
+                                         const int (&ro)[4], const int (&co)[4]) {
+  constexpr int NX = Ctx<KIND>::NX, NB = Ctx<KIND>::NB, OLI = Ctx<KIND>::OLI, OPM = Ctx<KIND>::OPM;
+  const bool xl = r < NX, ul = (r >= NX) && (r < NB);
+  const int islot = (KIND == LPVMPC_CONTROLLER) ? ((r == 0) ? 0 : ((r >= NX) ? (r - NX + 1) * 2 : 0)) : r;
+  const int ucomp = r - NX;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    h.tk[q] = sq + (uint32_t)(L.TK + ro[q]) * 8u;
+    h.kc[q] = sq + (uint32_t)(L.TK + 64 + (2 * q) * 8 + co[q]) * 8u;
+  }
+  h.v = sq + (uint32_t)(L.V + r) * 8u;
+  constexpr int ISBk = Ctx<KIND>::IS * 8;
+  const bool rows = (KIND == LPVMPC_CONTROLLER) ? (r == 0 || ul) : (xl || ul);
+  const uint32_t dm = sq + (uint32_t)(L.I + (N + 1) * Ctx<KIND>::IS) * 8u;   // block N+1: dummy rows, zero coupling
+  h.ib = rows ? sq + (uint32_t)(L.I + islot * 2) * 8u : dm;
+  h.il = rows ? sq + (uint32_t)(L.I + OLI + islot) * 8u : dm + (uint32_t)OLI * 8u;
+  h.istr = rows ? (uint32_t)ISBk : 0u;
+  h.pm = ul ? sq + (uint32_t)(L.I + OPM + ucomp) * 8u : dm + (uint32_t)OPM * 8u;
+  h.pm2 = ul ? h.pm + (uint32_t)ISBk : h.pm;
+  h.pstr = ul ? (uint32_t)ISBk : 0u;
+  h.gpub = gbuf + (uint32_t)(64 * (r >> 1) + 16 * g + 8 * (r & 1));
+  h.ggat = gbuf + (uint32_t)(16 * g);
+}
+
+// main warp: backward chain only; x~ -> XT, progress -> hw.prog; returns when every helper has finished the iteration
+template <int KIND>
+__device__ __forceinline__ void sweep_bwd_chain_hw(const Hot<KIND> &h, const int N, uint32_t &gsel, const int g, const uint32_t hws, const uint32_t seq,
+                                                   const uint32_t nh, const double cc) {
+  const int NL = N >> 1;
+  const int lane = threadIdx.x & 31;
+  const bool half = g & 1;
+  double gn[8];
+  if (lane == 0) {
+    *reinterpret_cast<volatile double *>(__cvta_shared_to_generic(hws + (uint32_t)offsetof(HwShared, cc))) = cc;
+    *reinterpret_cast<volatile uint32_t *>(__cvta_shared_to_generic(hws + (uint32_t)offsetof(HwShared, prog))) = 0u;
+  }
+  __syncwarp();
+  {
+    const uint32_t vm = h.v + (uint32_t)NL * VB;
+    const double xm_ = lds(vm);   // x~_m = W_m
+    sts<V_XT * 8>(vm, xm_);
+    sts(h.gpub ^ gsel, xm_);
+    gather_in(h.ggat, gsel, gn);   // (its __syncwarp orders the XT stores of all lanes before lane 0's release below)
+  }
+  if (lane == 0) { st_rel(hws + (uint32_t)offsetof(HwShared, go), seq); st_rel(hws + (uint32_t)offsetof(HwShared, prog), 1u); }
+#pragma unroll 1
+  for (int j = NL - 1; j >= 0; --j) {
+    const uint32_t k = (uint32_t)(half ? N - j : j), so = k * (uint32_t)TKB, vb = h.v + k * (uint32_t)VB;
+    const double xt = bwd_step(h.kc[0] + so, h.kc[1] + so, h.kc[2] + so, h.kc[3] + so, vb, h.gpub, h.ggat, gsel, gn);
+    sts<V_XT * 8>(vb, xt);
+    gather_in(h.ggat, gsel, gn);
+    if (lane == 0) st_prog(hws + (uint32_t)offsetof(HwShared, prog), (uint32_t)(NL - j + 1));
+  }
+  const uint32_t want = seq * nh;
+  while (ld_acq(hws + (uint32_t)offsetof(HwShared, done)) != want) {}
+  __syncwarp();
+}
+
+// helper warps: wait for an iteration, update the stages behind the chain, report, repeat until `quit`
+template <int KIND>
+__device__ __noinline__ void helper_loop(const Lay &L, const uint32_t sq, const uint32_t hws, const int hw, const int nh) {
+  const int lane = threadIdx.x & 31, g = lane >> 3, r = lane & 7;
+  int ro[4], co[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { ro[j] = chunk(r, j); co[j] = (((r >> 1) ^ j) << 1) | (r & 1); }
+  const int N = L.N, NL = N >> 1;
+  Hot<KIND> h;
+  init_hot<KIND>(h, L, sq, 0u, N, g, r, ro, co);
+  const HwShared *S = reinterpret_cast<const HwShared *>(__cvta_shared_to_generic(hws));
+  const int U = 4 * nh;
+  uint32_t seen = 0;
+  for (;;) {
+    uint32_t go;
+    for (;;) {
+      go = ld_acq(hws + (uint32_t)offsetof(HwShared, go));
+      if (go != seen) break;
+      if (ld_acq(hws + (uint32_t)offsetof(HwShared, quit))) return;
+    }
+    seen = go;
+    Upd<KIND> u;
+    {
+      const volatile HwShared *V = S;
+      u.rho = V->rho; u.rho_eq = V->rho_eq; u.rinv = V->rinv; u.rinv_eq = V->rinv_eq; u.sigma = V->sigma; u.alpha = V->alpha;
+      u.oma = V->oma; u.cc = V->cc; u.live = V->live != 0u; u.N = N;
+      u.eqm = V->eqm[r]; u.loosem = V->loosem[r];
+    }
+    // One update is a dependent chain of ~40 fp64 operations (630 cycles per round of 4 stages, measured); two rounds at a
+    // time give the warp two independent chains.  t = 0 -> m, 1 -> m-1, 2 -> m+1, 3 -> m-2, ...: the order in which the
+    // neighbours' x~ appear.
+    auto stage_of = [&](int t) { const int d = (t + 1) >> 1; return (t & 1) ? NL - d : NL + d; };
+    auto wait_for = [&](int tl) {   // until the x~ of the neighbours of stage t <= tl are there
+      const int dl = (tl + 1) >> 1;
+      const uint32_t need = (uint32_t)((dl + 1 < NL ? dl + 1 : NL) + 1);
+      while (ld_acq(hws + (uint32_t)offsetof(HwShared, prog)) < need) {}
+    };
+    int t0 = (hw - 1) * 4;
+#pragma unroll 1
+    for (; t0 + U + 3 <= N; t0 += 2 * U) {   // two full rounds
+      wait_for(t0 + U + 3);
+      const int ka = stage_of(t0 + g), kb = stage_of(t0 + U + g);
+      const uint32_t va = h.v + (uint32_t)ka * VB, ia = h.ib + (uint32_t)ka * h.istr, la = h.il + (uint32_t)ka * h.istr;
+      const uint32_t vb = h.v + (uint32_t)kb * VB, ib = h.ib + (uint32_t)kb * h.istr, lb = h.il + (uint32_t)kb * h.istr;
+      UpdIn ina, inb;
+      update_loads<KIND>(va, ia, la, h.pm + (uint32_t)ka * h.pstr, h.pm2 + (uint32_t)ka * h.pstr, ina);
+      update_loads<KIND>(vb, ib, lb, h.pm + (uint32_t)kb * h.pstr, h.pm2 + (uint32_t)kb * h.pstr, inb);
+      const double xa1 = lds<V_XT * 8>(va), xam = (ka > 0) ? lds<V_XT * 8>(va - VB) : 0.0, xap = (ka < N) ? lds<V_XT * 8>(va + VB) : 0.0;
+      const double xb1 = lds<V_XT * 8>(vb), xbm = (kb > 0) ? lds<V_XT * 8>(vb - VB) : 0.0, xbp = (kb < N) ? lds<V_XT * 8>(vb + VB) : 0.0;
+      UpdMid qa, qb;
+      update_part1<KIND>(u, ka, ia, ina, xa1, xam, xap, qa);
+      update_part1<KIND>(u, kb, ib, inb, xb1, xbm, xbp, qb);
+      update_part2<KIND>(u, va, xa1, qa);
+      update_part2<KIND>(u, vb, xb1, qb);
+    }
+#pragma unroll 1
+    for (; t0 <= N; t0 += U) {   // what is left: single, possibly partial rounds
+      wait_for((t0 + 3 <= N) ? t0 + 3 : N);
+      const int t = t0 + g;
+      if (t <= N) {
+        const int k = stage_of(t);
+        const uint32_t vj = h.v + (uint32_t)k * VB, ij = h.ib + (uint32_t)k * h.istr, lj = h.il + (uint32_t)k * h.istr;
+        const uint32_t pj = h.pm + (uint32_t)k * h.pstr, pj2 = h.pm2 + (uint32_t)k * h.pstr;
+        UpdIn in;
+        update_loads<KIND>(vj, ij, lj, pj, pj2, in);
+        const double x1 = lds<V_XT * 8>(vj);
+        const double xm = (k > 0) ? lds<V_XT * 8>(vj - VB) : 0.0;
+        const double xp = (k < N) ? lds<V_XT * 8>(vj + VB) : 0.0;
+        UpdMid q;
+        update_part1<KIND>(u, k, ij, in, x1, xm, xp, q);
+        update_part2<KIND>(u, vj, x1, q);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) add_rel(hws + (uint32_t)offsetof(HwShared, done), 1u);
+  }
+}
+
 // ---------------------------------------------------------------- per-QP scalars shared by the cold routines
 struct Info {
   double pri_res, dua_res, obj;
@@ -1910,14 +2080,15 @@ constexpr int kSyncEvery = 25;  // y_dyn is brought up to date and r re-projecte
 
 // ST: factor streamed from the slab (one QP per warp, one warp per CTA: every staging address is warp-uniform)
 // TW: twisted factorisation (one QP per warp, resident factor, even N: checked by the host)
-template <int KIND, int QPW, bool ST, bool TW = false>
-__global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant__ H8Params p) {
+// NH: helper warps (TW only; one QP per CTA: warp 0 runs the solver, warps 1 .. NH the element-wise updates of the ADMM step)
+template <int KIND, int QPW, bool ST, bool TW = false, int NH = 0>
+__global__ void __launch_bounds__(NH ? 32 * (NH + 1) : 64) lpv_solve_h8_kernel(const __grid_constant__ H8Params p) {
   static_assert(!ST || QPW == 1, "the streamed kernel holds one QP per warp");
   static_assert(!TW || (QPW == 1 && !ST), "the twisted kernel holds one QP per warp with the factor resident");
+  static_assert(NH == 0 || TW, "helper warps come with the twisted kernel");
   extern __shared__ __align__(16) double smem[];
   constexpr int NX = Ctx<KIND>::NX, NB = Ctx<KIND>::NB, NT = Ctx<KIND>::NT, NSL = Ctx<KIND>::NSL;
-  constexpr int OLI = Ctx<KIND>::OLI, OPM = Ctx<KIND>::OPM;
-  const int lane = threadIdx.x & 31, warp = ST ? 0 : (int)(threadIdx.x >> 5), wpc = ST ? 1 : (int)(blockDim.x >> 5);
+  const int lane = threadIdx.x & 31, warp = (ST || NH) ? 0 : (int)(threadIdx.x >> 5), wpc = (ST || NH) ? 1 : (int)(blockDim.x >> 5);
   const int g = lane >> 3, r = lane & 7;
   const Lay &L = p.L;
   const int N = L.N;
@@ -1947,6 +2118,17 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
   uint32_t gsel = 0;
   Strm sm;
   sm.t = 0u; sm.ahead = 0u; sm.rdy = 0u;
+  // helper warps: their mailbox sits behind the gather buffers; they never come back from helper_loop
+  const uint32_t hws = gbuf0 + (uint32_t)wpc * 512u + 256u;
+  uint32_t hw_seq = 0;
+  if (NH) {
+    if (threadIdx.x < (unsigned)(sizeof(HwShared) / 4)) reinterpret_cast<volatile uint32_t *>(__cvta_shared_to_generic(hws))[threadIdx.x] = 0u;
+    __syncthreads();
+    if (threadIdx.x >= 32) {
+      helper_loop<KIND>(L, smem_a, hws, (int)(threadIdx.x >> 5), NH);
+      return;
+    }
+  }
   if (ST) {  // this warp's mbarriers (one arrival: the issuing lane's expect_tx)
     if (lane < kRing) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar0 + 8u * (uint32_t)lane) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1973,23 +2155,7 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
       h.sc.issuer = ST && lane == 0;
       h.sc.ring = sq + (uint32_t)L.TK * 8u; h.sc.mbar = mbar0;
       h.sc.gsrc = c.cold + L.cTK; h.sc.N = N;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        h.tk[q] = sq + (uint32_t)(L.TK + c.ro[q]) * 8u;
-        h.kc[q] = sq + (uint32_t)(L.TK + 64 + (2 * q) * 8 + c.co[q]) * 8u;
-      }
-      h.v = sq + (uint32_t)(L.V + r) * 8u;
-      constexpr int ISBk = Ctx<KIND>::IS * 8;
-      const bool rows = (KIND == LPVMPC_CONTROLLER) ? (r == 0 || c.ul) : (c.xl || c.ul);
-      const uint32_t dm = sq + (uint32_t)(L.I + (N + 1) * Ctx<KIND>::IS) * 8u;   // block N+1: dummy rows, zero coupling
-      h.ib = rows ? sq + (uint32_t)(L.I + c.islot * 2) * 8u : dm;
-      h.il = rows ? sq + (uint32_t)(L.I + OLI + c.islot) * 8u : dm + (uint32_t)OLI * 8u;
-      h.istr = rows ? (uint32_t)ISBk : 0u;
-      h.pm = c.ul ? sq + (uint32_t)(L.I + OPM + ucomp) * 8u : dm + (uint32_t)OPM * 8u;
-      h.pm2 = c.ul ? h.pm + (uint32_t)ISBk : h.pm;
-      h.pstr = c.ul ? (uint32_t)ISBk : 0u;
-      h.gpub = gbuf + (uint32_t)(64 * (r >> 1) + 16 * g + 8 * (r & 1));
-      h.ggat = gbuf + (uint32_t)(16 * g);
+      init_hot<KIND>(h, L, sq, gbuf, N, g, r, c.ro, c.co);
     }
 
     Info I;
@@ -1999,6 +2165,10 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
       uint64_t eqm = 0, loosem = 0;
       flags = setup<KIND>(c, p, b, valid, &csc, &eqm, &loosem);
       c.eqm = eqm; c.loosem = loosem;
+      if (NH && g == 0) {
+        HwShared *H = reinterpret_cast<HwShared *>(__cvta_shared_to_generic(hws));
+        H->eqm[r] = eqm; H->loosem[r] = loosem;
+      }
     }
     I.csc = csc; I.cinv = 1.0 / csc;
     I.unscale = (S.scaling && !S.scaled_termination) ? 1 : 0;
@@ -2035,6 +2205,14 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
       if (ai) { const int nxt = (iter / ai + 1) * ai; stop = nxt < stop ? nxt : stop; }
       { const int nxt = iter + kSyncEvery; stop = nxt < stop ? nxt : stop; }
       u.rho = rho; u.rho_eq = rho_eq; u.rinv = 1.0 / rho; u.rinv_eq = 1.0 / rho_eq; u.live = live;
+      if (NH) {
+        if (lane == 0) {
+          HwShared *H = reinterpret_cast<HwShared *>(__cvta_shared_to_generic(hws));
+          H->rho = u.rho; H->rho_eq = u.rho_eq; H->rinv = u.rinv; H->rinv_eq = u.rinv_eq; H->sigma = u.sigma; H->alpha = u.alpha; H->oma = u.oma;
+          H->live = live ? 1u : 0u; H->N = (uint32_t)N;
+        }
+        __syncwarp();
+      }
 #pragma unroll 1
       for (; iter < stop; ++iter) {
         if (iter == stop - 1 && live) {  // keep the iterate before the last step of the chunk: delta_x, delta_y
@@ -2053,7 +2231,8 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
         if (TW) sweep_fwd_tw<KIND>(h, N, gsel, g);
         else if (QPW == 1) sweep_fwd_w1<KIND, ST>(h, sm, N, gsel, g);
         else sweep_fwd<KIND, ST>(h, sm, N, gsel);
-        if (TW) sweep_bwd_admm_tw<KIND>(h, u, gsel, g);
+        if (NH) sweep_bwd_chain_hw<KIND>(h, N, gsel, g, hws, ++hw_seq, NH, u.cc);
+        else if (TW) sweep_bwd_admm_tw<KIND>(h, u, gsel, g);
         else if (QPW == 1) sweep_bwd_admm_w1<KIND, ST>(h, sm, u, gsel, g);
         else sweep_bwd_admm<KIND, ST>(h, sm, u, gsel);
         if (iter == 0) first_in = 1;
@@ -2194,7 +2373,8 @@ __global__ void __launch_bounds__(64) lpv_solve_h8_kernel(const __grid_constant_
     if (ST) strm_drain(h.sc, sm);   // nothing may be in flight into the ring when the next QP's setup / factor starts
     __syncwarp();
   }
-  (void)NSL; (void)NB;
+  if (NH && lane == 0) st_rel(hws + (uint32_t)offsetof(HwShared, quit), 1u);
+  (void)NSL; (void)NB; (void)hw_seq;
 }
 
 }  // namespace h8

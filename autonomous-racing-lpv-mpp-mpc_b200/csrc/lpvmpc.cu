@@ -646,6 +646,7 @@ struct lpvmpc_handle {
   lpv::h8t::Lay TL16;        // H16T layout
   int wpc = 1;               // H8: warps per CTA
   bool twisted = false;      // H8, one QP per warp: twisted factorisation kernel
+  int helpers = 0;           // ... with this many helper warps per QP for the element-wise updates
   int qpw = 4;               // T8 / G8 / H8: QPs per warp
   unsigned *d_queue = nullptr;  // work-queue counter of the persistent T8 kernel
   int *d_perm = nullptr;        // visiting order of the batch (lpv_order_kernel)
@@ -832,6 +833,15 @@ template <int KIND>
 cudaError_t h8w_attr(size_t smem) {
   return cudaFuncSetAttribute(lpv::h8::lpv_solve_h8_kernel<KIND, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
+// twisted factorisation + NH helper warps: one QP per CTA of NH + 1 warps
+template <int KIND, int NH>
+void h8h_launch(int grid, size_t smem, cudaStream_t s, const lpv::h8::H8Params &hp) {
+  lpv::h8::lpv_solve_h8_kernel<KIND, 1, false, true, NH><<<grid, 32 * (NH + 1), smem, s>>>(hp);
+}
+template <int KIND, int NH>
+cudaError_t h8h_attr(size_t smem) {
+  return cudaFuncSetAttribute(lpv::h8::lpv_solve_h8_kernel<KIND, 1, false, true, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
 // streamed factor: one QP per warp, one warp per CTA
 template <int KIND>
 void h8s_launch(int grid, size_t smem, cudaStream_t s, const lpv::h8::H8Params &hp) {
@@ -855,6 +865,10 @@ int launch_h8(lpvmpc_handle *h, const Params &p, cudaStream_t s) {
   if (h->HL.ring) h8s_launch<KIND>(grid, h->ws_bytes, s, hp);
   else if (h->qpw == 4) h8_launch<KIND, 4>(grid, 32 * h->wpc, h->ws_bytes, s, hp);
   else if (h->qpw == 2) h8_launch<KIND, 2>(grid, 32 * h->wpc, h->ws_bytes, s, hp);
+  else if (h->twisted && h->helpers) {
+    if (KIND == LPVMPC_PLANNER) h8h_launch<LPVMPC_PLANNER, 1>(grid, h->ws_bytes, s, hp);
+    else h8h_launch<LPVMPC_CONTROLLER, 3>(grid, h->ws_bytes, s, hp);
+  }
   else if (h->twisted) h8w_launch<KIND>(grid, 32 * h->wpc, h->ws_bytes, s, hp);
   else h8_launch<KIND, 1>(grid, 32 * h->wpc, h->ws_bytes, s, hp);
   ++h->launches;
@@ -1169,7 +1183,25 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
       // one QP per warp, even horizon: twisted factorisation (both ends towards the middle stage); LPVMPC_H8_TWISTED=0: plain
       static const bool tw_on = [] { const char *e = std::getenv("LPVMPC_H8_TWISTED"); return !e || std::atoi(e) != 0; }();
       h->twisted = tw_on && (cfg->N % 2 == 0) && cfg->N >= 4;
-      if (h->twisted) CTRY(ctrl ? h8w_attr<LPVMPC_CONTROLLER>(h->ws_bytes) : h8w_attr<LPVMPC_PLANNER>(h->ws_bytes));
+      // helper warps for the element-wise updates (LPVMPC_H8_HELPERS=0: none): one QP per CTA, so the choice only stands when
+      // it was one warp per CTA anyway.  Controller (long horizons, one CTA per SM): 3 helpers.  Planner (3 CTAs per SM): ONE --
+      // a warp's registers live in its SM sub-partition (16 K registers), so at 224-255 registers per thread an SM holds 8
+      // warps: 3 CTAs of 2 (3 CTAs of 3 warps need <= 168 registers and spill: measured slower than no helpers)
+      static const bool hw_on = [] { const char *e = std::getenv("LPVMPC_H8_HELPERS"); return !e || std::atoi(e) != 0; }();
+      h->helpers = (h->twisted && hw_on && h->wpc == 1) ? (ctrl ? 3 : 1) : 0;
+      if (h->helpers) {
+        const size_t ws2 = h->ws_bytes + 512;   // the helpers' mailbox (lpv::h8::HwShared) behind the gather buffers
+        int ctas = (int)(sm_bytes / (ws2 + 1024));
+        if (ctas > 32) ctas = 32;
+        const int by_regs = ctrl ? 1 : 3;      // __launch_bounds__ of the two instantiations
+        if (ctas > by_regs) ctas = by_regs;
+        if (ctas >= best_ctas) {   // never at the price of fewer QPs per SM
+          h->ws_bytes = ws2; h->grid_cap = h->sm_count * (ctas < 1 ? 1 : ctas);
+          CTRY(ctrl ? (h8h_attr<LPVMPC_CONTROLLER, 3>(h->ws_bytes)) : (h8h_attr<LPVMPC_PLANNER, 1>(h->ws_bytes)));
+        } else h->helpers = 0;
+      }
+      if (h->helpers) {}
+      else if (h->twisted) CTRY(ctrl ? h8w_attr<LPVMPC_CONTROLLER>(h->ws_bytes) : h8w_attr<LPVMPC_PLANNER>(h->ws_bytes));
       else CTRY(ctrl ? (h8_attr<LPVMPC_CONTROLLER, 1>(h->ws_bytes)) : (h8_attr<LPVMPC_PLANNER, 1>(h->ws_bytes)));
     }
     CTRY(cudaMalloc(&h->d_queue, sizeof(unsigned)));

@@ -26,6 +26,18 @@ else:
     cfg = oracle.make_cfg("controller", N, W.CTRL_DT, W.CTRL_TT["Q"], W.CTRL_TT["R"], W.CTRL_TT["dR"], track)
     o = oracle.ctrl_batch(cfg, oracle.default_settings(polish=1), w["x0"], w["u_prev"], w["vel_ref"], w["curv_ref"], w["lap"], w["u_old"], threads=os.cpu_count())
 print("info", s.info())
+if len(sys.argv) > 3 and sys.argv[3] == "fixed":   # time of a fixed number of plain ADMM steps (no checks, no polish)
+    for iters in (100, 300):
+        s.update_settings(max_iter=iters, check_termination=0, adaptive_rho=0, polish=0)
+        tin = {k: torch.as_tensor(w[k]).to(dev) for k in keys}; tx0 = torch.as_tensor(w["x0"]).to(dev)
+        for _ in range(2): s.solve(tx0, **tin)
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+        for a, b in ev:
+            a.record(); s.solve(tx0, **tin); b.record()
+        torch.cuda.synchronize()
+        print("fixed %d iterations: kernel ms p50 %.4f" % (iters, np.percentile([a.elapsed_time(b) for a, b in ev], 50)))
+    sys.exit(0)
 r = s.solve(w["x0"], **{k: w[k] for k in keys})
 if o is not None:
     ok = np.isin(o["status"], (1, 2, -2))
