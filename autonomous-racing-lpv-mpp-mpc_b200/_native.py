@@ -13,7 +13,7 @@ _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "liblpvmpc.so")
 HASH_PATH = os.path.join(_PKG, "liblpvmpc.srchash")
 _SRC_DIR = os.path.join(_PKG, "csrc")
-_SOURCES = [os.path.join(_SRC_DIR, f) for f in ("lpvmpc.cu", "lpv_qp.cuh", "lpv_h8.cuh", "lpv_h8t.cuh", "lpv_h16t.cuh", "lpv_model.cuh", "lpv_loop.cuh")] + \
+_SOURCES = [os.path.join(_SRC_DIR, f) for f in ("lpvmpc.cu", "lpv_qp.cuh", "lpv_h8.cuh", "lpv_h8t.cuh", "lpv_h16t.cuh", "lpv_model.cuh", "lpv_loop.cuh", "lpv_aux.cuh")] + \
            [os.path.join(_ROOT, "include", "lpvmpc.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
@@ -96,7 +96,8 @@ EXPORTS = ["lpvmpc_abi_version", "lpvmpc_default_settings", "lpvmpc_device_count
            "lpvmpc_loop_init_host", "lpvmpc_loop_run_dev", "lpvmpc_loop_run_host", "lpvmpc_loop_view_dev",
            "lpvmpc_loop_read_host", "lpvmpc_plan_loop_init_host", "lpvmpc_plan_loop_init_dev", "lpvmpc_plan_loop_run_host",
            "lpvmpc_plan_loop_run_dev", "lpvmpc_plan_loop_view_dev", "lpvmpc_plan_loop_read_host", "lpvmpc_plan_refs_setup",
-           "lpvmpc_plan_refs_dev", "lpvmpc_plan_refs_host", "lpvmpc_track_inputs_dev", "lpvmpc_track_inputs_host"]
+           "lpvmpc_plan_refs_dev", "lpvmpc_plan_refs_host", "lpvmpc_track_inputs_dev", "lpvmpc_track_inputs_host",
+           "lpvmpc_anfis_abc_dev", "lpvmpc_anfis_abc_host", "lpvmpc_observer_step_dev", "lpvmpc_observer_step_host"]
 
 _lib = None
 
@@ -197,6 +198,10 @@ def lib():
                                           C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.lpvmpc_track_inputs_host.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.lpvmpc_anfis_abc_dev.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 9
+    L.lpvmpc_anfis_abc_host.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 8
+    L.lpvmpc_observer_step_dev.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 8 + [C.c_double, C.c_void_p, C.c_int32, C.c_void_p]
+    L.lpvmpc_observer_step_host.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 8 + [C.c_double, C.c_void_p, C.c_int32]
     if L.lpvmpc_abi_version() != ABI_VERSION:
         raise RuntimeError("liblpvmpc.so ABI version mismatch; rebuild with _native.build(force=True)")
     _lib = L

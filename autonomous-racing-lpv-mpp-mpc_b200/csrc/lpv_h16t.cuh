@@ -1305,10 +1305,10 @@ __global__ void __launch_bounds__(256, 1) lpv_solve_h16t_kernel(const __grid_con
       __syncthreads();
       if (threadIdx.x == 0) round_base_s = atomicAdd(p.queue, 2u * (unsigned)wpc);
       __syncthreads();
-      const unsigned rb = round_base_s;
+      const unsigned rb = round_base_s, rend = (unsigned)p.B;
       if ((int)rb >= p.B) break;
       base = rb + 2u * (unsigned)warp;
-      if ((int)base >= p.B) {
+      if (base >= rend) {
         if (p.cta_rounds > 1) __syncthreads();   // the phase barrier in front of the polish (below)
         continue;
       }

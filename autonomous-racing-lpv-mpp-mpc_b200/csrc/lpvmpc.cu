@@ -24,6 +24,7 @@
 #include "lpv_h8t.cuh"
 #include "lpv_h16t.cuh"
 #include "lpv_loop.cuh"
+#include "lpv_aux.cuh"
 
 namespace lpv {
 
@@ -896,7 +897,7 @@ int launch_h16t(lpvmpc_handle *h, const Params &p, cudaStream_t s) {
   lpv::h8t::H8Params hp;
   hp.L = h->TL16; hp.M = p.M; hp.S = p.S; hp.a = p.a; hp.B = p.B; hp.queue = h->d_queue; hp.cold = h->d_cold;
   hp.perm = batch_order(h, p, s);
-  static const int rounds = [] { const char *e = std::getenv("LPVMPC_H16T_ROUNDS"); return e ? std::atoi(e) : 2; }();   // 0: every warp pulls on its own, 1: rounds, 2: rounds + phase barrier before the polish
+  static const int rounds = [] { const char *e = std::getenv("LPVMPC_H16T_ROUNDS"); return e ? std::atoi(e) : 2; }();   // 0: every warp pulls on its own, 1: rounds, 2: + phase barrier before the polish (sharing the last round out evenly over the CTAs was measured: no gain)
   hp.cta_rounds = rounds;
   const int ctas = (p.B + 15) / 16;
   const int grid = ctas < h->grid_cap ? ctas : h->grid_cap;
@@ -1803,6 +1804,89 @@ int lpvmpc_track_inputs_host(lpvmpc_handle *h, int32_t B, const double *gstate, 
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   run_copies({{x0, h->h_stage + o_x, b_x}, {vel_ref, h->h_stage + o_v, b_v}, {curv_ref, h->h_stage + o_c, b_c}});
   if (ex) std::memcpy(ex, h->h_stage + o_e, b_e);
+  return LPVMPC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// TS-fuzzy (ANFIS) scheduling blend and the polytopic LPV observer (csrc/lpv_aux.cuh)
+int lpvmpc_anfis_abc_dev(lpvmpc_handle *h, int32_t n, const double *sched, const double *A_tab, const double *B_tab, const double *C_tab,
+                         const double *bell, double *A, double *B, double *C, void *stream) {
+  if (!h || !sched || !A_tab || !B_tab || !C_tab || !bell || !A || !B || !C) return fail(h, LPVMPC_E_ARG, "null handle/sched/tables/outputs");
+  if (n < 0) return fail(h, LPVMPC_E_ARG, "negative element count");
+  if (n == 0) return LPVMPC_OK;
+  ON_DEVICE(h);
+  lpv::aux::AnfisParams p;
+  p.sched = sched; p.A_tab = A_tab; p.B_tab = B_tab; p.C_tab = C_tab; p.bell = bell; p.A = A; p.B = B; p.C = C; p.n = n;
+  lpv::aux::lpv_anfis_abc_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p);
+  ++h->launches;
+  CUDA_TRY(h, cudaGetLastError());
+  return LPVMPC_OK;
+}
+int lpvmpc_anfis_abc_host(lpvmpc_handle *h, int32_t n, const double *sched, const double *A_tab, const double *B_tab, const double *C_tab,
+                          const double *bell, double *A, double *B, double *C) {
+  if (!h || !sched || !A_tab || !B_tab || !C_tab || !bell || !A || !B || !C) return fail(h, LPVMPC_E_ARG, "null handle/sched/tables/outputs");
+  if (n < 0) return fail(h, LPVMPC_E_ARG, "negative element count");
+  if (n == 0) return LPVMPC_OK;
+  ON_DEVICE(h);
+  const size_t D = sizeof(double), nb = (size_t)n;
+  const size_t b_s = 5 * D * nb, b_t = (96 + 64 + 32 + 30) * D, b_a = 3 * D * nb, b_b = 2 * D * nb, b_c = D * nb;
+  const size_t o_s = 0, o_t = o_s + align256(b_s), o_a = o_t + align256(b_t), o_b = o_a + align256(b_a), o_c = o_b + align256(b_b);
+  if (o_c + align256(b_c) > h->stage_bytes) return fail(h, LPVMPC_E_ARG, "staging overflow (more elements than the handle's arena holds)");
+  double *t = reinterpret_cast<double *>(h->h_stage + o_t);
+  run_copies({{h->h_stage + o_s, sched, b_s}});
+  std::memcpy(t, A_tab, 96 * D); std::memcpy(t + 96, B_tab, 64 * D); std::memcpy(t + 160, C_tab, 32 * D); std::memcpy(t + 192, bell, 30 * D);
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_stage, h->h_stage, o_a, cudaMemcpyHostToDevice, h->stream));
+  const double *dt_ = reinterpret_cast<const double *>(h->d_stage + o_t);
+  const int rc = lpvmpc_anfis_abc_dev(h, n, reinterpret_cast<const double *>(h->d_stage + o_s), dt_, dt_ + 96, dt_ + 160, dt_ + 192,
+                                      reinterpret_cast<double *>(h->d_stage + o_a), reinterpret_cast<double *>(h->d_stage + o_b),
+                                      reinterpret_cast<double *>(h->d_stage + o_c), h->stream);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_stage + o_a, h->d_stage + o_a, (o_c - o_a) + align256(b_c), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  run_copies({{A, h->h_stage + o_a, b_a}, {B, h->h_stage + o_b, b_b}, {C, h->h_stage + o_c, b_c}});
+  return LPVMPC_OK;
+}
+
+int lpvmpc_observer_step_dev(lpvmpc_handle *h, int32_t n, double *est, const double *y, const double *u, const double *lim_ls,
+                             const double *gains_ls, const double *lim_hs, const double *gains_hs, const double *C_obs, double dt,
+                             const int32_t *use_est, int32_t use_all, void *stream) {
+  if (!h || !est || !y || !u || !lim_ls || !gains_ls || !lim_hs || !gains_hs || !C_obs) return fail(h, LPVMPC_E_ARG, "null handle/state/measurement/tables");
+  if (n < 0 || !(dt > 0)) return fail(h, LPVMPC_E_ARG, "negative element count or dt <= 0");
+  if (n == 0) return LPVMPC_OK;
+  ON_DEVICE(h);
+  lpv::aux::ObserverParams p;
+  p.est = est; p.y = y; p.u = u; p.lim_ls = lim_ls; p.gains_ls = gains_ls; p.lim_hs = lim_hs; p.gains_hs = gains_hs; p.C_obs = C_obs;
+  p.use_est = use_est; p.use_all = use_all; p.dt = dt; p.n = n;
+  lpv::aux::lpv_observer_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p);
+  ++h->launches;
+  CUDA_TRY(h, cudaGetLastError());
+  return LPVMPC_OK;
+}
+int lpvmpc_observer_step_host(lpvmpc_handle *h, int32_t n, double *est, const double *y, const double *u, const double *lim_ls,
+                              const double *gains_ls, const double *lim_hs, const double *gains_hs, const double *C_obs, double dt,
+                              const int32_t *use_est, int32_t use_all) {
+  if (!h || !est || !y || !u || !lim_ls || !gains_ls || !lim_hs || !gains_hs || !C_obs) return fail(h, LPVMPC_E_ARG, "null handle/state/measurement/tables");
+  if (n < 0 || !(dt > 0)) return fail(h, LPVMPC_E_ARG, "negative element count or dt <= 0");
+  if (n == 0) return LPVMPC_OK;
+  ON_DEVICE(h);
+  const size_t D = sizeof(double), nb = (size_t)n;
+  const size_t b_e = 6 * D * nb, b_y = 5 * D * nb, b_u = 2 * D * nb, b_i = sizeof(int32_t) * nb, b_t = (12 + 480 + 12 + 480 + 30) * D;
+  const size_t o_e = 0, o_y = o_e + align256(b_e), o_u = o_y + align256(b_y), o_i = o_u + align256(b_u), o_t = o_i + align256(b_i);
+  if (o_t + align256(b_t) > h->stage_bytes) return fail(h, LPVMPC_E_ARG, "staging overflow (more elements than the handle's arena holds)");
+  run_copies({{h->h_stage + o_e, est, b_e}, {h->h_stage + o_y, y, b_y}, {h->h_stage + o_u, u, b_u}});
+  if (use_est) std::memcpy(h->h_stage + o_i, use_est, b_i);
+  double *t = reinterpret_cast<double *>(h->h_stage + o_t);
+  std::memcpy(t, lim_ls, 12 * D); std::memcpy(t + 12, gains_ls, 480 * D); std::memcpy(t + 492, lim_hs, 12 * D);
+  std::memcpy(t + 504, gains_hs, 480 * D); std::memcpy(t + 984, C_obs, 30 * D);
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_stage, h->h_stage, o_t + align256(b_t), cudaMemcpyHostToDevice, h->stream));
+  const double *dt_ = reinterpret_cast<const double *>(h->d_stage + o_t);
+  const int rc = lpvmpc_observer_step_dev(h, n, reinterpret_cast<double *>(h->d_stage + o_e), reinterpret_cast<const double *>(h->d_stage + o_y),
+                                          reinterpret_cast<const double *>(h->d_stage + o_u), dt_, dt_ + 12, dt_ + 492, dt_ + 504, dt_ + 984, dt,
+                                          use_est ? reinterpret_cast<const int32_t *>(h->d_stage + o_i) : nullptr, use_all, h->stream);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_stage + o_e, h->d_stage + o_e, b_e, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  run_copies({{est, h->h_stage + o_e, b_e}});
   return LPVMPC_OK;
 }
 

@@ -308,6 +308,36 @@ int lpvmpc_track_inputs_dev(lpvmpc_handle *h, int32_t B, const double *gstate, c
 int lpvmpc_track_inputs_host(lpvmpc_handle *h, int32_t B, const double *gstate, const int32_t *lap, const double *s_prev, const double *refs,
                              int32_t n_ref, const int32_t *index, double *x0, double *vel_ref, double *curv_ref, double *ex);
 
+/* ------------------------------------------------------------------------------------------------
+ * two auxiliary routines of the reference next to the hot path, batched, one thread per element.  Their
+ * vertex / gain tables are the caller's: the reference loads them from .mat files that are not in its repository.  Any
+ * handle serves (it supplies the device, the stream of the `_host` variants and their staging arena: n is limited by it).
+ *
+ * lpvmpc_anfis_abc_*: the TS-fuzzy (ANFIS) scheduling blend ABC_computation_5SV_new,
+ * ControllerObject/PathFollowingLPVMPC.py:530-602.  sched [n,5] = vx vy omega steer accel; bell [10,3] = (a, b, c) of the
+ * two generalised-bell memberships 1 / (1 + |(x - c) / a|^(2b)) of every scheduling variable (:551-552); vertex v of 32 has
+ * bits (vx, vy, omega, steer, accel) = bits 4..0 (:555-592); outputs = normalised-weight blends of the vertex tables
+ * A_tab [32,3], B_tab [32,2], C_tab [32] (:597-601): A [n,3], B [n,2], C [n].
+ */
+int lpvmpc_anfis_abc_dev(lpvmpc_handle *h, int32_t n, const double *sched, const double *A_tab, const double *B_tab, const double *C_tab,
+                         const double *bell, double *A, double *B, double *C, void *stream);
+int lpvmpc_anfis_abc_host(lpvmpc_handle *h, int32_t n, const double *sched, const double *A_tab, const double *B_tab, const double *C_tab,
+                          const double *bell, double *A, double *B, double *C);
+/*
+ * lpvmpc_observer_step_*: one step of the polytopic LPV observer, stateEstimator.py:349-492 (GS_LPV_Est with
+ * Continuous_AB_Comp :392-430 and L_Gain_Comp :433-492):  est <- est + dt (A_obs + L C_obs) est + dt B_obs u - dt L y.
+ * est [n,6] = vx vy omega x y yaw (in place); y [n,5] = vx omega x y yaw; u [n,2] = steer accel; lim_* [6,2]
+ * (SchedVars_Limits) and gains_* [6,5,16] (Llmi) of the low- and the high-speed polytope (the high-speed one when the
+ * scheduling vx > lim_ls[0][1]); C_obs [5,6]; use_est [n] (or NULL: use_all for every element): schedule on the
+ * estimate (the reference's curr_time > 0.02 branch, :369-373) or on the measurement (:374-378).
+ */
+int lpvmpc_observer_step_dev(lpvmpc_handle *h, int32_t n, double *est, const double *y, const double *u, const double *lim_ls,
+                             const double *gains_ls, const double *lim_hs, const double *gains_hs, const double *C_obs, double dt,
+                             const int32_t *use_est, int32_t use_all, void *stream);
+int lpvmpc_observer_step_host(lpvmpc_handle *h, int32_t n, double *est, const double *y, const double *u, const double *lim_ls,
+                              const double *gains_ls, const double *lim_hs, const double *gains_hs, const double *C_obs, double dt,
+                              const int32_t *use_est, int32_t use_all);
+
 #ifdef __cplusplus
 }
 #endif

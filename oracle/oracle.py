@@ -11,7 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liblpv_oracle.so")
-_SOURCES = ["lpv_ref.c", "osqp_ref.c", "loop_ref.c", "lpv_ref.h", "osqp_ref.h", "loop_ref.h", "Makefile"]
+_SOURCES = ["lpv_ref.c", "osqp_ref.c", "loop_ref.c", "aux_ref.c", "lpv_ref.h", "osqp_ref.h", "loop_ref.h", "aux_ref.h", "Makefile"]
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)
@@ -434,3 +434,29 @@ def track_inputs(gstate, s_prev, refs, N, dt, lap=None, index=None):
                          C.c_int(0 if index is None else int(index[b])), C.c_int(N), C.c_double(dt), _dp(out["x0"][b]),
                          _dp(out["vel_ref"][b]), _dp(out["curv_ref"][b]))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# SURVEY 8f row 4 (oracle/aux_ref.c): TS-fuzzy scheduling blend and the polytopic LPV observer
+def anfis_abc(sched, A_tab, B_tab, C_tab, bell):
+    """ABC_computation_5SV_new (PathFollowingLPVMPC.py:530-602) for a batch: sched [B,5] -> A [B,3], B [B,2], C [B]."""
+    sched, A_tab, B_tab, C_tab, bell = map(_f64, (sched, A_tab, B_tab, C_tab, bell))
+    n = sched.shape[0]
+    A, Bm, Cc = np.zeros((n, 3)), np.zeros((n, 2)), np.zeros(n)
+    f = lib().anfis_abc_ref
+    f.restype = C.c_double
+    for i in range(n):
+        Cc[i] = f(_dp(sched[i]), _dp(A_tab), _dp(B_tab), _dp(C_tab), _dp(bell), _dp(A[i]), _dp(Bm[i]))
+    return A, Bm, Cc
+
+
+def observer_step(est, y, u, lim_ls, gains_ls, lim_hs, gains_hs, C_obs, dt, use_est):
+    """GS_LPV_Est (stateEstimator.py:349-492) for a batch: est [B,6] -> new est [B,6]."""
+    est = _f64(est).copy()
+    y, u, lim_ls, gains_ls, lim_hs, gains_hs, C_obs = map(_f64, (y, u, lim_ls, gains_ls, lim_hs, gains_hs, C_obs))
+    use = np.broadcast_to(np.asarray(use_est, dtype=np.int32), (est.shape[0],))
+    f = lib().observer_step_ref
+    f.restype = None
+    for i in range(est.shape[0]):
+        f(_dp(est[i]), _dp(y[i]), _dp(u[i]), _dp(lim_ls), _dp(gains_ls), _dp(lim_hs), _dp(gains_hs), _dp(C_obs), C.c_double(dt), C.c_int(int(use[i])))
+    return est
