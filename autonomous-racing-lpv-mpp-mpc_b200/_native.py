@@ -92,7 +92,7 @@ class PlanLoopState(C.Structure):
 
 EXPORTS = ["lpvmpc_abi_version", "lpvmpc_default_settings", "lpvmpc_device_count", "lpvmpc_create", "lpvmpc_destroy",
            "lpvmpc_last_error", "lpvmpc_get_info", "lpvmpc_update_settings", "lpvmpc_schedule_dev",
-           "lpvmpc_schedule_host", "lpvmpc_solve_dev", "lpvmpc_solve_host", "lpvmpc_loop_default_cfg", "lpvmpc_loop_init_dev",
+           "lpvmpc_schedule_host", "lpvmpc_solve_dev", "lpvmpc_solve_host", "lpvmpc_solve_host_view", "lpvmpc_loop_default_cfg", "lpvmpc_loop_init_dev",
            "lpvmpc_loop_init_host", "lpvmpc_loop_run_dev", "lpvmpc_loop_run_host", "lpvmpc_loop_view_dev",
            "lpvmpc_loop_read_host", "lpvmpc_plan_loop_init_host", "lpvmpc_plan_loop_init_dev", "lpvmpc_plan_loop_run_host",
            "lpvmpc_plan_loop_run_dev", "lpvmpc_plan_loop_view_dev", "lpvmpc_plan_loop_read_host", "lpvmpc_plan_refs_setup",
@@ -177,6 +177,7 @@ def lib():
     L.lpvmpc_schedule_host.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Args), C.c_void_p]
     L.lpvmpc_solve_dev.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Args), C.c_void_p]
     L.lpvmpc_solve_host.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Args)]
+    L.lpvmpc_solve_host_view.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Args), C.POINTER(Args)]
     L.lpvmpc_loop_default_cfg.argtypes = [C.POINTER(LoopCfg)]
     L.lpvmpc_loop_default_cfg.restype = None
     L.lpvmpc_loop_init_dev.argtypes = [C.c_void_p, C.c_int32, C.POINTER(LoopCfg), C.c_void_p, C.c_void_p]

@@ -655,6 +655,9 @@ struct lpvmpc_handle {
   // staging for the host API
   char *d_stage = nullptr, *h_stage = nullptr;
   size_t stage_bytes = 0;
+  char *h_ring = nullptr;      // two pinned result arenas of lpvmpc_solve_host_view (allocated on its first call)
+  size_t ring_bytes = 0;
+  int ring_slot = 0;
   bool zc_in = false;          // host API: the kernel reads its inputs from the pinned arena (LPVMPC_ZERO_COPY_IN=1; measured equal to the H2D copy at ctrl4096, off by default)
   bool zc_out = true;          // host API: the kernel writes its results straight into the pinned arena (LPVMPC_ZERO_COPY_OUT=0: D2H copy)
   cudaStream_t stream = nullptr;
@@ -1285,6 +1288,7 @@ void lpvmpc_destroy(lpvmpc_handle *h) {
   cudaFree(h->d_loop); cudaFree(h->d_ploop); cudaFree(h->d_refs_W);
   if (h->loop_ev) cudaEventDestroy(h->loop_ev);
   if (h->h_stage) cudaFreeHost(h->h_stage);
+  if (h->h_ring) cudaFreeHost(h->h_ring);
   delete h;
 }
 
@@ -1389,13 +1393,27 @@ int lpvmpc_schedule_dev(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, int32
 }
 
 // Host-pointer variants: pack every non-NULL input into one pinned arena, one H2D, kernel, one D2H.
-static int run_host(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, int32_t *sched_err, bool solve) {
+// `views` (lpvmpc_solve_host_view): the results stay in pinned memory -- one of two result arenas used in turn -- and the
+// caller gets pointers into it instead of copies into its own arrays (valid until the call after the next one)
+static int run_host(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, int32_t *sched_err, bool solve, lpvmpc_args *views = nullptr) {
   int rc = validate_args(h, B, a, solve);
   if (rc) return rc;
+  if (views) std::memset(views, 0, sizeof(*views));
   if (B == 0) return LPVMPC_OK;
   ON_DEVICE(h);
   lpvmpc_args dev = *a;
   const std::vector<Field> fields = staged_fields(h);
+  char *ring = nullptr;   // this call's result arena (view mode)
+  if (views) {
+    if (!h->h_ring) {
+      size_t ob = 0;
+      for (const Field &f : fields) if (f.output) ob += align256(f.elem * (size_t)h->cfg.max_batch);
+      h->ring_bytes = ob;
+      CUDA_TRY(h, cudaMallocHost(&h->h_ring, 2 * ob));
+    }
+    h->ring_slot ^= 1;
+    ring = h->h_ring + (size_t)h->ring_slot * h->ring_bytes;
+  }
   size_t off = 0, in_end = 0, out_begin = 0;
   bool first_out = true;
   std::vector<size_t> offs(fields.size());
@@ -1409,7 +1427,7 @@ static int run_host(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, int32_t *
       if (!f.output) jobs.push_back({h->h_stage + off, cptr_at(a, f.off_args), bytes});
       // results: written by the kernel through the pinned arena's device mapping (posted PCIe writes behind the compute:
       // no D2H copy after the kernel); the kernels only ever write their outputs
-      ptr_at(&dev, f.off_args) = ((f.output ? h->zc_out : h->zc_in) ? h->h_stage : h->d_stage) + off;
+      ptr_at(&dev, f.off_args) = ((f.output ? h->zc_out : h->zc_in) ? ((f.output && ring) ? ring - out_begin : h->h_stage) : h->d_stage) + off;
       off += align256(bytes);
       if (!f.output) in_end = off;
     }
@@ -1423,9 +1441,23 @@ static int run_host(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, int32_t *
   rc = solve ? lpvmpc_solve_dev(h, B, &dev, h->stream) : lpvmpc_schedule_dev(h, B, &dev, d_se, h->stream);
   if (rc) return rc;
   const size_t d2h_begin = (h->zc_out && !first_out) ? se_off : out_begin;   // zero-copy results: only sched_err comes back by copy
-  if (off > d2h_begin)
-    CUDA_TRY(h, cudaMemcpyAsync(h->h_stage + d2h_begin, h->d_stage + d2h_begin, off - d2h_begin, cudaMemcpyDeviceToHost, h->stream));
+  if (off > d2h_begin) {
+    if (ring && !h->zc_out && se_off > out_begin) {   // view mode without zero-copy results: the D2H copy lands in the result arena
+      CUDA_TRY(h, cudaMemcpyAsync(ring, h->d_stage + out_begin, se_off - out_begin, cudaMemcpyDeviceToHost, h->stream));
+      if (off > se_off) CUDA_TRY(h, cudaMemcpyAsync(h->h_stage + se_off, h->d_stage + se_off, off - se_off, cudaMemcpyDeviceToHost, h->stream));
+    } else {
+      CUDA_TRY(h, cudaMemcpyAsync(h->h_stage + d2h_begin, h->d_stage + d2h_begin, off - d2h_begin, cudaMemcpyDeviceToHost, h->stream));
+    }
+  }
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (views) {
+    for (size_t i = 0; i < fields.size(); ++i) {
+      const Field &f = fields[i];
+      if (f.output && cptr_at(a, f.off_args)) ptr_at(views, f.off_args) = ring + (offs[i] - out_begin);
+    }
+    if (sched_err) std::memcpy(sched_err, h->h_stage + se_off, sizeof(int32_t) * (size_t)B);
+    return LPVMPC_OK;
+  }
   jobs.clear();
   for (size_t i = 0; i < fields.size(); ++i) {
     const Field &f = fields[i];
@@ -1438,6 +1470,10 @@ static int run_host(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, int32_t *
 }
 
 int lpvmpc_solve_host(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a) { return run_host(h, B, a, nullptr, true); }
+int lpvmpc_solve_host_view(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, lpvmpc_args *views) {
+  if (!views) return fail(h, LPVMPC_E_ARG, "null views");
+  return run_host(h, B, a, nullptr, true, views);
+}
 
 // ------------------------------------------------------------------------------------------------
 // closed-loop fleet

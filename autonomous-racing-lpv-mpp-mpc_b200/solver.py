@@ -175,16 +175,21 @@ class BatchSolver(object):
 
     # ------------------------------------------------------------------ the hot path
     def solve(self, x0, sched_mode=nat.SCHED_PREDICT, extra_outputs=(), x0_from_prediction=False, lap_all=1,
-              Cf_new=60.0, **inputs):
+              Cf_new=60.0, host_views=False, **inputs):
         """Schedule (per ``sched_mode``) + build + OSQP solve for a batch.
 
         numpy inputs -> host path, torch CUDA tensors -> device path (asynchronous on torch's current stream).
         Inputs by keyword as in ``lpvmpc_args``: A, Bm, C | u_prev, vel_ref, curv_ref, SS, lap, x_sched | traj;
         u_old, old_steering, max_ey, ey_lo, ey_hi.
+
+        ``host_views=True`` (host path): the result arrays are numpy VIEWS of the handle's pinned result arena
+        (``lpvmpc_solve_host_view``: no copy into fresh arrays); they stay valid until the call after the next one.
         """
         inputs = dict(inputs)
         inputs["x0"] = x0
         outs = tuple(self._DEFAULT_OUT) + tuple(o for o in extra_outputs if o not in self._DEFAULT_OUT)
+        if host_views and not any(self._is_torch(v) for v in inputs.values() if v is not None):
+            return self._solve_views(inputs, outs, sched_mode, x0_from_prediction, lap_all, Cf_new)
         B, a, res, keep, use_torch = self._prepare(inputs, outs, sched_mode, x0_from_prediction, lap_all, Cf_new)
         L = nat.lib()
         if use_torch:
@@ -194,6 +199,24 @@ class BatchSolver(object):
             res["_keepalive"] = keep
         else:
             nat.check(L.lpvmpc_solve_host(self._h, B, C.byref(a)), self._h)
+        return res
+
+    def _solve_views(self, inputs, outs, sched_mode, x0_from_prediction, lap_all, Cf_new):
+        import numpy as _np
+        B, a, res, keep, _ = self._prepare(inputs, (), sched_mode, x0_from_prediction, lap_all, Cf_new)
+        shapes = self._shapes(B)
+        for k in outs:
+            setattr(a, k, 1)                      # requested (the pointer's value is not used)
+        views = nat.Args()
+        nat.check(nat.lib().lpvmpc_solve_host_view(self._h, B, C.byref(a), C.byref(views)), self._h)
+        ctype = {"f8": C.c_double, "i4": C.c_int32, "u1": C.c_uint8}
+        for k in outs:
+            n = int(_np.prod(shapes[k]))
+            ptr = getattr(views, k)
+            if n == 0 or not ptr:
+                res[k] = _np.empty(shapes[k], dtype=self._OUT_DTYPES[k])
+                continue
+            res[k] = _np.ctypeslib.as_array((ctype[self._OUT_DTYPES[k]] * n).from_address(ptr)).reshape(shapes[k])
         return res
 
     def schedule(self, sched_mode=nat.SCHED_PREDICT, lap_all=1, Cf_new=60.0, **inputs):

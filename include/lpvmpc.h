@@ -186,6 +186,11 @@ int lpvmpc_schedule_host(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, int3
 /* schedule (per sched_mode) + build + OSQP solve (+ polish) + unpack */
 int lpvmpc_solve_dev(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, void *stream);
 int lpvmpc_solve_host(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a);
+/* As lpvmpc_solve_host, but the results are NOT copied into the caller's arrays: every output requested in `a` (non-NULL
+ * pointer; its value is not used) comes back in `views` as a pointer into pinned host memory owned by the handle -- one of
+ * two result arenas used in turn, so a result stays valid until the call after the next one on this handle.  Removes the
+ * last host copy of the call (2.4 MB per 4,096 controller QPs); the kernel has written the arena directly. */
+int lpvmpc_solve_host_view(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, lpvmpc_args *views);
 
 /* ------------------------------------------------------------------------------------------------
  * Closed-loop fleet (BASELINE configs[3], SURVEY 8b `lpvmpc_step_closed_loop`): B independent vehicles, each running the

@@ -247,3 +247,27 @@ def test_schedule_tma_kernel_chunks_and_tails(track):
         np.testing.assert_array_equal(bufB[2:].cpu().numpy().reshape(B, N, 6, 2), B_out)
         np.testing.assert_array_equal(bufS.cpu().numpy().reshape(B, N, 6), S_out)
         s.close()
+
+
+def test_host_views_equal_fresh_arrays(track):
+    """lpvmpc_solve_host_view: the results as views of the handle's pinned result arenas -- the same bits as the copying
+    call; a result stays intact over the next call (two arenas used in turn) and is overwritten by the one after."""
+    B = 300
+    w = W.controller_batch(B, 8, seed=77)
+    s = lp.BatchSolver("controller", 8, W.CTRL_DT, track=track, max_batch=512, **W.CTRL_TT)
+    kw = {k: w[k] for k in KEYS}
+    ref = s.solve(w["x0"], extra_outputs=("active_lo", "y"), **kw)
+    v1 = s.solve(w["x0"], extra_outputs=("active_lo", "y"), host_views=True, **kw)
+    for k in ("x_pred", "u_pred", "status", "iters", "obj", "active_lo", "y"):
+        np.testing.assert_array_equal(np.asarray(v1[k]), np.asarray(ref[k]))
+        assert not v1[k].flags["OWNDATA"]
+    keep = v1.u_pred.copy()
+    w2 = W.controller_batch(B, 8, seed=78)
+    v2 = s.solve(w2["x0"], host_views=True, **{k: w2[k] for k in KEYS})
+    np.testing.assert_array_equal(v1.u_pred, keep)                      # the other arena
+    assert not np.array_equal(v2.u_pred, keep)
+    ref2 = s.solve(w2["x0"], **{k: w2[k] for k in KEYS})
+    np.testing.assert_array_equal(np.asarray(v2.u_pred), ref2.u_pred)
+    e = s.solve(w["x0"][:0], host_views=True, **{k: w[k][:0] for k in KEYS})
+    assert e.u_pred.shape == (0, 8, 2)
+    s.close()
