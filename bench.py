@@ -774,13 +774,16 @@ def run_schedule(args):
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "kind": "stand-alone LPVPrediction (scheduling only: A_k, B_k, roll-out states to HBM; value = QPs SCHEDULED per second, no solve)",
                    "N": N, "batch_per_gpu": B, "l2": "flushed between steps (1 GiB memset outside the per-step event pairs); 250 MB per launch > L2",
-                   "kernel": "lpv_schedule_naive_kernel" if os.environ.get("LPVMPC_SCHED_NAIVE", "0") != "0" else "lpv_schedule_kernel"},
+                   "kernel": "lpv_schedule_naive_kernel" if os.environ.get("LPVMPC_SCHED_NAIVE", "0") != "0" else "lpv_schedule_tma_kernel (LPVMPC_SCHED_MODE, default 2)"},
         "e2e": {"value": B / e2e_s, "unit": "QP/s", "h2d_bytes_per_step": int(sum(np.asarray(v).nbytes for v in hin.values())),
                 "d2h_bytes_per_step": int(sum(v.nbytes for v in rh.values() if hasattr(v, "nbytes"))), "ms_per_step": 1e3 * e2e_s},
         "gpu_launches": int(launches), "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": ncu_traffic("sched65536", 0) if (B == 65536 and os.environ.get("LPVMPC_SCHED_MODE", "2") == "2") else None,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if not mp.get("_fallback") else "fallback (B200_PROFILING.md)",
-                     "kernel": "lpv_schedule_kernel<CONTROLLER>", "algorithmic_bytes_per_qp": in_b + out_b,
+                     "kernel": {"2": "lpv_schedule_tma_kernel (TMA tensor stores)", "1": "lpv_schedule_kernel<CONTROLLER, DIRECT> (256-bit stores)",
+                                "0": "lpv_schedule_kernel<CONTROLLER> (tile-staged stores)"}.get(os.environ.get("LPVMPC_SCHED_MODE", "2"), "?"),
+                     "algorithmic_bytes_per_qp": in_b + out_b,
                      "algorithmic_bytes_per_launch": (in_b + out_b) * B},
         "kernel_latency_ms": {"p50": float(np.percentile(step_ms, 50)), "max": float(step_ms.max())},
     }
