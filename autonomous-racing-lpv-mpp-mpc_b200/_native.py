@@ -16,8 +16,9 @@ _SRC_DIR = os.path.join(_PKG, "csrc")
 _SOURCES = [os.path.join(_SRC_DIR, f) for f in ("lpvmpc.cu", "lpv_qp.cuh", "lpv_h8.cuh", "lpv_h8t.cuh", "lpv_h16t.cuh", "lpv_model.cuh", "lpv_loop.cuh", "lpv_aux.cuh")] + \
            [os.path.join(_ROOT, "include", "lpvmpc.h")]
 
+# --split-compile=0: ptxas works on the kernels in parallel (45 s instead of 2 min 10 s on 8 cores; measured equal in speed)
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-shared"]
+              "--split-compile=0", "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-shared"]
 
 ABI_VERSION = 1
 CONTROLLER, PLANNER = 0, 1

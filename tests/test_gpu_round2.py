@@ -271,3 +271,38 @@ def test_host_views_equal_fresh_arrays(track):
     e = s.solve(w["x0"][:0], host_views=True, **{k: w[k][:0] for k in KEYS})
     assert e.u_pred.shape == (0, 8, 2)
     s.close()
+
+
+def test_helper_warp_kernels_repeat_bit_for_bit(track):
+    """The twisted H8 kernels hand the element-wise ADMM updates to helper warps through a shared-memory mailbox
+    (release / acquire on `go` / `done`, a relaxed progress counter behind the x~ stores).  compute-sanitizer's racecheck
+    cannot see that protocol (it reports the mailbox accesses as hazards), so: the same batch solved five times must give
+    the same bits every time -- any update that read an x~ too early would show up as a difference -- on top of the
+    parity tests against the oracle (test_planner_fixed_and_converged, test_long_horizon_controller_matches_oracle)."""
+    Np, Bp = 40, 300
+    wp = W.planner_batch(Bp, Np, seed=9)
+    sp = lp.BatchSolver("planner", Np, W.PLAN_DT, track=track, max_batch=Bp, **W.PLAN)
+    keys = ("SS", "u_prev", "u_old", "max_ey", "ey_lo", "ey_hi")
+    first = None
+    for _ in range(5):
+        r = sp.solve(wp["x0"], extra_outputs=("y",), **{k: wp[k] for k in keys})
+        got = (r.x_pred.copy(), r.u_pred.copy(), r.iters.copy(), r.status.copy(), r.y.copy())
+        if first is None:
+            first = got
+        else:
+            for a, b in zip(first, got):
+                np.testing.assert_array_equal(a, b)
+    sp.close()
+    N, B = 100, 150
+    w = W.controller_batch(B, N, seed=3, steer_scale=0.2)
+    s = lp.BatchSolver("controller", N, W.CTRL_DT, track=track, max_batch=B, **W.CTRL_TT)
+    first = None
+    for _ in range(4):
+        r = s.solve(w["x0"], extra_outputs=("y",), **{k: w[k] for k in KEYS})
+        got = (r.x_pred.copy(), r.u_pred.copy(), r.iters.copy(), r.y.copy())
+        if first is None:
+            first = got
+        else:
+            for a, b in zip(first, got):
+                np.testing.assert_array_equal(a, b)
+    s.close()

@@ -1,6 +1,6 @@
 """Small workloads for compute-sanitizer (memcheck / racecheck / synccheck): one launch of every kernel the library
 ships — solve kernels variant 1 (generic), 5 (H8, controller and planner, 4 / 1 QPs per warp), 6 (H8T, tensor memory),
-7 (H8S, TMA-streamed factor), 8 (H16T) when present, the visiting-order kernel, the stand-alone scheduling kernels,
+7 (H8S, TMA-streamed factor), 8 (H16T: CTA rounds), the twisted H8 kernels with helper warps (v5n100, p5) and the plain one (p5n39), the visiting-order kernel, the stand-alone scheduling kernels,
 the fleet / planner loop kernels, the reference and hand-off kernels.  Results are checked against the oracle so a
 sanitizer-clean run is also a correct one.
 
@@ -39,8 +39,7 @@ def ctrl(variant, N=8, B=10):
     return "variant %d N %d: ok (%d launches)" % (info["variant"], N, info["kernel_launches"])
 
 
-def plan(variant, B=5):
-    N = 40
+def plan(variant, B=5, N=40):
     w = W.planner_batch(B, N, seed=7)
     keys = ("SS", "u_prev", "u_old", "max_ey", "ey_lo", "ey_hi")
     s = lp.BatchSolver("planner", N, W.PLAN_DT, track=TRACK, max_batch=B, variant=variant, **W.PLAN, **SETTINGS)
@@ -93,8 +92,21 @@ def planfleet():
     return "planner loop + references: ok (%d ticks)" % int(out["ctr"][:, 0].sum())
 
 
+def aux():
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "aux.npz")))
+    s = lp.BatchSolver("controller", 8, W.CTRL_DT, track=TRACK, max_batch=64, **W.CTRL_TT)
+    r = lp.anfis_abc(s, g["an_sched"], g["an_A_tab"], g["an_B_tab"], g["an_C_tab"], g["an_bell"])
+    assert np.allclose(r["A"], g["an_A"], rtol=1e-12, atol=1e-14)
+    e = lp.observer_step(s, g["ob_est0"], g["ob_y"][0], g["ob_u"][0], g["ob_lim_ls"], g["ob_gains_ls"], g["ob_lim_hs"], g["ob_gains_hs"], g["ob_C"],
+                         dt=float(g["ob_dt"]), use_estimate=0)
+    assert np.allclose(e, g["ob_est"][0], rtol=1e-11, atol=1e-12)
+    s.close()
+    return "TS-fuzzy blend + observer kernels: ok"
+
+
 CASES = {
-    "v1": lambda: ctrl(1), "v5": lambda: ctrl(5), "v6": lambda: ctrl(6), "v7": lambda: ctrl(7),
+    "v1": lambda: ctrl(1), "v5": lambda: ctrl(5), "v6": lambda: ctrl(6), "v7": lambda: ctrl(7), "v8": lambda: ctrl(8, B=37),
+    "p5n39": lambda: plan(5, B=3, N=39), "aux": aux,
     "v5n20": lambda: ctrl(5, N=20, B=6), "v5n100": lambda: ctrl(5, N=100, B=2), "v7n160": lambda: ctrl(7, N=160, B=2),
     "p1": lambda: plan(1, B=2), "p5": lambda: plan(5), "p7": lambda: plan(7, B=3),
     "schedule": schedule, "fleet": fleet, "planfleet": planfleet,
@@ -103,8 +115,5 @@ CASES = {
 if __name__ == "__main__":
     names = sys.argv[1:] or list(CASES)
     for n in names:
-        if n == "v8":
-            print(n, ctrl(8))
-            continue
         print(n, CASES[n]())
     print("sanitize subset done")
