@@ -338,12 +338,14 @@ struct Hot {
 };
 
 // forward sweep: B holds the right-hand side on entry, W = T v on exit (both halves, local steps 0 .. NL)
-__device__ __forceinline__ void sweep_fwd(const Hot &h, const int NL, const int half, uint32_t &gsel) {
+template <bool UNROLL = false>
+__device__ __forceinline__ void sweep_fwd(const Hot &h, const int NLr, const int half, uint32_t &gsel) {
+  const int NL = UNROLL ? 4 : NLr;
   uint32_t tt = h.tT, tk = h.tKr, vb = h.v;
   TmRow a, b;
   tm_ld8(tt, a); tm_ld8(tk, b);
   double v = lds(vb);
-#pragma unroll 1
+#pragma unroll (UNROLL ? 4 : 1)
   for (int j = 0; j < NL; ++j) {
     sts(h.gpub ^ gsel, v);
     double bn = lds(vb + (uint32_t)h.vstr);
@@ -404,7 +406,9 @@ __device__ __forceinline__ void sweep_bwd_plain(const Hot &h, const int NL, uint
 // backward sweep fused with the element-wise ADMM update (hot).  Walking local steps NL-1 .. 0, the update of the stage
 // of local step j+1 runs behind the chain step that produces x~ of local step j.  The middle stage is updated by both
 // halves with its neighbours in canonical order (x~_{m-1}, x~_{m+1}): bit-identical values to the same addresses.
-__device__ __forceinline__ void sweep_bwd_admm(const Hot &h, const Upd<KIND> &u, const int NL, const int half, uint32_t &gsel) {
+template <bool UNROLL = false>
+__device__ __forceinline__ void sweep_bwd_admm(const Hot &h, const Upd<KIND> &u, const int NLr, const int half, uint32_t &gsel) {
+  const int NL = UNROLL ? 4 : NLr;
   double gn[8];
   uint32_t vb = h.vmid, ib = h.ibmid;
   uint32_t pb = h.pm + (uint32_t)(NL * h.pstr), pb2 = h.pm2 + (uint32_t)(NL * h.pstr);
@@ -432,7 +436,7 @@ __device__ __forceinline__ void sweep_bwd_admm(const Hot &h, const Upd<KIND> &u,
     vb -= (uint32_t)h.vstr; ib -= (uint32_t)h.istr; pb -= (uint32_t)h.pstr; pb2 -= (uint32_t)h.pstr;
     x2 = x1; x1 = xt;
   }
-#pragma unroll 1
+#pragma unroll (UNROLL ? 3 : 1)
   for (int j = NL - 2; j >= 0; --j) {
     UpdIn in;
     update_loads<KIND>(vb, ib, ib, pb, pb2, in);   // local step j+1, independent of the chain below
@@ -1407,8 +1411,8 @@ __global__ void __launch_bounds__(256, 1) lpv_solve_h16t_kernel(const __grid_con
           tm_wait_st();
         }
         u.cc = (iter == 0) ? 2.0 : alpha;
-        sweep_fwd(h, NL, half, gsel);
-        sweep_bwd_admm(h, u, NL, half, gsel);
+        sweep_fwd<true>(h, NL, half, gsel);          // N = 8: four local steps, unrolled (the host admits no other horizon)
+        sweep_bwd_admm<true>(h, u, NL, half, gsel);
         if (iter == 0) first_in = 1;
         ++nsync;
         zsel = 1.0;

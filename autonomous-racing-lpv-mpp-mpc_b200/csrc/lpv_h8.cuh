@@ -1100,11 +1100,28 @@ __device__ __forceinline__ void sweep_bwd_chain_hw(const Hot<KIND> &h, const int
     gather_in(h.ggat, gsel, gn);   // (its __syncwarp orders the XT stores of all lanes before lane 0's release below)
   }
   if (lane == 0) { st_rel(hws + (uint32_t)offsetof(HwShared, go), seq); st_rel(hws + (uint32_t)offsetof(HwShared, prog), 1u); }
+  // software-pipelined: the multiplier column and W of the NEXT chain step are requested before the all-gather of the current
+  // one (they do not depend on it), so their latency hides behind the publish -> gather round trip
+  const uint32_t kstr = half ? (uint32_t)TKB : (uint32_t)(-TKB), vstr = half ? (uint32_t)VB : (uint32_t)(-VB);   // towards the ends
+  uint32_t so = (uint32_t)(half ? N - (NL - 1) : NL - 1) * (uint32_t)TKB, vb = h.v + (uint32_t)(half ? N - (NL - 1) : NL - 1) * (uint32_t)VB;
+  double e0 = lds(h.kc[0] + so), e1 = lds<64>(h.kc[0] + so), e2 = lds(h.kc[1] + so), e3 = lds<64>(h.kc[1] + so);
+  double e4 = lds(h.kc[2] + so), e5 = lds<64>(h.kc[2] + so), e6 = lds(h.kc[3] + so), e7 = lds<64>(h.kc[3] + so);
+  double w = lds(vb);
 #pragma unroll 1
   for (int j = NL - 1; j >= 0; --j) {
-    const uint32_t k = (uint32_t)(half ? N - j : j), so = k * (uint32_t)TKB, vb = h.v + k * (uint32_t)VB;
-    const double xt = bwd_step(h.kc[0] + so, h.kc[1] + so, h.kc[2] + so, h.kc[3] + so, vb, h.gpub, h.ggat, gsel, gn);
+    double a0 = fma(e0, gn[0], w), a1 = e1 * gn[1];   // e = column of the (negated) multiplier
+    a0 = fma(e2, gn[2], a0); a1 = fma(e3, gn[3], a1);
+    a0 = fma(e4, gn[4], a0); a1 = fma(e5, gn[5], a1);
+    a0 = fma(e6, gn[6], a0); a1 = fma(e7, gn[7], a1);
+    const double xt = a0 + a1;
+    sts(h.gpub ^ gsel, xt);
     sts<V_XT * 8>(vb, xt);
+    if (j > 0) {
+      so += kstr; vb += vstr;
+      e0 = lds(h.kc[0] + so); e1 = lds<64>(h.kc[0] + so); e2 = lds(h.kc[1] + so); e3 = lds<64>(h.kc[1] + so);
+      e4 = lds(h.kc[2] + so); e5 = lds<64>(h.kc[2] + so); e6 = lds(h.kc[3] + so); e7 = lds<64>(h.kc[3] + so);
+      w = lds(vb);
+    }
     gather_in(h.ggat, gsel, gn);
     if (lane == 0) st_prog(hws + (uint32_t)offsetof(HwShared, prog), (uint32_t)(NL - j + 1));
   }
