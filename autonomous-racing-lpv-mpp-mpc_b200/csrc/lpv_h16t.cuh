@@ -117,8 +117,13 @@ struct Ctx {
 
 // Iterates a cold per-stage loop over my stages; `kv` is false on the left half's extra (dummy) trip, where k repeats my
 // first stage so that every address stays valid (stores and accumulations are guarded by kv).
+#ifndef H16_COLD_UNROLL
+#define H16_COLD_UNROLL 1
+#endif
+#define H16_STR2(x) #x
+#define H16_STR(x) H16_STR2(x)
 #define H16_COLD_LOOP(i, k, kv)                                   \
-  _Pragma("unroll 1") for (int i = 0; i <= c.NL; ++i)            \
+  _Pragma(H16_STR(unroll H16_COLD_UNROLL)) for (int i = 0; i <= c.NL; ++i)            \
     if (const bool kv = (i < c.nck); true)                        \
       if (const int k = c.kc0 + (kv ? i : 0); true)
 

@@ -42,6 +42,12 @@
 namespace lpv {
 namespace h8 {
 
+#ifndef H8_TW_UNROLL
+#define H8_TW_UNROLL 1   // unroll factor of the chain loops of the twisted sweeps
+#endif
+#define H8_STR2(x) #x
+#define H8_STR(x) H8_STR2(x)
+#define H8_TW_PRAGMA _Pragma(H8_STR(unroll H8_TW_UNROLL))
 constexpr int TKS = 128;  // doubles per stage of the factor: T_k (64) then K_{k+1} (64)
 constexpr int VS = 56;    // doubles per stage of the stage vectors
 enum { V_B = 0, V_X = 8, V_R = 16, V_XS = 24, V_DG = 32, V_CR = 40, V_XT = 48 };   // XT: x~ of the backward sweep (helper-warp kernels)
@@ -919,7 +925,7 @@ __device__ __forceinline__ void sweep_fwd_tw(const Hot<KIND> &h, const int N, ui
   uint32_t so = (half ? (uint32_t)N * (uint32_t)TKB : 0u) + (trole ? 0u : 512u);
   uint32_t vb = h.v + (half ? (uint32_t)N * (uint32_t)VB : 0u), wst = vb;
   double res = lds(vb);   // chain: v of local step 0 = b; T lanes: b as well, written back unchanged by their first store
-#pragma unroll 1
+H8_TW_PRAGMA
   for (int j = 0; j < NL; ++j) {
     sts(trole ? wst : (h.gpub ^ gsel), res);
     const double2 r0 = lds2(h.tk[0] + so), r1 = lds2(h.tk[1] + so), r2 = lds2(h.tk[2] + so), r3 = lds2(h.tk[3] + so);
@@ -1107,7 +1113,7 @@ __device__ __forceinline__ void sweep_bwd_chain_hw(const Hot<KIND> &h, const int
   double e0 = lds(h.kc[0] + so), e1 = lds<64>(h.kc[0] + so), e2 = lds(h.kc[1] + so), e3 = lds<64>(h.kc[1] + so);
   double e4 = lds(h.kc[2] + so), e5 = lds<64>(h.kc[2] + so), e6 = lds(h.kc[3] + so), e7 = lds<64>(h.kc[3] + so);
   double w = lds(vb);
-#pragma unroll 1
+H8_TW_PRAGMA
   for (int j = NL - 1; j >= 0; --j) {
     double a0 = fma(e0, gn[0], w), a1 = e1 * gn[1];   // e = column of the (negated) multiplier
     a0 = fma(e2, gn[2], a0); a1 = fma(e3, gn[3], a1);
