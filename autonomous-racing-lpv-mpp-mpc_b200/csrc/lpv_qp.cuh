@@ -53,7 +53,6 @@ struct Params {
   lpvmpc_args a;
   int B;
   double *gws;  // global workspace slabs (one per resident warp) when not in shared memory
-  int sched_stagger_ns = 0, sched_sms = 1;   // stand-alone scheduling kernel: start-up stagger of the CTAs sharing an SM
 };
 
 template <int KIND> struct Spec;

@@ -383,10 +383,6 @@ __global__ void __launch_bounds__(32 * kTmaWarps, 7) lpv_schedule_tma_kernel(con
   double m_u0 = 0.0, m_u1 = 0.0, m_a = 0.0, m_c = 0.0;
   if (N > 1) { m_u0 = up[NU]; m_u1 = up[NU + 1]; m_a = in0(1); m_c = in1(1); }
   const bool wantS = a.states_out && !estimate;
-  // Stagger the CTAs that share an SM (they are the CTAs b, b + #SMs, b + 2 #SMs, ... of the first wave): started together
-  // they would all compute and then all store; shifted against each other by a fraction of a stage their arithmetic and
-  // their store bursts overlap.  LPVMPC_SCHED_STAGGER_NS: nanoseconds per CTA rank on its SM (0 = off).
-  if (p.sched_stagger_ns > 0) __nanosleep((unsigned)p.sched_stagger_ns * (unsigned)((blockIdx.x / p.sched_sms) % 8u));
 #pragma unroll 1
   for (int i0 = 0; i0 < N; i0 += CH) {
     double bq[CH][3];
@@ -1381,10 +1377,7 @@ int lpvmpc_schedule_dev(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, int32
     if (a->sched_mode != LPVMPC_SCHED_ESTIMATE) enc(&maps.S, a->states_out, 6, lpv::kTmaChunk);
     if (ok) {
       const int g2 = (B + 32 * lpv::kTmaWarps - 1) / (32 * lpv::kTmaWarps);
-      static const int stagger = [] { const char *e = std::getenv("LPVMPC_SCHED_STAGGER_NS"); return e ? std::atoi(e) : 0; }();
-      lpv::Params ps = p;
-      ps.sched_stagger_ns = stagger; ps.sched_sms = h->sm_count;
-      lpv::lpv_schedule_tma_kernel<<<g2, 32 * lpv::kTmaWarps, 0, (cudaStream_t)stream>>>(ps, sched_err, maps);
+      lpv::lpv_schedule_tma_kernel<<<g2, 32 * lpv::kTmaWarps, 0, (cudaStream_t)stream>>>(p, sched_err, maps);
       ++h->launches;
       CUDA_TRY(h, cudaGetLastError());
       return stream_leave(h, (cudaStream_t)stream);
