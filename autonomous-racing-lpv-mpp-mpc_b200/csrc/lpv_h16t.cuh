@@ -1416,8 +1416,11 @@ __global__ void __launch_bounds__(256, 1) lpv_solve_h16t_kernel(const __grid_con
           tm_wait_st();
         }
         u.cc = (iter == 0) ? 2.0 : alpha;
-        sweep_fwd<true>(h, NL, half, gsel);          // N = 8: four local steps, unrolled (the host admits no other horizon)
-        sweep_bwd_admm<true>(h, u, NL, half, gsel);
+#ifndef H16T_UNROLL_SWEEPS
+#define H16T_UNROLL_SWEEPS 1
+#endif
+        sweep_fwd<H16T_UNROLL_SWEEPS != 0>(h, NL, half, gsel);          // N = 8: four local steps, unrolled (the host admits no other horizon)
+        sweep_bwd_admm<H16T_UNROLL_SWEEPS != 0>(h, u, NL, half, gsel);
         if (iter == 0) first_in = 1;
         ++nsync;
         zsel = 1.0;

@@ -502,14 +502,37 @@ __global__ void __launch_bounds__(1024) lpv_order_kernel(const double *__restric
     f = f < 0.0 ? 0.0 : (f > 255.0 ? 255.0 : f);
     return (int)f;
   };
-  for (int b = t; b < B; b += blockDim.x) atomicAdd(&hist[bucket(b)], 1);
+  // the first few elements of a thread keep their bucket in registers (a 4,096-QP batch: all of them)
+  constexpr int KEEP = 4;
+  int mine[KEEP];
+#pragma unroll
+  for (int j = 0; j < KEEP; ++j) {
+    const int b = t + j * (int)blockDim.x;
+    mine[j] = (b < B) ? bucket(b) : -1;
+    if (mine[j] >= 0) atomicAdd(&hist[mine[j]], 1);
+  }
+  for (int b = t + KEEP * (int)blockDim.x; b < B; b += blockDim.x) atomicAdd(&hist[bucket(b)], 1);
   __syncthreads();
-  if (t == 0) {
-    int acc = 0;
-    for (int i = 0; i < 256; ++i) { offs[i] = acc; acc += hist[i]; }
+  // exclusive prefix sum of the 256 bucket counts: warp scans + the 8 warp totals
+  __shared__ int wtot[8];
+  int incl = 0, cnt = 0;
+  if (t < 256) {
+    cnt = hist[t]; incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if ((t & 31) >= o) incl += v; }
+    if ((t & 31) == 31) wtot[t >> 5] = incl;
   }
   __syncthreads();
-  for (int b = t; b < B; b += blockDim.x) perm[atomicAdd(&offs[bucket(b)], 1)] = b;
+  if (t < 256) {
+    int base = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) base += (w < (t >> 5)) ? wtot[w] : 0;
+    offs[t] = base + incl - cnt;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < KEEP; ++j) if (mine[j] >= 0) perm[atomicAdd(&offs[mine[j]], 1)] = t + j * (int)blockDim.x;
+  for (int b = t + KEEP * (int)blockDim.x; b < B; b += blockDim.x) perm[atomicAdd(&offs[bucket(b)], 1)] = b;
 }
 
 }  // namespace lpv
