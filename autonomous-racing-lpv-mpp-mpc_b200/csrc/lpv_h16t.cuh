@@ -79,7 +79,7 @@ struct Ctx {
   double *S;     // my QP's shared region
   double *cold;  // my QP slot in the global slab
   const Lay *L;
-  int N, NL;     // horizon, local steps before the middle stage (N = 2 NL)
+  static constexpr int N = 8, NL = 4;   // horizon, local steps before the middle stage (N = 2 NL): this kernel is N = 8 only (lpvmpc_create)
   int r, h;      // component, half (0: left, stages ascending; 1: right, stages descending)
   int kc0, nck;  // cold ownership: stages kc0 .. kc0 + nck - 1 (left: 0 .. NL-1, right: NL .. N)
   int co[4];     // my column of a swizzled G block: offset inside row rr is co[rr >> 1]
@@ -1272,10 +1272,10 @@ __global__ void __launch_bounds__(256, 1) lpv_solve_h16t_kernel(const __grid_con
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
   const int gq0 = lane >> 4, half = (lane >> 3) & 1, r = lane & 7, g8 = lane >> 3;
   const Lay &L = p.L;
-  const int N = L.N, NL = N >> 1;
+  constexpr int N = Ctx::N, NL = Ctx::NL;
   Ctx c;
   c.S = smem; c.cold = p.cold;
-  c.L = &L; c.N = N; c.NL = NL; c.r = r; c.h = half;
+  c.L = &L; c.r = r; c.h = half;
   c.kc0 = half ? NL : 0; c.nck = half ? NL + 1 : NL;
   c.xl = r < NX; c.ul = (r >= NX) && (r < NB);
   c.islot = (r == 0) ? 0 : ((r >= NX) ? (r - NX + 1) * 2 : 0);
