@@ -126,6 +126,14 @@ struct Ctx {
   _Pragma(H16_STR(unroll H16_COLD_UNROLL)) for (int i = 0; i <= c.NL; ++i)            \
     if (const bool kv = (i < c.nck); true)                        \
       if (const int k = c.kc0 + (kv ? i : 0); true)
+// the two loops of a Ruiz pass (10 passes per QP: the bulk of setup): independent per stage, but unrolling them is slower
+#ifndef H16_RUIZ_UNROLL
+#define H16_RUIZ_UNROLL 1   // measured: 5 (full) 1.10 ms against 1.035 ms at 1
+#endif
+#define H16_RUIZ_LOOP(i, k, kv)                                   \
+  _Pragma(H16_STR(unroll H16_RUIZ_UNROLL)) for (int i = 0; i <= c.NL; ++i)            \
+    if (const bool kv = (i < c.nck); true)                        \
+      if (const int k = c.kc0 + (kv ? i : 0); true)
 
 // (P v)_(k, r), (A v) on my dynamics row, (A' t)_(k, r): as in lpv_h8t.cuh
 __device__ __forceinline__ double rowP(const Ctx &c, const double *PD, const double *PO, const double *v, int vs, int k) {
@@ -896,7 +904,7 @@ __device__ __noinline__ int setup(const Ctx c, const H8Params &p, const int b, c
   const int oL = c.NL * 8 + r;   // my slot at the right half's first stage
 #pragma unroll 1
   for (int it = 0; it < St.scaling; ++it) {
-    H16_COLD_LOOP(i, k, kv) {
+    H16_RUIZ_LOOP(i, k, kv) {
       const int o = k * 8 + r, ov = k * VS + r;
       if (kv) {
         double pa, qa;
@@ -939,7 +947,7 @@ __device__ __noinline__ int setup(const Ctx c, const H8Params &p, const int b, c
     // products as the left half forms, from the values before this pass touches them
     if (h && c.ul) npo_prev = ((sPO[oL - 8] * cp) * sDt[oL - 8]) * sDt[oL];
     __syncwarp();
-    H16_COLD_LOOP(i, k, kv) {
+    H16_RUIZ_LOOP(i, k, kv) {
       const int o = k * 8 + r, ov = k * VS + r;
       if (kv) {
         const double dt = sDt[o];
@@ -1562,6 +1570,7 @@ __global__ void __launch_bounds__(256, 1) lpv_solve_h16t_kernel(const __grid_con
 }
 
 #undef H16_COLD_LOOP
+#undef H16_RUIZ_LOOP
 
 }  // namespace h16t
 }  // namespace lpv
