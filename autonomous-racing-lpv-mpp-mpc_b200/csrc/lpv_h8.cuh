@@ -157,6 +157,47 @@ struct Ctx {
   bool xl, ul;   // state lane / input lane (neither: idle lane)
   int islot;     // first single-variable-row slot of my variable inside a stage (t adds 1)
   uint64_t eqm, loosem;  // planner: bit k = my box row at stage k is an equality / both bounds infinite
+  // Helper-warp kernels (one QP per CTA): EVERY warp of the CTA walks the cold per-stage loops -- warp w, group g takes the
+  // stages 4 w + g, + 4 nw, ... -- so a barrier between two loops is a CTA barrier and a reduction goes through `red`
+  // (16 doubles per warp in shared memory).  nw = 1: the warp is on its own (every other kernel).
+  int nw;
+  double *red;
+
+  __device__ __forceinline__ void sync() const { if (nw > 1) __syncthreads(); else __syncwarp(); }
+  // v[0 .. NV-1] reduced over the warps of the CTA (max or sum, in warp order: the same value in every warp); the values
+  // come in reduced over the warp
+  template <int NV, bool SUM>
+  __device__ __forceinline__ void cta_reduce(double (&v)[NV]) const {
+    static_assert(NV <= 16, "16 reduction slots per warp");
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) red[w * 16 + i] = v[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double acc = red[i];
+      for (int ww = 1; ww < nw; ++ww) { const double o = red[ww * 16 + i]; acc = SUM ? acc + o : ((o > acc) ? o : acc); }
+      v[i] = acc;
+    }
+    __syncthreads();
+  }
+  __device__ __forceinline__ double rmax(double v) const {
+    v = h8::wmax(v, ks > 1);
+    if (nw > 1) { double a[1] = {v}; cta_reduce<1, false>(a); v = a[0]; }
+    return v;
+  }
+  __device__ __forceinline__ double rsum(double v) const {
+    v = h8::wsum(v, ks > 1);
+    if (nw > 1) { double a[1] = {v}; cta_reduce<1, true>(a); v = a[0]; }
+    return v;
+  }
+  __device__ __forceinline__ int rany(int v) const {
+    v = h8::wany(v, ks > 1);
+    if (nw > 1) v = __syncthreads_or(v);
+    return v;
+  }
 
   __device__ __forceinline__ bool var_live(int k) const { return xl || (ul && k < N); }
   __device__ __forceinline__ bool has_in(int k) const {
@@ -1029,19 +1070,20 @@ __device__ __forceinline__ void sweep_bwd_admm_tw(const Hot<KIND> &h, const Upd<
 
 // ---------------------------------------------------------------- helper warps (twisted kernels, one QP per CTA)
 // The element-wise ADMM update is independent per stage, yet in the one-warp kernels it sits on the critical path: 11 update
-// rounds of 4 stages behind the 20 chain steps of a planner sweep.  Here the CTA has NH more warps that do nothing but
-// updates: the main warp runs the forward sweep and the backward CHAIN (x~_k goes to its own stage vector XT instead of
+// rounds of 4 stages behind the 20 chain steps of a planner sweep.  Here the CTA has NH more warps: inside an ADMM step
+// they do nothing but updates, and in every cold phase (setup, residuals, certificates, re-projection, polish) all
+// NH + 1 warps split the stages between them (Ctx::nw, Ctx::sync, Ctx::cta_reduce -- the cold phases are chains of exposed
+// L2 round trips per stage, and with few iterations per QP they outweigh the sweeps: profiles/r4a_*).  All warps follow the
+// same control flow; what belongs to the chains (factorisation, sweeps) is done by warp 0 between two CTA barriers.
+// In an ADMM step the main warp runs the forward sweep and the backward CHAIN (x~_k goes to its own stage vector XT instead of
 // being parked in B, so an update never reads a slot another update writes), publishes how far the chain has come, and the
 // 4 NH lane groups of the helpers update the stages behind it, in the order in which their neighbours' x~ appear
 // (m, m-1, m+1, m-2, ...).  When the chain ends only the last round of updates is still outstanding.
-//   main -> helpers: `go` (iteration sequence number, st.release after the parameters), `prog` (x~ known for local
+//   main -> helpers: `go` (iteration sequence number), `prog` (x~ known for local
 //                    distances 0 .. prog-1 from the middle stage, st.release after the XT stores)
 //   helpers -> main: `done` (atom.add.release after a helper's last update of the iteration)
-struct HwShared {
-  uint32_t go, prog, done, quit;
-  double rho, rho_eq, rinv, rinv_eq, sigma, alpha, oma, cc;
-  uint32_t live, N;
-  uint64_t eqm[8], loosem[8];
+struct HwShared {   // 512 bytes are set aside for it; the CTA's reduction scratch (Ctx::red) follows
+  uint32_t go, prog, done, pad;
 };
 __device__ __forceinline__ uint32_t ld_acq(uint32_t a) {
   uint32_t v;
@@ -1088,15 +1130,12 @@ __device__ __forceinline__ void init_hot(Hot<KIND> &h, const Lay &L, const uint3
 // main warp: backward chain only; x~ -> XT, progress -> hw.prog; returns when every helper has finished the iteration
 template <int KIND>
 __device__ __forceinline__ void sweep_bwd_chain_hw(const Hot<KIND> &h, const int N, uint32_t &gsel, const int g, const uint32_t hws, const uint32_t seq,
-                                                   const uint32_t nh, const double cc) {
+                                                   const uint32_t nh) {
   const int NL = N >> 1;
   const int lane = threadIdx.x & 31;
   const bool half = g & 1;
   double gn[8];
-  if (lane == 0) {
-    *reinterpret_cast<volatile double *>(__cvta_shared_to_generic(hws + (uint32_t)offsetof(HwShared, cc))) = cc;
-    *reinterpret_cast<volatile uint32_t *>(__cvta_shared_to_generic(hws + (uint32_t)offsetof(HwShared, prog))) = 0u;
-  }
+  if (lane == 0) *reinterpret_cast<volatile uint32_t *>(__cvta_shared_to_generic(hws + (uint32_t)offsetof(HwShared, prog))) = 0u;
   __syncwarp();
   {
     const uint32_t vm = h.v + (uint32_t)NL * VB;
@@ -1136,82 +1175,60 @@ H8_TW_PRAGMA
   __syncwarp();
 }
 
-// helper warps: wait for an iteration, update the stages behind the chain, report, repeat until `quit`
+// helper warps, one ADMM iteration: wait for the main warp's `go`, update the stages behind the chain, report
 template <int KIND>
-__device__ __noinline__ void helper_loop(const Lay &L, const uint32_t sq, const uint32_t hws, const int hw, const int nh) {
-  const int lane = threadIdx.x & 31, g = lane >> 3, r = lane & 7;
-  int ro[4], co[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) { ro[j] = chunk(r, j); co[j] = (((r >> 1) ^ j) << 1) | (r & 1); }
-  const int N = L.N, NL = N >> 1;
-  Hot<KIND> h;
-  init_hot<KIND>(h, L, sq, 0u, N, g, r, ro, co);
-  const HwShared *S = reinterpret_cast<const HwShared *>(__cvta_shared_to_generic(hws));
+__device__ __forceinline__ void helper_iter(const Hot<KIND> &h, const Upd<KIND> &u, const uint32_t hws, const uint32_t seq, const int hw, const int nh) {
+  const int lane = threadIdx.x & 31, g = lane >> 3;
+  const int N = u.N, NL = N >> 1;
   const int U = 4 * nh;
-  uint32_t seen = 0;
-  for (;;) {
-    uint32_t go;
-    for (;;) {
-      go = ld_acq(hws + (uint32_t)offsetof(HwShared, go));
-      if (go != seen) break;
-      if (ld_acq(hws + (uint32_t)offsetof(HwShared, quit))) return;
-    }
-    seen = go;
-    Upd<KIND> u;
-    {
-      const volatile HwShared *V = S;
-      u.rho = V->rho; u.rho_eq = V->rho_eq; u.rinv = V->rinv; u.rinv_eq = V->rinv_eq; u.sigma = V->sigma; u.alpha = V->alpha;
-      u.oma = V->oma; u.cc = V->cc; u.live = V->live != 0u; u.N = N;
-      u.eqm = V->eqm[r]; u.loosem = V->loosem[r];
-    }
-    // One update is a dependent chain of ~40 fp64 operations (630 cycles per round of 4 stages, measured); two rounds at a
-    // time give the warp two independent chains.  t = 0 -> m, 1 -> m-1, 2 -> m+1, 3 -> m-2, ...: the order in which the
-    // neighbours' x~ appear.
-    auto stage_of = [&](int t) { const int d = (t + 1) >> 1; return (t & 1) ? NL - d : NL + d; };
-    auto wait_for = [&](int tl) {   // until the x~ of the neighbours of stage t <= tl are there
-      const int dl = (tl + 1) >> 1;
-      const uint32_t need = (uint32_t)((dl + 1 < NL ? dl + 1 : NL) + 1);
-      while (ld_acq(hws + (uint32_t)offsetof(HwShared, prog)) < need) {}
-    };
-    int t0 = (hw - 1) * 4;
+  while (ld_acq(hws + (uint32_t)offsetof(HwShared, go)) != seq) {}
+  // One update is a dependent chain of ~40 fp64 operations (630 cycles per round of 4 stages, measured); two rounds at a
+  // time give the warp two independent chains.  t = 0 -> m, 1 -> m-1, 2 -> m+1, 3 -> m-2, ...: the order in which the
+  // neighbours' x~ appear.
+  auto stage_of = [&](int t) { const int d = (t + 1) >> 1; return (t & 1) ? NL - d : NL + d; };
+  auto wait_for = [&](int tl) {   // until the x~ of the neighbours of stage t <= tl are there
+    const int dl = (tl + 1) >> 1;
+    const uint32_t need = (uint32_t)((dl + 1 < NL ? dl + 1 : NL) + 1);
+    while (ld_acq(hws + (uint32_t)offsetof(HwShared, prog)) < need) {}
+  };
+  int t0 = (hw - 1) * 4;
 #pragma unroll 1
-    for (; t0 + U + 3 <= N; t0 += 2 * U) {   // two full rounds
-      wait_for(t0 + U + 3);
-      const int ka = stage_of(t0 + g), kb = stage_of(t0 + U + g);
-      const uint32_t va = h.v + (uint32_t)ka * VB, ia = h.ib + (uint32_t)ka * h.istr, la = h.il + (uint32_t)ka * h.istr;
-      const uint32_t vb = h.v + (uint32_t)kb * VB, ib = h.ib + (uint32_t)kb * h.istr, lb = h.il + (uint32_t)kb * h.istr;
-      UpdIn ina, inb;
-      update_loads<KIND>(va, ia, la, h.pm + (uint32_t)ka * h.pstr, h.pm2 + (uint32_t)ka * h.pstr, ina);
-      update_loads<KIND>(vb, ib, lb, h.pm + (uint32_t)kb * h.pstr, h.pm2 + (uint32_t)kb * h.pstr, inb);
-      const double xa1 = lds<V_XT * 8>(va), xam = (ka > 0) ? lds<V_XT * 8>(va - VB) : 0.0, xap = (ka < N) ? lds<V_XT * 8>(va + VB) : 0.0;
-      const double xb1 = lds<V_XT * 8>(vb), xbm = (kb > 0) ? lds<V_XT * 8>(vb - VB) : 0.0, xbp = (kb < N) ? lds<V_XT * 8>(vb + VB) : 0.0;
-      UpdMid qa, qb;
-      update_part1<KIND>(u, ka, ia, ina, xa1, xam, xap, qa);
-      update_part1<KIND>(u, kb, ib, inb, xb1, xbm, xbp, qb);
-      update_part2<KIND>(u, va, xa1, qa);
-      update_part2<KIND>(u, vb, xb1, qb);
-    }
-#pragma unroll 1
-    for (; t0 <= N; t0 += U) {   // what is left: single, possibly partial rounds
-      wait_for((t0 + 3 <= N) ? t0 + 3 : N);
-      const int t = t0 + g;
-      if (t <= N) {
-        const int k = stage_of(t);
-        const uint32_t vj = h.v + (uint32_t)k * VB, ij = h.ib + (uint32_t)k * h.istr, lj = h.il + (uint32_t)k * h.istr;
-        const uint32_t pj = h.pm + (uint32_t)k * h.pstr, pj2 = h.pm2 + (uint32_t)k * h.pstr;
-        UpdIn in;
-        update_loads<KIND>(vj, ij, lj, pj, pj2, in);
-        const double x1 = lds<V_XT * 8>(vj);
-        const double xm = (k > 0) ? lds<V_XT * 8>(vj - VB) : 0.0;
-        const double xp = (k < N) ? lds<V_XT * 8>(vj + VB) : 0.0;
-        UpdMid q;
-        update_part1<KIND>(u, k, ij, in, x1, xm, xp, q);
-        update_part2<KIND>(u, vj, x1, q);
-      }
-    }
-    __syncwarp();
-    if (lane == 0) add_rel(hws + (uint32_t)offsetof(HwShared, done), 1u);
+  for (; t0 + U + 3 <= N; t0 += 2 * U) {   // two full rounds
+    wait_for(t0 + U + 3);
+    const int ka = stage_of(t0 + g), kb = stage_of(t0 + U + g);
+    const uint32_t va = h.v + (uint32_t)ka * VB, ia = h.ib + (uint32_t)ka * h.istr, la = h.il + (uint32_t)ka * h.istr;
+    const uint32_t vb = h.v + (uint32_t)kb * VB, ib = h.ib + (uint32_t)kb * h.istr, lb = h.il + (uint32_t)kb * h.istr;
+    UpdIn ina, inb;
+    update_loads<KIND>(va, ia, la, h.pm + (uint32_t)ka * h.pstr, h.pm2 + (uint32_t)ka * h.pstr, ina);
+    update_loads<KIND>(vb, ib, lb, h.pm + (uint32_t)kb * h.pstr, h.pm2 + (uint32_t)kb * h.pstr, inb);
+    const double xa1 = lds<V_XT * 8>(va), xam = (ka > 0) ? lds<V_XT * 8>(va - VB) : 0.0, xap = (ka < N) ? lds<V_XT * 8>(va + VB) : 0.0;
+    const double xb1 = lds<V_XT * 8>(vb), xbm = (kb > 0) ? lds<V_XT * 8>(vb - VB) : 0.0, xbp = (kb < N) ? lds<V_XT * 8>(vb + VB) : 0.0;
+    UpdMid qa, qb;
+    update_part1<KIND>(u, ka, ia, ina, xa1, xam, xap, qa);
+    update_part1<KIND>(u, kb, ib, inb, xb1, xbm, xbp, qb);
+    update_part2<KIND>(u, va, xa1, qa);
+    update_part2<KIND>(u, vb, xb1, qb);
   }
+#pragma unroll 1
+  for (; t0 <= N; t0 += U) {   // what is left: single, possibly partial rounds
+    wait_for((t0 + 3 <= N) ? t0 + 3 : N);
+    const int t = t0 + g;
+    if (t <= N) {
+      const int k = stage_of(t);
+      const uint32_t vj = h.v + (uint32_t)k * VB, ij = h.ib + (uint32_t)k * h.istr, lj = h.il + (uint32_t)k * h.istr;
+      const uint32_t pj = h.pm + (uint32_t)k * h.pstr, pj2 = h.pm2 + (uint32_t)k * h.pstr;
+      UpdIn in;
+      update_loads<KIND>(vj, ij, lj, pj, pj2, in);
+      const double x1 = lds<V_XT * 8>(vj);
+      const double xm = (k > 0) ? lds<V_XT * 8>(vj - VB) : 0.0;
+      const double xp = (k < N) ? lds<V_XT * 8>(vj + VB) : 0.0;
+      UpdMid q;
+      update_part1<KIND>(u, k, ij, in, x1, xm, xp, q);
+      update_part2<KIND>(u, vj, x1, q);
+    }
+  }
+  __syncwarp();
+  if (lane == 0) add_rel(hws + (uint32_t)offsetof(HwShared, done), 1u);
 }
 
 // ---------------------------------------------------------------- per-QP scalars shared by the cold routines
@@ -1286,11 +1303,11 @@ __device__ __noinline__ void sync_yd(const Ctx<KIND> c, const bool live, const d
         if (live) YD[o] = YD[o] + rho_eq * (alpha * ax - cb * BE[o]);
       }
     }
-    __syncwarp();
+    c.sync();
 #pragma unroll 1
-    for (int k = 0; k <= N; ++k) XS[k * VS + r] = 0.0;
+    for (int k = c.k0; k <= N; k += c.ks) XS[k * VS + r] = 0.0;
   }
-  __syncwarp();
+  c.sync();
 }
 
 // Re-projects the recursion state from the explicit iterate:
@@ -1340,7 +1357,7 @@ __device__ __noinline__ void reproject(const Ctx<KIND> c, const bool doit, const
       }
     } else if (doit) { CR[ov] = 0.0; R[ov] = 0.0; BV[ov] = 0.0; }
   }
-  __syncwarp();
+  c.sync();
 }
 
 // residual norms at the current iterate (update_info); y_dyn must be in sync
@@ -1378,6 +1395,15 @@ __device__ __noinline__ void update_info(const Ctx<KIND> c, Info *ip, const doub
     }
   }
   const bool wd = c.ks > 1;
+  if (c.nw > 1) {   // the CTA's warps split the stages: one trip through shared memory for all fourteen norms
+    double v[14] = {wmax(a_rp, wd), wmax(a_z, wd), wmax(a_Ax, wd), wmax(a_rd, wd), wmax(a_q, wd), wmax(a_Aty, wd), wmax(a_Px, wd),
+                    wmax(b_rp, wd), wmax(b_z, wd), wmax(b_Ax, wd), wmax(b_rd, wd), wmax(b_q, wd), wmax(b_Aty, wd), wmax(b_Px, wd)};
+    c.template cta_reduce<14, false>(v);
+    I.n_rp = v[0]; I.n_z = v[1]; I.n_Ax = v[2]; I.n_rd = v[3]; I.n_q = v[4]; I.n_Aty = v[5]; I.n_Px = v[6];
+    if (I.unscale) { I.pri_res = v[7]; I.u_z = v[8]; I.u_Ax = v[9]; I.dua_res = I.cinv * v[10]; I.u_q = v[11]; I.u_Aty = v[12]; I.u_Px = v[13]; }
+    else { I.pri_res = I.n_rp; I.u_z = I.n_z; I.u_Ax = I.n_Ax; I.dua_res = I.n_rd; I.u_q = I.n_q; I.u_Aty = I.n_Aty; I.u_Px = I.n_Px; }
+    return;
+  }
   I.n_rp = wmax(a_rp, wd); I.n_z = wmax(a_z, wd); I.n_Ax = wmax(a_Ax, wd); I.n_rd = wmax(a_rd, wd); I.n_q = wmax(a_q, wd);
   I.n_Aty = wmax(a_Aty, wd); I.n_Px = wmax(a_Px, wd);
   if (I.unscale) {
@@ -1403,10 +1429,9 @@ __device__ __noinline__ bool primal_infeasible(const Ctx<KIND> c, const Info *ip
   const double *PVYI = c.cd(C_PVYI), *E = c.cd(C_E), *EI = c.cd(C_EI), *DINV = c.cd(C_DINV);
   double *DYD = c.cd(C_DYD), *DYI = c.cd(C_PYI), *XT = c.cd(C_ZT);
   const double ia = 1.0 / alpha, oma = 1.0 - alpha, cb = last_was_first ? 1.0 : alpha;
-  const bool wd = c.ks > 1;
 #pragma unroll 1
   for (int k = c.k0; k <= N; k += c.ks) { const int o = k * 8 + r; XT[o] = c.var_live(k) ? (X[k * VS + r] - oma * PVX[o]) * ia : 0.0; }
-  __syncwarp();
+  c.sync();
   double nrm = 0.0, lhs = 0.0;
 #pragma unroll 1
   for (int k = c.k0; k <= N; k += c.ks) {
@@ -1434,9 +1459,9 @@ __device__ __noinline__ bool primal_infeasible(const Ctx<KIND> c, const Info *ip
       }
     }
   }
-  nrm = wmax(nrm, wd);
-  lhs = wsum(lhs, wd);
-  __syncwarp();
+  nrm = c.rmax(nrm);
+  lhs = c.rsum(lhs);
+  c.sync();
   // the product with A' is only needed when the first two conditions of the certificate hold for some group
   if (!__any_sync(kFull, (nrm > eps) && (lhs < -eps * nrm))) return false;
   double mx = 0.0;
@@ -1447,7 +1472,7 @@ __device__ __noinline__ bool primal_infeasible(const Ctx<KIND> c, const Info *ip
       mx = absmax(mx, unscale ? DINV[k * 8 + r] * at : at);
     }
   }
-  mx = wmax(mx, wd);
+  mx = c.rmax(mx);
   return (nrm > eps) && (lhs < -eps * nrm) && (mx < eps * nrm);
 }
 
@@ -1462,7 +1487,6 @@ __device__ __noinline__ bool dual_infeasible(const Ctx<KIND> c, const Info *ip, 
   const double *PD = c.cd(C_PD), *PO = c.cd(C_PO);
   double *DX = c.cd(C_PX);
   double nrm = 0.0, qdx = 0.0;
-  const bool wd = c.ks > 1;
 #pragma unroll 1
   for (int k = c.k0; k <= N; k += c.ks) {
     const int o = k * 8 + r;
@@ -1471,8 +1495,8 @@ __device__ __noinline__ bool dual_infeasible(const Ctx<KIND> c, const Info *ip, 
     nrm = absmax(nrm, unscale ? D[o] * dx : dx);
     qdx += QV[o] * dx;
   }
-  nrm = wmax(nrm, wd); qdx = wsum(qdx, wd);
-  __syncwarp();
+  nrm = c.rmax(nrm); qdx = c.rsum(qdx);
+  c.sync();
   const double cs = unscale ? ip->csc : 1.0;
   // the products with P and A are only needed when the first two conditions of the certificate hold for some group
   if (!__any_sync(kFull, (nrm > eps) && (qdx < -cs * eps * nrm))) return false;
@@ -1499,8 +1523,8 @@ __device__ __noinline__ bool dual_infeasible(const Ctx<KIND> c, const Info *ip, 
       }
     }
   }
-  mx = wmax(mx, wd);
-  viol = wany(viol, wd);
+  mx = c.rmax(mx);
+  viol = c.rany(viol);
   return (nrm > eps) && (qdx < -cs * eps * nrm) && (mx < cs * eps * nrm) && !viol;
 }
 
@@ -1538,7 +1562,7 @@ __device__ __noinline__ double objective(const Ctx<KIND> c, const double *xv, co
 #pragma unroll 1
   for (int k = c.k0; k <= c.N; k += c.ks)
     if (c.var_live(k)) acc += (0.5 * rowP<KIND>(c, PD, PO, xv, vs, k) + QV[k * 8 + c.r]) * xv[k * vs + c.r];
-  return wsum(acc, c.ks > 1) * scale;
+  return c.rsum(acc) * scale;
 }
 
 // ---------------------------------------------------------------- setup: schedule + build + Ruiz (cold, once per QP)
@@ -1653,7 +1677,7 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
       }
     }
   }
-  __syncwarp();
+  c.sync();
   sched_err = gany(sched_err);
 
   // ---- build (PathFollowingLPVMPC.py:334-348, 397-464; LPV_MPC_Planner.py:145-181)
@@ -1701,7 +1725,7 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
         if (r < 2) ibk[OPMc + r] = 0.0;
       }
     }
-    __syncwarp();
+    c.sync();
 #pragma unroll 1
     for (int k = c.k0; k <= N; k += c.ks) {
       if (c.has_in(k)) {
@@ -1730,9 +1754,9 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
         }
       }
     }
-    __syncwarp();
+    c.sync();
   }
-  data_err = wany(data_err, c.ks > 1);
+  data_err = c.rany(data_err);
 
   // ---- Ruiz equilibration (OSQP scale_data)
   double csc = 1.0;
@@ -1768,7 +1792,7 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
       }
       sEt[o] = frsqrt(limit_scaling(ea));
     }
-    __syncwarp();
+    c.sync();
 #pragma unroll 1
     for (int k = c.k0; k <= N; k += c.ks) {
       const int o = k * 8 + r, ov = k * VS + r;
@@ -1793,7 +1817,7 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
       sD[o] = sD[o] * dt;
       sE[o] = sE[o] * sEt[o];
     }
-    __syncwarp();
+    c.sync();
     // cost scaling: mean of the column norms of P (summed per lane, then across the group)
     double qn = 0.0, ct = 0.0;
 #pragma unroll 1
@@ -1806,8 +1830,8 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
       }
       if (c.var_live(k)) { ct += pa; qn = absmax(qn, QV[k * VS + r]); }
     }
-    qn = wmax(qn, c.ks > 1);
-    ct = wsum(ct, c.ks > 1) / nz;
+    qn = c.rmax(qn);
+    ct = c.rsum(ct) / nz;
     qn = limit_scaling(qn);
     ct = ct > qn ? ct : qn;
     ct = limit_scaling(ct);
@@ -1815,7 +1839,7 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
 #pragma unroll 1
     for (int k = c.k0; k <= N; k += c.ks) { const int o = k * 8 + r; sPD[o] *= ct; QV[k * VS + r] *= ct; sPO[o] *= ct; }
     csc *= ct;
-    __syncwarp();
+    c.sync();
   }
   *csc_out = csc;
   // ---- scaled bounds, constraint classes, cold data to the slab, G to the slab
@@ -1841,7 +1865,7 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
         for (int j = 0; j < 4; ++j) { const double2 e = ld2(gs + 2 * j); st2(gd + 2 * j, e.x, e.y); }
       }
     }
-    __syncwarp();
+    c.sync();
 #pragma unroll 1
     for (int k = c.k0; k <= N; k += c.ks) {
       if (c.has_in(k)) {
@@ -1863,12 +1887,21 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
       eqm |= __shfl_xor_sync(kFull, eqm, 8); eqm |= __shfl_xor_sync(kFull, eqm, 16);
       loosem |= __shfl_xor_sync(kFull, loosem, 8); loosem |= __shfl_xor_sync(kFull, loosem, 16);
     }
+    if (c.nw > 1) {   // ... and the warps': lane r of a warp's first group leaves its masks in the reduction scratch
+      const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+      uint64_t *mr = reinterpret_cast<uint64_t *>(c.red);
+      if (lane < 8) { mr[w * 16 + lane] = eqm; mr[w * 16 + 8 + lane] = loosem; }
+      __syncthreads();
+      eqm = 0; loosem = 0;
+      for (int ww = 0; ww < c.nw; ++ww) { eqm |= mr[ww * 16 + r]; loosem |= mr[ww * 16 + 8 + r]; }
+      __syncthreads();
+    }
     *eqm_out = eqm; *loosem_out = loosem;
-    __syncwarp();
+    c.sync();
     // the scratch homes become hot vectors: XS = 0 (R, CR, B are set by refresh, DG by factor)
 #pragma unroll 1
     for (int k = c.k0; k <= N; k += c.ks) c.V(V_XS)[k * VS + r] = 0.0;
-    __syncwarp();
+    c.sync();
   }
   return (sched_err ? 1 : 0) | (data_err ? 2 : 0);
 }
@@ -1913,10 +1946,13 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, Strm *s
       }
     }
   }
-  __syncwarp();
+  c.sync();
   FW fw; fw.polish = 1; fw.rho = 0.0; fw.rho_eq = 0.0; fw.idel = idel;
   if (ST) strm_drain(h.sc, sm);
-  if (TW) factor_tw<KIND>(c, fw, delta, g & 1);
+  if (TW && c.nw > 1) {   // the chains belong to warp 0
+    if (threadIdx.x < 32) factor_tw<KIND>(c, fw, delta, g & 1);
+    __syncthreads();
+  } else if (TW) factor_tw<KIND>(c, fw, delta, g & 1);
   else factor<KIND>(c, fw, delta);
   auto bred_i = [&](int k, int t) { const double a = ACTI[c.ci(k, t)]; return (a == 1.0 || a == 3.0) ? c.lo_of(k, t) : c.ui(k, t); };
   // (A' t)_(k, r) with t_dyn stored [k*VS + q] and t_in = (ti0, ti1) of my single-variable rows
@@ -1946,8 +1982,11 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, Strm *s
   // iterate, DX the x part of the increment of the running K_reg solve, TMP a row temporary.
   double *DX = R2D, *TMP = c.V(V_CR);
   auto solve = [&]() {
-    __syncwarp();
-    if (TW) {
+    c.sync();
+    if (TW && c.nw > 1) {
+      if (threadIdx.x < 32) { sweep_fwd_tw<KIND>(h, N, gsel, g); sweep_bwd_plain_tw<KIND>(h, N, gsel, g); }
+      __syncthreads();
+    } else if (TW) {
       sweep_fwd_tw<KIND>(h, N, gsel, g);
       sweep_bwd_plain_tw<KIND>(h, N, gsel, g);
     } else {
@@ -1977,13 +2016,13 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, Strm *s
         }
         PX[ov] += ddx; DX[ov] += ddx;
       }
-      __syncwarp();
+      c.sync();
     }
   };
   // ---- s_0 = K_reg^-1 (-q, b_red): rhs = -q + A_red'(b_red / delta)
 #pragma unroll 1
   for (int k = c.k0; k <= N; k += c.ks) TMP[k * VS + r] = (c.xl && ACTD[k * 8 + r] != 0.0) ? idel * BE[k * 8 + r] : 0.0;
-  __syncwarp();
+  c.sync();
 #pragma unroll 1
   for (int k = c.k0; k <= N; k += c.ks) {
     double t2[2] = {0.0, 0.0};
@@ -2005,7 +2044,7 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, Strm *s
       for (int t = 0; t < NT; ++t) { const int oc = c.ci(k, t); PYI[oc] = (ACTI[oc] != 0.0) ? idel * (c.si(k, t) * xk - bred_i(k, t)) : 0.0; }
     }
   }
-  __syncwarp();
+  c.sync();
   inner();
 #pragma unroll 1
   for (int it = 0; it < St.polish_refine_iter; ++it) {
@@ -2015,7 +2054,7 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, Strm *s
       const int o = k * 8 + r, ov = k * VS + r;
       TMP[ov] = (c.xl && ACTD[o] != 0.0) ? fma(-idel, BE[o] - rowA_dyn<KIND>(c, ED, PX, VS, k), PYD[ov]) : 0.0;
     }
-    __syncwarp();
+    c.sync();
 #pragma unroll 1
     for (int k = c.k0; k <= N; k += c.ks) {
       const int o = k * 8 + r, ov = k * VS + r;
@@ -2033,7 +2072,7 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, Strm *s
     solve();
 #pragma unroll 1
     for (int k = c.k0; k <= N; k += c.ks) { const int ov = k * VS + r; const double ddx = BV[ov]; DX[ov] = ddx; PX[ov] += ddx; }
-    __syncwarp();
+    c.sync();
     // ty += (A ddx - r2) / delta = (A tx_new - b_red) / delta
 #pragma unroll 1
     for (int k = c.k0; k <= N; k += c.ks) {
@@ -2044,7 +2083,7 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, Strm *s
         for (int t = 0; t < NT; ++t) { const int oc = c.ci(k, t); if (ACTI[oc] != 0.0) PYI[oc] += idel * (c.si(k, t) * PX[ov] - bred_i(k, t)); }
       }
     }
-    __syncwarp();
+    c.sync();
     inner();
   }
   // pol z = A x, normal-cone projection, residuals, acceptance.  Polished z of the single-variable rows -> R2I.
@@ -2070,7 +2109,7 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, Strm *s
       }
     }
   }
-  __syncwarp();
+  c.sync();
 #pragma unroll 1
   for (int k = c.k0; k <= N; k += c.ks) {
     const int o = k * 8 + r;
@@ -2079,7 +2118,7 @@ __device__ __noinline__ int polish(const Ctx<KIND> c, const Hot<KIND> h, Strm *s
       a_rd = absmax(a_rd, unscale ? DINV[o] * rr : rr);
     }
   }
-  const double pol_pri = wmax(a_rp, c.ks > 1), pol_dua = (unscale ? I.cinv : 1.0) * wmax(a_rd, c.ks > 1);
+  const double pol_pri = c.rmax(a_rp), pol_dua = (unscale ? I.cinv : 1.0) * c.rmax(a_rd);
   const double pol_obj = objective<KIND>(c, PX, VS, St.scaling ? I.cinv : 1.0);
   const bool ok = (pol_pri < I.pri_res && pol_dua < I.dua_res) || (pol_pri < I.pri_res && I.dua_res < 1e-10) ||
                   (pol_dua < I.dua_res && I.pri_res < 1e-10);
@@ -2119,7 +2158,9 @@ __global__ void __launch_bounds__(NH ? 32 * (NH + 1) : 64) lpv_solve_h8_kernel(c
   c.S = smem; c.cold = p.cold;
   c.L = &L; c.N = N; c.r = r;
   c.kmask = ST ? (kRing - 1) : -1;
-  c.k0 = (QPW == 1) ? g : 0; c.ks = (QPW == 1) ? 4 : 1;
+  const int wid = NH ? (int)(threadIdx.x >> 5) : 0;   // helper-warp kernels: my warp among the CTA's NH + 1
+  c.nw = NH + 1;
+  c.k0 = (QPW == 1) ? 4 * wid + g : 0; c.ks = (QPW == 1) ? 4 * (NH + 1) : 1;
   c.xl = r < NX; c.ul = (r >= NX) && (r < NB);
   if (KIND == LPVMPC_CONTROLLER) c.islot = (r == 0) ? 0 : ((r >= NX) ? (r - NX + 1) * 2 : 0);
   else c.islot = r;
@@ -2141,16 +2182,14 @@ __global__ void __launch_bounds__(NH ? 32 * (NH + 1) : 64) lpv_solve_h8_kernel(c
   uint32_t gsel = 0;
   Strm sm;
   sm.t = 0u; sm.ahead = 0u; sm.rdy = 0u;
-  // helper warps: their mailbox sits behind the gather buffers; they never come back from helper_loop
+  // helper warps: the mailbox sits behind the gather buffers, the reduction scratch of the cold phases behind the mailbox
   const uint32_t hws = gbuf0 + (uint32_t)wpc * 512u + 256u;
   uint32_t hw_seq = 0;
+  c.red = NH ? reinterpret_cast<double *>(__cvta_shared_to_generic(hws + 512u)) : nullptr;
+  __shared__ unsigned base_s;
   if (NH) {
     if (threadIdx.x < (unsigned)(sizeof(HwShared) / 4)) reinterpret_cast<volatile uint32_t *>(__cvta_shared_to_generic(hws))[threadIdx.x] = 0u;
     __syncthreads();
-    if (threadIdx.x >= 32) {
-      helper_loop<KIND>(L, smem_a, hws, (int)(threadIdx.x >> 5), NH);
-      return;
-    }
   }
   if (ST) {  // this warp's mbarriers (one arrival: the issuing lane's expect_tx)
     if (lane < kRing) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar0 + 8u * (uint32_t)lane) : "memory");
@@ -2161,13 +2200,21 @@ __global__ void __launch_bounds__(NH ? 32 * (NH + 1) : 64) lpv_solve_h8_kernel(c
 
   for (;;) {
     unsigned base = 0;
-    if (lane == 0) base = atomicAdd(p.queue, (unsigned)QPW);
-    base = __shfl_sync(kFull, base, 0);
+    if (NH) {   // one QP per CTA (the barriers of the QP's cold phases separate this write from the previous round's reads)
+      if (threadIdx.x == 0) base_s = atomicAdd(p.queue, 1u);
+      __syncthreads();
+      base = base_s;
+    } else {
+      if (lane == 0) base = atomicAdd(p.queue, (unsigned)QPW);
+      base = __shfl_sync(kFull, base, 0);
+    }
     if ((int)base >= p.B) break;
     // Groups without a problem of their own (batch tail, or g >= QPW) mirror group 0 exactly: same problem, same
     // shared / scratch region, same values written by the same instruction; only user-visible outputs are guarded.
     const bool valid = (g < QPW) && ((int)(base + g) < p.B);
     const int gq = (QPW == 1) ? 0 : (valid ? g : 0);
+    // one QP per warp / CTA: its groups (and warps) split the stages of the output loops like those of every cold loop
+    const bool vout = (QPW == 1) ? ((int)base < p.B) : valid;
     const int b = p.perm ? p.perm[(int)base + gq] : (int)base + gq;
     c.S = wsm + gq * L.total;
     c.cold = p.cold + (wslot + gq) * L.cold_total;
@@ -2188,10 +2235,6 @@ __global__ void __launch_bounds__(NH ? 32 * (NH + 1) : 64) lpv_solve_h8_kernel(c
       uint64_t eqm = 0, loosem = 0;
       flags = setup<KIND>(c, p, b, valid, &csc, &eqm, &loosem);
       c.eqm = eqm; c.loosem = loosem;
-      if (NH && g == 0) {
-        HwShared *H = reinterpret_cast<HwShared *>(__cvta_shared_to_generic(hws));
-        H->eqm[r] = eqm; H->loosem[r] = loosem;
-      }
     }
     I.csc = csc; I.cinv = 1.0 / csc;
     I.unscale = (S.scaling && !S.scaled_termination) ? 1 : 0;
@@ -2205,7 +2248,8 @@ __global__ void __launch_bounds__(NH ? 32 * (NH + 1) : 64) lpv_solve_h8_kernel(c
     double rho_eq = kRhoEqOverIneq * rho;
     {
       FW fw; fw.polish = 0; fw.rho = rho; fw.rho_eq = rho_eq; fw.idel = 0.0;
-      if (TW) factor_tw<KIND>(c, fw, sigma, g & 1);
+      if (NH) { if (wid == 0) factor_tw<KIND>(c, fw, sigma, g & 1); __syncthreads(); }
+      else if (TW) factor_tw<KIND>(c, fw, sigma, g & 1);
       else factor<KIND>(c, fw, sigma);
     }
     reproject<KIND>(c, true, rho, rho_eq, sigma, 0.0, true);
@@ -2228,41 +2272,43 @@ __global__ void __launch_bounds__(NH ? 32 * (NH + 1) : 64) lpv_solve_h8_kernel(c
       if (ai) { const int nxt = (iter / ai + 1) * ai; stop = nxt < stop ? nxt : stop; }
       { const int nxt = iter + kSyncEvery; stop = nxt < stop ? nxt : stop; }
       u.rho = rho; u.rho_eq = rho_eq; u.rinv = 1.0 / rho; u.rinv_eq = 1.0 / rho_eq; u.live = live;
-      if (NH) {
-        if (lane == 0) {
-          HwShared *H = reinterpret_cast<HwShared *>(__cvta_shared_to_generic(hws));
-          H->rho = u.rho; H->rho_eq = u.rho_eq; H->rinv = u.rinv; H->rinv_eq = u.rinv_eq; H->sigma = u.sigma; H->alpha = u.alpha; H->oma = u.oma;
-          H->live = live ? 1u : 0u; H->N = (uint32_t)N;
-        }
-        __syncwarp();
-      }
 #pragma unroll 1
       for (; iter < stop; ++iter) {
-        if (iter == stop - 1 && live) {  // keep the iterate before the last step of the chunk: delta_x, delta_y
-          double *PVX = c.cd(C_PVX), *PVYI = c.cd(C_PVYI);
-          const double *X = c.V(V_X);
+        if (iter == stop - 1) {  // keep the iterate before the last step of the chunk: delta_x, delta_y
+          // (helper-warp kernels: the copy is split by stage over the CTA's warps, the updates of the previous step were split
+          // differently and so are those of this step -- a barrier on either side)
+          if (NH) __syncthreads();
+          if (live) {
+            double *PVX = c.cd(C_PVX), *PVYI = c.cd(C_PVYI);
+            const double *X = c.V(V_X);
 #pragma unroll 1
-          for (int k = c.k0; k <= N; k += c.ks) {
-            PVX[k * 8 + r] = X[k * VS + r];
-            if (c.has_in(k)) {
+            for (int k = c.k0; k <= N; k += c.ks) {
+              PVX[k * 8 + r] = X[k * VS + r];
+              if (c.has_in(k)) {
 #pragma unroll
-              for (int t = 0; t < NT; ++t) PVYI[c.ci(k, t)] = c.yi(k, t);
+                for (int t = 0; t < NT; ++t) PVYI[c.ci(k, t)] = c.yi(k, t);
+              }
             }
           }
+          if (NH) __syncthreads();
         }
         u.cc = (iter == 0) ? 2.0 : alpha;
-        if (TW) sweep_fwd_tw<KIND>(h, N, gsel, g);
+        if (NH) {
+          ++hw_seq;
+          if (wid == 0) { sweep_fwd_tw<KIND>(h, N, gsel, g); sweep_bwd_chain_hw<KIND>(h, N, gsel, g, hws, hw_seq, NH); }
+          else helper_iter<KIND>(h, u, hws, hw_seq, wid, NH);
+        }
+        else if (TW) { sweep_fwd_tw<KIND>(h, N, gsel, g); sweep_bwd_admm_tw<KIND>(h, u, gsel, g); }
         else if (QPW == 1) sweep_fwd_w1<KIND, ST>(h, sm, N, gsel, g);
         else sweep_fwd<KIND, ST>(h, sm, N, gsel);
-        if (NH) sweep_bwd_chain_hw<KIND>(h, N, gsel, g, hws, ++hw_seq, NH, u.cc);
-        else if (TW) sweep_bwd_admm_tw<KIND>(h, u, gsel, g);
+        if (NH || TW) {}
         else if (QPW == 1) sweep_bwd_admm_w1<KIND, ST>(h, sm, u, gsel, g);
         else sweep_bwd_admm<KIND, ST>(h, sm, u, gsel);
         if (iter == 0) first_in = 1;
         ++nsync;
         zsel = 1.0;
       }
-      __syncwarp();
+      c.sync();
       const int last_was_first = (iter == 1);
       rho_eq_last = rho_eq;
       sync_yd<KIND>(c, live, rho_eq, alpha, nsync, first_in);
@@ -2289,9 +2335,10 @@ __global__ void __launch_bounds__(NH ? 32 * (NH + 1) : 64) lpv_solve_h8_kernel(c
             // groups that do not update must keep their factor: re-factorising with unchanged rho reproduces it
             if (upd) { rho = rho_new; rho_eq = kRhoEqOverIneq * rho; ++rho_updates; }
             FW fw; fw.polish = 0; fw.rho = rho; fw.rho_eq = rho_eq; fw.idel = 0.0;
-            __syncwarp();
+            c.sync();
             if (ST) strm_drain(h.sc, sm);
-            if (TW) factor_tw<KIND>(c, fw, sigma, g & 1);
+            if (NH) { if (wid == 0) factor_tw<KIND>(c, fw, sigma, g & 1); __syncthreads(); }
+            else if (TW) factor_tw<KIND>(c, fw, sigma, g & 1);
             else factor<KIND>(c, fw, sigma);
             new_cr = true;
           }
@@ -2327,11 +2374,11 @@ __global__ void __launch_bounds__(NH ? 32 * (NH + 1) : 64) lpv_solve_h8_kernel(c
       return nx + (c.xl ? (k * NX + r) : (nx + k * 2 + ucomp));
     };
     auto ref_var = [&](int k) { return c.xl ? (k * NX + r) : (nx + k * 2 + ucomp); };
-    if (valid && (a.xs || a.zs || a.ys)) {
+    if (vout && (a.xs || a.zs || a.ys)) {
       const double *X = c.V(V_X);
       const double *YD = c.cd(C_YD), *BE = c.cd(C_BE);
 #pragma unroll 1
-      for (int k = 0; k <= N; ++k) {
+      for (int k = c.k0; k <= N; k += c.ks) {
         const int o = k * 8 + r;
         if (c.var_live(k) && a.xs) a.xs[(size_t)b * nz + ref_var(k)] = X[k * VS + r];
         if (c.xl) {
@@ -2355,11 +2402,11 @@ __global__ void __launch_bounds__(NH ? 32 * (NH + 1) : 64) lpv_solve_h8_kernel(c
       polished_sets = do_pol;
     }
     // ---- outputs
-    if (valid) {
+    if (vout) {
       const double *X = c.V(V_X);
       const double *YD = c.cd(C_YD), *D = c.cd(C_D), *E = c.cd(C_E), *EI = c.cd(C_EI), *ACTD = c.cd(C_ACTD), *ACTI = c.cd(C_ACTI);
 #pragma unroll 1
-      for (int k = 0; k <= N; ++k) {
+      for (int k = c.k0; k <= N; k += c.ks) {
         const int o = k * 8 + r;
         const double v = has_sol ? D[o] * X[k * VS + r] : nan("");
         if (c.xl) a.x_pred[(size_t)b * nx + k * NX + r] = v;
@@ -2383,7 +2430,7 @@ __global__ void __launch_bounds__(NH ? 32 * (NH + 1) : 64) lpv_solve_h8_kernel(c
           }
         }
       }
-      if (r == 0) {
+      if (r == 0 && valid) {
         a.status[b] = status;
         if (a.iters) a.iters[b] = iter_done;
         if (a.rho_updates) a.rho_updates[b] = rho_updates;
@@ -2394,10 +2441,9 @@ __global__ void __launch_bounds__(NH ? 32 * (NH + 1) : 64) lpv_solve_h8_kernel(c
       }
     }
     if (ST) strm_drain(h.sc, sm);   // nothing may be in flight into the ring when the next QP's setup / factor starts
-    __syncwarp();
+    c.sync();
   }
-  if (NH && lane == 0) st_rel(hws + (uint32_t)offsetof(HwShared, quit), 1u);
-  (void)NSL; (void)NB; (void)hw_seq;
+  (void)NSL; (void)NB; (void)hw_seq; (void)wid;
 }
 
 }  // namespace h8

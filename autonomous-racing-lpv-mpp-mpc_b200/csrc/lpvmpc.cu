@@ -1219,7 +1219,7 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
       static const bool hw_on = [] { const char *e = std::getenv("LPVMPC_H8_HELPERS"); return !e || std::atoi(e) != 0; }();
       h->helpers = (h->twisted && hw_on && h->wpc == 1) ? (ctrl ? 3 : 1) : 0;
       if (h->helpers) {
-        const size_t ws2 = h->ws_bytes + 512;   // the helpers' mailbox (lpv::h8::HwShared) behind the gather buffers
+        const size_t ws2 = h->ws_bytes + 512 + 1024;   // the helpers' mailbox (lpv::h8::HwShared) behind the gather buffers, then the CTA's reduction scratch (4 warps x 16 doubles)
         int ctas = (int)(sm_bytes / (ws2 + 1024));
         if (ctas > 32) ctas = 32;
         const int by_regs = ctrl ? 1 : 3;      // __launch_bounds__ of the two instantiations
