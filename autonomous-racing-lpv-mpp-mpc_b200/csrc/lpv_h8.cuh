@@ -966,19 +966,26 @@ __device__ __forceinline__ void sweep_fwd_tw(const Hot<KIND> &h, const int N, ui
   uint32_t so = (half ? (uint32_t)N * (uint32_t)TKB : 0u) + (trole ? 0u : 512u);
   uint32_t vb = h.v + (half ? (uint32_t)N * (uint32_t)VB : 0u), wst = vb;
   double res = lds(vb);   // chain: v of local step 0 = b; T lanes: b as well, written back unchanged by their first store
+  // Software-pipelined: the matrix row and the right-hand side of the NEXT step are requested behind the products of this
+  // one, so that their 20 shared-memory wavefronts drain while the sums, the publish and the barrier run, and the all-gather
+  // loads -- the critical path -- find the pipe empty (profiles/r4a_*: with the row loads in front of the barrier a step
+  // waited 36 of its 146 cycles for them).  The last step's prefetch reads the middle stage's slot and is not used.
+  double2 r0 = lds2(h.tk[0] + so), r1 = lds2(h.tk[1] + so), r2 = lds2(h.tk[2] + so), r3 = lds2(h.tk[3] + so);
+  double bn = lds(vb + vstr);
+  if (trole || (half && NL == 1)) bn = 0.0;   // the middle stage's right-hand side enters once: through the left half
 H8_TW_PRAGMA
   for (int j = 0; j < NL; ++j) {
     sts(trole ? wst : (h.gpub ^ gsel), res);
-    const double2 r0 = lds2(h.tk[0] + so), r1 = lds2(h.tk[1] + so), r2 = lds2(h.tk[2] + so), r3 = lds2(h.tk[3] + so);
-    double bn = lds(vb + vstr);
-    if (trole || (half && j == NL - 1)) bn = 0.0;   // the middle stage's right-hand side enters once: through the left half
     __syncwarp();
     const uint32_t gg = ggat ^ gsel;
     const double2 g0 = lds2(gg), g1 = lds2<64>(gg), g2 = lds2<128>(gg), g3 = lds2<192>(gg);
     double c0 = fma(r0.x, g0.x, bn), c1 = r1.x * g1.x, c2 = r2.x * g2.x, c3 = r3.x * g3.x;
     c0 = fma(r0.y, g0.y, c0); c1 = fma(r1.y, g1.y, c1); c2 = fma(r2.y, g2.y, c2); c3 = fma(r3.y, g3.y, c3);
-    res = (c0 + c1) + (c2 + c3);
     wst = vb; vb += vstr; so += tstr; gsel ^= 256u;
+    r0 = lds2(h.tk[0] + so); r1 = lds2(h.tk[1] + so); r2 = lds2(h.tk[2] + so); r3 = lds2(h.tk[3] + so);
+    bn = lds(vb + vstr);
+    if (trole || (half && j + 1 == NL - 1)) bn = 0.0;
+    res = (c0 + c1) + (c2 + c3);
   }
   if (trole) sts(wst, res);   // W of local step NL-1
   const double vm = res + __shfl_xor_sync(kFull, res, 8);   // chain lanes: v_m = (b_m - K_m v_{m-1}) + (- J_m v_{m+1})
@@ -1158,15 +1165,16 @@ H8_TW_PRAGMA
     a0 = fma(e2, gn[2], a0); a1 = fma(e3, gn[3], a1);
     a0 = fma(e4, gn[4], a0); a1 = fma(e5, gn[5], a1);
     a0 = fma(e6, gn[6], a0); a1 = fma(e7, gn[7], a1);
-    const double xt = a0 + a1;
-    sts(h.gpub ^ gsel, xt);
-    sts<V_XT * 8>(vb, xt);
-    if (j > 0) {
+    const uint32_t vcur = vb;
+    if (j > 0) {   // (in front of the publish: the loads drain behind the products instead of ahead of the all-gather)
       so += kstr; vb += vstr;
       e0 = lds(h.kc[0] + so); e1 = lds<64>(h.kc[0] + so); e2 = lds(h.kc[1] + so); e3 = lds<64>(h.kc[1] + so);
       e4 = lds(h.kc[2] + so); e5 = lds<64>(h.kc[2] + so); e6 = lds(h.kc[3] + so); e7 = lds<64>(h.kc[3] + so);
       w = lds(vb);
     }
+    const double xt = a0 + a1;
+    sts(h.gpub ^ gsel, xt);
+    sts<V_XT * 8>(vcur, xt);
     gather_in(h.ggat, gsel, gn);
     if (lane == 0) st_prog(hws + (uint32_t)offsetof(HwShared, prog), (uint32_t)(NL - j + 1));
   }
