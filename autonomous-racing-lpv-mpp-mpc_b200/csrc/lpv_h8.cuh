@@ -42,6 +42,19 @@
 namespace lpv {
 namespace h8 {
 
+// -DLPV_H8_PHASE_TIMING (development builds, tools/h8_phase_timing.py): thread 0 of a helper-warp CTA adds up the clock
+// cycles it spends in each phase of a QP; read back through lpvmpc_debug_phase_cycles (only exported by such builds)
+#ifdef LPV_H8_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[16];
+#define H8_PH(i) do { const long long ph_t1 = clock64(); ph[i] += ph_t1 - ph_t0; ph_t0 = ph_t1; } while (0)
+#define H8_PH_PARAMS , long long *ph, long long &ph_t0
+#define H8_PH_ARGS , ph, ph_t0
+#else
+#define H8_PH(i) do { } while (0)
+#define H8_PH_PARAMS
+#define H8_PH_ARGS
+#endif
+
 #ifndef H8_TW_UNROLL
 #define H8_TW_UNROLL 1   // unroll factor of the chain loops of the twisted sweeps
 #endif
@@ -967,9 +980,11 @@ __device__ __forceinline__ void sweep_fwd_tw(const Hot<KIND> &h, const int N, ui
   uint32_t vb = h.v + (half ? (uint32_t)N * (uint32_t)VB : 0u), wst = vb;
   double res = lds(vb);   // chain: v of local step 0 = b; T lanes: b as well, written back unchanged by their first store
   // Software-pipelined: the matrix row and the right-hand side of the NEXT step are requested behind the products of this
-  // one, so that their 20 shared-memory wavefronts drain while the sums, the publish and the barrier run, and the all-gather
-  // loads -- the critical path -- find the pipe empty (profiles/r4a_*: with the row loads in front of the barrier a step
-  // waited 36 of its 146 cycles for them).  The last step's prefetch reads the middle stage's slot and is not used.
+  // one and arrive while the sums, the publish and the barrier run (profiles/r4a_*: with the row loads in front of the
+  // barrier a step waited 36 of its 146 cycles for them before it could reach the barrier).  What is left is the warp's
+  // own shared-memory instruction rate -- one LDS / STS per 8.7 cycles from a single warp whatever its width
+  // (profiles/r1_smem_probe.jsonl) -- at 10 such instructions per step.  The last step's prefetch reads the middle stage's
+  // slot and is not used.
   double2 r0 = lds2(h.tk[0] + so), r1 = lds2(h.tk[1] + so), r2 = lds2(h.tk[2] + so), r3 = lds2(h.tk[3] + so);
   double bn = lds(vb + vstr);
   if (trole || (half && NL == 1)) bn = 0.0;   // the middle stage's right-hand side enters once: through the left half
@@ -1137,7 +1152,7 @@ __device__ __forceinline__ void init_hot(Hot<KIND> &h, const Lay &L, const uint3
 // main warp: backward chain only; x~ -> XT, progress -> hw.prog; returns when every helper has finished the iteration
 template <int KIND>
 __device__ __forceinline__ void sweep_bwd_chain_hw(const Hot<KIND> &h, const int N, uint32_t &gsel, const int g, const uint32_t hws, const uint32_t seq,
-                                                   const uint32_t nh) {
+                                                   const uint32_t nh H8_PH_PARAMS) {
   const int NL = N >> 1;
   const int lane = threadIdx.x & 31;
   const bool half = g & 1;
@@ -1152,8 +1167,8 @@ __device__ __forceinline__ void sweep_bwd_chain_hw(const Hot<KIND> &h, const int
     gather_in(h.ggat, gsel, gn);   // (its __syncwarp orders the XT stores of all lanes before lane 0's release below)
   }
   if (lane == 0) { st_rel(hws + (uint32_t)offsetof(HwShared, go), seq); st_rel(hws + (uint32_t)offsetof(HwShared, prog), 1u); }
-  // software-pipelined: the multiplier column and W of the NEXT chain step are requested before the all-gather of the current
-  // one (they do not depend on it), so their latency hides behind the publish -> gather round trip
+  H8_PH(13);
+  // software-pipelined: the multiplier column and W of the NEXT chain step are requested a step ahead
   const uint32_t kstr = half ? (uint32_t)TKB : (uint32_t)(-TKB), vstr = half ? (uint32_t)VB : (uint32_t)(-VB);   // towards the ends
   uint32_t so = (uint32_t)(half ? N - (NL - 1) : NL - 1) * (uint32_t)TKB, vb = h.v + (uint32_t)(half ? N - (NL - 1) : NL - 1) * (uint32_t)VB;
   double e0 = lds(h.kc[0] + so), e1 = lds<64>(h.kc[0] + so), e2 = lds(h.kc[1] + so), e3 = lds<64>(h.kc[1] + so);
@@ -1165,19 +1180,22 @@ H8_TW_PRAGMA
     a0 = fma(e2, gn[2], a0); a1 = fma(e3, gn[3], a1);
     a0 = fma(e4, gn[4], a0); a1 = fma(e5, gn[5], a1);
     a0 = fma(e6, gn[6], a0); a1 = fma(e7, gn[7], a1);
-    const uint32_t vcur = vb;
-    if (j > 0) {   // (in front of the publish: the loads drain behind the products instead of ahead of the all-gather)
-      so += kstr; vb += vstr;
-      e0 = lds(h.kc[0] + so); e1 = lds<64>(h.kc[0] + so); e2 = lds(h.kc[1] + so); e3 = lds<64>(h.kc[1] + so);
-      e4 = lds(h.kc[2] + so); e5 = lds<64>(h.kc[2] + so); e6 = lds(h.kc[3] + so); e7 = lds<64>(h.kc[3] + so);
-      w = lds(vb);
-    }
     const double xt = a0 + a1;
     sts(h.gpub ^ gsel, xt);
-    sts<V_XT * 8>(vcur, xt);
+    sts<V_XT * 8>(vb, xt);
     gather_in(h.ggat, gsel, gn);
+    // the next step's column goes into the shared-memory pipe behind the all-gather loads; measured equal to requesting it
+    // in front of the publish (same-box A/B): the step is bound by the warp's shared-memory instruction rate (8.7 cycles per
+    // LDS / STS from one warp, 16 of them here against 10 in the forward sweep -- the column comes in 64-bit pieces), not by
+    // the order in the pipe.  The last step re-reads its own column: no branch in the loop body
+    if (j > 0) { so += kstr; vb += vstr; }
+    e0 = lds(h.kc[0] + so); e1 = lds<64>(h.kc[0] + so); w = lds(vb);
+    e2 = lds(h.kc[1] + so); e3 = lds<64>(h.kc[1] + so);
+    e4 = lds(h.kc[2] + so); e5 = lds<64>(h.kc[2] + so);
+    e6 = lds(h.kc[3] + so); e7 = lds<64>(h.kc[3] + so);
     if (lane == 0) st_prog(hws + (uint32_t)offsetof(HwShared, prog), (uint32_t)(NL - j + 1));
   }
+  H8_PH(14);
   const uint32_t want = seq * nh;
   while (ld_acq(hws + (uint32_t)offsetof(HwShared, done)) != want) {}
   __syncwarp();
@@ -2206,6 +2224,12 @@ __global__ void __launch_bounds__(NH ? 32 * (NH + 1) : 64) lpv_solve_h8_kernel(c
     __syncwarp();
   }
 
+#ifdef LPV_H8_PHASE_TIMING
+  long long ph[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) ph[i] = 0;
+  long long ph_t0 = clock64();
+#endif
   for (;;) {
     unsigned base = 0;
     if (NH) {   // one QP per CTA (the barriers of the QP's cold phases separate this write from the previous round's reads)
@@ -2244,6 +2268,7 @@ __global__ void __launch_bounds__(NH ? 32 * (NH + 1) : 64) lpv_solve_h8_kernel(c
       flags = setup<KIND>(c, p, b, valid, &csc, &eqm, &loosem);
       c.eqm = eqm; c.loosem = loosem;
     }
+    H8_PH(0);
     I.csc = csc; I.cinv = 1.0 / csc;
     I.unscale = (S.scaling && !S.scaled_termination) ? 1 : 0;
     I.pri_res = 0.0; I.dua_res = 0.0; I.obj = nan("");
@@ -2260,7 +2285,9 @@ __global__ void __launch_bounds__(NH ? 32 * (NH + 1) : 64) lpv_solve_h8_kernel(c
       else if (TW) factor_tw<KIND>(c, fw, sigma, g & 1);
       else factor<KIND>(c, fw, sigma);
     }
+    H8_PH(1);
     reproject<KIND>(c, true, rho, rho_eq, sigma, 0.0, true);
+    H8_PH(2);
     bool live = (flags == 0);
     const bool failed = flags != 0;
     int iter_done = 0, rho_updates = 0;
@@ -2280,6 +2307,7 @@ __global__ void __launch_bounds__(NH ? 32 * (NH + 1) : 64) lpv_solve_h8_kernel(c
       if (ai) { const int nxt = (iter / ai + 1) * ai; stop = nxt < stop ? nxt : stop; }
       { const int nxt = iter + kSyncEvery; stop = nxt < stop ? nxt : stop; }
       u.rho = rho; u.rho_eq = rho_eq; u.rinv = 1.0 / rho; u.rinv_eq = 1.0 / rho_eq; u.live = live;
+      H8_PH(9);
 #pragma unroll 1
       for (; iter < stop; ++iter) {
         if (iter == stop - 1) {  // keep the iterate before the last step of the chunk: delta_x, delta_y
@@ -2299,11 +2327,12 @@ __global__ void __launch_bounds__(NH ? 32 * (NH + 1) : 64) lpv_solve_h8_kernel(c
             }
           }
           if (NH) __syncthreads();
+          H8_PH(3);
         }
         u.cc = (iter == 0) ? 2.0 : alpha;
         if (NH) {
           ++hw_seq;
-          if (wid == 0) { sweep_fwd_tw<KIND>(h, N, gsel, g); sweep_bwd_chain_hw<KIND>(h, N, gsel, g, hws, hw_seq, NH); }
+          if (wid == 0) { sweep_fwd_tw<KIND>(h, N, gsel, g); H8_PH(4); sweep_bwd_chain_hw<KIND>(h, N, gsel, g, hws, hw_seq, NH H8_PH_ARGS); H8_PH(5); }
           else helper_iter<KIND>(h, u, hws, hw_seq, wid, NH);
         }
         else if (TW) { sweep_fwd_tw<KIND>(h, N, gsel, g); sweep_bwd_admm_tw<KIND>(h, u, gsel, g); }
@@ -2317,9 +2346,11 @@ __global__ void __launch_bounds__(NH ? 32 * (NH + 1) : 64) lpv_solve_h8_kernel(c
         zsel = 1.0;
       }
       c.sync();
+      H8_PH(9);
       const int last_was_first = (iter == 1);
       rho_eq_last = rho_eq;
       sync_yd<KIND>(c, live, rho_eq, alpha, nsync, first_in);
+      H8_PH(6);
       nsync = 0; first_in = 0;
       const bool can_check = ct && (iter % ct == 0);
       const bool can_adapt = ai && (iter % ai == 0);
@@ -2329,8 +2360,10 @@ __global__ void __launch_bounds__(NH ? 32 * (NH + 1) : 64) lpv_solve_h8_kernel(c
         Info J = I;
         update_info<KIND>(c, &J, zsel);
         if (live) { I = J; iter_done = iter; }
+        H8_PH(7);
         if (can_check) {
           if (check_termination<KIND>(c, S, &I, live, 0, rho_eq_last, last_was_first, true)) live = false;  // frozen: stores are predicated on `live`
+          H8_PH(8);
         }
         if (can_adapt) {
           const double pr = I.n_rp / ((I.n_z > I.n_Ax ? I.n_z : I.n_Ax) + 1e-10);
@@ -2348,12 +2381,14 @@ __global__ void __launch_bounds__(NH ? 32 * (NH + 1) : 64) lpv_solve_h8_kernel(c
             if (NH) { if (wid == 0) factor_tw<KIND>(c, fw, sigma, g & 1); __syncthreads(); }
             else if (TW) factor_tw<KIND>(c, fw, sigma, g & 1);
             else factor<KIND>(c, fw, sigma);
+            H8_PH(1);
             new_cr = true;
           }
         }
       }
       // re-project r (and the pending right-hand side) from the explicit iterate: removes the drift of the recursion
       if (iter < S.max_iter && __any_sync(kFull, live)) reproject<KIND>(c, live, rho, rho_eq, sigma, zsel, new_cr);
+      H8_PH(2);
     }
     if (!checked_last && __any_sync(kFull, live)) {
       Info J = I;
@@ -2402,6 +2437,7 @@ __global__ void __launch_bounds__(NH ? 32 * (NH + 1) : 64) lpv_solve_h8_kernel(c
         }
       }
     }
+    H8_PH(10);
     int polish_status = 0;
     const bool do_pol = S.polish && status == LPVMPC_SOLVED;
     bool polished_sets = false;
@@ -2409,6 +2445,7 @@ __global__ void __launch_bounds__(NH ? 32 * (NH + 1) : 64) lpv_solve_h8_kernel(c
       polish_status = polish<KIND, ST, TW>(c, h, &sm, S, &I, do_pol, gsel);
       polished_sets = do_pol;
     }
+    H8_PH(11);
     // ---- outputs
     if (vout) {
       const double *X = c.V(V_X);
@@ -2450,7 +2487,14 @@ __global__ void __launch_bounds__(NH ? 32 * (NH + 1) : 64) lpv_solve_h8_kernel(c
     }
     if (ST) strm_drain(h.sc, sm);   // nothing may be in flight into the ring when the next QP's setup / factor starts
     c.sync();
+    H8_PH(12);
   }
+#ifdef LPV_H8_PHASE_TIMING
+  if (NH && threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) atomicAdd(&g_phase_cycles[i], (unsigned long long)ph[i]);
+  }
+#endif
   (void)NSL; (void)NB; (void)hw_seq; (void)wid;
 }
 

@@ -1030,6 +1030,15 @@ void run_copies(const std::vector<CopyJob> &jobs) {
 extern "C" {
 
 int lpvmpc_abi_version(void) { return LPVMPC_ABI_VERSION; }
+#ifdef LPV_H8_PHASE_TIMING
+// development builds only: cycles per phase added up by the helper-warp H8 kernels (lpv_h8.cuh), optionally cleared
+int lpvmpc_debug_phase_cycles(unsigned long long *out16, int reset) {
+  unsigned long long z[16] = {0};
+  if (out16 && cudaMemcpyFromSymbol(out16, lpv::h8::g_phase_cycles, sizeof(z)) != cudaSuccess) return -1;
+  if (reset && cudaMemcpyToSymbol(lpv::h8::g_phase_cycles, z, sizeof(z)) != cudaSuccess) return -1;
+  return 0;
+}
+#endif
 
 void lpvmpc_default_settings(lpvmpc_settings *s) {
   if (!s) return;
@@ -1219,7 +1228,7 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
       static const bool hw_on = [] { const char *e = std::getenv("LPVMPC_H8_HELPERS"); return !e || std::atoi(e) != 0; }();
       h->helpers = (h->twisted && hw_on && h->wpc == 1) ? (ctrl ? 3 : 1) : 0;
       if (h->helpers) {
-        const size_t ws2 = h->ws_bytes + 512 + 1024;   // the helpers' mailbox (lpv::h8::HwShared) behind the gather buffers, then the CTA's reduction scratch (4 warps x 16 doubles)
+        const size_t ws2 = h->ws_bytes + 512 + 1536;   // the helpers' mailbox (lpv::h8::HwShared) behind the gather buffers, then the CTA's reduction scratch (4 warps x 16 doubles)
         int ctas = (int)(sm_bytes / (ws2 + 1024));
         if (ctas > 32) ctas = 32;
         const int by_regs = ctrl ? 1 : 3;      // __launch_bounds__ of the two instantiations
