@@ -56,6 +56,14 @@ using h8t::kSyncEvery;
 
 constexpr int KIND = LPVMPC_CONTROLLER;
 constexpr int NX = 6, NB = 8, NT = 2, NSL = 6, OPM = 24, IS = 26, GS = NX * 8;
+// Offsets (doubles) of the blocks of a QP's shared-memory region: the layout lpvmpc.cu's make_h16t_layout computes for the
+// one horizon this kernel is built for, as compile-time constants (lpvmpc_create checks them against the host's layout with
+// layout_matches).  Through the `Lay` in the kernel parameters every accessor of a cold routine paid a generic load from
+// parameter memory in front of its address (121 LD.E in the kernel's SASS, reloaded behind every asm volatile).
+constexpr int kN8 = 8;
+constexpr int kLV = 0, kLI = kLV + (kN8 + 1) * h8t::VS, kLG = kLI + (kN8 + 2) * IS, kLCS = kLG + kN8 * NX * 8;
+static_assert(((kN8 + 1) * h8t::VS) % 2 == 0 && ((kN8 + 2) * IS) % 2 == 0 && (kN8 * NX * 8) % 2 == 0, "blocks are padded to even sizes on the host");
+inline bool layout_matches(const Lay &L) { return L.N == kN8 && L.V == kLV && L.I == kLI && L.G == kLG && L.CS == kLCS; }
 
 // reductions over the 8 lanes of a half (pivot rows) and over the 16 lanes of a QP
 __device__ __forceinline__ double h8shfl(double v, int src) { return __shfl_sync(kFull, v, src, 8); }
@@ -78,7 +86,6 @@ __device__ __forceinline__ int qany(int v) {
 struct Ctx {
   double *S;     // my QP's shared region
   double *cold;  // my QP slot in the global slab
-  const Lay *L;
   static constexpr int N = 8, NL = 4;   // horizon, local steps before the middle stage (N = 2 NL): this kernel is N = 8 only (lpvmpc_create)
   int r, h;      // component, half (0: left, stages ascending; 1: right, stages descending)
   int kc0, nck;  // cold ownership: stages kc0 .. kc0 + nck - 1 (left: 0 .. NL-1, right: NL .. N)
@@ -93,20 +100,20 @@ struct Ctx {
   __device__ __forceinline__ bool owns(int k) const { return k >= kc0 && k < kc0 + nck; }
   __device__ __forceinline__ int kstage(int j) const { return h ? N - j : j; }   // stage of local step j
   __device__ __forceinline__ double *cd(int arr) const {
-    return (arr < C_NSMEM) ? (S + L->CS + arr * (N + 1) * 8) : (cold + (arr - C_NSMEM) * (N + 1) * 8);
+    return (arr < C_NSMEM) ? (S + kLCS + arr * (N + 1) * 8) : (cold + (arr - C_NSMEM) * (N + 1) * 8);
   }
-  __device__ __forceinline__ double *Gb(int k) const { return S + L->G + k * GS; }
-  __device__ __forceinline__ double *V(int arr) const { return S + L->V + arr; }
+  __device__ __forceinline__ double *Gb(int k) const { return S + kLG + k * GS; }
+  __device__ __forceinline__ double *V(int arr) const { return S + kLV + arr; }
   // factorisation scratch rows (8 doubles each) in dead stage-vector slots: previous pivot inverse / parked block
-  __device__ __forceinline__ double *Tp(int row) const { return S + L->V + row * VS + (h ? V_CR : V_B); }
-  __device__ __forceinline__ double *Ob(int row) const { return S + L->V + row * VS + (h ? V_XS : V_R); }
+  __device__ __forceinline__ double *Tp(int row) const { return S + kLV + row * VS + (h ? V_CR : V_B); }
+  __device__ __forceinline__ double *Ob(int row) const { return S + kLV + row * VS + (h ? V_XS : V_R); }
   // tensor-memory columns (the same for every lane of the warp): local step j, cold slot i
   __device__ __forceinline__ uint32_t tT(int j) const { return tm + (uint32_t)(16 * j); }
   __device__ __forceinline__ uint32_t tKr(int j) const { return tm + (uint32_t)(16 * (NL + 1) + 16 * (j - 1)); }
   __device__ __forceinline__ uint32_t tKc(int j) const { return tm + (uint32_t)(16 * (2 * NL + 1) + 16 * (j - 1)); }
   __device__ __forceinline__ uint32_t tP(int i) const { return tm + (uint32_t)(16 * (3 * NL + 1) + 8 * i); }
   __device__ __forceinline__ uint32_t tQ(int i) const { return tP(i); }   // certificates (ADMM) / polish duals (afterwards)
-  __device__ __forceinline__ double *Ib(int k) const { return S + L->I + k * IS; }
+  __device__ __forceinline__ double *Ib(int k) const { return S + kLI + k * IS; }
   __device__ __forceinline__ double &zi(int k, int t) const { return Ib(k)[(islot + t) * 2]; }
   __device__ __forceinline__ double &yi(int k, int t) const { return Ib(k)[(islot + t) * 2 + 1]; }
   __device__ __forceinline__ double &si(int k, int t) const { return Ib(k)[NSL * 2 + (islot + t) * 2]; }
@@ -747,7 +754,6 @@ __device__ __noinline__ double objective(const Ctx c, const double *xv, const in
 // As in lpv_h8t.cuh, the stage loops split over the halves.  Returns flags: bit 0 = Curvature() failed, bit 1 = bad data.
 __device__ __noinline__ int setup(const Ctx c, const H8Params &p, const int b, const bool valid, double *csc_out) {
   const int N = c.N, r = c.r, h = c.h;
-  const Lay &L = *c.L;
   const Model &M = p.M;
   const lpvmpc_args &a = p.a;
   const lpvmpc_settings &St = p.S;
@@ -758,7 +764,7 @@ __device__ __noinline__ int setup(const Ctx c, const H8Params &p, const int b, c
   double x0r = 0.0;
   double *sPD = c.cd(C_PD), *sPO = c.cd(C_PO), *sD = c.cd(C_Q), *sE = c.cd(C_BE), *sEI = c.cd(C_ED), *sDt = c.cd(C_YD);
   double *sEt = c.cd(C_DINV), *sEti = c.cd(C_EINV);
-  double *Gs = S + L.G;
+  double *Gs = S + kLG;
   __syncwarp();
   // ---- schedule: G_k = -[A_k B_k] (unscaled); every lane walks the serial roll-out, the owner of stage k keeps row r
   if (a.sched_mode == LPVMPC_SCHED_GIVEN) {
@@ -1283,7 +1289,7 @@ __global__ void __launch_bounds__(256, 1) lpv_solve_h16t_kernel(const __grid_con
   constexpr int N = Ctx::N, NL = Ctx::NL;
   Ctx c;
   c.S = smem; c.cold = p.cold;
-  c.L = &L; c.r = r; c.h = half;
+  c.r = r; c.h = half;
   c.kc0 = half ? NL : 0; c.nck = half ? NL + 1 : NL;
   c.xl = r < NX; c.ul = (r >= NX) && (r < NB);
   c.islot = (r == 0) ? 0 : ((r >= NX) ? (r - NX + 1) * 2 : 0);
@@ -1348,26 +1354,26 @@ __global__ void __launch_bounds__(256, 1) lpv_solve_h16t_kernel(const __grid_con
       constexpr int ISB = IS * 8;
       const int k0 = half ? N : 0, sgn = half ? -1 : 1;
       h.tT = c.tT(0); h.tKr = c.tKr(1); h.tKc = c.tKc(1);
-      h.v = sq + (uint32_t)(L.V + k0 * VS + r) * 8u;
+      h.v = sq + (uint32_t)(kLV + k0 * VS + r) * 8u;
       h.vstr = sgn * VB;
       const bool rows = (r == 0 || c.ul);
-      const uint32_t dm = sq + (uint32_t)(L.I + (N + 1) * IS) * 8u;   // block N+1: dummy rows, zero coupling
+      const uint32_t dm = sq + (uint32_t)(kLI + (N + 1) * IS) * 8u;   // block N+1: dummy rows, zero coupling
       // single-variable rows exist at stages 0 .. N-1: local step 0 of the right half (stage N) has the dummy block's
       // layout right behind it, so the signed stride walks from block N (all dummies after setup) down to block m
-      h.ib = rows ? sq + (uint32_t)(L.I + k0 * IS + c.islot * 2) * 8u : dm;
+      h.ib = rows ? sq + (uint32_t)(kLI + k0 * IS + c.islot * 2) * 8u : dm;
       h.istr = rows ? sgn * ISB : 0;
       // slew coupling: pm(k) couples u_{k-1}, u_k.  The update of local step j sees x~ of local step j-1 (the one just
       // computed: argument xm) and of local step j+1 (xp): left half xm = stage k-1 -> pm(k), xp -> pm(k+1);
       // right half xm = stage k+1 -> pm(k+1), xp = stage k-1 -> pm(k)
-      const uint32_t pk0 = sq + (uint32_t)(L.I + k0 * IS + OPM + (c.ul ? ucomp : 0)) * 8u;
+      const uint32_t pk0 = sq + (uint32_t)(kLI + k0 * IS + OPM + (c.ul ? ucomp : 0)) * 8u;
       h.pm = c.ul ? (half ? pk0 + (uint32_t)ISB : pk0) : dm + (uint32_t)OPM * 8u;
       h.pm2 = c.ul ? (half ? pk0 : pk0 + (uint32_t)ISB) : dm + (uint32_t)OPM * 8u;
       h.pstr = c.ul ? sgn * ISB : 0;
       h.gpub = gbuf + (uint32_t)(64 * (r >> 1) + 16 * g8 + 8 * (r & 1));
       h.ggat = gbuf + (uint32_t)(16 * g8);
-      h.vmid = sq + (uint32_t)(L.V + NL * VS + r) * 8u;
-      h.ibmid = rows ? sq + (uint32_t)(L.I + NL * IS + c.islot * 2) * 8u : dm;
-      const uint32_t pkm = sq + (uint32_t)(L.I + NL * IS + OPM + (c.ul ? ucomp : 0)) * 8u;
+      h.vmid = sq + (uint32_t)(kLV + NL * VS + r) * 8u;
+      h.ibmid = rows ? sq + (uint32_t)(kLI + NL * IS + c.islot * 2) * 8u : dm;
+      const uint32_t pkm = sq + (uint32_t)(kLI + NL * IS + OPM + (c.ul ? ucomp : 0)) * 8u;
       h.pmid = c.ul ? pkm : dm + (uint32_t)OPM * 8u;
       h.pmid2 = c.ul ? pkm + (uint32_t)ISB : dm + (uint32_t)OPM * 8u;
     }

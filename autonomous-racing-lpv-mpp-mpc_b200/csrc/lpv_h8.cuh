@@ -150,6 +150,18 @@ __device__ __forceinline__ double frsqrt(double x) {
 }
 __device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 __device__ __forceinline__ void st2(double *p, double a, double b) { *reinterpret_cast<double2 *>(p) = make_double2(a, b); }
+// slab (global memory) loads that stay where they are written: the compiler neither sinks them into the conditional block
+// that uses the value nor reorders them (the cold loops request every operand of a stage before the first use)
+__device__ __forceinline__ double ldg_v(const double *p) {
+  double v;
+  asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(__cvta_generic_to_global(p)));
+  return v;
+}
+__device__ __forceinline__ double2 ldg2_v(const double *p) {
+  double2 v;
+  asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(__cvta_generic_to_global(p)));
+  return v;
+}
 __device__ __forceinline__ int swz(int rr) { return (rr >> 1) & 3; }
 // offset of logical 16-byte chunk j of row rr inside a swizzled 8-wide block
 __device__ __forceinline__ int chunk(int rr, int j) { return rr * 8 + ((j ^ swz(rr)) << 1); }
@@ -1386,10 +1398,14 @@ __device__ __noinline__ void reproject(const Ctx<KIND> c, const bool doit, const
   c.sync();
 }
 
-// residual norms at the current iterate (update_info); y_dyn must be in sync
+// residual norms at the current iterate (update_info); y_dyn must be in sync.
+// Every slab (L2) operand of a stage is requested at the top of the stage's iteration, with clamped indices and no
+// condition in front of it: behind the conditions (state lane / row present / k < N ...) the loads sat in different basic
+// blocks and a stage cost one exposed L2 round trip per block (six to eight of ~700 cycles; the slab cannot live in L1,
+// shared memory takes the SM's array).  The arithmetic is unchanged: the same products in the same order.
 template <int KIND>
 __device__ __noinline__ void update_info(const Ctx<KIND> c, Info *ip, const double zsel) {
-  constexpr int NT = Ctx<KIND>::NT;
+  constexpr int NT = Ctx<KIND>::NT, NX = Ctx<KIND>::NX;
   Info &I = *ip;
   const int N = c.N, r = c.r;
   const double *X = c.V(V_X);
@@ -1397,27 +1413,70 @@ __device__ __noinline__ void update_info(const Ctx<KIND> c, Info *ip, const doub
   const double *EINV = c.cd(C_EINV), *EIINV = c.cd(C_EIINV), *DINV = c.cd(C_DINV), *PD = c.cd(C_PD), *PO = c.cd(C_PO);
   double a_rp = 0, a_z = 0, a_Ax = 0, b_rp = 0, b_z = 0, b_Ax = 0;
   double a_rd = 0, a_q = 0, a_Aty = 0, a_Px = 0, b_rd = 0, b_q = 0, b_Aty = 0, b_Px = 0;
+  const int rg = c.xl ? r : 0;   // a row of G that exists (only state lanes use theirs)
 #pragma unroll 1
   for (int k = c.k0; k <= N; k += c.ks) {
-    const int o = k * 8 + r;
+    const int o = k * 8 + r, ov = k * VS + r;
+    const int km = k > 0 ? k - 1 : 0, kp = k < N ? k + 1 : N, kg = k < N ? k : N - 1;
+    // ---- slab operands, up front
+    const double ed = ldg_v(ED + o), be = ldg_v(BE + o), einv = ldg_v(EINV + o), pd = ldg_v(PD + o), po0 = ldg_v(PO + o), pom = ldg_v(PO + km * 8 + r);
+    const double yd = ldg_v(YD + o), qv = ldg_v(QV + o), dinv = ldg_v(DINV + o);
+    const double *gm = c.Gb(km) + rg * 8;
+    const double2 t0 = ldg2_v(gm), t1 = ldg2_v(gm + 2), t2 = ldg2_v(gm + 4), t3 = ldg2_v(gm + 6);
+    const double *gk = c.Gb(kg);
+    double gc[NX], ydn[NX], eiinv[NT];
+#pragma unroll
+    for (int rr = 0; rr < NX; ++rr) { gc[rr] = ldg_v(gk + rr * 8 + r); ydn[rr] = ldg_v(YD + kp * 8 + rr); }
+#pragma unroll
+    for (int t = 0; t < NT; ++t) eiinv[t] = ldg_v(EIINV + c.ci(k, t));
+    const bool hin = c.has_in(k);
+    // ---- the arithmetic of rowA_dyn / rowP / colA on them
     if (c.xl) {
-      const double Ax = rowA_dyn<KIND>(c, ED, X, VS, k), z = zsel * BE[o], rr = Ax - z, ei = EINV[o];
+      double Ax = ed * X[ov];
+      if (k > 0) {
+        double g[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) g[q] = X[(k - 1) * VS + q];
+        double a0 = t0.x * g[0], a1 = t1.x * g[2], a2 = t2.x * g[4], a3 = t3.x * g[6];
+        a0 = fma(t0.y, g[1], a0); a1 = fma(t1.y, g[3], a1); a2 = fma(t2.y, g[5], a2); a3 = fma(t3.y, g[7], a3);
+        Ax += (a0 + a1) + (a2 + a3);
+      }
+      const double z = zsel * be, rr = Ax - z, ei = einv;
       a_rp = absmax(a_rp, rr); a_z = absmax(a_z, z); a_Ax = absmax(a_Ax, Ax);
       b_rp = absmax(b_rp, ei * rr); b_z = absmax(b_z, ei * z); b_Ax = absmax(b_Ax, ei * Ax);
     }
-    if (c.has_in(k)) {
+    if (hin) {
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
-        const double ax = c.si(k, t) * X[k * VS + r], z = c.zi(k, t), rr = ax - z, ei = EIINV[c.ci(k, t)];
+        const double ax = c.si(k, t) * X[ov], z = c.zi(k, t), rr = ax - z, ei = eiinv[t];
         a_rp = absmax(a_rp, rr); a_z = absmax(a_z, z); a_Ax = absmax(a_Ax, ax);
         b_rp = absmax(b_rp, ei * rr); b_z = absmax(b_z, ei * z); b_Ax = absmax(b_Ax, ei * ax);
       }
     }
     if (c.var_live(k)) {
-      const double Px = rowP<KIND>(c, PD, PO, X, VS, k), Aty = colA<KIND>(c, ED, YD, nullptr, true, k);
-      const double rr = (QV[o] + Px) + Aty, di = DINV[o];
-      a_rd = absmax(a_rd, rr); a_q = absmax(a_q, QV[o]); a_Aty = absmax(a_Aty, Aty); a_Px = absmax(a_Px, Px);
-      b_rd = absmax(b_rd, di * rr); b_q = absmax(b_q, di * QV[o]); b_Aty = absmax(b_Aty, di * Aty); b_Px = absmax(b_Px, di * Px);
+      double Px = pd * X[ov];
+      if (c.ul) {
+        if (k > 0 && k < N) Px = fma(pom, X[ov - VS], Px);
+        if (k < N - 1) Px = fma(po0, X[ov + VS], Px);
+        if (k == N) Px = 0.0;
+      }
+      double Aty = c.xl ? ed * yd : 0.0;
+      if (k < N) {
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int rr = 0; rr < NX; rr += 2) {
+          a0 = fma(gc[rr], ydn[rr], a0);
+          if (rr + 1 < NX) a1 = fma(gc[rr + 1], ydn[rr + 1], a1);
+        }
+        Aty += a0 + a1;
+      }
+      if (hin) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) Aty = fma(c.si(k, t), c.yi(k, t), Aty);
+      }
+      const double rr = (qv + Px) + Aty, di = dinv;
+      a_rd = absmax(a_rd, rr); a_q = absmax(a_q, qv); a_Aty = absmax(a_Aty, Aty); a_Px = absmax(a_Px, Px);
+      b_rd = absmax(b_rd, di * rr); b_q = absmax(b_q, di * qv); b_Aty = absmax(b_Aty, di * Aty); b_Px = absmax(b_Px, di * Px);
     }
   }
   const bool wd = c.ks > 1;

@@ -1160,7 +1160,7 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
     h->TL16 = make_h16t_layout(cfg->kind, cfg->N);
     const size_t h16t_bytes = (size_t)h->TL16.total * sizeof(double) * 16 + 8 * 512 + 512;
     const bool h16t_ok = pdiag && cfg->steering_delay == 0 && cfg->kind == LPVMPC_CONTROLLER && cfg->N == 8 &&
-                         h16t_bytes + 64 <= (size_t)h->smem_optin;
+                         h16t_bytes + 64 <= (size_t)h->smem_optin && lpv::h16t::layout_matches(h->TL16);   // (the kernel holds the layout as constants)
     if (cfg->variant == 8 && !h16t_ok) { h->err = "variant 8 (H16T) needs controller, N=8, diagonal Q and R, steering_delay=0"; return bail(LPVMPC_E_UNSUPPORTED); }
     static const bool auto16 = [] { const char *e = std::getenv("LPVMPC_AUTO_H16T"); return !e || std::atoi(e) != 0; }();   // LPVMPC_AUTO_H16T=0: H8T
     if (cfg->variant == 8 || (cfg->variant == 0 && h16t_ok && auto16)) h->variant = 8;
