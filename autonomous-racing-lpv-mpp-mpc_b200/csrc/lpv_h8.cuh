@@ -95,6 +95,11 @@ template <int KIND> struct Dims;
 template <> struct Dims<LPVMPC_CONTROLLER> { static constexpr int NX = 6, NT = 2, NSL = 6, OLI = 24, OPM = 24, IS = 26; };
 template <> struct Dims<LPVMPC_PLANNER> { static constexpr int NX = 5, NT = 1, NSL = 7, OLI = 28, OPM = 36, IS = 38; };
 
+// what Ctx takes for granted about the host's layout
+inline bool layout_matches(const Lay &L, int nx) {
+  return L.TK == 0 && L.cG == C_COUNT * (L.N + 1) * 8 && L.cTK == L.cG + L.N * nx * 8;
+}
+
 __device__ __forceinline__ double gshfl(double v, int src) { return __shfl_sync(kFull, v, src, 8); }
 __device__ __forceinline__ double gmax(double v) {
 #pragma unroll
@@ -172,7 +177,11 @@ struct Ctx {
   static constexpr int OLI = Dims<KIND>::OLI, OPM = Dims<KIND>::OPM, IS = Dims<KIND>::IS;
   double *S;     // my QP's shared region
   double *cold;  // my QP slot in the global slab
-  const Lay *L;
+  // The layout by value (lpvmpc.cu: make_h8_layout; checked at create with layout_matches): the factor starts the region, the
+  // stage vectors follow at oV, the single-variable rows at oI; the slab holds C_COUNT vectors, then G, then (streamed factor)
+  // the factor.  Through a `const Lay *` into the kernel parameters every accessor of a cold routine paid a generic load from
+  // parameter memory in front of its address.
+  int oV, oI, ring;
   int N, r;
   int kmask;     // stage -> factor block slot: -1 (resident: slot k) or ring - 1
   int k0, ks;    // stages of the cold per-stage loops handled by my group: k0, k0 + ks, ... (0, 1; or group index, 4 when the
@@ -230,12 +239,14 @@ struct Ctx {
     return xl || (ul && k < N);
   }
   __device__ __forceinline__ double *cd(int arr) const { return cold + arr * (N + 1) * 8; }
-  __device__ __forceinline__ double *Tb(int k) const { return S + L->TK + (k & kmask) * TKS; }
-  __device__ __forceinline__ double *Kb(int k) const { return S + L->TK + ((k - 1) & kmask) * TKS + 64; }
-  __device__ __forceinline__ const double *Gb(int k) const { return cold + L->cG + k * (NX * 8); }
-  __device__ __forceinline__ double *V(int arr) const { return S + L->V + arr; }          // element (k, q) at [k*VS + q]
+  __device__ __forceinline__ int cG() const { return C_COUNT * (N + 1) * 8; }
+  __device__ __forceinline__ int cTK() const { return cG() + N * NX * 8; }
+  __device__ __forceinline__ double *Tb(int k) const { return S + (k & kmask) * TKS; }
+  __device__ __forceinline__ double *Kb(int k) const { return S + ((k - 1) & kmask) * TKS + 64; }
+  __device__ __forceinline__ const double *Gb(int k) const { return cold + cG() + k * (NX * 8); }
+  __device__ __forceinline__ double *V(int arr) const { return S + oV + arr; }          // element (k, q) at [k*VS + q]
   // single-variable rows in shared memory: z, y, coefficient, upper (and lower: planner) bound of my row t at stage k
-  __device__ __forceinline__ double *Ib(int k) const { return S + L->I + k * IS; }
+  __device__ __forceinline__ double *Ib(int k) const { return S + oI + k * IS; }
   __device__ __forceinline__ double &zi(int k, int t) const { return Ib(k)[(islot + t) * 2]; }
   __device__ __forceinline__ double &yi(int k, int t) const { return Ib(k)[(islot + t) * 2 + 1]; }
   __device__ __forceinline__ double &si(int k, int t) const { return Ib(k)[NSL * 2 + (islot + t) * 2]; }
@@ -391,8 +402,8 @@ __device__ __noinline__ void factor(const Ctx<KIND> c, const FW fw, const double
 #pragma unroll
     for (int j = 0; j < 4; ++j) st2(Tk + c.ro[j], s[2 * j], s[2 * j + 1]);
     __syncwarp();
-    if (c.L->ring) {  // streamed factor: block k-1 = [T_{k-1} | K_k] is final, block N = [T_N | -] after the last stage
-      double *dst = c.cold + c.L->cTK;
+    if (c.ring) {  // streamed factor: block k-1 = [T_{k-1} | K_k] is final, block N = [T_N | -] after the last stage
+      double *dst = c.cold + c.cTK();
       if (k > 0) {
         const double *src = c.Tb(k - 1);
         double *d = dst + (size_t)(k - 1) * TKS;
@@ -407,7 +418,7 @@ __device__ __noinline__ void factor(const Ctx<KIND> c, const FW fw, const double
       }
     }
   }
-  if (c.L->ring) {  // the slab copy is read by the async proxy (TMA) from here on, and the ring is overwritten by it
+  if (c.ring) {  // the slab copy is read by the async proxy (TMA) from here on, and the ring is overwritten by it
     __threadfence_block();
     asm volatile("fence.proxy.async;" ::: "memory");
     __syncwarp();
@@ -1658,7 +1669,6 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
                                  uint64_t *eqm_out, uint64_t *loosem_out) {
   constexpr int NX = Ctx<KIND>::NX, NB = Ctx<KIND>::NB, NT = Ctx<KIND>::NT, GS = NX * 8;
   const int N = c.N, r = c.r;
-  const Lay &L = *c.L;
   const Model &M = p.M;
   const lpvmpc_args &a = p.a;
   const lpvmpc_settings &St = p.S;
@@ -1669,7 +1679,7 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
   int sched_err = 0, data_err = 0;
   double x0r = 0.0;
   // scratch in the factor area ((N+1)*128 - 64 doubles): 8 arrays of NS8, then G (N x GS, plain rows), then nz doubles
-  double *sD = L.ring ? c.cold + L.cTK : S + L.TK, *sE = sD + NS8, *sEI = sE + NS8, *sDt = sEI + NS8, *sEt = sDt + NS8, *sEti = sEt + NS8;
+  double *sD = c.ring ? c.cold + c.cTK() : S, *sE = sD + NS8, *sEI = sE + NS8, *sDt = sEI + NS8, *sEt = sDt + NS8, *sEti = sEt + NS8;
   double *sPD = sEti + NS8, *sPO = sPD + NS8;
   double *Gs = sPO + NS8;
   // ---- schedule: G_k = -[A_k B_k] (unscaled), my row
@@ -1940,7 +1950,7 @@ __device__ __noinline__ int setup(const Ctx<KIND> c, const H8Params &p, const in
       cQ[o] = c.var_live(k) ? QV[ov] : 0.0; cBE[o] = sE[o] * BE[ov]; cED[o] = ED[ov]; cYD[o] = 0.0;
       if (c.ul) c.pm(k, ucomp) = (k > 0 && k < N) ? sPO[o - 8] : 0.0;   // couples u_{k-1}, u_k
     }
-    double *Gd = c.cold + L.cG;
+    double *Gd = c.cold + c.cG();
 #pragma unroll 1
     for (int k = c.k0; k < N; k += c.ks) {
       if (c.xl) {
@@ -2229,7 +2239,7 @@ constexpr int kSyncEvery = 25;  // y_dyn is brought up to date and r re-projecte
 // TW: twisted factorisation (one QP per warp, resident factor, even N: checked by the host)
 // NH: helper warps (TW only; one QP per CTA: warp 0 runs the solver, warps 1 .. NH the element-wise updates of the ADMM step)
 template <int KIND, int QPW, bool ST, bool TW = false, int NH = 0>
-__global__ void __launch_bounds__(NH ? 32 * (NH + 1) : 64) lpv_solve_h8_kernel(const __grid_constant__ H8Params p) {
+__global__ void __launch_bounds__(NH ? 32 * (NH + 1) : 64, 1) lpv_solve_h8_kernel(const __grid_constant__ H8Params p) {
   static_assert(!ST || QPW == 1, "the streamed kernel holds one QP per warp");
   static_assert(!TW || (QPW == 1 && !ST), "the twisted kernel holds one QP per warp with the factor resident");
   static_assert(NH == 0 || TW, "helper warps come with the twisted kernel");
@@ -2241,7 +2251,7 @@ __global__ void __launch_bounds__(NH ? 32 * (NH + 1) : 64) lpv_solve_h8_kernel(c
   const int N = L.N;
   Ctx<KIND> c;
   c.S = smem; c.cold = p.cold;
-  c.L = &L; c.N = N; c.r = r;
+  c.oV = L.V; c.oI = L.I; c.ring = L.ring; c.N = N; c.r = r;
   c.kmask = ST ? (kRing - 1) : -1;
   const int wid = NH ? (int)(threadIdx.x >> 5) : 0;   // helper-warp kernels: my warp among the CTA's NH + 1
   c.nw = NH + 1;

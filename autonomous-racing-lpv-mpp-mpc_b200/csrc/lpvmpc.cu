@@ -1133,14 +1133,14 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
     if (cfg->variant < 0 || cfg->variant > 8) { h->err = "unknown kernel variant"; return bail(LPVMPC_E_ARG); }
     // H8 kernel: same restrictions as G8, smaller shared-memory footprint (cold data in an L2 slab)
     h->HL = make_h8_layout(cfg->kind, cfg->N, 0);
-    const bool h8_ok = pdiag && cfg->steering_delay == 0 && (size_t)h->HL.total * sizeof(double) + 1024 <= (size_t)h->smem_optin &&
+    const bool h8_ok = lpv::h8::layout_matches(h->HL, cfg->kind == LPVMPC_CONTROLLER ? 6 : 5) && pdiag && cfg->steering_delay == 0 && (size_t)h->HL.total * sizeof(double) + 1024 <= (size_t)h->smem_optin &&
                        (cfg->kind == LPVMPC_CONTROLLER || cfg->N <= 63);
     if (cfg->variant == 5 && !h8_ok) { h->err = "variant 5 (H8) needs diagonal Q and R, steering_delay=0, planner N<=63 and a per-QP state that fits shared memory"; return bail(LPVMPC_E_UNSUPPORTED); }
     if (cfg->variant == 5 || (cfg->variant == 0 && h8_ok)) h->variant = 5;
     // H8S = H8 with the factor streamed from the slab through a ring of 4 stage blocks (variant 7): N <= 254, stage
     // vectors and single-variable rows must still fit shared memory
     const lpv::h8::Lay SL4 = make_h8_layout(cfg->kind, cfg->N, 4);
-    const bool h8s_ok = pdiag && cfg->steering_delay == 0 && cfg->N <= 254 && (size_t)SL4.total * sizeof(double) + 2048 <= (size_t)h->smem_optin &&
+    const bool h8s_ok = lpv::h8::layout_matches(SL4, cfg->kind == LPVMPC_CONTROLLER ? 6 : 5) && pdiag && cfg->steering_delay == 0 && cfg->N <= 254 && (size_t)SL4.total * sizeof(double) + 2048 <= (size_t)h->smem_optin &&
                         (cfg->kind == LPVMPC_CONTROLLER || cfg->N <= 63);
     if (cfg->variant == 7 && !h8s_ok) { h->err = "variant 7 (H8S) needs diagonal Q and R, steering_delay=0, planner N<=63, N<=254"; return bail(LPVMPC_E_UNSUPPORTED); }
     if (cfg->variant == 7) { h->variant = 5; h->HL = SL4; }
@@ -1224,7 +1224,8 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
       // helper warps for the element-wise updates (LPVMPC_H8_HELPERS=0: none): one QP per CTA, so the choice only stands when
       // it was one warp per CTA anyway.  Controller (long horizons, one CTA per SM): 3 helpers.  Planner (3 CTAs per SM): ONE --
       // a warp's registers live in its SM sub-partition (16 K registers), so at 224-255 registers per thread an SM holds 8
-      // warps: 3 CTAs of 2 (3 CTAs of 3 warps need <= 168 registers and spill: measured slower than no helpers)
+      // warps: 3 CTAs of 2.  3 CTAs of 3 or 4 warps need <= 168 registers: with that cap forced (__launch_bounds__(96, 4) /
+      // (128, 3): 300 bytes of spills) plan16384 takes 319 / 315 ms against 297 ms with one helper at 255 registers, same box
       static const bool hw_on = [] { const char *e = std::getenv("LPVMPC_H8_HELPERS"); return !e || std::atoi(e) != 0; }();
       h->helpers = (h->twisted && hw_on && h->wpc == 1) ? (ctrl ? 3 : 1) : 0;
       if (h->helpers) {
