@@ -16,9 +16,12 @@ _SRC_DIR = os.path.join(_PKG, "csrc")
 _SOURCES = [os.path.join(_SRC_DIR, f) for f in ("lpvmpc.cu", "lpv_qp.cuh", "lpv_h8.cuh", "lpv_h8t.cuh", "lpv_h16t.cuh", "lpv_model.cuh", "lpv_loop.cuh", "lpv_aux.cuh")] + \
            [os.path.join(_ROOT, "include", "lpvmpc.h")]
 
-# --split-compile=0: ptxas works on the kernels in parallel (45 s instead of 2 min 10 s on 8 cores; measured equal in speed)
+# No --split-compile: with it ptxas works on the kernels in parallel (45 s instead of 2 min 25 s) but the result is not
+# reproducible -- two builds of the same sources differ in register allocation, inlining and size (458 k against 485 k SASS
+# lines; the helper-warp H8 kernels came out at 168 or at 255 registers) and the one-QP-per-warp workloads moved by up to
+# 13 % from build to build.  Development builds can pass it through LPVMPC_NVCC_EXTRA.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
-              "--split-compile=0", "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-shared"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-shared"]
 
 ABI_VERSION = 1
 CONTROLLER, PLANNER = 0, 1
