@@ -135,7 +135,7 @@ struct Ctx {
       if (const int k = c.kc0 + (kv ? i : 0); true)
 // the two loops of a Ruiz pass (10 passes per QP: the bulk of setup): independent per stage, but unrolling them is slower
 #ifndef H16_RUIZ_UNROLL
-#define H16_RUIZ_UNROLL 1   // measured: 5 (full) 1.10 ms against 1.035 ms at 1
+#define H16_RUIZ_UNROLL 1   // measured (reproducible builds, same box): 5 (full) 1.003 ms against 0.986 ms at 1; H16_COLD_UNROLL 2: 0.995 ms
 #endif
 #define H16_RUIZ_LOOP(i, k, kv)                                   \
   _Pragma(H16_STR(unroll H16_RUIZ_UNROLL)) for (int i = 0; i <= c.NL; ++i)            \
