@@ -1344,12 +1344,25 @@ __device__ __noinline__ void sync_yd(const Ctx<KIND> c, const bool live, const d
   const double *BE = c.cd(C_BE), *ED = c.cd(C_ED);
   const double cb = alpha * n + (first ? (1.0 - alpha) : 0.0);
   if (n > 0) {
+    const int rg = c.xl ? r : 0;
 #pragma unroll 1
     for (int k = c.k0; k <= N; k += c.ks) {
+      const int o = k * 8 + r, km = k > 0 ? k - 1 : 0;
+      // slab operands up front (see update_info); then rowA_dyn(c, ED, XS, VS, k) on them
+      const double ed = ldg_v(ED + o), yd = ldg_v(YD + o), be = ldg_v(BE + o);
+      const double *gm = c.Gb(km) + rg * 8;
+      const double2 t0 = ldg2_v(gm), t1 = ldg2_v(gm + 2), t2 = ldg2_v(gm + 4), t3 = ldg2_v(gm + 6);
       if (c.xl) {
-        const int o = k * 8 + r;
-        const double ax = rowA_dyn<KIND>(c, ED, XS, VS, k);
-        if (live) YD[o] = YD[o] + rho_eq * (alpha * ax - cb * BE[o]);
+        double ax = ed * XS[k * VS + r];
+        if (k > 0) {
+          double g[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) g[q] = XS[(k - 1) * VS + q];
+          double a0 = t0.x * g[0], a1 = t1.x * g[2], a2 = t2.x * g[4], a3 = t3.x * g[6];
+          a0 = fma(t0.y, g[1], a0); a1 = fma(t1.y, g[3], a1); a2 = fma(t2.y, g[5], a2); a3 = fma(t3.y, g[7], a3);
+          ax += (a0 + a1) + (a2 + a3);
+        }
+        if (live) YD[o] = yd + rho_eq * (alpha * ax - cb * be);
       }
     }
     c.sync();
@@ -1373,8 +1386,16 @@ __device__ __noinline__ void reproject(const Ctx<KIND> c, const bool doit, const
 #pragma unroll 1
   for (int k = c.k0; k <= N; k += c.ks) {
     const int o = k * 8 + r, ov = k * VS + r;
+    // slab operands of the common path up front (see update_info)
+    const int kp = k < N ? k + 1 : N, kg = k < N ? k : N - 1;
+    const double ed0 = ldg_v(ED + o), yd0 = ldg_v(YD + o), qv0 = ldg_v(QV + o);
+    double gc[NX], ydn[NX];
+    {
+      const double *gq = c.Gb(kg);
+#pragma unroll
+      for (int rr = 0; rr < NX; ++rr) { gc[rr] = ldg_v(gq + rr * 8 + r); ydn[rr] = ldg_v(YD + kp * 8 + rr); }
+    }
     if (c.var_live(k)) {
-      const double *gk = c.Gb(k);
       double crd = CR[ov];
       if (new_cr) {
         double acc = c.xl ? ED[o] * BE[o] : 0.0;
@@ -1382,16 +1403,25 @@ __device__ __noinline__ void reproject(const Ctx<KIND> c, const bool doit, const
           double g[8];
 #pragma unroll
           for (int rr = 0; rr < 8; ++rr) g[rr] = (rr < NX) ? BE[(k + 1) * 8 + rr] : 0.0;
-          acc += pcoldot<NX>(gk, r, g);
+          double a0 = 0.0, a1 = 0.0;   // pcoldot<NX>(G_k, r, g) on the column already loaded
+#pragma unroll
+          for (int rr = 0; rr < NX; rr += 2) {
+            a0 = fma(gc[rr], g[rr], a0);
+            if (rr + 1 < NX) a1 = fma(gc[rr + 1], g[rr + 1], a1);
+          }
+          acc += a0 + a1;
         }
         crd = rho_eq * acc;
       }
-      double aty = c.xl ? ED[o] * YD[o] : 0.0;
-      if (k < N) {
-        double g[8];
+      double aty = c.xl ? ed0 * yd0 : 0.0;
+      if (k < N) {   // pcoldot<NX>(G_k, r, y_dyn of stage k + 1) on the operands above
+        double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-        for (int rr = 0; rr < 8; ++rr) g[rr] = (rr < NX) ? YD[(k + 1) * 8 + rr] : 0.0;
-        aty += pcoldot<NX>(gk, r, g);
+        for (int rr = 0; rr < NX; rr += 2) {
+          a0 = fma(gc[rr], ydn[rr], a0);
+          if (rr + 1 < NX) a1 = fma(gc[rr + 1], ydn[rr + 1], a1);
+        }
+        aty += a0 + a1;
       }
       double sin = 0.0;
       if (c.has_in(k)) {
@@ -1400,7 +1430,7 @@ __device__ __noinline__ void reproject(const Ctx<KIND> c, const bool doit, const
         for (int t = 0; t < NT; ++t) sin = fma(c.si(k, t), rt * c.zi(k, t) - c.yi(k, t), sin);
       }
       if (doit) {
-        const double rr = (zsel * crd - aty) - QV[o];
+        const double rr = (zsel * crd - aty) - qv0;
         CR[ov] = crd; R[ov] = rr;
         BV[ov] = fma(sigma, X[ov], rr) + sin;
       }
@@ -1523,34 +1553,55 @@ __device__ __noinline__ bool primal_infeasible(const Ctx<KIND> c, const Info *ip
   const double *X = c.V(V_X);
   const double *BE = c.cd(C_BE), *ED = c.cd(C_ED), *PVX = c.cd(C_PVX);
   const double *PVYI = c.cd(C_PVYI), *E = c.cd(C_E), *EI = c.cd(C_EI), *DINV = c.cd(C_DINV);
-  double *DYD = c.cd(C_DYD), *DYI = c.cd(C_PYI), *XT = c.cd(C_ZT);
+  double *DYD = c.cd(C_DYD), *DYI = c.cd(C_PYI);
+  double *XT = c.V(V_XT);   // [k*VS + q]: the stage vector x~ of the backward sweep, free between two ADMM steps (it was a slab vector: an L2 round trip per read)
   const double ia = 1.0 / alpha, oma = 1.0 - alpha, cb = last_was_first ? 1.0 : alpha;
 #pragma unroll 1
-  for (int k = c.k0; k <= N; k += c.ks) { const int o = k * 8 + r; XT[o] = c.var_live(k) ? (X[k * VS + r] - oma * PVX[o]) * ia : 0.0; }
+  for (int k = c.k0; k <= N; k += c.ks) { const int o = k * 8 + r; XT[k * VS + r] = c.var_live(k) ? (X[k * VS + r] - oma * PVX[o]) * ia : 0.0; }
   c.sync();
   double nrm = 0.0, lhs = 0.0;
+  const int rg = c.xl ? r : 0;   // a row of G that exists (only state lanes use theirs)
 #pragma unroll 1
   for (int k = c.k0; k <= N; k += c.ks) {
     const int o = k * 8 + r;
+    const int km = k > 0 ? k - 1 : 0;
+    // slab operands up front (see update_info)
+    const double ed = ldg_v(ED + o), be = ldg_v(BE + o), e = ldg_v(E + o);
+    const double *gm = c.Gb(km) + rg * 8;
+    const double2 t0 = ldg2_v(gm), t1 = ldg2_v(gm + 2), t2 = ldg2_v(gm + 4), t3 = ldg2_v(gm + 6);
+    double pvyi[NT], ei[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) { pvyi[t] = ldg_v(PVYI + c.ci(k, t)); ei[t] = ldg_v(EI + c.ci(k, t)); }
     double d = 0.0;
-    if (c.xl) d = rho_eq * (alpha * rowA_dyn<KIND>(c, ED, XT, 8, k) - cb * BE[o]);  // equality rows: no projection
+    if (c.xl) {  // equality rows: no projection.  rowA_dyn(c, ED, XT, VS, k) on the operands above
+      double ax = ed * XT[k * VS + r];
+      if (k > 0) {
+        double g[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) g[q] = XT[(k - 1) * VS + q];
+        double a0 = t0.x * g[0], a1 = t1.x * g[2], a2 = t2.x * g[4], a3 = t3.x * g[6];
+        a0 = fma(t0.y, g[1], a0); a1 = fma(t1.y, g[3], a1); a2 = fma(t2.y, g[5], a2); a3 = fma(t3.y, g[7], a3);
+        ax += (a0 + a1) + (a2 + a3);
+      }
+      d = rho_eq * (alpha * ax - cb * be);
+    }
     DYD[o] = d;
     if (c.xl) {
-      nrm = absmax(nrm, unscale ? E[o] * d : d);
-      lhs += BE[o] * ((d > 0) ? d : 0) + BE[o] * ((d < 0) ? d : 0);
+      nrm = absmax(nrm, unscale ? e * d : d);
+      lhs += be * ((d > 0) ? d : 0) + be * ((d < 0) ? d : 0);
     }
     if (c.has_in(k)) {
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
         const int oc = c.ci(k, t);
-        double di = c.yi(k, t) - PVYI[oc];
+        double di = c.yi(k, t) - pvyi[t];
         const double lo = c.lo_of(k, t), up = c.ui(k, t);
         if (up > kInfty * kMinScaling) {
           if (lo < -kInfty * kMinScaling) di = 0.0;
           else di = (di < 0.0) ? di : 0.0;
         } else if (lo < -kInfty * kMinScaling) di = (di > 0.0) ? di : 0.0;
         DYI[oc] = di;
-        nrm = absmax(nrm, unscale ? EI[oc] * di : di);
+        nrm = absmax(nrm, unscale ? ei[t] * di : di);
         lhs += up * ((di > 0) ? di : 0) + lo * ((di < 0) ? di : 0);
       }
     }
@@ -1581,13 +1632,13 @@ __device__ __noinline__ bool dual_infeasible(const Ctx<KIND> c, const Info *ip, 
   const double *QV = c.cd(C_Q), *ED = c.cd(C_ED);
   const double *PVX = c.cd(C_PVX), *D = c.cd(C_D), *DINV = c.cd(C_DINV), *EINV = c.cd(C_EINV), *EIINV = c.cd(C_EIINV);
   const double *PD = c.cd(C_PD), *PO = c.cd(C_PO);
-  double *DX = c.cd(C_PX);
+  double *DX = c.V(V_XT);   // [k*VS + q], as in primal_infeasible (which is done with it: its reductions end in a barrier)
   double nrm = 0.0, qdx = 0.0;
 #pragma unroll 1
   for (int k = c.k0; k <= N; k += c.ks) {
     const int o = k * 8 + r;
     const double dx = c.var_live(k) ? X[k * VS + r] - PVX[o] : 0.0;
-    DX[o] = dx;
+    DX[k * VS + r] = dx;
     nrm = absmax(nrm, unscale ? D[o] * dx : dx);
     qdx += QV[o] * dx;
   }
@@ -1602,18 +1653,18 @@ __device__ __noinline__ bool dual_infeasible(const Ctx<KIND> c, const Info *ip, 
   for (int k = c.k0; k <= N; k += c.ks) {
     const int o = k * 8 + r;
     if (c.var_live(k)) {
-      const double Pdx = rowP<KIND>(c, PD, PO, DX, 8, k);
+      const double Pdx = rowP<KIND>(c, PD, PO, DX, VS, k);
       mx = absmax(mx, unscale ? DINV[o] * Pdx : Pdx);
     }
     if (c.xl) {
-      double v = rowA_dyn<KIND>(c, ED, DX, 8, k);
+      double v = rowA_dyn<KIND>(c, ED, DX, VS, k);
       if (unscale) v = EINV[o] * v;
       if (v > eps * nrm || v < -eps * nrm) viol = 1;
     }
     if (c.has_in(k)) {
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
-        double v = c.si(k, t) * DX[o];
+        double v = c.si(k, t) * DX[k * VS + r];
         if (unscale) v = EIINV[c.ci(k, t)] * v;
         if (((c.ui(k, t) < kInfty * kMinScaling) && (v > eps * nrm)) || ((c.lo_of(k, t) > -kInfty * kMinScaling) && (v < -eps * nrm))) viol = 1;
       }
