@@ -681,7 +681,9 @@ struct lpvmpc_handle {
   char *h_ring = nullptr;      // two pinned result arenas of lpvmpc_solve_host_view (allocated on its first call)
   size_t ring_bytes = 0;
   int ring_slot = 0;
-  bool zc_in = false;          // host API: the kernel reads its inputs from the pinned arena (LPVMPC_ZERO_COPY_IN=1; measured equal to the H2D copy at ctrl4096, off by default)
+  bool zc_in = false;          // host API, solve calls: the kernel reads its inputs from the pinned arena instead of one H2D in front of it (default for the
+                               // H16T kernel: ctrl4096 end to end 1.117 -> 1.081 ms; LPVMPC_ZERO_COPY_IN=0 / 1 overrides.  The one-QP-per-warp kernels walk a serial
+                               // roll-out over their inputs -- a PCIe round trip per stage -- and keep the copy)
   bool zc_out = true;          // host API: the kernel writes its results straight into the pinned arena (LPVMPC_ZERO_COPY_OUT=0: D2H copy)
   cudaStream_t stream = nullptr;
   // The _dev entry points launch on the caller's stream but share per-handle device scratch (work queue, visiting order,
@@ -1307,6 +1309,7 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
   CTRY(cudaMalloc(&h->d_stage, per));
   CTRY(cudaMallocHost(&h->h_stage, per));
   if (const char *e = std::getenv("LPVMPC_ZERO_COPY_OUT")) h->zc_out = std::atoi(e) != 0;
+  h->zc_in = (h->variant == 8);
   if (const char *e = std::getenv("LPVMPC_ZERO_COPY_IN")) h->zc_in = std::atoi(e) != 0;
 #undef CTRY
   *out = h;
@@ -1437,6 +1440,7 @@ static int run_host(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, int32_t *
   if (B == 0) return LPVMPC_OK;
   ON_DEVICE(h);
   lpvmpc_args dev = *a;
+  const bool zin = solve && h->zc_in;
   const std::vector<Field> fields = staged_fields(h);
   char *ring = nullptr;   // this call's result arena (view mode)
   if (views) {
@@ -1462,7 +1466,7 @@ static int run_host(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, int32_t *
       if (!f.output) jobs.push_back({h->h_stage + off, cptr_at(a, f.off_args), bytes});
       // results: written by the kernel through the pinned arena's device mapping (posted PCIe writes behind the compute:
       // no D2H copy after the kernel); the kernels only ever write their outputs
-      ptr_at(&dev, f.off_args) = ((f.output ? h->zc_out : h->zc_in) ? ((f.output && ring) ? ring - out_begin : h->h_stage) : h->d_stage) + off;
+      ptr_at(&dev, f.off_args) = ((f.output ? h->zc_out : zin) ? ((f.output && ring) ? ring - out_begin : h->h_stage) : h->d_stage) + off;
       off += align256(bytes);
       if (!f.output) in_end = off;
     }
@@ -1472,7 +1476,7 @@ static int run_host(lpvmpc_handle *h, int32_t B, const lpvmpc_args *a, int32_t *
   int32_t *d_se = nullptr;
   if (sched_err) { d_se = reinterpret_cast<int32_t *>(h->d_stage + off); off += align256(sizeof(int32_t) * (size_t)B); }
   if (off > h->stage_bytes) return fail(h, LPVMPC_E_ARG, "staging overflow");
-  if (in_end && !h->zc_in) CUDA_TRY(h, cudaMemcpyAsync(h->d_stage, h->h_stage, in_end, cudaMemcpyHostToDevice, h->stream));
+  if (in_end && !zin) CUDA_TRY(h, cudaMemcpyAsync(h->d_stage, h->h_stage, in_end, cudaMemcpyHostToDevice, h->stream));
   rc = solve ? lpvmpc_solve_dev(h, B, &dev, h->stream) : lpvmpc_schedule_dev(h, B, &dev, d_se, h->stream);
   if (rc) return rc;
   const size_t d2h_begin = (h->zc_out && !first_out) ? se_off : out_begin;   // zero-copy results: only sched_err comes back by copy

@@ -639,6 +639,8 @@ def run_ours(args):
                   "smem_bytes_per_qp": info0["smem_bytes_per_qp"]},
         "e2e": {"value": e2e_value, "unit": "QP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * e2e_total / args.steps,
+                "h2d": ("kernel reads its inputs from the pinned host arena the call packed them into (zero-copy: the bytes cross PCIe inside the launch)"
+                        if (os.environ.get("LPVMPC_ZERO_COPY_IN", "1" if info0["variant"] == 8 else "0") != "0") else "one cudaMemcpyAsync in front of the kernel"),
                 "d2h": ("kernel writes the results into the pinned host arena (zero-copy, posted PCIe writes behind the compute)"
                         if os.environ.get("LPVMPC_ZERO_COPY_OUT", "1") != "0" else "one cudaMemcpyAsync after the kernel"),
                 "results": "numpy views of the handle's pinned result arenas (lpvmpc_solve_host_view; two arenas used in turn)",
