@@ -55,12 +55,19 @@ __device__ unsigned long long g_phase_cycles[16];
 #define H8_PH_ARGS
 #endif
 
-#ifndef H8_TW_UNROLL
-#define H8_TW_UNROLL 2   // unroll factor of the chain loops of the twisted sweeps (2 against 1: plan16384 294.9 -> 292.1 ms, ctrl1024N100 25.23 -> 25.16 ms, same box, reproducible builds)
+// Unroll factors of the chain loops of the twisted sweeps, per problem kind (the loops sit in templates on KIND).  Measured with
+// reproducible builds on one box: planner (3 CTAs per SM share the instruction cache) 1: 285.8, 2: 280.9, 4: 275.5, 5: 278.9,
+// 8: 291.0, 10: 282.5 ms per plan16384; long-horizon controller (1 CTA per SM) 1: 24.72, 2: 24.57, 4: 23.66, 5: 23.48,
+// 8: 23.35, 10: 23.27 ms per ctrl1024N100.
+#ifndef H8_TW_UNROLL_PLAN
+#define H8_TW_UNROLL_PLAN 4
+#endif
+#ifndef H8_TW_UNROLL_CTRL
+#define H8_TW_UNROLL_CTRL 10
 #endif
 #define H8_STR2(x) #x
 #define H8_STR(x) H8_STR2(x)
-#define H8_TW_PRAGMA _Pragma(H8_STR(unroll H8_TW_UNROLL))
+#define H8_TW_PRAGMA _Pragma(H8_STR(unroll (KIND == LPVMPC_PLANNER ? H8_TW_UNROLL_PLAN : H8_TW_UNROLL_CTRL)))
 constexpr int TKS = 128;  // doubles per stage of the factor: T_k (64) then K_{k+1} (64)
 constexpr int VS = 56;    // doubles per stage of the stage vectors
 enum { V_B = 0, V_X = 8, V_R = 16, V_XS = 24, V_DG = 32, V_CR = 40, V_XT = 48 };   // XT: x~ of the backward sweep (helper-warp kernels)
