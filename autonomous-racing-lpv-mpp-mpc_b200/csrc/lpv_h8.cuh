@@ -65,8 +65,12 @@ __device__ unsigned long long g_phase_cycles[16];
 #ifndef H8_TW_UNROLL_CTRL
 #define H8_TW_UNROLL_CTRL 10
 #endif
+#ifndef H8_COLD_UNROLL
+#define H8_COLD_UNROLL 1   // unroll factor of the cold per-stage loops that request their slab operands up front (measured, reproducible builds, same box: 2: ctrl1024N100 23.27 -> 23.64 ms, plan16384 274.7 -> 282.4 ms; 4: 23.85 / 303.9 ms)
+#endif
 #define H8_STR2(x) #x
 #define H8_STR(x) H8_STR2(x)
+#define H8_COLD_PRAGMA _Pragma(H8_STR(unroll H8_COLD_UNROLL))
 #define H8_TW_PRAGMA _Pragma(H8_STR(unroll (KIND == LPVMPC_PLANNER ? H8_TW_UNROLL_PLAN : H8_TW_UNROLL_CTRL)))
 constexpr int TKS = 128;  // doubles per stage of the factor: T_k (64) then K_{k+1} (64)
 constexpr int VS = 56;    // doubles per stage of the stage vectors
@@ -1352,7 +1356,7 @@ __device__ __noinline__ void sync_yd(const Ctx<KIND> c, const bool live, const d
   const double cb = alpha * n + (first ? (1.0 - alpha) : 0.0);
   if (n > 0) {
     const int rg = c.xl ? r : 0;
-#pragma unroll 1
+H8_COLD_PRAGMA
     for (int k = c.k0; k <= N; k += c.ks) {
       const int o = k * 8 + r, km = k > 0 ? k - 1 : 0;
       // slab operands up front (see update_info); then rowA_dyn(c, ED, XS, VS, k) on them
@@ -1390,7 +1394,7 @@ __device__ __noinline__ void reproject(const Ctx<KIND> c, const bool doit, const
   double *BV = c.V(V_B), *R = c.V(V_R), *CR = c.V(V_CR);
   const double *X = c.V(V_X);
   const double *YD = c.cd(C_YD), *BE = c.cd(C_BE), *ED = c.cd(C_ED), *QV = c.cd(C_Q);
-#pragma unroll 1
+H8_COLD_PRAGMA
   for (int k = c.k0; k <= N; k += c.ks) {
     const int o = k * 8 + r, ov = k * VS + r;
     // slab operands of the common path up front (see update_info)
@@ -1462,7 +1466,7 @@ __device__ __noinline__ void update_info(const Ctx<KIND> c, Info *ip, const doub
   double a_rp = 0, a_z = 0, a_Ax = 0, b_rp = 0, b_z = 0, b_Ax = 0;
   double a_rd = 0, a_q = 0, a_Aty = 0, a_Px = 0, b_rd = 0, b_q = 0, b_Aty = 0, b_Px = 0;
   const int rg = c.xl ? r : 0;   // a row of G that exists (only state lanes use theirs)
-#pragma unroll 1
+H8_COLD_PRAGMA
   for (int k = c.k0; k <= N; k += c.ks) {
     const int o = k * 8 + r, ov = k * VS + r;
     const int km = k > 0 ? k - 1 : 0, kp = k < N ? k + 1 : N, kg = k < N ? k : N - 1;
@@ -1568,7 +1572,7 @@ __device__ __noinline__ bool primal_infeasible(const Ctx<KIND> c, const Info *ip
   c.sync();
   double nrm = 0.0, lhs = 0.0;
   const int rg = c.xl ? r : 0;   // a row of G that exists (only state lanes use theirs)
-#pragma unroll 1
+H8_COLD_PRAGMA
   for (int k = c.k0; k <= N; k += c.ks) {
     const int o = k * 8 + r;
     const int km = k > 0 ? k - 1 : 0;
