@@ -2303,7 +2303,7 @@ constexpr int kSyncEvery = 25;  // y_dyn is brought up to date and r re-projecte
 
 // ST: factor streamed from the slab (one QP per warp, one warp per CTA: every staging address is warp-uniform)
 // TW: twisted factorisation (one QP per warp, resident factor, even N: checked by the host)
-// NH: helper warps (TW only; one QP per CTA: warp 0 runs the solver, warps 1 .. NH the element-wise updates of the ADMM step)
+// NH: helper warps (TW only; one QP per CTA: warp 0 runs the chains, warps 1 .. NH the element-wise updates of the ADMM step, all of them the cold phases)
 template <int KIND, int QPW, bool ST, bool TW = false, int NH = 0>
 __global__ void __launch_bounds__(NH ? 32 * (NH + 1) : 64, 1) lpv_solve_h8_kernel(const __grid_constant__ H8Params p) {
   static_assert(!ST || QPW == 1, "the streamed kernel holds one QP per warp");

@@ -898,6 +898,7 @@ int launch_h8(lpvmpc_handle *h, const Params &p, cudaStream_t s) {
   else if (h->qpw == 2) h8_launch<KIND, 2>(grid, 32 * h->wpc, h->ws_bytes, s, hp);
   else if (h->twisted && h->helpers) {
     if (KIND == LPVMPC_PLANNER) h8h_launch<LPVMPC_PLANNER, 1>(grid, h->ws_bytes, s, hp);
+    else if (h->helpers == 7) h8h_launch<LPVMPC_CONTROLLER, 7>(grid, h->ws_bytes, s, hp);
     else h8h_launch<LPVMPC_CONTROLLER, 3>(grid, h->ws_bytes, s, hp);
   }
   else if (h->twisted) h8w_launch<KIND>(grid, 32 * h->wpc, h->ws_bytes, s, hp);
@@ -1224,12 +1225,13 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
       static const bool tw_on = [] { const char *e = std::getenv("LPVMPC_H8_TWISTED"); return !e || std::atoi(e) != 0; }();
       h->twisted = tw_on && (cfg->N % 2 == 0) && cfg->N >= 4;
       // helper warps for the element-wise updates (LPVMPC_H8_HELPERS=0: none): one QP per CTA, so the choice only stands when
-      // it was one warp per CTA anyway.  Controller (long horizons, one CTA per SM): 3 helpers.  Planner (3 CTAs per SM): ONE --
+      // it was one warp per CTA anyway.  Controller (long horizons, one CTA per SM): 7 helpers (the cold phases split 32 ways).  Planner (3 CTAs per SM): ONE --
       // a warp's registers live in its SM sub-partition (16 K registers), so at 224-255 registers per thread an SM holds 8
       // warps: 3 CTAs of 2.  3 CTAs of 3 or 4 warps need <= 168 registers: with that cap forced (__launch_bounds__(96, 4) /
       // (128, 3): 300 bytes of spills) plan16384 takes 319 / 315 ms against 297 ms with one helper at 255 registers, same box
       static const bool hw_on = [] { const char *e = std::getenv("LPVMPC_H8_HELPERS"); return !e || std::atoi(e) != 0; }();
-      h->helpers = (h->twisted && hw_on && h->wpc == 1) ? (ctrl ? 3 : 1) : 0;
+      static const int ctrl_nh = [] { const char *e = std::getenv("LPVMPC_H8_CTRL_HELPERS"); return (e && std::atoi(e) == 3) ? 3 : 7; }();   // LPVMPC_H8_CTRL_HELPERS=3: three helpers (ctrl1024N100 23.23 ms against 22.44 ms with seven, same binary)
+      h->helpers = (h->twisted && hw_on && h->wpc == 1) ? (ctrl ? ctrl_nh : 1) : 0;
       if (h->helpers) {
         const size_t ws2 = h->ws_bytes + 512 + 1536;   // the helpers' mailbox (lpv::h8::HwShared) behind the gather buffers, then the CTA's reduction scratch (4 warps x 16 doubles)
         int ctas = (int)(sm_bytes / (ws2 + 1024));
@@ -1238,7 +1240,7 @@ int lpvmpc_create(const lpvmpc_cfg *cfg, lpvmpc_handle **out) {
         if (ctas > by_regs) ctas = by_regs;
         if (ctas >= best_ctas) {   // never at the price of fewer QPs per SM
           h->ws_bytes = ws2; h->grid_cap = h->sm_count * (ctas < 1 ? 1 : ctas);
-          CTRY(ctrl ? (h8h_attr<LPVMPC_CONTROLLER, 3>(h->ws_bytes)) : (h8h_attr<LPVMPC_PLANNER, 1>(h->ws_bytes)));
+          CTRY(ctrl ? (h->helpers == 7 ? h8h_attr<LPVMPC_CONTROLLER, 7>(h->ws_bytes) : h8h_attr<LPVMPC_CONTROLLER, 3>(h->ws_bytes)) : (h8h_attr<LPVMPC_PLANNER, 1>(h->ws_bytes)));
         } else h->helpers = 0;
       }
       if (h->helpers) {}
