@@ -75,6 +75,9 @@ __device__ unsigned long long g_phase_cycles[16];
 #define H8_HELPER_UNROLL 1   // unroll factor of the helpers' two-rounds-at-a-time loop (2: ctrl1024N100 23.27 -> 23.15 ms, plan16384 275.3 -> 277.5 ms)
 #endif
 #define H8_HELPER_PRAGMA _Pragma(H8_STR(unroll H8_HELPER_UNROLL))
+#ifndef H8_HELPER_SINGLES
+#define H8_HELPER_SINGLES 4   // from this many helper warps on, the helpers update one round at a time
+#endif
 #define H8_TW_PRAGMA _Pragma(H8_STR(unroll (KIND == LPVMPC_PLANNER ? H8_TW_UNROLL_PLAN : H8_TW_UNROLL_CTRL)))
 constexpr int TKS = 128;  // doubles per stage of the factor: T_k (64) then K_{k+1} (64)
 constexpr int VS = 56;    // doubles per stage of the stage vectors
@@ -1256,8 +1259,10 @@ __device__ __forceinline__ void helper_iter(const Hot<KIND> &h, const Upd<KIND> 
     while (ld_acq(hws + (uint32_t)offsetof(HwShared, prog)) < need) {}
   };
   int t0 = (hw - 1) * 4;
+  // (with many helpers -- long horizons, one CTA per SM -- every helper has slack: single rounds, each as soon as its x~ are
+  // there, so that after the chain's last step only ONE round is outstanding instead of a pair that waited for its later half)
 H8_HELPER_PRAGMA
-  for (; t0 + U + 3 <= N; t0 += 2 * U) {   // two full rounds
+  for (; nh < H8_HELPER_SINGLES && t0 + U + 3 <= N; t0 += 2 * U) {   // two full rounds
     wait_for(t0 + U + 3);
     const int ka = stage_of(t0 + g), kb = stage_of(t0 + U + g);
     const uint32_t va = h.v + (uint32_t)ka * VB, ia = h.ib + (uint32_t)ka * h.istr, la = h.il + (uint32_t)ka * h.istr;
