@@ -75,6 +75,9 @@ __device__ unsigned long long g_phase_cycles[16];
 #define H8_HELPER_UNROLL 1   // unroll factor of the helpers' two-rounds-at-a-time loop (2: ctrl1024N100 23.27 -> 23.15 ms, plan16384 275.3 -> 277.5 ms)
 #endif
 #define H8_HELPER_PRAGMA _Pragma(H8_STR(unroll H8_HELPER_UNROLL))
+#ifndef H8_HELPER_TRIPLE
+#define H8_HELPER_TRIPLE 0   // 1: the helpers take three rounds at a time where they can (measured: plan16384 275.7 -> 286.9 ms: the third round delays the start of the other two)
+#endif
 #ifndef H8_HELPER_SINGLES
 #define H8_HELPER_SINGLES 4   // from this many helper warps on, the helpers update one round at a time
 #endif
@@ -1259,6 +1262,30 @@ __device__ __forceinline__ void helper_iter(const Hot<KIND> &h, const Upd<KIND> 
     while (ld_acq(hws + (uint32_t)offsetof(HwShared, prog)) < need) {}
   };
   int t0 = (hw - 1) * 4;
+#if H8_HELPER_TRIPLE
+#pragma unroll 1
+  for (; nh < H8_HELPER_SINGLES && t0 + 2 * U + 3 <= N; t0 += 3 * U) {   // three full rounds: three independent chains
+    wait_for(t0 + 2 * U + 3);
+    const int ka = stage_of(t0 + g), kb = stage_of(t0 + U + g), kc = stage_of(t0 + 2 * U + g);
+    const uint32_t va = h.v + (uint32_t)ka * VB, ia = h.ib + (uint32_t)ka * h.istr, la = h.il + (uint32_t)ka * h.istr;
+    const uint32_t vb = h.v + (uint32_t)kb * VB, ib = h.ib + (uint32_t)kb * h.istr, lb = h.il + (uint32_t)kb * h.istr;
+    const uint32_t vc = h.v + (uint32_t)kc * VB, ic = h.ib + (uint32_t)kc * h.istr, lc = h.il + (uint32_t)kc * h.istr;
+    UpdIn ina, inb, inc;
+    update_loads<KIND>(va, ia, la, h.pm + (uint32_t)ka * h.pstr, h.pm2 + (uint32_t)ka * h.pstr, ina);
+    update_loads<KIND>(vb, ib, lb, h.pm + (uint32_t)kb * h.pstr, h.pm2 + (uint32_t)kb * h.pstr, inb);
+    update_loads<KIND>(vc, ic, lc, h.pm + (uint32_t)kc * h.pstr, h.pm2 + (uint32_t)kc * h.pstr, inc);
+    const double xa1 = lds<V_XT * 8>(va), xam = (ka > 0) ? lds<V_XT * 8>(va - VB) : 0.0, xap = (ka < N) ? lds<V_XT * 8>(va + VB) : 0.0;
+    const double xb1 = lds<V_XT * 8>(vb), xbm = (kb > 0) ? lds<V_XT * 8>(vb - VB) : 0.0, xbp = (kb < N) ? lds<V_XT * 8>(vb + VB) : 0.0;
+    const double xc1 = lds<V_XT * 8>(vc), xcm = (kc > 0) ? lds<V_XT * 8>(vc - VB) : 0.0, xcp = (kc < N) ? lds<V_XT * 8>(vc + VB) : 0.0;
+    UpdMid qa, qb, qc;
+    update_part1<KIND>(u, ka, ia, ina, xa1, xam, xap, qa);
+    update_part1<KIND>(u, kb, ib, inb, xb1, xbm, xbp, qb);
+    update_part1<KIND>(u, kc, ic, inc, xc1, xcm, xcp, qc);
+    update_part2<KIND>(u, va, xa1, qa);
+    update_part2<KIND>(u, vb, xb1, qb);
+    update_part2<KIND>(u, vc, xc1, qc);
+  }
+#endif
   // (with many helpers -- long horizons, one CTA per SM -- every helper has slack: single rounds, each as soon as its x~ are
   // there, so that after the chain's last step only ONE round is outstanding instead of a pair that waited for its later half)
 H8_HELPER_PRAGMA
